@@ -1,0 +1,74 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_golden(name):
+    """tests/golden/<name>.npz -> {group: {key: torch tensor}} (None for the NaN 'no grad' marker)."""
+    raw = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    out = {}
+    for k in raw.files:
+        group, key = k.split("/", 1)
+        arr = raw[k]
+        t = torch.from_numpy(np.array(arr))
+        if group == "grads" and t.numel() == 1 and torch.isnan(t).all():
+            t = None
+        out.setdefault(group, {})[key] = t
+    return out
+
+
+def oracle_graph(arrays):
+    """golden 'graph' group -> the dict the oracle consumes (dgl.batch restatement)."""
+    from oracle import reference_ops as R
+    from immunostruct_b200.synthetic import split_graphs
+    return R.dgl_batch(split_graphs(arrays))
+
+
+def rel_err(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def assert_grads_close(got: dict, ref: dict, tol: float, floor_frac: float = 1e-2):
+    """Per-parameter max-abs error <= tol * max(|ref|max of that parameter, floor_frac * largest
+    gradient magnitude of the whole model).  The floor keeps parameters whose true gradient is
+    exactly zero (e.g. the key bias under softmax shift-invariance) from being compared on noise.
+    ``ref[k] is None`` demands that the product also reports NO gradient (``None``)."""
+    gmax = max(float(v.abs().max()) for v in ref.values() if v is not None)
+    bad = []
+    for k, r in ref.items():
+        g = got[k]
+        if r is None:
+            if g is not None:
+                bad.append((k, "expected grad None"))
+            continue
+        if g is None:
+            bad.append((k, "missing grad"))
+            continue
+        err = float((g.detach().double().cpu() - r.double()).abs().max())
+        lim = tol * max(float(r.abs().max()), floor_frac * gmax)
+        if not err <= lim:
+            bad.append((k, f"err {err:.3e} > {lim:.3e}"))
+    assert not bad, bad
