@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Headline benchmark: pMHC graphs/s of the ImmunoStruct hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): HybridModelv2 inference (eval, no_grad) over synthetic pMHC
+graphs of the named shape (200 residues, directed 10-NN contacts, 283x21 sequence one-hots), batch
+512 per GPU, fp32.  A "step" is one pass of the hot path over one batch of 512 graphs: on-device
+collation (CSR + CSC + segment offsets) -> 6 EGNN layers -> per-graph attention + mean pool -> VAE
+and property branches -> fusion attention -> classifier -> sigmoid.
+  * ``value``  : graphs/s with inputs resident in HBM (a pool of batches larger than L2 is cycled);
+  * ``e2e``    : same metric through the public API from pinned HOST buffers (GraphBatch.to(device),
+                 model(...), probabilities copied back) -- H2D and D2H inside the timed region;
+  * ``train``  : fwd + bwd + Adam step (BCE_loss with sequence loss) at the same batch per GPU, with
+                 the NCCL gradient all-reduce when N > 1 (weak scaling);
+  * ``roofline``: the dominant kernel (EGNN edge forward) timed alone with CUDA events;
+  * ``cpu_baseline``: the CPU oracle port of the same forward on this box's host cores (bounded sample).
+``--impl reference`` times the reference's CPU path (oracle port; the reference is pure Python +
+dgl/torch_geometric and cannot travel to this box) with all host threads on the same metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 512
+N_NODES, KNN = 200, 10
+VAE_IN = 5943
+POOL = 8                    # resident input batches cycled through (8 x 42 MB > 126 MB of L2)
+FLOP_PER_EDGE_EDGE_KERNEL = 2 * 64 * 64 * 2 + 2 * 64      # two 64x64 per-edge GEMMs + the w4 dot
+BYTES_PER_EDGE_EDGE_KERNEL = 2 * 256 + 3 * 4 + 4           # P[src] + Q[dst] rows (L2-resident gathers) + ids + attr
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12          # 74.4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+def make_pool(batch, n_batches, seed, device):
+    from immunostruct_b200.synthetic import synthetic_dense, synthetic_graph_arrays
+    pool = []
+    for i in range(n_batches):
+        arr = synthetic_graph_arrays(batch, N_NODES, KNN, seed=seed + 31 * i, device=device)
+        dense = synthetic_dense(batch, seed=seed + 31 * i, device=device)
+        pool.append((arr, dense))
+    return pool
+
+
+def oracle_inference(params, arr, dense, eps):
+    from immunostruct_b200.synthetic import split_graphs
+    from oracle import reference_ops as R
+    with torch.no_grad():
+        g = R.dgl_batch(split_graphs(arr))
+        out = R.hybrid_forward(params, g, dense["seq"], dense["prop"], eps)
+        return torch.sigmoid(out[3]).squeeze()
+
+
+def cpu_reference_arm(args):
+    """The reference's CPU implementation of the path (oracle port), all host threads."""
+    import immunostruct_b200 as I
+    torch.set_num_threads(os.cpu_count() or 1)
+    sample = 64
+    pool = make_pool(sample, 2, seed=1, device="cpu")
+    torch.manual_seed(1)
+    params = {k: v.detach() for k, v in I.model_map["HybridModelv2"](vae_input_dim=VAE_IN, device="cpu").state_dict().items()}
+    eps = torch.randn(sample, 32)
+    for i in range(args.warmup):
+        oracle_inference(params, *pool[i % 2], eps)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        oracle_inference(params, *pool[i % 2], eps)
+    dt = time.perf_counter() - t0
+    v = sample * args.steps / dt
+    cores = torch.get_num_threads()
+    print(json.dumps({
+        "impl": "reference", "metric": "pMHC graphs/sec (HybridModelv2 inference, fp32)", "value": v,
+        "unit": "graphs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "IEDB HybridModelv2 inference, batch 512 per GPU, 200-node 10-NN graphs, fp32",
+                   "step_sample": f"{sample} graphs per step (bounded sample of the 512-graph batch)"},
+        "cpu_baseline": {"value": v, "unit": "graphs/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} x {sample}-graph batches, oracle/reference_ops.py hybrid_forward, torch CPU"},
+        "e2e": {"value": v, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            cpu_reference_arm(args)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+
+    import torch.distributed as dist
+    import immunostruct_b200 as I
+    from immunostruct_b200 import _C
+    from immunostruct_b200.distributed import GradientAllReducer, broadcast_parameters
+    from immunostruct_b200.graph import GraphBatch
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, W = args.batch, args.steps, args.warmup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    torch.manual_seed(1)
+    model = I.model_map["HybridModelv2"](vae_input_dim=VAE_IN, device=dev).to(dev)
+    broadcast_parameters(model)
+    pool = make_pool(B, POOL, seed=1 + 1000 * rank, device=dev)
+    keys = ("x", "src", "dst", "edge_attr", "node_counts", "edge_counts")
+
+    def infer_step(arr, dense):
+        gb = GraphBatch.from_arrays(*(arr[k] for k in keys), max_nodes=N_NODES)
+        out = model(gb, dense["seq"], dense["prop"])[3]
+        return torch.sigmoid(out).squeeze()
+
+    # ---- device-resident inference throughput (the headline `value`) ---------------------------
+    model.eval()
+    launches0 = None
+    with torch.no_grad():
+        for i in range(W):
+            infer_step(*pool[i % POOL])
+        barrier()
+        launches0 = _C.LAUNCHES
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clk:
+            e0.record()
+            for i in range(K):
+                probs = infer_step(*pool[i % POOL])
+            e1.record()
+            barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = _C.LAUNCHES - launches0
+    value = world * B * K / (ms / 1e3)
+
+    # ---- end to end from pinned host buffers through the public API -----------------------------
+    host = []
+    for arr, dense in pool[:4]:
+        gbh = GraphBatch.from_arrays(*(arr[k].cpu() for k in keys), max_nodes=N_NODES).pin_memory()
+        host.append((gbh, dense["seq"].cpu().pin_memory(), dense["prop"].cpu().pin_memory()))
+    h2d = sum(t.numel() * t.element_size() for t in (host[0][0].ndata["x"], host[0][0]._src_local, host[0][0]._dst_local,
+                                                     host[0][0].edata["edge_attr"], host[0][0]._node_counts,
+                                                     host[0][0]._edge_counts, host[0][1], host[0][2]))
+    out_host = torch.empty(B, pin_memory=True)
+
+    def e2e_step(item):
+        gbh, seq, prop = item
+        gb = gbh.to(dev, non_blocking=True)
+        out = model(gb, seq.to(dev, non_blocking=True), prop.to(dev, non_blocking=True))[3]
+        out_host.copy_(torch.sigmoid(out).squeeze(), non_blocking=True)
+
+    with torch.no_grad():
+        for i in range(W):
+            e2e_step(host[i % 4])
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            e2e_step(host[i % 4])
+        e1.record()
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * B * K / (ms_e2e / 1e3)
+
+    # ---- training step: fwd + bwd + Adam (+ NCCL gradient all-reduce) ---------------------------
+    train = None
+    if not args.no_train:
+        model.train()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+        losses = I.Losses(VAE_IN, [0.81, 0.19], sequence=True)
+        reducer = GradientAllReducer(model.parameters())
+        kt = max(3, min(K, 10))
+
+        def train_step(arr, dense):
+            gb = GraphBatch.from_arrays(*(arr[k] for k in keys), max_nodes=N_NODES)
+            opt.zero_grad(set_to_none=True)
+            recon, mu, logvar, out = model(gb, dense["seq"], dense["prop"])
+            loss = losses.BCE_loss(recon, dense["seq"], mu, logvar, out, dense["target"])
+            loss.backward()
+            reducer.step()
+            opt.step()
+            return loss
+
+        for i in range(W):
+            train_step(*pool[i % POOL])
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(kt):
+            loss = train_step(*pool[i % POOL])
+        e1.record()
+        barrier()
+        ms_t = max_over_ranks(e0.elapsed_time(e1))
+        train = {"value": world * B * kt / (ms_t / 1e3), "unit": "graphs/s", "steps": kt, "ms_per_step": ms_t / kt,
+                 "global_batch": world * B, "optimizer": "Adam", "loss": "BCE_loss(sequence=True)",
+                 "final_loss": float(loss), "allreduce_bytes": reducer.nbytes}
+        model.eval()
+
+    # ---- roofline of the dominant kernel (EGNN edge forward), timed alone ------------------------
+    roofline = None
+    if rank == 0:
+        arr, dense = pool[0]
+        gb = GraphBatch.from_arrays(*(arr[k] for k in keys), max_nodes=N_NODES)
+        layer = model.GCN_layers[1]
+        W1, b1, W2, b2, W3, b3, w4 = [t.detach().contiguous() for t in layer.kernel_params()[:7]]
+        n, e = gb.n_nodes, gb.n_edges
+        h = torch.randn(n, 64, device=dev)
+        PQ, hn, xo = torch.empty(n, 128, device=dev), torch.empty(n, 64, device=dev), torch.empty(n, 3, device=dev)
+        x = arr["x"][:, 20:]
+        _C.egnn_node_pre_fwd(h, W1, b1, PQ)
+        flush = torch.empty(64 * 1024 * 1024, device=dev)          # 256 MB > L2
+        times = []
+        for it in range(3 + 10):
+            flush.zero_()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            _C.egnn_edge_fwd(gb, PQ, x, arr["edge_attr"], 64, W1, W2, b2, W3, b3, w4, True, hn, xo)
+            s1.record()
+            torch.cuda.synchronize()
+            if it >= 3:
+                times.append(s0.elapsed_time(s1))
+        t_k = statistics.mean(times) / 1e3
+        hbm_peak, src = measured_peaks()
+        tflops = e * FLOP_PER_EDGE_EDGE_KERNEL / t_k / 1e12
+        gbs = (e * BYTES_PER_EDGE_EDGE_KERNEL + n * (256 + 12 + 12 + 4)) / t_k / 1e9
+        roofline = {"kernel": "is::edge_fwd_kernel<true> (EGNN edge forward, fp32 SIMT)", "bound": "fp32_fma",
+                    "achieved": tflops, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tflops / FP32_PEAK_TFLOPS,
+                    "traffic": None, "launch_ms": t_k * 1e3, "edges_per_launch": e,
+                    "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": src},
+                    "note": "compute-bound on the FP32 pipe (SURVEY 8(d)); peak = 148 SM x 128 FMA x 2 x 1.965 GHz"}
+
+    # ---- CPU baseline (oracle port) on this box's host cores, rank 0 at N=1 only ------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        sample = 64
+        cpool = make_pool(sample, 1, seed=1, device="cpu")
+        params = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        eps = torch.randn(sample, 32)
+        oracle_inference(params, *cpool[0], eps)
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < 3 or time.perf_counter() - t0 < 10.0:
+            ref_probs = oracle_inference(params, *cpool[0], eps)
+            reps += 1
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": sample * reps / dt, "unit": "graphs/s", "cores": torch.get_num_threads(),
+                        "kind": "port", "sample": f"{reps} x {sample}-graph batches (same graph shape), "
+                                                  "oracle/reference_ops.py hybrid_forward, torch CPU fp32"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "pMHC graphs/sec (HybridModelv2 inference, fp32)", "value": value, "unit": "graphs/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "IEDB HybridModelv2 inference, batch 512 per GPU, 200-node 10-NN graphs, "
+                                   "283x21 sequence, fp32 (BASELINE configs[1])",
+                       "batch_per_gpu": B, "nodes_per_graph": N_NODES, "edges_per_graph": N_NODES * KNN,
+                       "parallelism": f"dp{world}", "l2": f"{POOL} resident input batches (~42 MB each) cycled: inputs > L2"},
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": "graphs/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": B * 4},
+            "gpu_launches": launches,
+            "train": train, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

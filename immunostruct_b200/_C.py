@@ -1,0 +1,236 @@
+"""ctypes binding of ``libimmunostruct_b200.so`` (the C ABI declared in include/immunostruct_b200.h).
+
+Every function here takes torch CUDA tensors, checks device / dtype / layout, and enqueues the
+kernel on torch's current stream.  There is NO CPU fallback: a missing library or a CPU tensor
+raises.  The caller owns (pre-allocates) every output and scratch buffer.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+from .build import LIB_PATH
+
+_lib = None
+
+_i64, _i32, _f32, _vp = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+
+
+class ExtensionMissing(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ExtensionMissing(
+                f"{LIB_PATH} not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). immunostruct_b200 has no CPU or eager fallback.")
+        _lib = ctypes.CDLL(LIB_PATH)
+    return _lib
+
+
+def exported_symbols():
+    """Names declared in include/immunostruct_b200.h (used by the CPU symbol-presence test)."""
+    return ["is_num_sms", "is_egnn_node_grid", "is_egnn_edge_bwd_grid", "is_attn_max_nodes",
+            "is_loss_num_partials", "is_collate_csr", "is_egnn_node_pre_fwd", "is_egnn_edge_fwd",
+            "is_egnn_node_post_fwd", "is_egnn_node_post_bwd", "is_egnn_edge_bwd", "is_egnn_node_pre_bwd",
+            "is_reduce_partials", "is_attn_pool_fwd", "is_attn_pool_bwd", "is_fusion_attn_fwd",
+            "is_fusion_attn_bwd", "is_loss_fwd", "is_loss_bwd"]
+
+
+def _check(rc: int, name: str):
+    if rc != 0:
+        kind = {-1: "bad argument", -2: "unsupported size"}.get(rc, f"cudaError {rc}")
+        raise RuntimeError(f"{name} failed: {kind}")
+
+
+def _t(t, dtype, name, contiguous=True):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (immunostruct_b200 has no CPU path), got {t.device}")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if contiguous and not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous tensor")
+    return _vp(t.data_ptr())
+
+
+def _rows(t, name):
+    """[n, k] fp32 view whose rows are contiguous (inner stride 1); returns (ptr, leading dim)."""
+    if not t.is_cuda or t.dtype != torch.float32 or t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise ValueError(f"{name}: expected a CUDA fp32 [n,k] tensor with unit inner stride")
+    return _vp(t.data_ptr()), _i64(t.stride(0))
+
+
+def _stream():
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+LAUNCHES = 0          # number of immunostruct_b200 kernels enqueued so far (bench.py reports the delta)
+_KERNELS_PER_CALL = {"is_collate_csr": 2, "is_loss_fwd": 2, "is_loss_bwd": 2}
+
+
+def _call(name, *args):
+    global LAUNCHES
+    fn = getattr(lib(), name)
+    fn.restype = ctypes.c_int
+    _check(fn(*args), name)
+    LAUNCHES += _KERNELS_PER_CALL.get(name, 1)
+
+
+# ---- sizing queries ----------------------------------------------------------------------------
+def num_sms() -> int:
+    return int(lib().is_num_sms())
+
+
+def egnn_node_grid(n_nodes: int) -> int:
+    fn = lib().is_egnn_node_grid
+    fn.argtypes = [_i64]
+    return int(fn(n_nodes))
+
+
+def egnn_edge_bwd_grid(n_nodes: int) -> int:
+    fn = lib().is_egnn_edge_bwd_grid
+    fn.argtypes = [_i64]
+    return int(fn(n_nodes))
+
+
+def attn_max_nodes() -> int:
+    return int(lib().is_attn_max_nodes())
+
+
+def loss_num_partials() -> int:
+    return int(lib().is_loss_num_partials())
+
+
+# ---- collation ---------------------------------------------------------------------------------
+def collate_csr(src_local, dst_local, node_counts, edge_counts, n_nodes, n_edges, out):
+    i64, i32 = torch.int64, torch.int32
+    _call("is_collate_csr", _t(src_local, i64, "src"), _t(dst_local, i64, "dst"),
+          _t(node_counts, i64, "node_counts"), _t(edge_counts, i64, "edge_counts"),
+          _i32(node_counts.numel()), _i64(n_nodes), _i64(n_edges),
+          _t(out["node_off"], i64, "node_off"), _t(out["edge_off"], i64, "edge_off"),
+          _t(out["edge_index"], i64, "edge_index"), _t(out["batch"], i64, "batch"),
+          _t(out["indptr"], i32, "indptr"), _t(out["csr_src"], i32, "csr_src"),
+          _t(out["csr_dst"], i32, "csr_dst"), _t(out["csr_eid"], i32, "csr_eid"),
+          _t(out["outptr"], i32, "outptr"), _t(out["csc_pos"], i32, "csc_pos"),
+          _t(out["scratch"], i32, "scratch"), _t(out["stats"], i32, "stats"), _stream())
+
+
+# ---- EGNN --------------------------------------------------------------------------------------
+def _csr(g):
+    i32 = torch.int32
+    return (_t(g.indptr, i32, "indptr"), _t(g.csr_src, i32, "csr_src"), _t(g.csr_dst, i32, "csr_dst"),
+            _t(g.csr_eid, i32, "csr_eid"))
+
+
+def egnn_node_pre_fwd(h, W1, b1, PQ):
+    f32 = torch.float32
+    hp, ldh = _rows(h, "h")
+    _call("is_egnn_node_pre_fwd", hp, ldh, _i32(h.shape[1]), _t(W1, f32, "W1"), _t(b1, f32, "b1"),
+          _t(PQ, f32, "PQ"), _i64(h.shape[0]), _stream())
+
+
+def egnn_edge_fwd(g, PQ, x, edge_attr, F, W1, W2, b2, W3, b3, w4, update_coords, hn, x_out):
+    f32 = torch.float32
+    xp, ldx = _rows(x, "x")
+    _call("is_egnn_edge_fwd", *_csr(g), _t(PQ, f32, "PQ"), xp, ldx, _t(edge_attr, f32, "edge_attr"),
+          _t(W1, f32, "W1"), _i32(F), _t(W2, f32, "W2"), _t(b2, f32, "b2"), _t(W3, f32, "W3"),
+          _t(b3, f32, "b3"), _t(w4, f32, "w4"), _i32(1 if update_coords else 0), _t(hn, f32, "hn"),
+          _t(x_out, f32, "x_out"), _i64(PQ.shape[0]), _t(g.status, torch.int32, "status"), _stream())
+
+
+def egnn_node_post_fwd(h, hn, W5, b5, W6, b6, h_out):
+    f32 = torch.float32
+    hp, ldh = _rows(h, "h")
+    _call("is_egnn_node_post_fwd", hp, ldh, _i32(h.shape[1]), _t(hn, f32, "hn"), _t(W5, f32, "W5"),
+          _t(b5, f32, "b5"), _t(W6, f32, "W6"), _t(b6, f32, "b6"), _t(h_out, f32, "h_out"),
+          _i64(h.shape[0]), _stream())
+
+
+def egnn_node_post_bwd(gh_out, h, hn, W5, b5, W6, gh_direct, ghn, partials):
+    f32 = torch.float32
+    hp, ldh = _rows(h, "h")
+    _call("is_egnn_node_post_bwd", _t(gh_out, f32, "gh_out"), hp, ldh, _i32(h.shape[1]), _t(hn, f32, "hn"),
+          _t(W5, f32, "W5"), _t(b5, f32, "b5"), _t(W6, f32, "W6"), _t(gh_direct, f32, "gh_direct"),
+          _t(ghn, f32, "ghn"), _t(partials, f32, "partials"), _i64(h.shape[0]), _stream())
+
+
+def egnn_edge_bwd(g, PQ, x, edge_attr, F, W1, W2, b2, W3, b3, w4, ghn, gx_out, gz1, gQ, gD, gxd, partials):
+    f32 = torch.float32
+    xp, ldx = _rows(x, "x")
+    _call("is_egnn_edge_bwd", *_csr(g), _t(PQ, f32, "PQ"), xp, ldx, _t(edge_attr, f32, "edge_attr"),
+          _t(W1, f32, "W1"), _i32(F), _t(W2, f32, "W2"), _t(b2, f32, "b2"), _t(W3, f32, "W3"),
+          _t(b3, f32, "b3"), _t(w4, f32, "w4"), _t(ghn, f32, "ghn"), _t(gx_out, f32, "gx_out"),
+          _t(gz1, f32, "gz1"), _t(gQ, f32, "gQ"), _t(gD, f32, "gD"), _t(gxd, f32, "gxd"),
+          _t(partials, f32, "partials"), _i64(PQ.shape[0]), _t(g.status, torch.int32, "status"), _stream())
+
+
+def egnn_node_pre_bwd(gz1, gQ, gD, gxd, gx_out, gh_direct, g, h, W1, gh, gx, partials):
+    f32, i32 = torch.float32, torch.int32
+    hp, ldh = _rows(h, "h")
+    _call("is_egnn_node_pre_bwd", _t(gz1, f32, "gz1"), _t(gQ, f32, "gQ"), _t(gD, f32, "gD"), _t(gxd, f32, "gxd"),
+          _t(gx_out, f32, "gx_out"), _t(gh_direct, f32, "gh_direct"), _t(g.outptr, i32, "outptr"),
+          _t(g.csc_pos, i32, "csc_pos"), hp, ldh, _i32(h.shape[1]), _t(W1, f32, "W1"), _t(gh, f32, "gh"),
+          _t(gx, f32, "gx"), _t(partials, f32, "partials"), _i64(h.shape[0]), _stream())
+
+
+def reduce_partials(partials, out):
+    f32 = torch.float32
+    _call("is_reduce_partials", _t(partials, f32, "partials"), _i32(partials.shape[0]), _i64(partials.shape[1]),
+          _t(out, f32, "out"), _stream())
+
+
+# ---- attention + pooling -----------------------------------------------------------------------
+def attn_pool_fwd(QKV, node_off, n_head, max_nodes, O, LSE, pooled, attn=None, attn_off=None):
+    f32, i64 = torch.float32, torch.int64
+    _call("is_attn_pool_fwd", _t(QKV, f32, "QKV"), _t(node_off, i64, "node_off"), _i32(node_off.numel() - 1),
+          _i32(n_head), _i32(max_nodes), _t(O, f32, "O"), _t(LSE, f32, "LSE"), _t(pooled, f32, "pooled"),
+          _t(attn, f32, "attn"), _t(attn_off, i64, "attn_off"), _stream())
+
+
+def attn_pool_bwd(QKV, O, LSE, node_off, n_head, max_nodes, g_pooled, gO_full, gQKV):
+    f32, i64 = torch.float32, torch.int64
+    _call("is_attn_pool_bwd", _t(QKV, f32, "QKV"), _t(O, f32, "O"), _t(LSE, f32, "LSE"),
+          _t(node_off, i64, "node_off"), _i32(node_off.numel() - 1), _i32(n_head), _i32(max_nodes),
+          _t(g_pooled, f32, "g_pooled"), _t(gO_full, f32, "gO_full"), _t(gQKV, f32, "gQKV"), _stream())
+
+
+# ---- fusion attention --------------------------------------------------------------------------
+def fusion_attn_fwd(c, n_head, coef, out):
+    f32 = torch.float32
+    _call("is_fusion_attn_fwd", _t(c, f32, "c"), _i32(c.shape[0]), _i32(c.shape[1]), _i32(n_head),
+          _t(coef, f32, "coef"), _t(out, f32, "out"), _stream())
+
+
+def fusion_attn_bwd(c, n_head, coef, gout, gc, gcoef_part):
+    f32 = torch.float32
+    _call("is_fusion_attn_bwd", _t(c, f32, "c"), _i32(c.shape[0]), _i32(c.shape[1]), _i32(n_head),
+          _t(coef, f32, "coef"), _t(gout, f32, "gout"), _t(gc, f32, "gc"), _t(gcoef_part, f32, "gcoef_part"),
+          _stream())
+
+
+# ---- losses ------------------------------------------------------------------------------------
+def loss_fwd(recon, seq, mu, logvar, logits, y, mode, pos_weight, w_pred, w_mse, w_kld, partial, out):
+    f32 = torch.float32
+    _call("is_loss_fwd", _t(recon, f32, "recon"), _t(seq, f32, "seq"),
+          _i64(recon.numel() if recon is not None else 0), _t(mu, f32, "mu"), _t(logvar, f32, "logvar"),
+          _i64(mu.numel() if mu is not None else 0), _t(logits, f32, "logits"), _t(y, f32, "y"),
+          _i64(logits.numel()), _i32(mode), _f32(pos_weight), _f32(w_pred), _f32(w_mse), _f32(w_kld),
+          _t(partial, f32, "partial"), _t(out, f32, "out"), _stream())
+
+
+def loss_bwd(recon, seq, mu, logvar, logits, y, mode, pos_weight, w_pred, w_mse, w_kld, gout,
+             g_recon, g_mu, g_logvar, g_logits):
+    f32 = torch.float32
+    _call("is_loss_bwd", _t(recon, f32, "recon"), _t(seq, f32, "seq"),
+          _i64(recon.numel() if recon is not None else 0), _t(mu, f32, "mu"), _t(logvar, f32, "logvar"),
+          _i64(mu.numel() if mu is not None else 0), _t(logits, f32, "logits"), _t(y, f32, "y"),
+          _i64(logits.numel()), _i32(mode), _f32(pos_weight), _f32(w_pred), _f32(w_mse), _f32(w_kld),
+          _t(gout, f32, "gout"), _t(g_recon, f32, "g_recon"), _t(g_mu, f32, "g_mu"),
+          _t(g_logvar, f32, "g_logvar"), _t(g_logits, f32, "g_logits"), _stream())

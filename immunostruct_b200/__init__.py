@@ -1,0 +1,8 @@
+"""immunostruct_b200 -- B200-native (sm_100a) implementation of ImmunoStruct's training / inference
+hot path behind the reference's own plug-in API (``model_map``, ``Losses``, ``PairedContrastiveLoss``,
+``collate`` / ``batch``).  See DESIGN.md and INTEGRATION.md."""
+from .graph import Graph, GraphBatch, batch, collate, collate_amino_acid, graph  # noqa: F401
+from .layers import EGNNConv, MultiHeadAttention, SelfAttention  # noqa: F401
+from .loss import Losses  # noqa: F401
+from .contrastive import PairedContrastiveLoss  # noqa: F401
+from .mapping import model_map  # noqa: F401

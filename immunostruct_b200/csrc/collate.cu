@@ -1,0 +1,149 @@
+// On-device collation of a graph batch: the device-side replacement of ``dgl.batch`` as called by
+// ``collate`` / ``collate_amino_acid`` (immunostruct/data/utils.py:160-176 / 178-196) plus the
+// destination-sorted CSR that DGL builds lazily on first ``update_all`` and its CSC transpose
+// (SURVEY.md section 8(a) row 1).  All outputs are integers and must be BIT-EXACT against the
+// oracle (oracle/reference_ops.py: dgl_batch, batch_vector, csr_from_coo).
+//
+// Input  : graph-local COO endpoints concatenated graph-major (src_local/dst_local int64 [E]),
+//          per-graph node and edge counts (int64 [B]).
+// Output : node_off/edge_off int64 [B+1] (segment offsets), edge_index int64 [2,E] (global ids,
+//          edge order preserved), batch int64 [N]; CSR by destination (stable in edge id):
+//          indptr int32 [N+1], csr_src/csr_dst/csr_eid int32 [E]; CSC transpose by source:
+//          outptr int32 [N+1], csc_pos int32 [E] (CSR position of every out-edge, stable in edge id);
+//          stats int32 [4] = {max in-degree, #endpoints out of range, 0, 0}.
+#include "common.cuh"
+
+namespace is {
+
+// exclusive scan of two int64 count arrays with one CTA (B is a few thousand at most)
+__global__ void offsets_kernel(const int64_t* __restrict__ node_counts, const int64_t* __restrict__ edge_counts,
+                               int B, int64_t* __restrict__ node_off, int64_t* __restrict__ edge_off) {
+    __shared__ int64_t s_n[1024], s_e[1024];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int per = (B + nt - 1) / nt;
+    const int b0 = min(B, tid * per), b1 = min(B, b0 + per);
+    int64_t sn = 0, se = 0;
+    for (int b = b0; b < b1; ++b) { sn += node_counts[b]; se += edge_counts[b]; }
+    s_n[tid] = sn; s_e[tid] = se;
+    __syncthreads();
+    if (tid == 0) {
+        int64_t an = 0, ae = 0;
+        for (int t = 0; t < nt; ++t) {
+            int64_t vn = s_n[t], ve = s_e[t];
+            s_n[t] = an; s_e[t] = ae;
+            an += vn; ae += ve;
+        }
+        node_off[B] = an; edge_off[B] = ae;
+    }
+    __syncthreads();
+    sn = s_n[tid]; se = s_e[tid];
+    for (int b = b0; b < b1; ++b) {
+        node_off[b] = sn; edge_off[b] = se;
+        sn += node_counts[b]; se += edge_counts[b];
+    }
+}
+
+// one warp per graph: globalise endpoints, histogram, scan, stable fill of CSR and CSC
+__global__ void __launch_bounds__(128)
+collate_kernel(const int64_t* __restrict__ src_local, const int64_t* __restrict__ dst_local,
+               const int64_t* __restrict__ node_off, const int64_t* __restrict__ edge_off, int B,
+               int64_t* __restrict__ edge_index /* [2,E] */, int64_t E, int64_t* __restrict__ batch,
+               int* __restrict__ indptr, int* __restrict__ csr_src, int* __restrict__ csr_dst, int* __restrict__ csr_eid,
+               int* __restrict__ outptr, int* __restrict__ csc_pos,
+               int* __restrict__ cur_in, int* __restrict__ cur_out /* scratch int32 [N] each */,
+               int* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= B) return;
+    const int64_t n0 = node_off[g], n1 = node_off[g + 1], e0 = edge_off[g], e1 = edge_off[g + 1];
+    const int ng = (int)(n1 - n0);
+    // phase 0: batch vector, zero the degree counters
+    for (int64_t n = n0 + lane; n < n1; n += 32) { batch[n] = g; cur_in[n] = 0; cur_out[n] = 0; }
+    __syncwarp();
+    // phase 1: globalise + degree histograms (integer atomics: order-independent result)
+    int bad = 0;
+    for (int64_t e = e0 + lane; e < e1; e += 32) {
+        int64_t s = src_local[e], d = dst_local[e];
+        if (s < 0 || s >= ng || d < 0 || d >= ng) { bad++; s = 0; d = 0; }
+        s += n0; d += n0;
+        edge_index[e] = s;
+        edge_index[E + e] = d;
+        atomicAdd(cur_in + d, 1);
+        atomicAdd(cur_out + s, 1);
+    }
+    if (bad) atomicAdd(stats + 1, bad);
+    __syncwarp();
+    // phase 2: exclusive scans -> indptr / outptr (global positions), cursors, max in-degree
+    int run_in = (int)e0, run_out = (int)e0, maxdeg = 0;
+    for (int64_t nb = n0; nb < n1; nb += 32) {
+        const int64_t n = nb + lane;
+        const int di = (n < n1) ? cur_in[n] : 0, dout = (n < n1) ? cur_out[n] : 0;
+        maxdeg = max(maxdeg, di);
+        int si = di, so = dout;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int ti = __shfl_up_sync(0xffffffffu, si, o), to = __shfl_up_sync(0xffffffffu, so, o);
+            if (lane >= o) { si += ti; so += to; }
+        }
+        if (n < n1) {
+            indptr[n] = run_in + si - di; outptr[n] = run_out + so - dout;
+            cur_in[n] = run_in + si - di; cur_out[n] = run_out + so - dout;
+        }
+        run_in += __shfl_sync(0xffffffffu, si, 31);
+        run_out += __shfl_sync(0xffffffffu, so, 31);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, o));
+    if (lane == 0) {
+        atomicMax(stats, maxdeg);
+        if (g == B - 1) { indptr[n1] = (int)e1; outptr[n1] = (int)e1; }
+    }
+    __syncwarp();
+    // phase 3: stable fill, 32 edges per step in ascending edge id
+    for (int64_t eb = e0; eb < e1; eb += 32) {
+        const int64_t e = eb + lane;
+        const bool act = e < e1;
+        const int s = act ? (int)edge_index[e] : -1 - lane, d = act ? (int)edge_index[E + e] : -1 - lane;
+        const unsigned md = __match_any_sync(0xffffffffu, d), ms = __match_any_sync(0xffffffffu, s);
+        const unsigned lt = (1u << lane) - 1u;
+        int pos_csr = 0;
+        if (act) {
+            pos_csr = cur_in[d] + __popc(md & lt);
+            csr_src[pos_csr] = s; csr_dst[pos_csr] = d; csr_eid[pos_csr] = (int)e;
+        }
+        __syncwarp();
+        if (act && (md & lt) == 0) cur_in[d] += __popc(md);       // group leader advances the cursor
+        if (act) csc_pos[cur_out[s] + __popc(ms & lt)] = pos_csr;
+        __syncwarp();
+        if (act && (ms & lt) == 0) cur_out[s] += __popc(ms);
+        __syncwarp();
+    }
+}
+
+}  // namespace is
+
+using namespace is;
+
+extern "C" {
+
+// Replaces dgl.batch (data/utils.py:163,169-170) + DGL's lazy CSC build.  scratch: int32 [2*N].
+int is_collate_csr(const int64_t* src_local, const int64_t* dst_local, const int64_t* node_counts,
+                   const int64_t* edge_counts, int n_graphs, int64_t n_nodes, int64_t n_edges,
+                   int64_t* node_off, int64_t* edge_off, int64_t* edge_index, int64_t* batch,
+                   int* indptr, int* csr_src, int* csr_dst, int* csr_eid, int* outptr, int* csc_pos,
+                   int* scratch, int* stats, void* stream) {
+    if (n_graphs <= 0 || n_nodes < 0 || n_edges < 0 || n_nodes > 0x7fffffff || n_edges > 0x7fffffff) return IS_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(stats, 0, 4 * sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
+    offsets_kernel<<<1, 1024, 0, st>>>(node_counts, edge_counts, n_graphs, node_off, edge_off);
+    IS_LAUNCH_CHECK();
+    const int wpb = 4;
+    collate_kernel<<<(n_graphs + wpb - 1) / wpb, wpb * 32, 0, st>>>(
+        src_local, dst_local, node_off, edge_off, n_graphs, edge_index, n_edges, batch, indptr, csr_src, csr_dst,
+        csr_eid, outptr, csc_pos, scratch, scratch + n_nodes, stats);
+    IS_LAUNCH_CHECK();
+    return IS_OK;
+}
+
+}  // extern "C"

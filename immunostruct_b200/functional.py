@@ -1,0 +1,243 @@
+"""Differentiable host wrappers around the C-ABI kernels (``torch.autograd.Function`` per fused op).
+
+Nothing here computes on the host: each ``forward`` / ``backward`` allocates outputs with torch and
+enqueues kernels through ``immunostruct_b200._C``.  Gradients are deterministic (fixed-order
+reductions; per-CTA partials summed in CTA order by ``is_reduce_partials``).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _C
+
+H = 64   # hidden width of the EGNN MLPs and of the node embedding (hybrid_models.py:247)
+
+
+def _new(like, *shape):
+    return torch.empty(*shape, dtype=torch.float32, device=like.device)
+
+
+# ==================================================================================================
+# EGNN layer
+# ==================================================================================================
+class _EGNNLayer(torch.autograd.Function):
+    """dgl.nn.EGNNConv.forward (reference call site models/hybrid_models.py:89-90 / :323-324).
+
+    forward(graph, update_coords, h, x, edge_attr, W1, b1, W2, b2, W3, b3, w4, W5, b5, W6, b6)
+      -> (h_out [N,64], x_out [N,3] or None when ``update_coords`` is False)
+    The per-edge activations are NOT saved; the backward recomputes them tile by tile.
+    """
+
+    @staticmethod
+    def forward(ctx, graph, update_coords, h, x, edge_attr, W1, b1, W2, b2, W3, b3, w4, W5, b5, W6, b6):
+        n, f = h.shape
+        if W2.shape != (H, H) or W6.shape != (H, H) or W1.shape != (H, 2 * f + 2) or W5.shape != (H, f + H):
+            raise NotImplementedError("EGNN kernels are specialised for hidden = out = 64 and edge_feat_size = 1")
+        params = [t.contiguous() for t in (W1, b1, W2, b2, W3, b3, w4, W5, b5, W6, b6)]
+        W1, b1, W2, b2, W3, b3, w4, W5, b5, W6, b6 = params
+        edge_attr = edge_attr.contiguous()
+        PQ, hn, h_out = _new(h, n, 2 * H), _new(h, n, H), _new(h, n, H)
+        x_out = _new(h, n, 3) if update_coords else None
+        _C.egnn_node_pre_fwd(h, W1, b1, PQ)
+        _C.egnn_edge_fwd(graph, PQ, x, edge_attr, f, W1, W2, b2, W3, b3, w4, update_coords, hn, x_out)
+        _C.egnn_node_post_fwd(h, hn, W5, b5, W6, b6, h_out)
+        ctx.graph = graph
+        ctx.update_coords = update_coords
+        ctx.save_for_backward(h, x, edge_attr, PQ, hn, *params)
+        ctx.set_materialize_grads(False)
+        return h_out, x_out
+
+    @staticmethod
+    def backward(ctx, gh_out, gx_out):
+        h, x, edge_attr, PQ, hn, W1, b1, W2, b2, W3, b3, w4, W5, b5, W6, b6 = ctx.saved_tensors
+        g = ctx.graph
+        n, f = h.shape
+        e = g.n_edges
+        k = f + H
+        need_gh, need_gx = ctx.needs_input_grad[2], ctx.needs_input_grad[3]
+        if need_gh and f != H:
+            raise NotImplementedError("gradient w.r.t. the 20-wide input features is not needed by any model")
+        if gh_out is None:
+            gh_out = torch.zeros(n, H, dtype=torch.float32, device=h.device)
+        gh_out = gh_out.contiguous()
+        has_coord = ctx.update_coords and gx_out is not None
+        if has_coord:
+            gx_out = gx_out.contiguous()
+        else:
+            gx_out = None
+
+        grid_n, grid_e = _C.egnn_node_grid(n), _C.egnn_edge_bwd_grid(n)
+        # node_post backward
+        ghn = _new(h, n, H)
+        gh_direct = _new(h, n, H) if need_gh else None
+        p_post = _new(h, grid_n, H * k + H + H * H + H)
+        _C.egnn_node_post_bwd(gh_out, h, hn, W5, b5, W6, gh_direct, ghn, p_post)
+        # edge backward
+        gz1, gQ, gD, gxd = _new(h, e, H), _new(h, n, H), _new(h, e, 3), _new(h, n, 3)
+        p_edge = _new(h, grid_e, 2 * H * H + 5 * H)
+        _C.egnn_edge_bwd(g, PQ, x, edge_attr, f, W1, W2, b2, W3, b3, w4, ghn, gx_out, gz1, gQ, gD, gxd, p_edge)
+        # node_pre backward (source-side reduction through the CSC transpose)
+        gh = _new(h, n, H) if need_gh else None
+        gx = _new(h, n, 3) if need_gx else None
+        p_pre = _new(h, grid_n, 2 * H * f + H)
+        _C.egnn_node_pre_bwd(gz1, gQ, gD, gxd, gx_out, gh_direct, g, h, W1, gh, gx, p_pre)
+        # deterministic reduction of the per-CTA weight-gradient partials
+        r_post, r_edge, r_pre = _new(h, p_post.shape[1]), _new(h, p_edge.shape[1]), _new(h, p_pre.shape[1])
+        _C.reduce_partials(p_post, r_post)
+        _C.reduce_partials(p_edge, r_edge)
+        _C.reduce_partials(p_pre, r_pre)
+
+        gW5 = r_post[:H * k].view(H, k)
+        gb5 = r_post[H * k:H * k + H]
+        gW6 = r_post[H * k + H:H * k + H + H * H].view(H, H)
+        gb6 = r_post[H * k + H + H * H:]
+        gW2 = r_edge[:H * H].view(H, H)
+        gb2 = r_edge[2 * H * H:2 * H * H + H]
+        gwr = r_edge[2 * H * H + 3 * H:2 * H * H + 4 * H]
+        gwa = r_edge[2 * H * H + 4 * H:2 * H * H + 5 * H]
+        if has_coord:
+            gW3 = r_edge[H * H:2 * H * H].view(H, H)
+            gb3 = r_edge[2 * H * H + H:2 * H * H + 2 * H]
+            gw4 = r_edge[2 * H * H + 2 * H:2 * H * H + 3 * H].view(1, H)
+        else:
+            gW3 = gb3 = gw4 = None            # coord_mlp never influenced the loss: report NO gradient
+        gWs = r_pre[:H * f].view(H, f)
+        gWd = r_pre[H * f:2 * H * f].view(H, f)
+        gb1 = r_pre[2 * H * f:]
+        gW1 = torch.cat([gWs, gWd, gwr.unsqueeze(1), gwa.unsqueeze(1)], dim=1)
+        return (None, None, gh, gx, None, gW1, gb1, gW2, gb2, gW3, gb3, gw4, gW5, gb5, gW6, gb6)
+
+
+def egnn_layer(graph, h, x, edge_attr, params, update_coords=True):
+    """params = (W1, b1, W2, b2, W3, b3, w4, W5, b5, W6, b6); returns (h_out, x_out|None)."""
+    return _EGNNLayer.apply(graph, update_coords, h, x, edge_attr, *params)
+
+
+# ==================================================================================================
+# per-graph attention + mean pool
+# ==================================================================================================
+class _AttnPool(torch.autograd.Function):
+    """softmax(QK^T/sqrt(d)) V per graph and head, plus the per-graph mean of the rows.
+
+    forward(graph, n_head, want_attn, QKV [N,192]) -> (O [N,64], pooled [B,64], attn or None)
+    ``attn`` is the dense weights tensor [B, H, n, n] (equal node counts) when requested.
+    """
+
+    @staticmethod
+    def forward(ctx, graph, n_head, want_attn, QKV):
+        QKV = QKV.contiguous()
+        n = QKV.shape[0]
+        b = graph.n_graphs
+        O, LSE, pooled = _new(QKV, n, H), _new(QKV, n, n_head), _new(QKV, b, H)
+        attn = attn_off = None
+        if want_attn:
+            m = graph.max_nodes
+            if m * b != n:
+                raise NotImplementedError("return_attention needs equal node counts per graph (as the reference does)")
+            attn = _new(QKV, b, n_head, m, m)
+            attn_off = torch.arange(b, device=QKV.device, dtype=torch.int64) * (n_head * m * m)
+        _C.attn_pool_fwd(QKV, graph.node_off, n_head, graph.max_nodes, O, LSE, pooled, attn, attn_off)
+        ctx.graph, ctx.n_head = graph, n_head
+        ctx.save_for_backward(QKV, O, LSE)
+        ctx.set_materialize_grads(False)
+        if want_attn:
+            ctx.mark_non_differentiable(attn)
+        return O, pooled, attn
+
+    @staticmethod
+    def backward(ctx, gO, g_pooled, _g_attn):
+        QKV, O, LSE = ctx.saved_tensors
+        gQKV = _new(QKV, *QKV.shape)
+        if gO is None and g_pooled is None:
+            gQKV.zero_()
+            return None, None, None, gQKV
+        gO = gO.contiguous() if gO is not None else None
+        g_pooled = g_pooled.contiguous() if g_pooled is not None else None
+        _C.attn_pool_bwd(QKV, O, LSE, ctx.graph.node_off, ctx.n_head, ctx.graph.max_nodes, g_pooled, gO, gQKV)
+        return None, None, None, gQKV
+
+
+def attention_pool(graph, QKV, n_head=1, want_attn=False):
+    return _AttnPool.apply(graph, n_head, want_attn, QKV)
+
+
+# ==================================================================================================
+# fusion attention (closed form)
+# ==================================================================================================
+class _FusionAttn(torch.autograd.Function):
+    """out[b,i] = btilde + sum_h (alpha_h E^h_i + beta_h); see csrc/fusion.cu.  coef = [A|C|alpha|beta|btilde]."""
+
+    @staticmethod
+    def forward(ctx, c, coef, n_head):
+        c, coef = c.contiguous(), coef.contiguous()
+        out = _new(c, *c.shape)
+        _C.fusion_attn_fwd(c, n_head, coef, out)
+        ctx.n_head = n_head
+        ctx.save_for_backward(c, coef)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        c, coef = ctx.saved_tensors
+        hh = ctx.n_head
+        gout = gout.contiguous()
+        gc, part = _new(c, *c.shape), _new(c, c.shape[0], 4 * hh)
+        _C.fusion_attn_bwd(c, hh, coef, gout, gc, part)
+        gcoef = torch.cat([part.sum(0), gout.sum().reshape(1)])
+        return gc, gcoef, None
+
+
+def fusion_attention(c, coef, n_head):
+    return _FusionAttn.apply(c, coef, n_head)
+
+
+# ==================================================================================================
+# fused loss
+# ==================================================================================================
+class _FusedLoss(torch.autograd.Function):
+    """w_pred * pred(out, y) + w_mse * MSE(recon, seq) + w_kld * KLD(mu, logvar)  (utils/loss.py:13-31)."""
+
+    @staticmethod
+    def forward(ctx, recon, seq, mu, logvar, logits, y, mode, pos_weight, w_pred, w_mse, w_kld):
+        ctx.logits_shape = logits.shape
+        logits = logits.reshape(-1).contiguous()
+        y = y.reshape(-1).contiguous().float()
+        if logits.numel() != y.numel():
+            raise ValueError("prediction and target must have the same number of elements")
+        if w_mse != 0.0 or w_kld != 0.0:
+            recon, seq = recon.contiguous(), seq.reshape(recon.shape[0], -1).contiguous()
+            if recon.shape != seq.shape:
+                raise ValueError(f"recon {tuple(recon.shape)} vs sequence {tuple(seq.shape)}")
+            mu, logvar = mu.contiguous(), logvar.contiguous()
+        else:
+            recon = seq = mu = logvar = None
+        out = _new(logits, 4)
+        partial = _new(logits, _C.loss_num_partials())
+        _C.loss_fwd(recon, seq, mu, logvar, logits, y, mode, pos_weight, w_pred, w_mse, w_kld, partial, out)
+        ctx.cfg = (mode, pos_weight, w_pred, w_mse, w_kld)
+        ctx.has_seq = recon is not None
+        saved = (logits, y) + ((recon, seq, mu, logvar) if recon is not None else ())
+        ctx.save_for_backward(*saved)
+        ctx.mark_non_differentiable(out)
+        return out[0].clone(), out
+
+    @staticmethod
+    def backward(ctx, gout, _gcomp):
+        mode, pos_weight, w_pred, w_mse, w_kld = ctx.cfg
+        if ctx.has_seq:
+            logits, y, recon, seq, mu, logvar = ctx.saved_tensors
+            g_recon, g_mu, g_lv = _new(recon, *recon.shape), _new(mu, *mu.shape), _new(mu, *mu.shape)
+        else:
+            logits, y = ctx.saved_tensors
+            recon = seq = mu = logvar = g_recon = g_mu = g_lv = None
+        g_logits = _new(logits, logits.numel())
+        gout = gout.reshape(1).contiguous().float()
+        _C.loss_bwd(recon, seq, mu, logvar, logits, y, mode, pos_weight, w_pred, w_mse, w_kld, gout,
+                    g_recon, g_mu, g_lv, g_logits)
+        return g_recon, None, g_mu, g_lv, g_logits.view(ctx.logits_shape), None, None, None, None, None, None
+
+
+def fused_loss(recon, seq, mu, logvar, logits, y, mode, pos_weight, w_pred, w_mse, w_kld, return_components=False):
+    total, comps = _FusedLoss.apply(recon, seq, mu, logvar, logits, y, int(mode), float(pos_weight),
+                                    float(w_pred), float(w_mse), float(w_kld))
+    return (total, comps) if return_components else total

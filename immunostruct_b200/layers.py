@@ -1,0 +1,151 @@
+"""nn.Module building blocks with the reference's parameter names (state_dict compatible).
+
+* ``EGNNConv``  -- stands in for ``dgl.nn.EGNNConv`` (constructed at models/hybrid_models.py:29-31):
+  same sub-module layout (``edge_mlp.{0,2}``, ``node_mlp.{0,2}``, ``coord_mlp.{0,2}``), forward runs
+  the fused CUDA layer (csrc/egnn.cu).
+* ``SelfAttention`` / ``MultiHeadAttention`` -- reference ``models/layers.py:6-22 / 51-106``.  Their
+  generic ``forward(x)`` keeps the reference semantics (returns output and dense weights); the models
+  use the fused entry points ``pooled(...)`` (per-graph attention + global mean pool in one kernel)
+  and ``fused_mean(...)`` (fusion attention over scalar tokens in closed form).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import functional as IF
+
+
+class EGNNConv(nn.Module):
+    def __init__(self, in_size, hidden_size, out_size, edge_feat_size=0):
+        super().__init__()
+        if hidden_size != 64 or out_size != 64 or edge_feat_size != 1 or in_size not in (20, 64):
+            raise NotImplementedError(
+                "immunostruct_b200.EGNNConv is specialised for the reference's configuration: "
+                "in_size in {20, 64}, hidden = out = 64, edge_feat_size = 1")
+        self.in_size, self.hidden_size, self.out_size, self.edge_feat_size = in_size, hidden_size, out_size, edge_feat_size
+        act = nn.SiLU()
+        # same construction order and shapes as upstream DGL
+        self.edge_mlp = nn.Sequential(nn.Linear(in_size * 2 + edge_feat_size + 1, hidden_size), act,
+                                      nn.Linear(hidden_size, hidden_size), act)
+        self.node_mlp = nn.Sequential(nn.Linear(in_size + hidden_size, hidden_size), act,
+                                      nn.Linear(hidden_size, out_size))
+        self.coord_mlp = nn.Sequential(nn.Linear(hidden_size, hidden_size), act,
+                                       nn.Linear(hidden_size, 1, bias=False))
+
+    def kernel_params(self):
+        return (self.edge_mlp[0].weight, self.edge_mlp[0].bias, self.edge_mlp[2].weight, self.edge_mlp[2].bias,
+                self.coord_mlp[0].weight, self.coord_mlp[0].bias, self.coord_mlp[2].weight,
+                self.node_mlp[0].weight, self.node_mlp[0].bias, self.node_mlp[2].weight, self.node_mlp[2].bias)
+
+    def forward(self, graph, node_feat, coord_feat, edge_feat=None, update_coords: bool = True):
+        """Returns ``(h', x')``.  With ``update_coords=False`` (used by the models for the last layer,
+        whose coordinates the reference discards, hybrid_models.py:323-326) ``x'`` is ``coord_feat``
+        unchanged and the coordinate MLP is skipped."""
+        if edge_feat is None:
+            raise ValueError("edge_feat is required (edge_feat_size = 1)")
+        h_out, x_out = IF.egnn_layer(graph, node_feat, coord_feat, edge_feat, self.kernel_params(), update_coords)
+        return h_out, (x_out if update_coords else coord_feat)
+
+
+def _dense_attention(q, k, v):
+    w = torch.softmax(q @ k.transpose(-2, -1) / math.sqrt(k.shape[-1]), dim=-1)
+    return w @ v, w
+
+
+class SelfAttention(nn.Module):
+    """Single-head attention without output projection (reference layers.py:6-22)."""
+
+    n_head = 1
+
+    def __init__(self, feature_dim):
+        super().__init__()
+        self.query = nn.Linear(feature_dim, feature_dim)
+        self.key = nn.Linear(feature_dim, feature_dim)
+        self.value = nn.Linear(feature_dim, feature_dim)
+
+    def forward(self, x):
+        return _dense_attention(self.query(x), self.key(x), self.value(x))
+
+    def _qkv(self, h):
+        w = torch.cat([self.query.weight, self.key.weight, self.value.weight], 0)
+        b = torch.cat([self.query.bias, self.key.bias, self.value.bias], 0)
+        return F.linear(h, w, b)
+
+    def pooled(self, graph, h, want_attn=False, want_nodes=False):
+        """h [N_total,64] -> (per-graph mean of the attention output [B,64], weights|None, per-node out|None)."""
+        O, pooled, attn = IF.attention_pool(graph, self._qkv(h), 1, want_attn)
+        if want_attn:
+            attn = attn.squeeze(1)         # SelfAttention returns [B, n, n]
+        return pooled, attn, (O if want_nodes else None)
+
+
+class MultiHeadAttention(nn.Module):
+    """Reference layers.py:51-106 (w_q, w_k, w_v, w_concat)."""
+
+    def __init__(self, feature_dim, n_head, input_dim=None):
+        super().__init__()
+        assert feature_dim % n_head == 0, "Embedding dimension must be 0 modulo number of heads."
+        if not input_dim:
+            input_dim = feature_dim
+        self.n_head, self.feature_dim, self.input_dim = n_head, feature_dim, input_dim
+        self.w_q = nn.Linear(input_dim, feature_dim)
+        self.w_k = nn.Linear(input_dim, feature_dim)
+        self.w_v = nn.Linear(input_dim, feature_dim)
+        self.w_concat = nn.Linear(feature_dim, feature_dim)
+
+    def split(self, t):
+        b, l, d = t.size()
+        return t.view(b, l, self.n_head, d // self.n_head).transpose(1, 2)
+
+    def concat(self, t):
+        b, h, l, d = t.size()
+        return t.transpose(1, 2).contiguous().view(b, l, h * d)
+
+    def forward(self, x, mask=None):
+        q, k, v = self.split(self.w_q(x)), self.split(self.w_k(x)), self.split(self.w_v(x))
+        score = (q @ k.transpose(2, 3)) / math.sqrt(k.shape[-1])
+        if mask is not None:
+            score = score.masked_fill(mask == 0, -10000)
+        score = torch.softmax(score, dim=-1)
+        return self.w_concat(self.concat(score @ v)), score
+
+    # ---- fused entry points used by the models ---------------------------------------------------
+    def _qkv(self, h):
+        w = torch.cat([self.w_q.weight, self.w_k.weight, self.w_v.weight], 0)
+        b = torch.cat([self.w_q.bias, self.w_k.bias, self.w_v.bias], 0)
+        return F.linear(h, w, b)
+
+    def pooled(self, graph, h, want_attn=False, want_nodes=False):
+        """Per-graph attention over node embeddings + global mean pool.  The mean commutes with the
+        affine ``w_concat``, so the projection is applied to the pooled [B,64] rows."""
+        if self.feature_dim != 64 or self.input_dim != 64:
+            raise NotImplementedError("fused per-graph attention is specialised for 64 channels")
+        O, pooled, attn = IF.attention_pool(graph, self._qkv(h), self.n_head, want_attn)
+        nodes = self.w_concat(O) if want_nodes else None
+        return self.w_concat(pooled), attn, nodes
+
+    def fusion_coefficients(self):
+        """[A(H) | C(H) | alpha(H) | beta(H) | btilde] of the closed form in csrc/fusion.cu."""
+        if self.input_dim != 1:
+            raise NotImplementedError("closed-form fusion attention needs scalar tokens (input_dim = 1)")
+        hh, dh = self.n_head, self.feature_dim // self.n_head
+        wq, wk, wv = self.w_q.weight[:, 0], self.w_k.weight[:, 0], self.w_v.weight[:, 0]
+        s = 1.0 / math.sqrt(dh)
+        A = (wq * wk).view(hh, dh).sum(1) * s
+        C = (self.w_q.bias * wk).view(hh, dh).sum(1) * s
+        wt = self.w_concat.weight.mean(0)
+        alpha = (wt * wv).view(hh, dh).sum(1)
+        beta = (wt * self.w_v.bias).view(hh, dh).sum(1)
+        # the key bias only shifts every score of a row by a constant, which softmax ignores: its
+        # gradient is exactly zero.  Keep it in the graph so that it receives a (zero) .grad like in
+        # the reference (optimizers with weight decay treat None and 0 differently).
+        btilde = self.w_concat.bias.mean() + 0.0 * self.w_k.bias.sum()
+        return torch.cat([A, C, alpha, beta, btilde.reshape(1)])
+
+    def fused_mean(self, combined):
+        """``mean(self(combined.unsqueeze(2))[0], dim=2)`` (hybrid_models.py:344-347) in one kernel."""
+        return IF.fusion_attention(combined, self.fusion_coefficients(), self.n_head)

@@ -1,0 +1,105 @@
+"""Shared pieces of the reference's model zoo, factored once (the reference repeats them per class).
+
+``StructureTrunk``: EGNN stack -> per-graph attention -> global mean pool
+(models/hybrid_models.py:82-97 / :316-331, identical in every structure-bearing model).
+``SequenceVAE``: encode_vae / reparameterize / decode_vae (hybrid_models.py:63-74).
+Attribute names equal the reference's so that ``state_dict`` keys and shapes match exactly.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .graph import GraphBatch
+from .layers import EGNNConv, MultiHeadAttention, SelfAttention
+
+
+def _require_device_batch(graph_data):
+    if not isinstance(graph_data, GraphBatch):
+        raise TypeError("graph_data must be an immunostruct_b200.GraphBatch (see immunostruct_b200.batch)")
+    if not graph_data.ndata["x"].is_cuda:
+        raise RuntimeError("immunostruct_b200 models run on CUDA only; call graph_data.to(device) first "
+                           "(there is no CPU fallback)")
+
+
+class StructureTrunk:
+    """Mixin: builds ``GCN_layers`` + ``self_attention`` and runs them."""
+
+    def _build_trunk(self, gcn_layers, hidden, attention, heads=1):
+        self.gat_hidden_channels = hidden
+        self.GCN_layers = nn.ModuleList([EGNNConv(20, hidden, hidden, 1)])
+        for _ in range(gcn_layers):
+            self.GCN_layers.append(EGNNConv(hidden, hidden, hidden, 1))
+        self.self_attention = SelfAttention(hidden) if attention == "sa" else MultiHeadAttention(hidden, heads)
+
+    def structure_embedding(self, graph_data, want_attn=False, want_nodes=False):
+        """-> (pooled [B,64], attention weights or None, per-node attention output or None).
+
+        The per-graph ``batch_tensor`` of the reference (B host syncs per forward,
+        hybrid_models.py:86-87) is replaced by the segment offsets cached on the GraphBatch."""
+        _require_device_batch(graph_data)
+        xin = graph_data.ndata["x"]
+        node_feat, coord_feat, edge_feat = xin[:, :20], xin[:, 20:], graph_data.edata["edge_attr"]
+        last = len(self.GCN_layers) - 1
+        for i, layer in enumerate(self.GCN_layers):
+            # the last layer's coordinates are never consumed (hybrid_models.py:323-326)
+            node_feat, coord_feat = layer(graph_data, node_feat, coord_feat, edge_feat, update_coords=i != last)
+        return self.self_attention.pooled(graph_data, node_feat, want_attn=want_attn, want_nodes=want_nodes)
+
+
+class SequenceVAE:
+    """Mixin: the sequence VAE branch (five Linear layers; cuBLAS GEMMs through torch)."""
+
+    def _build_vae(self, vae_input_dim, vae_hidden_dim, vae_latent_dim, cond_dim):
+        self.vae_input_dim, self.vae_hidden_dim, self.vae_latent_dim = vae_input_dim, vae_hidden_dim, vae_latent_dim
+        self.vae_fc1 = nn.Linear(vae_input_dim, vae_hidden_dim)
+        self.vae_fc21 = nn.Linear(vae_hidden_dim, vae_latent_dim)
+        self.vae_fc22 = nn.Linear(vae_hidden_dim, vae_latent_dim)
+        self.vae_fc3 = nn.Linear(vae_latent_dim + cond_dim, vae_hidden_dim)
+        self.vae_fc4 = nn.Linear(vae_hidden_dim, vae_input_dim)
+
+    def encode_vae(self, x):
+        h1 = F.relu(self.vae_fc1(x))
+        return self.vae_fc21(h1), self.vae_fc22(h1)
+
+    def reparameterize(self, mu, logvar):
+        # sampled in eval mode too, exactly like the reference (hybrid_models.py:301-304)
+        std = torch.exp(0.5 * logvar)
+        eps = torch.randn_like(std)
+        return mu + eps * std
+
+    def decode_vae(self, z):
+        return self.vae_fc4(F.relu(self.vae_fc3(z)))
+
+    def vae_branch(self, sequence_data, cond=None):
+        mu, logvar = self.encode_vae(sequence_data.reshape(-1, self.vae_input_dim))
+        z = self.reparameterize(mu, logvar)
+        if cond is not None:
+            z = torch.cat([z, cond], dim=1)
+        return self.decode_vae(z), mu, logvar, z
+
+
+def property_mlp(out_dim):
+    return nn.Sequential(nn.Linear(2, 32), nn.ReLU(True), nn.Dropout(0.1), nn.Linear(32, out_dim), nn.ReLU(True))
+
+
+def classifier_mlp(in_dim, with_out=True):
+    layers = [nn.Flatten(1), nn.Linear(in_dim, 32), nn.ReLU(True), nn.Dropout(0.1)]
+    if with_out:
+        layers.append(nn.Linear(32, 1))
+    return nn.Sequential(*layers)
+
+
+class LoadTrained:
+    """``load_trained(path, new_head, map_location)`` (hybrid_models.py:310-313, :197-200 for SSL)."""
+
+    _head_attr = "classifier"
+
+    def load_trained(self, path, new_head=False, map_location=None):
+        self.load_state_dict(torch.load(path, map_location=map_location))
+        if new_head:
+            if self._head_attr == "classifier":
+                self.classifier = self.get_classifier().to(self.device)
+            else:
+                self.classifier_head = nn.Linear(self.mlp_features, 1).to(self.device)

@@ -1,0 +1,97 @@
+/* immunostruct_b200 -- C ABI of the B200 (sm_100a) kernels behind the ImmunoStruct hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  The reference is pure
+ * Python/PyTorch and has no FFI of its own; each entry point below names the reference call
+ * (file:line under immunostruct/) whose GPU work it replaces.  The Python host layer
+ * (immunostruct_b200/_C.py) binds these with ctypes; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (including scratch / partial buffers);
+ *     launchers never allocate and never synchronise; work is enqueued on `stream` (a cudaStream_t);
+ *   - return value: 0 = enqueued; < 0 = argument error (-1 bad argument, -2 unsupported size);
+ *     > 0 = cudaError_t of the failed launch;
+ *   - all floating tensors are fp32, row-major, contiguous unless a leading dimension is passed;
+ *     graph ids are int64 at the reference-facing surface (DGL default) and int32 inside the CSR;
+ *   - no floating-point atomics: results are bit-reproducible on a given device.
+ */
+#ifndef IMMUNOSTRUCT_B200_H
+#define IMMUNOSTRUCT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- device / sizing queries ------------------------------------------------------------------ */
+int is_num_sms(void);
+int is_egnn_node_grid(int64_t n_nodes);       /* #partial blocks written by node_post_bwd / node_pre_bwd */
+int is_egnn_edge_bwd_grid(int64_t n_nodes);   /* #partial blocks written by edge_bwd */
+int is_attn_max_nodes(void);                  /* largest graph the attention kernels stage on chip */
+int is_loss_num_partials(void);
+
+/* ---- collation: dgl.batch (data/utils.py:163,169-170) + DGL's lazy dst-sorted CSC + its transpose.
+ * scratch: int32[2*n_nodes]; stats: int32[4] = {max in-degree, #endpoints out of range, 0, 0}. */
+int is_collate_csr(const int64_t* src_local, const int64_t* dst_local, const int64_t* node_counts,
+                   const int64_t* edge_counts, int n_graphs, int64_t n_nodes, int64_t n_edges,
+                   int64_t* node_off, int64_t* edge_off, int64_t* edge_index, int64_t* batch,
+                   int* indptr, int* csr_src, int* csr_dst, int* csr_eid, int* outptr, int* csc_pos,
+                   int* scratch, int* stats, void* stream);
+
+/* ---- EGNNConv (dgl.nn.EGNNConv, models/hybrid_models.py:29-31,89-90) --------
+ * F = input feature width (20 for layer 0, 64 afterwards).  W1 = edge_mlp.0.weight [64, 2F+2],
+ * W2/b2 = edge_mlp.2, W3/b3 = coord_mlp.0, w4 = coord_mlp.2.weight [1,64], W5/b5 = node_mlp.0
+ * [64, F+64], W6/b6 = node_mlp.2.  PQ [n,128], hn [n,64]; status: int32 set to 1 if a node has
+ * more than 128 in-edges (unsupported). */
+int is_egnn_node_pre_fwd(const float* h, int64_t ldh, int F, const float* W1, const float* b1, float* PQ,
+                         int64_t n_nodes, void* stream);
+int is_egnn_edge_fwd(const int* indptr, const int* csr_src, const int* csr_dst, const int* csr_eid,
+                     const float* PQ, const float* x, int64_t ldx, const float* edge_attr,
+                     const float* W1, int F, const float* W2, const float* b2,
+                     const float* W3, const float* b3, const float* w4, int update_coords,
+                     float* hn, float* x_out, int64_t n_nodes, int* status, void* stream);
+int is_egnn_node_post_fwd(const float* h, int64_t ldh, int F, const float* hn, const float* W5, const float* b5,
+                          const float* W6, const float* b6, float* h_out, int64_t n_nodes, void* stream);
+int is_egnn_node_post_bwd(const float* gh_out, const float* h, int64_t ldh, int F, const float* hn,
+                          const float* W5, const float* b5, const float* W6,
+                          float* gh_direct, float* ghn, float* partials, int64_t n_nodes, void* stream);
+int is_egnn_edge_bwd(const int* indptr, const int* csr_src, const int* csr_dst, const int* csr_eid,
+                     const float* PQ, const float* x, int64_t ldx, const float* edge_attr,
+                     const float* W1, int F, const float* W2, const float* b2,
+                     const float* W3, const float* b3, const float* w4,
+                     const float* ghn, const float* gx_out,
+                     float* gz1, float* gQ, float* gD, float* gxd, float* partials,
+                     int64_t n_nodes, int* status, void* stream);
+int is_egnn_node_pre_bwd(const float* gz1, const float* gQ, const float* gD, const float* gxd,
+                         const float* gx_out, const float* gh_direct,
+                         const int* outptr, const int* csc_pos, const float* h, int64_t ldh, int F,
+                         const float* W1, float* gh, float* gx, float* partials, int64_t n_nodes, void* stream);
+int is_reduce_partials(const float* partials, int nparts, int64_t stride, float* out, void* stream);
+
+/* ---- per-graph attention + global_mean_pool (models/layers.py:13-22,29-48,67-78;
+ * models/hybrid_models.py:92-97 / 326-331).  QKV [n,192], O [n,64], LSE [n,H], pooled [B,64]. */
+int is_attn_pool_fwd(const float* QKV, const int64_t* node_off, int n_graphs, int n_head, int max_nodes,
+                     float* O, float* LSE, float* pooled, float* attn, const int64_t* attn_off, void* stream);
+int is_attn_pool_bwd(const float* QKV, const float* O, const float* LSE, const int64_t* node_off, int n_graphs,
+                     int n_head, int max_nodes, const float* g_pooled, const float* gO_full, float* gQKV, void* stream);
+
+/* ---- fusion attention over the fused scalars + mean(dim=2) (models/hybrid_models.py:275,344-347;
+ * comparative_models.py:392,484-486).  coef: [A(H) | C(H) | alpha(H) | beta(H) | btilde]. */
+int is_fusion_attn_fwd(const float* c, int n_samples, int L, int n_head, const float* coef, float* out, void* stream);
+int is_fusion_attn_bwd(const float* c, int n_samples, int L, int n_head, const float* coef, const float* gout,
+                       float* gc, float* gcoef_part, void* stream);
+
+/* ---- losses (utils/loss.py:13-31).  mode 0 = BCE-with-logits(pos_weight), 1 = MSE regression.
+ * out: float[4] = {total, prediction, recon MSE, KLD}. */
+int is_loss_fwd(const float* recon, const float* seq, int64_t n_recon, const float* mu, const float* logvar,
+                int64_t n_lat, const float* logits, const float* y, int64_t B, int mode, float pos_weight,
+                float w_pred, float w_mse, float w_kld, float* partial, float* out, void* stream);
+int is_loss_bwd(const float* recon, const float* seq, int64_t n_recon, const float* mu, const float* logvar,
+                int64_t n_lat, const float* logits, const float* y, int64_t B, int mode, float pos_weight,
+                float w_pred, float w_mse, float w_kld, const float* gout,
+                float* g_recon, float* g_mu, float* g_logvar, float* g_logits, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMMUNOSTRUCT_B200_H */

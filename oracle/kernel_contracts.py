@@ -1,0 +1,282 @@
+"""Per-kernel CPU contracts: what every C-ABI entry point must write, restated with torch ops.
+
+TEST INFRASTRUCTURE ONLY (see oracle/reference_ops.py header).  Two uses:
+  * ``tests/test_kernels_gpu.py`` runs each CUDA kernel and the matching function below on the same
+    inputs and compares outputs (the functions use autograd for every gradient, so they are an
+    independent derivation of the hand-written backward kernels);
+  * ``tests/test_host_glue.py`` monkeypatches ``immunostruct_b200._C`` with these functions so that
+    the product's host logic (autograd wiring, buffer plumbing, model classes) can be exercised
+    end-to-end on a CPU-only box against the full-model oracle and the golden vectors.
+Signatures mirror ``immunostruct_b200/_C.py`` one to one (outputs are written in place).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import reference_ops as R
+
+FAKE_GRID = 3   # number of per-CTA partial blocks the fake "device" reports
+
+
+def _silu(z):
+    return z * torch.sigmoid(z)
+
+
+# ---- sizing -------------------------------------------------------------------------------------
+def num_sms():
+    return FAKE_GRID
+
+
+def egnn_node_grid(n_nodes):
+    return FAKE_GRID
+
+
+def egnn_edge_bwd_grid(n_nodes):
+    return FAKE_GRID
+
+
+def attn_max_nodes():
+    return 256
+
+
+def loss_num_partials():
+    return 592
+
+
+# ---- collation ----------------------------------------------------------------------------------
+def collate_csr(src_local, dst_local, node_counts, edge_counts, n_nodes, n_edges, out):
+    b = node_counts.numel()
+    node_off = torch.zeros(b + 1, dtype=torch.int64)
+    node_off[1:] = torch.cumsum(node_counts, 0)
+    edge_off = torch.zeros(b + 1, dtype=torch.int64)
+    edge_off[1:] = torch.cumsum(edge_counts, 0)
+    shift = torch.repeat_interleave(node_off[:-1], edge_counts)
+    src, dst = src_local + shift, dst_local + shift
+    csr = R.csr_from_coo(src, dst, n_nodes)
+    out["node_off"].copy_(node_off)
+    out["edge_off"].copy_(edge_off)
+    out["edge_index"].copy_(torch.stack([src, dst]))
+    out["batch"].copy_(R.batch_vector(node_counts))
+    for k in ("indptr", "csr_src", "csr_dst", "csr_eid", "outptr", "csc_pos"):
+        out[k].copy_(csr[k])
+    deg = torch.bincount(dst, minlength=n_nodes)
+    ng = torch.repeat_interleave(node_counts, edge_counts)
+    bad = int(((src_local < 0) | (src_local >= ng) | (dst_local < 0) | (dst_local >= ng)).sum())
+    out["stats"].copy_(torch.tensor([int(deg.max()) if n_edges else 0, bad, 0, 0], dtype=torch.int32))
+
+
+# ---- EGNN forward -------------------------------------------------------------------------------
+def egnn_node_pre_fwd(h, W1, b1, PQ):
+    f = h.shape[1]
+    PQ[:, :64] = h @ W1[:, :f].T
+    PQ[:, 64:] = h @ W1[:, f:2 * f].T + b1
+
+
+def _edge_forward(g, PQ, diff, a, f, W1, W2, b2, W3, b3, w4, z1_add=None):
+    s, d = g.csr_src.long(), g.csr_dst.long()
+    r = (diff * diff).sum(-1, keepdim=True)
+    dhat = diff / (r.sqrt() + 1e-30)
+    z1 = PQ[s, :64] + PQ[d, 64:] + r * W1[:, 2 * f] + a * W1[:, 2 * f + 1]
+    if z1_add is not None:
+        z1 = z1 + z1_add
+    m = _silu(F.linear(_silu(z1), W2, b2))
+    n = PQ.shape[0]
+    hn = torch.zeros(n, 64, dtype=PQ.dtype).index_add_(0, d, m)
+    xn = None
+    if W3 is not None:
+        c = F.linear(_silu(F.linear(m, W3, b3)), w4)
+        deg = torch.bincount(d, minlength=n).clamp(min=1).to(PQ.dtype).unsqueeze(1)
+        xn = torch.zeros(n, 3, dtype=PQ.dtype).index_add_(0, d, c * dhat) / deg
+    return hn, xn
+
+
+def _edge_inputs(g, x, edge_attr):
+    s, d = g.csr_src.long(), g.csr_dst.long()
+    return x[s] - x[d], edge_attr.reshape(-1)[g.csr_eid.long()].unsqueeze(1)
+
+
+def egnn_edge_fwd(g, PQ, x, edge_attr, f, W1, W2, b2, W3, b3, w4, update_coords, hn, x_out):
+    diff, a = _edge_inputs(g, x, edge_attr)
+    with torch.no_grad():
+        hn_, xn = _edge_forward(g, PQ, diff, a, f, W1, W2, b2, W3 if update_coords else None, b3, w4)
+    hn.copy_(hn_)
+    if update_coords:
+        x_out.copy_(x + xn)
+
+
+def egnn_node_post_fwd(h, hn, W5, b5, W6, b6, h_out):
+    h_out.copy_(F.linear(_silu(F.linear(torch.cat([h, hn], 1), W5, b5)), W6, b6))
+
+
+# ---- EGNN backward (autograd = independent derivation) -------------------------------------------
+def _partials(rows, *tensors):
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    out = torch.zeros(rows, flat.numel())
+    out[0] = flat
+    return out
+
+
+@torch.enable_grad()
+def egnn_node_post_bwd(gh_out, h, hn, W5, b5, W6, gh_direct, ghn, partials):
+    leaves = [t.detach().clone().requires_grad_(True) for t in (h, hn, W5, b5, W6)]
+    b6 = torch.zeros(64, requires_grad=True)
+    out = F.linear(_silu(F.linear(torch.cat(leaves[:2], 1), leaves[2], leaves[3])), leaves[4], b6)
+    gh, ghn_, gW5, gb5, gW6, gb6 = torch.autograd.grad(out, leaves + [b6], gh_out)
+    if gh_direct is not None:
+        gh_direct.copy_(gh)
+    ghn.copy_(ghn_)
+    partials.copy_(_partials(partials.shape[0], gW5, gb5, gW6, gb6))
+
+
+@torch.enable_grad()
+def egnn_edge_bwd(g, PQ, x, edge_attr, f, W1, W2, b2, W3, b3, w4, ghn, gx_out, gz1, gQ, gD, gxd, partials):
+    diff, a = _edge_inputs(g, x, edge_attr)
+    has_coord = gx_out is not None
+    diff = diff.detach().clone().requires_grad_(True)
+    z1_add = torch.zeros(diff.shape[0], 64, requires_grad=True)
+    wr = W1[:, 2 * f].detach().clone().requires_grad_(True)
+    wa = W1[:, 2 * f + 1].detach().clone().requires_grad_(True)
+    W1p = torch.cat([W1[:, :2 * f].detach(), wr.unsqueeze(1), wa.unsqueeze(1)], 1)
+    ps = [t.detach().clone().requires_grad_(True) for t in ((W2, b2, W3, b3, w4) if has_coord else (W2, b2))]
+    if has_coord:
+        hn, xn = _edge_forward(g, PQ, diff, a, f, W1p, *ps, z1_add=z1_add)
+        obj = (hn * ghn).sum() + (xn * gx_out).sum()
+    else:
+        hn, _ = _edge_forward(g, PQ, diff, a, f, W1p, ps[0], ps[1], None, None, None, z1_add=z1_add)
+        obj = (hn * ghn).sum()
+    grads = torch.autograd.grad(obj, [z1_add, diff, wr, wa] + ps)
+    d = g.csr_dst.long()
+    n = PQ.shape[0]
+    gz1.copy_(grads[0])
+    gD.copy_(grads[1])
+    gQ.copy_(torch.zeros(n, 64).index_add_(0, d, grads[0]))
+    gxd.copy_(-torch.zeros(n, 3).index_add_(0, d, grads[1]))
+    z64, z1 = torch.zeros(64, 64), torch.zeros(64)
+    if has_coord:
+        gW2, gb2, gW3, gb3, gw4 = grads[4:]
+    else:
+        (gW2, gb2), gW3, gb3, gw4 = grads[4:], z64, z1, z1
+    partials.copy_(_partials(partials.shape[0], gW2, gW3, gb2, gb3, gw4, grads[2], grads[3]))
+
+
+def egnn_node_pre_bwd(gz1, gQ, gD, gxd, gx_out, gh_direct, g, h, W1, gh, gx, partials):
+    f = h.shape[1]
+    n = h.shape[0]
+    deg_out = (g.outptr[1:] - g.outptr[:-1]).long()
+    owner = torch.repeat_interleave(torch.arange(n), deg_out)
+    pos = g.csc_pos.long()
+    gP = torch.zeros(n, 64).index_add_(0, owner, gz1[pos])
+    if gh is not None:
+        v = gP @ W1[:, :f] + gQ @ W1[:, f:2 * f]
+        gh.copy_(v + gh_direct if gh_direct is not None else v)
+    if gx is not None:
+        v = gxd + torch.zeros(n, 3).index_add_(0, owner, gD[pos])
+        gx.copy_(v + gx_out if gx_out is not None else v)
+    partials.copy_(_partials(partials.shape[0], gP.T @ h, gQ.T @ h, gQ.sum(0)))
+
+
+def reduce_partials(partials, out):
+    out.copy_(partials.sum(0))
+
+
+# ---- attention + pooling ------------------------------------------------------------------------
+def _attn_graph(qkv, n_head):
+    n = qkv.shape[0]
+    dh = 64 // n_head
+    q, k, v = (qkv[:, i * 64:(i + 1) * 64].reshape(n, n_head, dh).transpose(0, 1) for i in range(3))
+    s = q @ k.transpose(1, 2) / math.sqrt(dh)
+    w = torch.softmax(s, -1)
+    o = (w @ v).transpose(0, 1).reshape(n, 64)
+    return o, w, torch.logsumexp(s, -1).transpose(0, 1)
+
+
+def attn_pool_fwd(QKV, node_off, n_head, max_nodes, O, LSE, pooled, attn=None, attn_off=None):
+    off = node_off.tolist()
+    for gi in range(len(off) - 1):
+        a, b = off[gi], off[gi + 1]
+        o, w, lse = _attn_graph(QKV[a:b], n_head)
+        O[a:b] = o
+        LSE[a:b] = lse
+        pooled[gi] = o.mean(0)
+        if attn is not None:
+            attn.view(-1)[int(attn_off[gi]):int(attn_off[gi]) + w.numel()] = w.reshape(-1)
+
+
+@torch.enable_grad()
+def attn_pool_bwd(QKV, O, LSE, node_off, n_head, max_nodes, g_pooled, gO_full, gQKV):
+    off = node_off.tolist()
+    for gi in range(len(off) - 1):
+        a, b = off[gi], off[gi + 1]
+        leaf = QKV[a:b].detach().clone().requires_grad_(True)
+        o, _, _ = _attn_graph(leaf, n_head)
+        go = torch.zeros_like(o)
+        if g_pooled is not None:
+            go = go + g_pooled[gi] / (b - a)
+        if gO_full is not None:
+            go = go + gO_full[a:b]
+        gQKV[a:b] = torch.autograd.grad(o, leaf, go)[0]
+
+
+# ---- fusion attention (closed form; the dense equivalence is tested separately) -----------------
+def _fusion(c, coef, n_head):
+    hh = n_head
+    A, C, al, be, bt = coef[:hh], coef[hh:2 * hh], coef[2 * hh:3 * hh], coef[3 * hh:4 * hh], coef[4 * hh]
+    gamma = c.unsqueeze(-1) * A + C                                    # [B, L, H]
+    logits = gamma.unsqueeze(2) * c.unsqueeze(1).unsqueeze(-1)         # [B, i, j, H]
+    p = torch.softmax(logits, dim=2)
+    E = (p * c.unsqueeze(1).unsqueeze(-1)).sum(2)                      # [B, L, H]
+    return bt + (E * al + be).sum(-1)
+
+
+def fusion_attn_fwd(c, n_head, coef, out):
+    with torch.no_grad():
+        out.copy_(_fusion(c, coef, n_head))
+
+
+@torch.enable_grad()
+def fusion_attn_bwd(c, n_head, coef, gout, gc, gcoef_part):
+    cl = c.detach().clone().requires_grad_(True)
+    per_sample = coef.detach().unsqueeze(0).repeat(c.shape[0], 1).requires_grad_(True)
+    outs = torch.stack([_fusion(cl[i:i + 1], per_sample[i], n_head)[0] for i in range(c.shape[0])])
+    g_c, g_coef = torch.autograd.grad(outs, [cl, per_sample], gout)
+    gc.copy_(g_c)
+    gcoef_part.copy_(g_coef[:, :4 * n_head])
+
+
+# ---- losses -------------------------------------------------------------------------------------
+def _loss(recon, seq, mu, logvar, logits, y, mode, pos_weight, w_pred, w_mse, w_kld):
+    if mode == 0:
+        pred = F.binary_cross_entropy_with_logits(logits, y, pos_weight=torch.tensor(pos_weight))
+    else:
+        pred = F.mse_loss(logits, y)
+    mse = F.mse_loss(recon, seq) if w_mse != 0 else torch.zeros(())
+    kld = R.kld(mu, logvar) if w_kld != 0 else torch.zeros(())
+    return w_pred * pred + w_mse * mse + w_kld * kld, pred, mse, kld
+
+
+def loss_fwd(recon, seq, mu, logvar, logits, y, mode, pos_weight, w_pred, w_mse, w_kld, partial, out):
+    with torch.no_grad():
+        out.copy_(torch.stack(_loss(recon, seq, mu, logvar, logits, y, mode, pos_weight, w_pred, w_mse, w_kld)))
+
+
+@torch.enable_grad()
+def loss_bwd(recon, seq, mu, logvar, logits, y, mode, pos_weight, w_pred, w_mse, w_kld, gout,
+             g_recon, g_mu, g_logvar, g_logits):
+    lg = logits.detach().clone().requires_grad_(True)
+    if w_mse != 0:
+        rc, m, lv = (t.detach().clone().requires_grad_(True) for t in (recon, mu, logvar))
+        total = _loss(rc, seq, m, lv, lg, y, mode, pos_weight, w_pred, w_mse, w_kld)[0]
+        grads = torch.autograd.grad(total, [rc, m, lv, lg], gout.reshape(()))
+        g_recon.copy_(grads[0]); g_mu.copy_(grads[1]); g_logvar.copy_(grads[2]); g_logits.copy_(grads[3])
+    else:
+        total = _loss(None, None, None, None, lg, y, mode, pos_weight, w_pred, 0.0, 0.0)[0]
+        g_logits.copy_(torch.autograd.grad(total, lg, gout.reshape(()))[0])
+
+
+ALL = ["num_sms", "egnn_node_grid", "egnn_edge_bwd_grid", "attn_max_nodes", "loss_num_partials", "collate_csr",
+       "egnn_node_pre_fwd", "egnn_edge_fwd", "egnn_node_post_fwd", "egnn_node_post_bwd", "egnn_edge_bwd",
+       "egnn_node_pre_bwd", "reduce_partials", "attn_pool_fwd", "attn_pool_bwd", "fusion_attn_fwd",
+       "fusion_attn_bwd", "loss_fwd", "loss_bwd"]

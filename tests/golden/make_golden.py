@@ -179,9 +179,21 @@ def structure_case(model_map, fname, seed):
          grads=grads, meta={"gcn_layers": 2})
 
 
+def state_dict_shapes(model_map):
+    import json
+    out = {}
+    for name, cls in model_map.items():
+        m = cls(vae_input_dim=5943, device="cpu")
+        out[name] = {k: list(v.shape) for k, v in m.state_dict().items()}
+    with open(os.path.join(OUT, "state_dict_shapes.json"), "w") as f:
+        json.dump(out, f, indent=0, sort_keys=True)
+    print("state_dict_shapes.json", len(out), "classes")
+
+
 def main():
     torch.set_num_threads(1)
     model_map, Losses, PCL = shim.load_reference()
+    state_dict_shapes(model_map)
     hybrid_case(model_map, Losses, "HybridModelv2", "hybrid_v2.npz", gcn_layers=5, seed=1)
     hybrid_case(model_map, Losses, "HybridModel", "hybrid_v1.npz", gcn_layers=1, seed=2)
     comparative_case(model_map, Losses, PCL, "comparative_v2.npz", seed=3)

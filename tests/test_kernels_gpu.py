@@ -1,0 +1,340 @@
+"""Every CUDA kernel, called through the C ABI (ctypes), against its CPU contract
+(oracle/kernel_contracts.py) on the same seeded inputs.  Integer outputs bit-exact; fp32 within 1e-5
+of the result's scale (the north star's fp32 tolerance)."""
+import types
+
+import pytest
+import torch
+
+from immunostruct_b200 import _C
+from immunostruct_b200.graph import GraphBatch
+from immunostruct_b200.synthetic import synthetic_graph_arrays
+from oracle import kernel_contracts as KC
+from oracle import reference_ops as R
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 1e-5
+
+
+def close(got, ref, tol=TOL, what=""):
+    got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    scale = float(ref.abs().max().clamp_min(1e-6))
+    err = float((got - ref).abs().max())
+    _log(f"{what}: err {err:.3e} scale {scale:.3e} rel {err / scale:.2e} nan={bool(torch.isnan(got).any())}")
+    assert err <= tol * scale, f"{what}: max abs err {err:.3e} vs scale {scale:.3e} (rel {err / scale:.2e})"
+
+
+def _log(msg):
+    import os
+    os.makedirs("gpurun_out", exist_ok=True)
+    test = os.environ.get("PYTEST_CURRENT_TEST", "").split("::")[-1]
+    with open("gpurun_out/kernel_errors.txt", "a") as f:
+        f.write(f"{test} | {msg}\n")
+
+
+def random_multigraph_arrays(seed, node_counts, mean_deg):
+    """Ragged batch with multi-edges, self-free random endpoints, isolated nodes and varying in-degree."""
+    gen = torch.Generator().manual_seed(seed)
+    xs, srcs, dsts, ecs = [], [], [], []
+    for n in node_counts:
+        e = int(n * mean_deg) if n > 1 else 0
+        dst = torch.randint(0, max(n - 2, 1), (e,), generator=gen)        # last two nodes get no in-edges
+        src = (dst + 1 + torch.randint(0, n - 1, (e,), generator=gen)) % n  # never a self loop
+        x = torch.zeros(n, 23)
+        x[torch.arange(n), torch.randint(0, 20, (n,), generator=gen)] = 1.0
+        x[:, 20:] = torch.randn(n, 3, generator=gen) * 4.0
+        xs.append(x); srcs.append(src); dsts.append(dst); ecs.append(e)
+    return {"x": torch.cat(xs), "src": torch.cat(srcs), "dst": torch.cat(dsts),
+            "edge_attr": torch.rand(sum(ecs), 1, generator=gen) + 0.5,
+            "node_counts": torch.tensor(node_counts), "edge_counts": torch.tensor(ecs)}
+
+
+CASES = {
+    "knn_small": lambda: synthetic_graph_arrays(5, 37, 6, seed=3, n_pad=4, coord_scale=4.0),
+    "knn_200": lambda: synthetic_graph_arrays(3, 200, 10, seed=4, n_pad=10),
+    "ragged_multi": lambda: random_multigraph_arrays(5, [17, 1, 64, 33, 150, 2], 7.5),
+}
+
+
+def to_dev(arrays):
+    return GraphBatch.from_arrays(*(arrays[k].to(DEV) for k in
+                                    ("x", "src", "dst", "edge_attr", "node_counts", "edge_counts")))
+
+
+def cpu_graph(gb):
+    ns = types.SimpleNamespace()
+    for f in ("indptr", "csr_src", "csr_dst", "csr_eid", "outptr", "csc_pos", "node_off"):
+        setattr(ns, f, getattr(gb, f).cpu())
+    ns.n_edges, ns.n_graphs, ns.max_nodes = gb.n_edges, gb.n_graphs, gb.max_nodes
+    return ns
+
+
+@pytest.fixture(params=sorted(CASES))
+def case(request):
+    arrays = CASES[request.param]()
+    gb = to_dev(arrays)
+    return arrays, gb, cpu_graph(gb)
+
+
+def rnd(gen, *shape, scale=1.0):
+    return torch.randn(*shape, generator=gen) * scale
+
+
+def egnn_weights(gen, f):
+    s = 0.25
+    return dict(W1=rnd(gen, 64, 2 * f + 2, scale=s), b1=rnd(gen, 64, scale=s), W2=rnd(gen, 64, 64, scale=s),
+                b2=rnd(gen, 64, scale=s), W3=rnd(gen, 64, 64, scale=s), b3=rnd(gen, 64, scale=s),
+                w4=rnd(gen, 1, 64, scale=s), W5=rnd(gen, 64, f + 64, scale=s), b5=rnd(gen, 64, scale=s),
+                W6=rnd(gen, 64, 64, scale=s), b6=rnd(gen, 64, scale=s))
+
+
+def dev(*ts):
+    return [t.to(DEV) if t is not None else None for t in ts]
+
+
+# ---- collation: bit exact ----------------------------------------------------------------------
+def test_collate_bit_exact(case):
+    arrays, gb, _ = case
+    from immunostruct_b200.synthetic import split_graphs
+    ref = R.dgl_batch(split_graphs(arrays))
+    csr = R.csr_from_coo(ref["src"], ref["dst"], ref["num_nodes"])
+    assert torch.equal(gb.edge_index.cpu(), torch.stack([ref["src"], ref["dst"]]))
+    assert torch.equal(gb.batch.cpu(), R.batch_vector(ref["batch_num_nodes"]))
+    off = torch.zeros(gb.n_graphs + 1, dtype=torch.int64)
+    off[1:] = torch.cumsum(ref["batch_num_nodes"], 0)
+    assert torch.equal(gb.node_off.cpu(), off)
+    for k in ("indptr", "csr_src", "csr_dst", "csr_eid", "outptr", "csc_pos"):
+        assert torch.equal(getattr(gb, k).cpu(), csr[k]), k
+    deg = torch.bincount(ref["dst"], minlength=ref["num_nodes"])
+    assert gb.stats.cpu().tolist()[:2] == [int(deg.max()), 0]
+    gb.validate()
+
+
+def test_collate_flags_bad_endpoints():
+    arrays = CASES["knn_small"]()
+    arrays["src"][5] = 1000
+    gb = to_dev(arrays)
+    with pytest.raises(ValueError, match="outside"):
+        gb.validate()
+
+
+def test_cpu_tensors_are_rejected():
+    with pytest.raises(RuntimeError, match="CUDA"):
+        _C.egnn_node_pre_fwd(torch.zeros(4, 64), torch.zeros(64, 130), torch.zeros(64), torch.zeros(4, 128))
+
+
+# ---- EGNN forward ------------------------------------------------------------------------------
+@pytest.mark.parametrize("f", [20, 64])
+def test_egnn_forward_kernels(case, f):
+    arrays, gb, cg = case
+    gen = torch.Generator().manual_seed(11)
+    n = gb.n_nodes
+    w = egnn_weights(gen, f)
+    h = arrays["x"][:, :20].clone() if f == 20 else rnd(gen, n, 64)
+    x = arrays["x"][:, 20:].clone()
+    ea = arrays["edge_attr"].float()
+    # strided views for the 20-wide layer, exactly as the model slices ndata['x']
+    x23 = arrays["x"].to(DEV)
+    h_d = x23[:, :20] if f == 20 else h.to(DEV)
+    x_d = x23[:, 20:]
+    wd = {k: v.to(DEV) for k, v in w.items()}
+    PQ_d, PQ = torch.empty(n, 128, device=DEV), torch.empty(n, 128)
+    _C.egnn_node_pre_fwd(h_d, wd["W1"], wd["b1"], PQ_d)
+    KC.egnn_node_pre_fwd(h, w["W1"], w["b1"], PQ)
+    close(PQ_d, PQ, what="PQ")
+    for upd in (True, False):
+        hn_d, xo_d = torch.empty(n, 64, device=DEV), torch.empty(n, 3, device=DEV)
+        hn, xo = torch.empty(n, 64), torch.empty(n, 3)
+        _C.egnn_edge_fwd(gb, PQ_d, x_d, ea.to(DEV), f, wd["W1"], wd["W2"], wd["b2"], wd["W3"], wd["b3"], wd["w4"],
+                         upd, hn_d, xo_d if upd else None)
+        KC.egnn_edge_fwd(cg, PQ, x, ea, f, w["W1"], w["W2"], w["b2"], w["W3"], w["b3"], w["w4"], upd, hn, xo)
+        close(hn_d, hn, what=f"hn upd={upd}")
+        if upd:
+            close(xo_d - x_d, xo - x, what="x' - x")
+            close(xo_d, xo, what="x'")
+    ho_d, ho = torch.empty(n, 64, device=DEV), torch.empty(n, 64)
+    _C.egnn_node_post_fwd(h_d, hn_d, wd["W5"], wd["b5"], wd["W6"], wd["b6"], ho_d)
+    KC.egnn_node_post_fwd(h, hn, w["W5"], w["b5"], w["W6"], w["b6"], ho)
+    close(ho_d, ho, what="h'")
+    assert int(gb.status.item()) == 0
+
+
+# ---- EGNN backward -----------------------------------------------------------------------------
+@pytest.mark.parametrize("f,coord", [(64, True), (64, False), (20, True)])
+def test_egnn_backward_kernels(case, f, coord):
+    arrays, gb, cg = case
+    gen = torch.Generator().manual_seed(13)
+    n, e = gb.n_nodes, gb.n_edges
+    w = egnn_weights(gen, f)
+    wd = {k: v.to(DEV) for k, v in w.items()}
+    h = arrays["x"][:, :20].clone() if f == 20 else rnd(gen, n, 64)
+    x = arrays["x"][:, 20:].clone()
+    ea = arrays["edge_attr"].float()
+    x23 = arrays["x"].to(DEV)
+    h_d = x23[:, :20] if f == 20 else h.to(DEV)
+    x_d = x23[:, 20:]
+    PQ, hn = torch.empty(n, 128), torch.empty(n, 64)
+    KC.egnn_node_pre_fwd(h, w["W1"], w["b1"], PQ)
+    KC.egnn_edge_fwd(cg, PQ, x, ea, f, w["W1"], w["W2"], w["b2"], w["W3"], w["b3"], w["w4"], False, hn, None)
+    PQ_d, hn_d = PQ.to(DEV), hn.to(DEV)
+    gh_out, gx_out = rnd(gen, n, 64), (rnd(gen, n, 3) if coord else None)
+    need_gh = f == 64
+    k = f + 64
+    # node_post backward
+    grid_n = _C.egnn_node_grid(n)
+    ghd_d = torch.empty(n, 64, device=DEV) if need_gh else None
+    ghn_d, pp_d = torch.empty(n, 64, device=DEV), torch.empty(grid_n, 64 * k + 64 + 4096 + 64, device=DEV)
+    ghd = torch.empty(n, 64) if need_gh else None
+    ghn, pp = torch.empty(n, 64), torch.empty(KC.FAKE_GRID, 64 * k + 64 + 4096 + 64)
+    _C.egnn_node_post_bwd(gh_out.to(DEV), h_d, hn_d, wd["W5"], wd["b5"], wd["W6"], ghd_d, ghn_d, pp_d)
+    KC.egnn_node_post_bwd(gh_out, h, hn, w["W5"], w["b5"], w["W6"], ghd, ghn, pp)
+    close(ghn_d, ghn, what="ghn")
+    if need_gh:
+        close(ghd_d, ghd, what="gh_direct")
+    rp_d = torch.empty(pp_d.shape[1], device=DEV)
+    _C.reduce_partials(pp_d, rp_d)
+    rp = pp.sum(0)
+    for name, a, b in (("gW5", 0, 64 * k), ("gb5", 64 * k, 64 * k + 64), ("gW6", 64 * k + 64, 64 * k + 64 + 4096),
+                       ("gb6", 64 * k + 64 + 4096, 64 * k + 128 + 4096)):
+        close(rp_d[a:b], rp[a:b], what=name)
+    # edge backward
+    grid_e = _C.egnn_edge_bwd_grid(n)
+    outs_d = [torch.empty(e, 64, device=DEV), torch.empty(n, 64, device=DEV), torch.empty(e, 3, device=DEV),
+              torch.empty(n, 3, device=DEV), torch.empty(grid_e, 8512, device=DEV)]
+    outs = [torch.empty(e, 64), torch.empty(n, 64), torch.empty(e, 3), torch.empty(n, 3), torch.empty(KC.FAKE_GRID, 8512)]
+    _C.egnn_edge_bwd(gb, PQ_d, x_d, ea.to(DEV), f, wd["W1"], wd["W2"], wd["b2"], wd["W3"], wd["b3"], wd["w4"],
+                     ghn_d, gx_out.to(DEV) if coord else None, *outs_d)
+    KC.egnn_edge_bwd(cg, PQ, x, ea, f, w["W1"], w["W2"], w["b2"], w["W3"], w["b3"], w["w4"], ghn, gx_out, *outs)
+    for name, a, b in zip(("gz1", "gQ", "gD", "gxd"), outs_d[:4], outs[:4]):
+        close(a, b, what=name)
+    re_d = torch.empty(8512, device=DEV)
+    _C.reduce_partials(outs_d[4], re_d)
+    re = outs[4].sum(0)
+    names = [("gW2", 0, 4096), ("gb2", 8192, 8256), ("gwr", 8384, 8448), ("gwa", 8448, 8512)]
+    if coord:
+        names += [("gW3", 4096, 8192), ("gb3", 8256, 8320), ("gw4", 8320, 8384)]
+    for name, a, b in names:
+        close(re_d[a:b], re[a:b], what=name)
+    # node_pre backward
+    gz1_d, gQ_d, gD_d, gxd_d = outs_d[:4]
+    gz1, gQ, gD, gxd = outs[:4]
+    gh_d = torch.empty(n, 64, device=DEV) if need_gh else None
+    gx_d = torch.empty(n, 3, device=DEV)
+    p3_d = torch.empty(grid_n, 2 * 64 * f + 64, device=DEV)
+    gh = torch.empty(n, 64) if need_gh else None
+    gx, p3 = torch.empty(n, 3), torch.empty(KC.FAKE_GRID, 2 * 64 * f + 64)
+    _C.egnn_node_pre_bwd(gz1_d, gQ_d, gD_d, gxd_d, gx_out.to(DEV) if coord else None, ghd_d, gb, h_d, wd["W1"],
+                         gh_d, gx_d, p3_d)
+    KC.egnn_node_pre_bwd(gz1, gQ, gD, gxd, gx_out, ghd, cg, h, w["W1"], gh, gx, p3)
+    close(gx_d, gx, what="gx")
+    if need_gh:
+        close(gh_d, gh, what="gh")
+    r3_d = torch.empty(p3_d.shape[1], device=DEV)
+    _C.reduce_partials(p3_d, r3_d)
+    r3 = p3.sum(0)
+    for name, a, b in (("gWs", 0, 64 * f), ("gWd", 64 * f, 128 * f), ("gb1", 128 * f, 128 * f + 64)):
+        close(r3_d[a:b], r3[a:b], what=name)
+    assert int(gb.status.item()) == 0
+
+
+def test_backward_is_deterministic(case):
+    """Same inputs twice -> bit-identical gradients (no floating-point atomics anywhere)."""
+    arrays, gb, _ = case
+    gen = torch.Generator().manual_seed(17)
+    n, e = gb.n_nodes, gb.n_edges
+    w = {k: v.to(DEV) for k, v in egnn_weights(gen, 64).items()}
+    PQ, ghn, gx_out = dev(rnd(gen, n, 128), rnd(gen, n, 64), rnd(gen, n, 3))
+    x_d, ea = arrays["x"].to(DEV)[:, 20:], arrays["edge_attr"].float().to(DEV)
+    res = []
+    for _ in range(2):
+        outs = [torch.empty(e, 64, device=DEV), torch.empty(n, 64, device=DEV), torch.empty(e, 3, device=DEV),
+                torch.empty(n, 3, device=DEV), torch.empty(_C.egnn_edge_bwd_grid(n), 8512, device=DEV)]
+        _C.egnn_edge_bwd(gb, PQ, x_d, ea, 64, w["W1"], w["W2"], w["b2"], w["W3"], w["b3"], w["w4"], ghn, gx_out, *outs)
+        red = torch.empty(8512, device=DEV)
+        _C.reduce_partials(outs[4], red)
+        res.append([o.clone() for o in outs[:4]] + [red])
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+
+
+# ---- attention + pooling -----------------------------------------------------------------------
+@pytest.mark.parametrize("n_head", [1, 8])
+def test_attention_pool_kernels(case, n_head):
+    arrays, gb, cg = case
+    gen = torch.Generator().manual_seed(19)
+    n, b = gb.n_nodes, gb.n_graphs
+    QKV = rnd(gen, n, 192, scale=0.7)
+    O, LSE, pooled = torch.empty(n, 64), torch.empty(n, n_head), torch.empty(b, 64)
+    O_d, LSE_d, pooled_d = (torch.empty_like(t, device=DEV) for t in (O, LSE, pooled))
+    _C.attn_pool_fwd(QKV.to(DEV), gb.node_off, n_head, gb.max_nodes, O_d, LSE_d, pooled_d)
+    KC.attn_pool_fwd(QKV, cg.node_off, n_head, gb.max_nodes, O, LSE, pooled)
+    close(O_d, O, what="O"); close(LSE_d, LSE, what="LSE"); close(pooled_d, pooled, what="pooled")
+    g_pooled, gO = rnd(gen, b, 64), rnd(gen, n, 64)
+    for gp, go in ((g_pooled, None), (g_pooled, gO), (None, gO)):
+        gQKV, gQKV_d = torch.empty(n, 192), torch.empty(n, 192, device=DEV)
+        _C.attn_pool_bwd(QKV.to(DEV), O_d, LSE_d, gb.node_off, n_head, gb.max_nodes,
+                         gp.to(DEV) if gp is not None else None, go.to(DEV) if go is not None else None, gQKV_d)
+        KC.attn_pool_bwd(QKV, O, LSE, cg.node_off, n_head, gb.max_nodes, gp, go, gQKV)
+        close(gQKV_d, gQKV, what=f"gQKV pooled={gp is not None} full={go is not None}")
+
+
+def test_attention_weights_output():
+    arrays = CASES["knn_small"]()
+    gb = to_dev(arrays)
+    gen = torch.Generator().manual_seed(23)
+    n, b, m, hh = gb.n_nodes, gb.n_graphs, gb.max_nodes, 8
+    QKV = rnd(gen, n, 192)
+    attn_d = torch.empty(b, hh, m, m, device=DEV)
+    off = torch.arange(b, device=DEV, dtype=torch.int64) * (hh * m * m)
+    O_d, LSE_d, pooled_d = torch.empty(n, 64, device=DEV), torch.empty(n, hh, device=DEV), torch.empty(b, 64, device=DEV)
+    _C.attn_pool_fwd(QKV.to(DEV), gb.node_off, hh, m, O_d, LSE_d, pooled_d, attn_d, off)
+    ref = torch.stack([KC._attn_graph(QKV[i * m:(i + 1) * m], hh)[1] for i in range(b)])
+    close(attn_d, ref, what="attention weights")
+
+
+# ---- fusion attention --------------------------------------------------------------------------
+@pytest.mark.parametrize("L,H", [(104, 8), (208, 8), (7, 2)])
+def test_fusion_attention_kernels(L, H):
+    gen = torch.Generator().manual_seed(29)
+    b = 9
+    c, coef, gout = rnd(gen, b, L), rnd(gen, 4 * H + 1, scale=0.8), rnd(gen, b, L)
+    out, out_d = torch.empty(b, L), torch.empty(b, L, device=DEV)
+    _C.fusion_attn_fwd(c.to(DEV), H, coef.to(DEV), out_d)
+    KC.fusion_attn_fwd(c, H, coef, out)
+    close(out_d, out, what="fusion out")
+    gc, gp = torch.empty(b, L), torch.empty(b, 4 * H)
+    gc_d, gp_d = torch.empty(b, L, device=DEV), torch.empty(b, 4 * H, device=DEV)
+    _C.fusion_attn_bwd(c.to(DEV), H, coef.to(DEV), gout.to(DEV), gc_d, gp_d)
+    KC.fusion_attn_bwd(c, H, coef, gout, gc, gp)
+    close(gc_d, gc, what="fusion gc")
+    close(gp_d.sum(0), gp.sum(0), what="fusion gcoef")
+
+
+# ---- losses ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode,seqflag", [(0, True), (1, True), (0, False), (1, False)])
+def test_loss_kernels(mode, seqflag):
+    gen = torch.Generator().manual_seed(31)
+    b, s, z = 37, 5943, 32
+    recon, seq = rnd(gen, b, s), (torch.rand(b, s, generator=gen) < 0.05).float()
+    mu, lv, logits = rnd(gen, b, z), rnd(gen, b, z, scale=0.3), rnd(gen, b, scale=2.0)
+    y = (torch.rand(b, generator=gen) < 0.3).float() if mode == 0 else rnd(gen, b)
+    wts = ((5.0, 0.1, 0.1) if mode == 0 else (2.0, 0.5, 0.5)) if seqflag else (1.0, 0.0, 0.0)
+    args = (recon, seq, mu, lv) if seqflag else (None, None, None, None)
+    out, out_d = torch.empty(4), torch.empty(4, device=DEV)
+    part = torch.empty(_C.loss_num_partials(), device=DEV)
+    _C.loss_fwd(*dev(*args), logits.to(DEV), y.to(DEV), mode, 4.25, *wts, part, out_d)
+    KC.loss_fwd(*args, logits, y, mode, 4.25, *wts, None, out)
+    close(out_d[:1], out[:1], what="loss")
+    close(out_d, out, what="loss components")
+    gout = torch.tensor([0.7])
+    g = [torch.empty(b, s), torch.empty(b, z), torch.empty(b, z), torch.empty(b)]
+    g_d = [torch.empty_like(t, device=DEV) for t in g]
+    if not seqflag:
+        g[:3], g_d[:3] = [None] * 3, [None] * 3
+    _C.loss_bwd(*dev(*args), logits.to(DEV), y.to(DEV), mode, 4.25, *wts, gout.to(DEV), *g_d)
+    KC.loss_bwd(*args, logits, y, mode, 4.25, *wts, gout, *g)
+    for name, a, bb in zip(("g_recon", "g_mu", "g_logvar", "g_logits"), g_d, g):
+        if a is not None:
+            close(a, bb, what=name)

@@ -1,0 +1,183 @@
+"""End-to-end parity of the product models on the GPU: golden vectors produced by the unmodified
+reference code, the full-model CPU oracle at the benchmark's graph shape, and size-independent
+properties (determinism, edge-order invariance, padding semantics) at full batch sizes.
+Tolerances: 1e-5 relative on logits / loss (north star, fp32), gradients 1e-5 of the parameter's
+scale with a floor (conftest.assert_grads_close)."""
+import pytest
+import torch
+
+import immunostruct_b200 as I
+from immunostruct_b200.synthetic import synthetic_dense, synthetic_graph_arrays, split_graphs
+from oracle import reference_ops as R
+
+from conftest import assert_grads_close, load_golden, rel_err
+from helpers import build_model, graph_batch, inject_eps, named_grads
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 1e-5
+
+
+def _d(t):
+    return t.to(DEV)
+
+
+@pytest.mark.parametrize("name,cls", [("hybrid_v2", "HybridModelv2"), ("hybrid_v1", "HybridModel")])
+def test_hybrid_golden(name, cls):
+    gd = load_golden(name)
+    model = build_model(cls, gd, device=DEV)
+    g = graph_batch(gd["graph"], DEV).validate()
+    d, o = gd["dense"], gd["out"]
+    inject_eps(model, d["eps"], d["eps"], d["eps"])
+    recon, mu, logvar, out = model(g, _d(d["seq"]), _d(d["prop"]))
+    for got, key in ((recon, "recon"), (mu, "mu"), (logvar, "logvar"), (out, "logits")):
+        assert rel_err(got, o[key]) < TOL, key
+    # closer to the fp64 run of the reference than 1e-5 as well
+    assert rel_err(out, o["logits64"]) < TOL
+    losses = I.Losses(231, [float(gd["meta"]["pos_weight"]), 1.0], sequence=True)
+    loss = losses.BCE_loss(recon, _d(d["seq"]), mu, logvar, out, _d(d["target"]))
+    assert rel_err(loss, o["loss_bce"]) < TOL
+    assert rel_err(losses.regression_loss(recon, _d(d["seq"]), mu, logvar, out, _d(d["target"] * 0.5 - 0.1)),
+                   o["loss_reg"]) < TOL
+    loss.backward()
+    assert_grads_close(named_grads(model), gd["grads"], TOL)
+    emb = model(g, _d(d["seq"]), _d(d["prop"]), return_embedding=True)[0]
+    att = model(g, _d(d["seq"]), _d(d["prop"]), return_attention=True)[0]
+    assert rel_err(emb, o["embedding"]) < TOL
+    assert att.shape == o["attention"].shape and rel_err(att, o["attention"]) < TOL
+
+
+def test_comparative_golden():
+    gd = load_golden("comparative_v2")
+    model = build_model("HybridModelv2_Comparative", gd, device=DEV)
+    gc, gw = graph_batch(gd["graph_c"], DEV), graph_batch(gd["graph_w"], DEV)
+    d, o = gd["dense"], gd["out"]
+    inject_eps(model, d["eps_c"], d["eps_w"], d["eps_c"])
+    embs, recons, mus, logvars, out = model.forward_comparative(
+        (gc, gw), (_d(d["seq_c"]), _d(d["seq_w"])), (_d(d["prop_c"]), _d(d["prop_w"])))
+    assert rel_err(out, o["logits"]) < TOL
+    assert rel_err(embs[0], o["emb_c"]) < TOL and rel_err(embs[1], o["emb_w"]) < TOL
+    losses = I.Losses(231, [float(gd["meta"]["pos_weight"]), 1.0], sequence=True)
+    pcl = I.PairedContrastiveLoss(embedding_dim=104, device=DEV)
+    pcl.load_state_dict(gd["projector"])
+    y = _d(d["target"])
+    l_c = losses.BCE_loss(recons[0], _d(d["seq_c"]), mus[0], logvars[0], out, y)
+    l_w = losses.BCE_loss(recons[1], _d(d["seq_w"]), mus[1], logvars[1], out, y)
+    l_con = pcl(embs[0], embs[1], y)
+    assert rel_err(l_con, o["loss_contrastive"]) < 5e-5      # B x B and 128 x 128 sums of squares
+    loss = (l_c + l_w) / 2 + float(gd["meta"]["coeff_contrastive"]) * l_con
+    assert rel_err(loss, o["loss"]) < TOL
+    loss.backward()
+    assert_grads_close(named_grads(model), gd["grads"], 2e-5)
+    assert rel_err(model(gc, _d(d["seq_c"]), _d(d["prop_c"]))[3], o["single_logits"]) < TOL
+
+
+def test_structure_v2_golden():
+    gd = load_golden("structure_v2")
+    model = I.model_map["StructureModelv2"](vae_input_dim=231, device=DEV, gcn_layers=1)
+    model.load_state_dict(gd["weights"])
+    model.to(DEV).eval()
+    g = graph_batch(gd["graph"], DEV)
+    _, _, _, out, node_pred = model(g, _d(gd["dense"]["seq"]), _d(gd["dense"]["prop"]))
+    assert rel_err(out, gd["out"]["logits"]) < TOL and rel_err(node_pred, gd["out"]["node_pred"]) < TOL
+    (out.sum() + node_pred.pow(2).sum()).backward()
+    assert_grads_close(named_grads(model), gd["grads"], TOL)
+
+
+def _bench_shape_case(b, seed, n_pad=0, scale=2.0):
+    arr = synthetic_graph_arrays(b, 200, 10, seed=seed, n_pad=n_pad)
+    dense = synthetic_dense(b, seed=seed)
+    torch.manual_seed(seed)
+    model = I.model_map["HybridModelv2"](vae_input_dim=5943, device=DEV)
+    with torch.no_grad():
+        for k, p in model.named_parameters():
+            if k.startswith("GCN_layers") and k.endswith("weight"):
+                p.mul_(scale)
+    eps = torch.randn(b, 32, generator=torch.Generator().manual_seed(seed + 3))
+    return arr, dense, model, eps
+
+
+def test_benchmark_shape_against_full_model_oracle():
+    """N = 200, k = 10, vae_input_dim 5943 (BASELINE config shape), padded variant: logits, loss and
+    every parameter gradient against the CPU oracle."""
+    b = 6
+    arr, dense, model, eps = _bench_shape_case(b, seed=5, n_pad=10)
+    p = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    g = R.dgl_batch(split_graphs(arr))
+    recon, mu, logvar, out = R.hybrid_forward(p, g, dense["seq"], dense["prop"], eps)
+    loss_ref = R.bce_loss(recon, dense["seq"], mu, logvar, out, dense["target"], 4.25)
+    loss_ref.backward()
+    model = model.to(DEV).eval()
+    inject_eps(model, eps)
+    gb = graph_batch(arr, DEV).validate()
+    r2, m2, lv2, o2 = model(gb, _d(dense["seq"]), _d(dense["prop"]))
+    losses = I.Losses(5943, [4.25, 1.0], sequence=True)
+    loss = losses.BCE_loss(r2, _d(dense["seq"]), m2, lv2, o2, _d(dense["target"]))
+    assert rel_err(o2, out) < TOL and rel_err(r2, recon) < TOL and rel_err(loss, loss_ref) < TOL
+    loss.backward()
+    assert_grads_close(named_grads(model), {k: v.grad for k, v in p.items()}, TOL)
+
+
+def test_full_batch_properties():
+    """Batch 512 (BASELINE inference batch): bit-determinism, edge-order invariance within tolerance,
+    per-graph independence (a graph's output does not depend on its batch neighbours)."""
+    b = 512
+    arr, dense, model, eps = _bench_shape_case(b, seed=9)
+    model = model.to(DEV).eval()
+    seq, prop = _d(dense["seq"]), _d(dense["prop"])
+    with torch.no_grad():
+        outs = []
+        for _ in range(2):
+            inject_eps(model, eps)
+            outs.append(model(graph_batch(arr, DEV), seq, prop))
+        for a, c in zip(outs[0], outs[1]):
+            assert torch.equal(a, c)
+        # shuffle the edge order inside every graph: sums are re-associated, nothing else changes
+        e = int(arr["edge_counts"][0])
+        perm = torch.stack([torch.randperm(e) + i * e for i in range(b)]).reshape(-1)
+        arr2 = dict(arr, src=arr["src"][perm], dst=arr["dst"][perm], edge_attr=arr["edge_attr"][perm])
+        inject_eps(model, eps)
+        shuffled = model(graph_batch(arr2, DEV), seq, prop)
+        assert rel_err(shuffled[3], outs[0][3]) < TOL
+        # the first 8 graphs alone give the same logits as inside the batch of 512
+        sub = synthetic_graph_arrays(b, 200, 10, seed=9)
+        n8, e8 = 8 * 200, 8 * e
+        arr8 = {"x": sub["x"][:n8], "src": sub["src"][:e8], "dst": sub["dst"][:e8], "edge_attr": sub["edge_attr"][:e8],
+                "node_counts": sub["node_counts"][:8], "edge_counts": sub["edge_counts"][:8]}
+        inject_eps(model, eps[:8])
+        small = model(graph_batch(arr8, DEV), seq[:8], prop[:8])
+        assert rel_err(small[3], outs[0][3][:8]) < TOL
+    assert torch.isfinite(outs[0][3]).all()
+
+
+def test_last_layer_coord_mlp_has_no_grad_and_training_step_runs():
+    """Reference behaviour: layer-5 coord_mlp parameters keep grad None, so
+    Adam/AdamW skip them.  Also runs two optimiser steps in train mode (dropout + randn_like live)."""
+    b = 16
+    arr, dense, model, _ = _bench_shape_case(b, seed=13, scale=1.0)
+    model = model.to(DEV).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    losses = I.Losses(5943, [4.25, 1.0], sequence=True)
+    gb = graph_batch(arr, DEV)
+    vals = []
+    for _ in range(2):
+        opt.zero_grad()
+        recon, mu, logvar, out = model(gb, _d(dense["seq"]), _d(dense["prop"]))
+        loss = losses.BCE_loss(recon, _d(dense["seq"]), mu, logvar, out, _d(dense["target"]))
+        loss.backward()
+        opt.step()
+        vals.append(float(loss))
+    last = len(model.GCN_layers) - 1
+    for k, p in model.named_parameters():
+        if k.startswith(f"GCN_layers.{last}.coord_mlp"):
+            assert p.grad is None, k
+        else:
+            assert p.grad is not None and torch.isfinite(p.grad).all(), k
+    assert all(v == v for v in vals)
+
+
+def test_contrastive_gate_on_device():
+    pcl = I.PairedContrastiveLoss(embedding_dim=104, device=DEV)
+    e1, e2 = torch.randn(8, 104, device=DEV), torch.randn(8, 104, device=DEV)
+    assert float(pcl(e1, e2, torch.ones(8, device=DEV))) == 0.0
+    assert float(pcl(e1, e2, torch.tensor([0., 1, 0, 1, 1, 0, 0, 1], device=DEV))) > 0.0
