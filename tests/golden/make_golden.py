@@ -71,7 +71,9 @@ def scaled_init(model, seed, scale):
 
 
 def pack(prefix, d):
-    return {f"{prefix}{k}": (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v))
+    # fp64 reference values are stored rounded to fp32 (6e-8 relative: far below the 1e-5 tolerance)
+    cast = (lambda v: v.float()) if prefix.startswith("grads64") else (lambda v: v)
+    return {f"{prefix}{k}": (cast(v.detach().cpu()).numpy() if torch.is_tensor(v) else np.asarray(v))
             for k, v in d.items()}
 
 
@@ -118,13 +120,16 @@ def hybrid_case(model_map, Losses, cls, fname, gcn_layers, seed):
     g64 = dict(g, x=g["x"].double(), edge_attr=g["edge_attr"].double())
     with _Eps([eps]):
         r64 = m64(shim.graph_from_dict(g64), seq.double(), prop.double())
+    losses.BCE_loss(r64[0], seq.double(), r64[1], r64[2], r64[3], y.double()).backward()
+    grads64 = {k_: (p.grad if p.grad is not None else torch.full((1,), float("nan")))
+               for k_, p in m64.named_parameters()}
     save(fname,
          graph=graph_inputs(arr), dense={"seq": seq, "prop": prop, "target": y, "eps": eps},
          weights=dict(model.state_dict()),
          out={"recon": recon, "mu": mu, "logvar": logvar, "logits": out, "embedding": emb,
               "attention": attn, "h_last": trunk["h_last"], "x_last": trunk["x_last"],
               "loss_bce": loss, "loss_reg": loss_reg, "logits64": r64[3], "recon64": r64[0]},
-         grads=grads,
+         grads=grads, grads64=grads64,
          meta={"gcn_layers": gcn_layers + 1, "pos_weight": 2.0, "vae_hidden_dim": 32,
                "n_nodes": n, "k": k})
 
@@ -138,6 +143,7 @@ def comparative_case(model_map, Losses, PCL, fname, seed):
     scaled_init(model, seed, 1.6).eval()
     torch.manual_seed(seed + 5)
     pcl = PCL(embedding_dim=104)
+    pcl_state = {k_: v.clone() for k_, v in pcl.state_dict().items()}     # before BatchNorm running stats move
     losses = Losses(SEQ[0] * SEQ[1], [3.0, 1.0], sequence=True)
     with _Eps([eps_c, eps_w]):
         embs, recons, mus, logvars, out = model.forward_comparative(
@@ -152,16 +158,32 @@ def comparative_case(model_map, Losses, PCL, fname, seed):
              for k_, p in model.named_parameters()}
     with _Eps([eps_c]):
         single = model(shim.graph_from_dict(g_c), seq_c, prop_c)
+    # fp64 run of the same reference code (model, losses and contrastive module in double)
+    m64 = model_map["HybridModelv2_Comparative"](vae_input_dim=SEQ[0] * SEQ[1], device="cpu",
+                                                 gcn_layers=1, vae_hidden_dim=32).double().eval()
+    m64.load_state_dict({k_: v.double() for k_, v in model.state_dict().items()})
+    pcl64 = PCL(embedding_dim=104).double()
+    pcl64.load_state_dict({k_: v.double() if v.is_floating_point() else v for k_, v in pcl_state.items()})
+    dd = lambda gg: shim.graph_from_dict(dict(gg, x=gg["x"].double(), edge_attr=gg["edge_attr"].double()))
+    with _Eps([eps_c, eps_w]):
+        e64, r64, mu64, lv64, o64 = m64.forward_comparative((dd(g_c), dd(g_w)), (seq_c.double(), seq_w.double()),
+                                                            (prop_c.double(), prop_w.double()))
+    y64 = y.double()
+    l64 = (losses.BCE_loss(r64[0], seq_c.double(), mu64[0], lv64[0], o64, y64)
+           + losses.BCE_loss(r64[1], seq_w.double(), mu64[1], lv64[1], o64, y64)) / 2 + 0.01 * pcl64(e64[0], e64[1], y64)
+    l64.backward()
+    grads64 = {k_: (p.grad if p.grad is not None else torch.full((1,), float("nan")))
+               for k_, p in m64.named_parameters()}
     save(fname,
          graph_c=graph_inputs(arr_c), graph_w=graph_inputs(arr_w),
          dense={"seq_c": seq_c, "seq_w": seq_w, "prop_c": prop_c, "prop_w": prop_w, "target": y,
                 "eps_c": eps_c, "eps_w": eps_w},
-         weights=dict(model.state_dict()), projector=dict(pcl.state_dict()),
+         weights=dict(model.state_dict()), projector=pcl_state,
          out={"emb_c": embs[0], "emb_w": embs[1], "recon_c": recons[0], "recon_w": recons[1],
               "mu_c": mus[0], "mu_w": mus[1], "logvar_c": logvars[0], "logvar_w": logvars[1],
               "logits": out, "loss_contrastive": l_con, "loss": loss,
               "single_logits": single[3], "single_recon": single[0]},
-         grads=grads, meta={"gcn_layers": 2, "pos_weight": 3.0, "coeff_contrastive": 0.01})
+         grads=grads, grads64=grads64, meta={"gcn_layers": 2, "pos_weight": 3.0, "coeff_contrastive": 0.01})
 
 
 def structure_case(model_map, fname, seed):

@@ -41,7 +41,7 @@ def random_multigraph_arrays(seed, node_counts, mean_deg):
     for n in node_counts:
         e = int(n * mean_deg) if n > 1 else 0
         dst = torch.randint(0, max(n - 2, 1), (e,), generator=gen)        # last two nodes get no in-edges
-        src = (dst + 1 + torch.randint(0, n - 1, (e,), generator=gen)) % n  # never a self loop
+        src = (dst + 1 + torch.randint(0, max(n - 1, 1), (e,), generator=gen)) % n  # never a self loop
         x = torch.zeros(n, 23)
         x[torch.arange(n), torch.randint(0, 20, (n,), generator=gen)] = 1.0
         x[:, 20:] = torch.randn(n, 3, generator=gen) * 4.0
@@ -121,7 +121,7 @@ def test_collate_flags_bad_endpoints():
 
 
 def test_cpu_tensors_are_rejected():
-    with pytest.raises(RuntimeError, match="CUDA"):
+    with pytest.raises((RuntimeError, ValueError), match="CUDA"):
         _C.egnn_node_pre_fwd(torch.zeros(4, 64), torch.zeros(64, 130), torch.zeros(64), torch.zeros(4, 128))
 
 

@@ -40,7 +40,7 @@ def test_hybrid_golden(name, cls):
     assert rel_err(losses.regression_loss(recon, _d(d["seq"]), mu, logvar, out, _d(d["target"] * 0.5 - 0.1)),
                    o["loss_reg"]) < TOL
     loss.backward()
-    assert_grads_close(named_grads(model), gd["grads"], TOL)
+    assert_grads_close(named_grads(model), gd["grads"], TOL, truth=gd["grads64"])
     emb = model(g, _d(d["seq"]), _d(d["prop"]), return_embedding=True)[0]
     att = model(g, _d(d["seq"]), _d(d["prop"]), return_attention=True)[0]
     assert rel_err(emb, o["embedding"]) < TOL
@@ -68,7 +68,7 @@ def test_comparative_golden():
     loss = (l_c + l_w) / 2 + float(gd["meta"]["coeff_contrastive"]) * l_con
     assert rel_err(loss, o["loss"]) < TOL
     loss.backward()
-    assert_grads_close(named_grads(model), gd["grads"], 2e-5)
+    assert_grads_close(named_grads(model), gd["grads"], TOL, truth=gd["grads64"])
     assert rel_err(model(gc, _d(d["seq_c"]), _d(d["prop_c"]))[3], o["single_logits"]) < TOL
 
 
@@ -84,7 +84,11 @@ def test_structure_v2_golden():
     assert_grads_close(named_grads(model), gd["grads"], TOL)
 
 
-def _bench_shape_case(b, seed, n_pad=0, scale=2.0):
+def _bench_shape_case(b, seed, n_pad=0, scale=1.0):
+    """HybridModelv2 at the BASELINE shape with default initialisation (at 200 nodes / in-degree 10 the
+    logits already differ between graphs in the 2nd digit; scaling the EGNN weights up saturates the
+    per-graph softmax and, from about 2x, overflows fp32 through the six un-normalised
+    sum-aggregations in reference and product alike)."""
     arr = synthetic_graph_arrays(b, 200, 10, seed=seed, n_pad=n_pad)
     dense = synthetic_dense(b, seed=seed)
     torch.manual_seed(seed)
@@ -97,16 +101,25 @@ def _bench_shape_case(b, seed, n_pad=0, scale=2.0):
     return arr, dense, model, eps
 
 
+def _oracle_run(state, arr, dense, eps, dtype):
+    p = {k: v.detach().clone().to(dtype).requires_grad_(True) for k, v in state.items()}
+    g = R.dgl_batch(split_graphs(arr))
+    g = dict(g, x=g["x"].to(dtype), edge_attr=g["edge_attr"].to(dtype))
+    recon, mu, logvar, out = R.hybrid_forward(p, g, dense["seq"].to(dtype), dense["prop"].to(dtype), eps.to(dtype))
+    loss = R.bce_loss(recon, dense["seq"].to(dtype), mu, logvar, out, dense["target"].to(dtype), 4.25)
+    loss.backward()
+    return recon, out, loss, {k: v.grad for k, v in p.items()}
+
+
 def test_benchmark_shape_against_full_model_oracle():
     """N = 200, k = 10, vae_input_dim 5943 (BASELINE config shape), padded variant: logits, loss and
-    every parameter gradient against the CPU oracle."""
+    every parameter gradient against the CPU oracle (fp32 = the reference's arithmetic, fp64 = truth)."""
     b = 6
     arr, dense, model, eps = _bench_shape_case(b, seed=5, n_pad=10)
-    p = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
-    g = R.dgl_batch(split_graphs(arr))
-    recon, mu, logvar, out = R.hybrid_forward(p, g, dense["seq"], dense["prop"], eps)
-    loss_ref = R.bce_loss(recon, dense["seq"], mu, logvar, out, dense["target"], 4.25)
-    loss_ref.backward()
+    state = {k: v.cpu() for k, v in model.state_dict().items()}
+    recon, out, loss_ref, grads32 = _oracle_run(state, arr, dense, eps, torch.float32)
+    _, out64, _, grads64 = _oracle_run(state, arr, dense, eps, torch.float64)
+    assert float(out.std()) > 1e-4 * float(out.abs().mean())          # outputs do depend on the graph
     model = model.to(DEV).eval()
     inject_eps(model, eps)
     gb = graph_batch(arr, DEV).validate()
@@ -114,8 +127,9 @@ def test_benchmark_shape_against_full_model_oracle():
     losses = I.Losses(5943, [4.25, 1.0], sequence=True)
     loss = losses.BCE_loss(r2, _d(dense["seq"]), m2, lv2, o2, _d(dense["target"]))
     assert rel_err(o2, out) < TOL and rel_err(r2, recon) < TOL and rel_err(loss, loss_ref) < TOL
+    assert rel_err(o2, out64) < TOL
     loss.backward()
-    assert_grads_close(named_grads(model), {k: v.grad for k, v in p.items()}, TOL)
+    assert_grads_close(named_grads(model), grads32, TOL, truth=grads64)
 
 
 def test_full_batch_properties():
@@ -154,7 +168,7 @@ def test_last_layer_coord_mlp_has_no_grad_and_training_step_runs():
     """Reference behaviour: layer-5 coord_mlp parameters keep grad None, so
     Adam/AdamW skip them.  Also runs two optimiser steps in train mode (dropout + randn_like live)."""
     b = 16
-    arr, dense, model, _ = _bench_shape_case(b, seed=13, scale=1.0)
+    arr, dense, model, _ = _bench_shape_case(b, seed=13)
     model = model.to(DEV).train()
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
     losses = I.Losses(5943, [4.25, 1.0], sequence=True)
