@@ -71,7 +71,7 @@ attn_fwd_kernel(const float* __restrict__ QKV, const int64_t* __restrict__ node_
 #pragma unroll
             for (int jj = 0; jj < IS_ATT_NMAX / 32; ++jj) {
                 const int j = jj * 32 + lane;
-                const float e = (j < n) ? __expf(s[jj] - mx) : 0.0f;
+                const float e = (j < n) ? expf(s[jj] - mx) : 0.0f;
                 s[jj] = e;
                 z += e;
             }
@@ -88,7 +88,7 @@ attn_fwd_kernel(const float* __restrict__ QKV, const int64_t* __restrict__ node_
                 }
             }
             __syncwarp();
-            if (lane == 0) LSE[(n0 + i) * H + h] = mx + __logf(z);
+            if (lane == 0) LSE[(n0 + i) * H + h] = mx + logf(z);
             // O[i][h*dh + k] = sum_j p_j V[j][h*dh + k]; lanes over k (two k per lane when dh = 64)
             for (int k = lane; k < dh; k += 32) {
                 float o = 0.0f;
@@ -167,7 +167,7 @@ attn_bwd_kernel(const float* __restrict__ QKV, const float* __restrict__ O, cons
                 const float* vr = S1 + j * IS_ATT_LD + h * dh;
                 float a = 0.0f, gp = 0.0f;
                 for (int k = 0; k < dh; ++k) { a = fmaf(q[h * dh + k], kr[k], a); gp = fmaf(go[h * dh + k], vr[k], gp); }
-                const float pj = __expf(a * scale - lse);
+                const float pj = expf(a * scale - lse);
                 pr[j] = pj * (gp - D);
             }
             __syncwarp();
@@ -205,7 +205,7 @@ attn_bwd_kernel(const float* __restrict__ QKV, const float* __restrict__ O, cons
                 const float* gr = S1 + i * IS_ATT_LD + h * dh;
                 float a = 0.0f, gp = 0.0f;
                 for (int k = 0; k < dh; ++k) { a = fmaf(qr[k], kk[h * dh + k], a); gp = fmaf(gr[k], vv[h * dh + k], gp); }
-                const float pij = __expf(a * scale - __ldg(LSE + (n0 + i) * H + h));
+                const float pij = expf(a * scale - __ldg(LSE + (n0 + i) * H + h));
                 pc[i] = pij;
                 pr[i] = pij * (gp - Dn[i * 8 + h]);
             }

@@ -31,7 +31,9 @@
 
 namespace is {
 
-__device__ __forceinline__ float sigmoidf_fast(float z) { return __fdividef(1.0f, 1.0f + __expf(-z)); }
+// accurate exp + correctly rounded reciprocal: the fast intrinsics (__expf, __fdividef) cost ~1e-5 of
+// gradient parity against the fp32 reference (measured on the B200: tests/test_models_gpu.py)
+__device__ __forceinline__ float sigmoidf_fast(float z) { return __frcp_rn(1.0f + expf(-z)); }
 __device__ __forceinline__ float silu(float z) { return z * sigmoidf_fast(z); }
 // d/dz [z * sigmoid(z)] = s * (1 + z * (1 - s))
 __device__ __forceinline__ float dsilu(float z) {

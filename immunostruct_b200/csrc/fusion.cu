@@ -29,7 +29,7 @@ __device__ __forceinline__ void fusion_pair(const float* __restrict__ c, int L, 
     Z = 0.0f; S1 = 0.0f; S2 = 0.0f;
     for (int j = 0; j < L; ++j) {
         const float cj = c[j];
-        const float e = __expf(gamma * cj - mx);
+        const float e = expf(gamma * cj - mx);
         Z += e; S1 = fmaf(e, cj, S1); S2 = fmaf(e * cj, cj, S2);
     }
 }
@@ -137,7 +137,7 @@ fusion_bwd_kernel(const float* __restrict__ cin, int L, int H, const float* __re
             for (int h = 0; h < H; ++h) {
                 const int idx = i * H + h;
                 const float gam = s_gam[idx];
-                const float p = __expf(gam * cj - s_mx[idx]) * s_rz[idx];
+                const float p = expf(gam * cj - s_mx[idx]) * s_rz[idx];
                 s = fmaf(goi * coef[2 * H + h] * p, 1.0f + gam * (cj - s_E[idx]), s);
             }
         }
