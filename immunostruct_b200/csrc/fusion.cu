@@ -107,7 +107,14 @@ fusion_bwd_kernel(const float* __restrict__ cin, int L, int H, const float* __re
         const float gamma = coef[h] * c[i] + coef[H + h];
         float mx, Z, S1, S2;
         fusion_pair(c, L, gamma, cmax, cmin, mx, Z, S1, S2);
-        const float rz = 1.0f / Z, E = S1 * rz, var = S2 * rz - E * E;
+        const float rz = 1.0f / Z, E = S1 * rz;
+        // variance by a second pass around the mean: E[c^2] - E[c]^2 cancels catastrophically in fp32
+        float var = 0.0f;
+        for (int j = 0; j < L; ++j) {
+            const float dcj = c[j] - E;
+            var = fmaf(expf(gamma * c[j] - mx), dcj * dcj, var);
+        }
+        var *= rz;
         s_gam[idx] = gamma; s_mx[idx] = mx; s_rz[idx] = rz; s_E[idx] = E;
         s_gg[idx] = go[i] * coef[2 * H + h] * var;             // dL/dgamma_ih
     }
