@@ -39,7 +39,7 @@ def exported_symbols():
             "is_loss_num_partials", "is_collate_csr", "is_egnn_node_pre_fwd", "is_egnn_edge_fwd",
             "is_egnn_node_post_fwd", "is_egnn_node_post_bwd", "is_egnn_edge_bwd", "is_egnn_node_pre_bwd",
             "is_reduce_partials", "is_attn_pool_fwd", "is_attn_pool_bwd", "is_fusion_attn_fwd",
-            "is_fusion_attn_bwd", "is_loss_fwd", "is_loss_bwd"]
+            "is_fusion_attn_bwd", "is_loss_fwd", "is_loss_bwd", "is_umma_selftest"]
 
 
 def _check(rc: int, name: str):
@@ -234,3 +234,10 @@ def loss_bwd(recon, seq, mu, logvar, logits, y, mode, pos_weight, w_pred, w_mse,
           _i64(logits.numel()), _i32(mode), _f32(pos_weight), _f32(w_pred), _f32(w_mse), _f32(w_kld),
           _t(gout, f32, "gout"), _t(g_recon, f32, "g_recon"), _t(g_mu, f32, "g_mu"),
           _t(g_logvar, f32, "g_logvar"), _t(g_logits, f32, "g_logits"), _stream())
+
+
+# ---- tcgen05 self-test ---------------------------------------------------------------------------
+def umma_selftest(A, B, D, mode):
+    """D[128,64] = A[128,64] @ B[64,64]^T on the tensor cores; mode 0 bf16, 1 tf32, 2 3xTF32."""
+    f32 = torch.float32
+    _call("is_umma_selftest", _t(A, f32, "A"), _t(B, f32, "B"), _t(D, f32, "D"), _i32(mode), _stream())

@@ -1,0 +1,137 @@
+// Hand-written tcgen05 (5th-generation tensor core) helpers for sm_100a: shared-memory matrix
+// descriptors, instruction descriptors, TMEM allocation, MMA issue, commit/mbarrier, TMEM loads.
+//
+// Operand layout used everywhere in this project: K-major, SWIZZLE_NONE ("interleave") canonical
+// layout.  The unit is the 8-row x 16-byte CORE MATRIX, stored as 128 contiguous bytes (row r of the
+// core matrix at byte 16 r).  Core matrices are placed
+//     LBO bytes apart along K   (16 bytes of K = 8 bf16 or 4 tf32 elements per step),
+//     SBO bytes apart along M/N (8 rows per step),
+// so element (row, kbyte) of a tile lives at  (row/8)*SBO + (kbyte/16)*LBO + (row%8)*16 + kbyte%16.
+// One tcgen05.mma consumes 32 bytes of K (two core matrices: K = 16 for bf16, 8 for tf32).
+// LBO is padded to 144 bytes (not 128) so that the 16-byte stores of the SIMT producers -- 8 lanes
+// writing the 8 K-chunks of one row -- fall into 8 different bank groups.
+//
+// Bit layouts follow the PTX ISA "matrix descriptor" / "instruction descriptor" tables (cross-checked
+// against cute/arch/mma_sm100_desc.hpp in the CUTLASS headers shipped with this image).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace is {
+namespace umma {
+
+constexpr uint32_t kLBO = 144;                       // bytes between K-adjacent core matrices
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 64-bit shared-memory matrix descriptor (SWIZZLE_NONE, version 1 = Blackwell)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);                  // [0,14)  start address >> 4
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;        // [16,30) leading-dimension byte offset >> 4
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;        // [32,46) stride-dimension byte offset >> 4
+    d |= (uint64_t)1 << 46;                                  // [46,48) descriptor version = 1
+    return d;                                                // base_offset = 0, lbo_mode = 0, layout = SWIZZLE_NONE
+}
+
+// 32-bit instruction descriptor: D fp32, A/B both `fmt` (1 = bf16, 2 = tf32), K-major A and B, dense
+__device__ __forceinline__ constexpr uint32_t make_instr_desc(uint32_t fmt, uint32_t M, uint32_t N) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// ---- TMEM allocation (one full warp executes these) ------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// ---- fences ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy smem writes -> visible to the async proxy (tensor core operand reads)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- mbarrier -------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    const uint32_t addr = smem_u32(bar);
+    while (!done) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    }
+}
+
+// ---- MMA issue (ONE thread) ------------------------------------------------------------------------
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T ; kind::f16 covers fp16/bf16 inputs, kind::tf32 tf32 inputs
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on `bar` once every previously issued MMA of this thread has completed
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns ---------------------------
+// taddr = base + (lane_quarter * 32 << 16) + first column.  Thread t receives lane (quarter*32 + t).
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- operand packing helpers ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float tf32_round(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// byte offset of element (row, k) inside a canonical K-major tile with `kchunks` 16-byte chunks per row
+template <int ELEM_BYTES>
+__device__ __forceinline__ uint32_t canon_off(int row, int k, int kchunks) {
+    constexpr int per = 16 / ELEM_BYTES;
+    return (uint32_t)((row >> 3) * (kchunks * kLBO) + (k / per) * kLBO + (row & 7) * 16 + (k % per) * ELEM_BYTES);
+}
+
+}  // namespace umma
+}  // namespace is

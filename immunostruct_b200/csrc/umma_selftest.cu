@@ -1,0 +1,114 @@
+// Self-test of the hand-written tcgen05 path: D[128,64] = A[128,64] * B[64,64]^T for one tile, with the
+// exact device helpers (canonical layout, descriptors, MMA issue, commit, TMEM load) that the fused
+// EGNN tensor-core kernels use.  mode 0: bf16 operands; 1: tf32; 2: 3xTF32 split (fp32-accurate).
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace is {
+
+template <int MODE>
+__global__ void __launch_bounds__(128)
+umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D) {
+    using namespace umma;
+    constexpr int EB = MODE == 0 ? 2 : 4;                 // operand element bytes
+    constexpr int KCH = 64 * EB / 16;                     // 16-byte chunks per row (8 for bf16, 16 for tf32)
+    constexpr uint32_t SBO = KCH * kLBO;
+    constexpr uint32_t A_BYTES = 16 * SBO, B_BYTES = 8 * SBO;
+    constexpr int NSPLIT = MODE == 2 ? 2 : 1;             // hi (+ lo) copies
+    extern __shared__ __align__(128) uint8_t sm[];
+    uint8_t* sA = sm;                                     // [NSPLIT][A_BYTES]
+    uint8_t* sB = sm + NSPLIT * A_BYTES;                  // [NSPLIT][B_BYTES]
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (warp == 0) tmem_alloc(&tmem_base, 64);
+    if (tid == 32) mbar_init(&mbar, 1);
+    // stage operands in the canonical layout
+    for (int idx = tid; idx < 128 * 64; idx += 128) {
+        const int r = idx >> 6, k = idx & 63;
+        const float a = A[idx];
+        const uint32_t off = canon_off<EB>(r, k, KCH);
+        if (MODE == 0) {
+            *reinterpret_cast<__nv_bfloat16*>(sA + off) = __float2bfloat16_rn(a);
+        } else {
+            const float hi = tf32_round(a);
+            *reinterpret_cast<float*>(sA + off) = hi;
+            if (MODE == 2) *reinterpret_cast<float*>(sA + A_BYTES + off) = tf32_round(a - hi);
+        }
+    }
+    for (int idx = tid; idx < 64 * 64; idx += 128) {
+        const int r = idx >> 6, k = idx & 63;
+        const float b = B[idx];
+        const uint32_t off = canon_off<EB>(r, k, KCH);
+        if (MODE == 0) {
+            *reinterpret_cast<__nv_bfloat16*>(sB + off) = __float2bfloat16_rn(b);
+        } else {
+            const float hi = tf32_round(b);
+            *reinterpret_cast<float*>(sB + off) = hi;
+            if (MODE == 2) *reinterpret_cast<float*>(sB + B_BYTES + off) = tf32_round(b - hi);
+        }
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tbase = tmem_base;
+    if (tid == 0) {
+        const uint32_t idesc = make_instr_desc(MODE == 0 ? 1u : 2u, 128, 64);
+        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+        uint32_t acc = 0;
+        // small terms first: A_lo*B_hi, A_hi*B_lo, then A_hi*B_hi
+        for (int term = (MODE == 2 ? 0 : 2); term < 3; ++term) {
+            const uint32_t aoff = (term == 0) ? A_BYTES : 0, boff = (term == 1) ? B_BYTES : 0;
+            for (int ks = 0; ks < KCH / 2; ++ks) {
+                const uint64_t da = make_smem_desc(a0 + aoff + ks * 2 * kLBO, kLBO, SBO);
+                const uint64_t db = make_smem_desc(b0 + boff + ks * 2 * kLBO, kLBO, SBO);
+                if (MODE == 0) mma_bf16(tbase, da, db, idesc, acc); else mma_tf32(tbase, da, db, idesc, acc);
+                acc = 1;
+            }
+        }
+        mma_commit(&mbar);
+    }
+    mbar_wait(&mbar, 0);
+    fence_after_sync();
+    float v[32];
+    for (int half = 0; half < 2; ++half) {
+        tmem_ld32(tbase + ((uint32_t)(warp * 32) << 16) + half * 32, v);
+        const int row = warp * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) D[row * 64 + half * 32 + c] = v[c];
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 64);
+}
+
+}  // namespace is
+
+using namespace is;
+
+extern "C" int is_umma_selftest(const float* A, const float* B, float* D, int mode, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e;
+    if (mode == 0) {
+        size_t smem = 24 * 8 * umma::kLBO + 128;
+        e = cudaFuncSetAttribute(umma_selftest_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        umma_selftest_kernel<0><<<1, 128, smem, st>>>(A, B, D);
+    } else if (mode == 1) {
+        size_t smem = 24 * 16 * umma::kLBO + 128;
+        e = cudaFuncSetAttribute(umma_selftest_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        umma_selftest_kernel<1><<<1, 128, smem, st>>>(A, B, D);
+    } else if (mode == 2) {
+        size_t smem = 2 * 24 * 16 * umma::kLBO + 128;
+        e = cudaFuncSetAttribute(umma_selftest_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        umma_selftest_kernel<2><<<1, 128, smem, st>>>(A, B, D);
+    } else {
+        return IS_ERR_ARG;
+    }
+    IS_LAUNCH_CHECK();
+    return IS_OK;
+}

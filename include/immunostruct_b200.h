@@ -91,6 +91,10 @@ int is_loss_bwd(const float* recon, const float* seq, int64_t n_recon, const flo
                 float w_pred, float w_mse, float w_kld, const float* gout,
                 float* g_recon, float* g_mu, float* g_logvar, float* g_logits, void* stream);
 
+/* ---- tcgen05 self-test: D[128,64] = A[128,64] * B[64,64]^T through the hand-written UMMA helpers
+ * (csrc/umma.cuh).  mode 0 = bf16 operands, 1 = tf32, 2 = 3xTF32 split (fp32-accurate). */
+int is_umma_selftest(const float* A, const float* B, float* D, int mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
