@@ -13,6 +13,25 @@ from . import _C
 H = 64   # hidden width of the EGNN MLPs and of the node embedding (hybrid_models.py:247)
 
 
+# Arithmetic of the EGNN edge GEMMs in the FORWARD pass (the backward always recomputes in fp32 SIMT):
+#   "fp32"   : fp32 SIMT FMA kernels (csrc/egnn.cu)
+#   "tf32x3" : tcgen05 tensor cores with the 3xTF32 split -- fp32-accurate (csrc/egnn_tc.cu)
+#   "bf16"   : tcgen05 tensor cores, bf16 operands, fp32 accumulate, fast SiLU (1e-2 tolerance mode)
+_PRECISIONS = {"fp32": None, "tf32x3": _C.PREC_TF32X3, "bf16": _C.PREC_BF16}
+_precision = "tf32x3"
+
+
+def set_precision(name: str) -> None:
+    global _precision
+    if name not in _PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
+    _precision = name
+
+
+def get_precision() -> str:
+    return _precision
+
+
 def _new(like, *shape):
     return torch.empty(*shape, dtype=torch.float32, device=like.device)
 
@@ -39,7 +58,11 @@ class _EGNNLayer(torch.autograd.Function):
         PQ, hn, h_out = _new(h, n, 2 * H), _new(h, n, H), _new(h, n, H)
         x_out = _new(h, n, 3) if update_coords else None
         _C.egnn_node_pre_fwd(h, W1, b1, PQ)
-        _C.egnn_edge_fwd(graph, PQ, x, edge_attr, f, W1, W2, b2, W3, b3, w4, update_coords, hn, x_out)
+        prec = _PRECISIONS[_precision]
+        if prec is None:
+            _C.egnn_edge_fwd(graph, PQ, x, edge_attr, f, W1, W2, b2, W3, b3, w4, update_coords, hn, x_out)
+        else:
+            _C.egnn_edge_fwd_tc(graph, PQ, x, edge_attr, f, W1, W2, b2, W3, b3, w4, update_coords, prec, hn, x_out)
         _C.egnn_node_post_fwd(h, hn, W5, b5, W6, b6, h_out)
         ctx.graph = graph
         ctx.update_coords = update_coords

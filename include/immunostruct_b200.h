@@ -50,6 +50,13 @@ int is_egnn_edge_fwd(const int* indptr, const int* csr_src, const int* csr_dst, 
                      const float* W1, int F, const float* W2, const float* b2,
                      const float* W3, const float* b3, const float* w4, int update_coords,
                      float* hn, float* x_out, int64_t n_nodes, int* status, void* stream);
+/* tcgen05 / TMEM variant of is_egnn_edge_fwd: the two per-tile 128x64x64 GEMMs run on the tensor
+ * cores.  precision 0 = bf16 operands (fp32 accumulate), 2 = 3xTF32 split (fp32-accurate). */
+int is_egnn_edge_fwd_tc(const int* indptr, const int* csr_src, const int* csr_dst, const int* csr_eid,
+                        const float* PQ, const float* x, int64_t ldx, const float* edge_attr,
+                        const float* W1, int F, const float* W2, const float* b2,
+                        const float* W3, const float* b3, const float* w4, int update_coords, int precision,
+                        float* hn, float* x_out, int64_t n_nodes, int* status, void* stream);
 int is_egnn_node_post_fwd(const float* h, int64_t ldh, int F, const float* hn, const float* W5, const float* b5,
                           const float* W6, const float* b6, float* h_out, int64_t n_nodes, void* stream);
 int is_egnn_node_post_bwd(const float* gh_out, const float* h, int64_t ldh, int F, const float* hn,

@@ -107,6 +107,11 @@ def egnn_edge_fwd(g, PQ, x, edge_attr, f, W1, W2, b2, W3, b3, w4, update_coords,
         x_out.copy_(x + xn)
 
 
+def egnn_edge_fwd_tc(g, PQ, x, edge_attr, f, W1, W2, b2, W3, b3, w4, update_coords, precision, hn, x_out):
+    """Same contract as egnn_edge_fwd; the tensor-core kernel only changes the GEMM arithmetic."""
+    egnn_edge_fwd(g, PQ, x, edge_attr, f, W1, W2, b2, W3, b3, w4, update_coords, hn, x_out)
+
+
 def egnn_node_post_fwd(h, hn, W5, b5, W6, b6, h_out):
     h_out.copy_(F.linear(_silu(F.linear(torch.cat([h, hn], 1), W5, b5)), W6, b6))
 
@@ -277,6 +282,6 @@ def loss_bwd(recon, seq, mu, logvar, logits, y, mode, pos_weight, w_pred, w_mse,
 
 
 ALL = ["num_sms", "egnn_node_grid", "egnn_edge_bwd_grid", "attn_max_nodes", "loss_num_partials", "collate_csr",
-       "egnn_node_pre_fwd", "egnn_edge_fwd", "egnn_node_post_fwd", "egnn_node_post_bwd", "egnn_edge_bwd",
+       "egnn_node_pre_fwd", "egnn_edge_fwd", "egnn_edge_fwd_tc", "egnn_node_post_fwd", "egnn_node_post_bwd", "egnn_edge_bwd",
        "egnn_node_pre_bwd", "reduce_partials", "attn_pool_fwd", "attn_pool_bwd", "fusion_attn_fwd",
        "fusion_attn_bwd", "loss_fwd", "loss_bwd"]

@@ -161,6 +161,31 @@ def test_egnn_forward_kernels(case, f):
     assert int(gb.status.item()) == 0
 
 
+@pytest.mark.parametrize("prec,tol", [(_C.PREC_TF32X3, 1e-5), (_C.PREC_BF16, 2e-2)])
+@pytest.mark.parametrize("f", [20, 64])
+def test_egnn_edge_forward_tensor_core(case, f, prec, tol):
+    """tcgen05 edge kernel vs the same CPU contract: 3xTF32 at the fp32 tolerance, bf16 at 2e-2."""
+    arrays, gb, cg = case
+    gen = torch.Generator().manual_seed(37)
+    n = gb.n_nodes
+    w = egnn_weights(gen, f)
+    wd = {k: v.to(DEV) for k, v in w.items()}
+    PQ = rnd(gen, n, 128)
+    x = arrays["x"][:, 20:].clone()
+    ea = arrays["edge_attr"].float()
+    x_d = arrays["x"].to(DEV)[:, 20:]
+    for upd in (True, False):
+        hn_d, xo_d = torch.empty(n, 64, device=DEV), torch.empty(n, 3, device=DEV)
+        hn, xo = torch.empty(n, 64), torch.empty(n, 3)
+        _C.egnn_edge_fwd_tc(gb, PQ.to(DEV), x_d, ea.to(DEV), f, wd["W1"], wd["W2"], wd["b2"], wd["W3"], wd["b3"],
+                            wd["w4"], upd, prec, hn_d, xo_d if upd else None)
+        KC.egnn_edge_fwd(cg, PQ, x, ea, f, w["W1"], w["W2"], w["b2"], w["W3"], w["b3"], w["w4"], upd, hn, xo)
+        close(hn_d, hn, tol, what=f"tc hn prec={prec} upd={upd}")
+        if upd:
+            close(xo_d - x_d, xo - x, tol, what=f"tc x'-x prec={prec}")
+    assert int(gb.status.item()) == 0
+
+
 # ---- EGNN backward -----------------------------------------------------------------------------
 @pytest.mark.parametrize("f,coord", [(64, True), (64, False), (20, True)])
 def test_egnn_backward_kernels(case, f, coord):
