@@ -50,17 +50,20 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "bf16"],
+                    help="EGNN edge-GEMM arithmetic of the headline run (tf32x3 = fp32-accurate tensor cores)")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
 def measured_peaks():
+    """(HBM GB/s, dense bf16 TFLOP/s burst, source) from the driver-written MEASURED_PEAKS.json."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured"
-    return 6650.0, "fallback"
+        return float(d["hbm_gbs"]), float(d["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, "fallback"
 
 
 class ClockSampler:
@@ -194,6 +197,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
+    I.set_precision(args.precision)
     torch.manual_seed(1)
     model = I.model_map["HybridModelv2"](vae_input_dim=VAE_IN, device=dev).to(dev)
     broadcast_parameters(model)
@@ -253,6 +257,26 @@ def main():
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = world * B * K / (ms_e2e / 1e3)
 
+    # ---- the same device-resident step in the other arithmetic modes (short runs) -----------------
+    other = {}
+    with torch.no_grad():
+        for prec in ("fp32", "tf32x3", "bf16"):
+            if prec == args.precision:
+                continue
+            I.set_precision(prec)
+            for i in range(W):
+                infer_step(*pool[i % POOL])
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(K):
+                infer_step(*pool[i % POOL])
+            e1.record()
+            barrier()
+            ms_o = max_over_ranks(e0.elapsed_time(e1))
+            other[prec] = {"value": world * B * K / (ms_o / 1e3), "unit": "graphs/s", "ms_per_step": ms_o / K}
+    I.set_precision(args.precision)
+
     # ---- training step: fwd + bwd + Adam (+ NCCL gradient all-reduce) ---------------------------
     train = None
     if not args.no_train:
@@ -284,7 +308,7 @@ def main():
         ms_t = max_over_ranks(e0.elapsed_time(e1))
         train = {"value": world * B * kt / (ms_t / 1e3), "unit": "graphs/s", "steps": kt, "ms_per_step": ms_t / kt,
                  "global_batch": world * B, "optimizer": "Adam", "loss": "BCE_loss(sequence=True)",
-                 "final_loss": float(loss), "allreduce_bytes": reducer.nbytes}
+                 "final_loss": float(loss.detach()), "allreduce_bytes": reducer.nbytes}
         model.eval()
 
     # ---- roofline of the dominant kernel (EGNN edge forward), timed alone ------------------------
@@ -300,25 +324,43 @@ def main():
         x = arr["x"][:, 20:]
         _C.egnn_node_pre_fwd(h, W1, b1, PQ)
         flush = torch.empty(64 * 1024 * 1024, device=dev)          # 256 MB > L2
-        times = []
-        for it in range(3 + 10):
-            flush.zero_()
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record()
-            _C.egnn_edge_fwd(gb, PQ, x, arr["edge_attr"], 64, W1, W2, b2, W3, b3, w4, True, hn, xo)
-            s1.record()
-            torch.cuda.synchronize()
-            if it >= 3:
-                times.append(s0.elapsed_time(s1))
-        t_k = statistics.mean(times) / 1e3
-        hbm_peak, src = measured_peaks()
-        tflops = e * FLOP_PER_EDGE_EDGE_KERNEL / t_k / 1e12
-        gbs = (e * BYTES_PER_EDGE_EDGE_KERNEL + n * (256 + 12 + 12 + 4)) / t_k / 1e9
-        roofline = {"kernel": "is::edge_fwd_kernel<true> (EGNN edge forward, fp32 SIMT)", "bound": "fp32_fma",
-                    "achieved": tflops, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tflops / FP32_PEAK_TFLOPS,
-                    "traffic": None, "launch_ms": t_k * 1e3, "edges_per_launch": e,
+        hbm_peak, tensor_peak, src = measured_peaks()
+
+        def time_kernel(fn):
+            times = []
+            for it in range(3 + 10):
+                flush.zero_()
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record()
+                fn()
+                s1.record()
+                torch.cuda.synchronize()
+                if it >= 3:
+                    times.append(s0.elapsed_time(s1))
+            return statistics.mean(times) / 1e3
+
+        variants = {
+            "fp32": lambda: _C.egnn_edge_fwd(gb, PQ, x, arr["edge_attr"], 64, W1, W2, b2, W3, b3, w4, True, hn, xo),
+            "tf32x3": lambda: _C.egnn_edge_fwd_tc(gb, PQ, x, arr["edge_attr"], 64, W1, W2, b2, W3, b3, w4, True, _C.PREC_TF32X3, hn, xo),
+            "bf16": lambda: _C.egnn_edge_fwd_tc(gb, PQ, x, arr["edge_attr"], 64, W1, W2, b2, W3, b3, w4, True, _C.PREC_BF16, hn, xo),
+        }
+        t_all = {k: time_kernel(fn) for k, fn in variants.items()}
+        t_k = t_all[args.precision]
+        flops = e * FLOP_PER_EDGE_EDGE_KERNEL
+        nbytes = e * BYTES_PER_EDGE_EDGE_KERNEL + n * (256 + 12 + 12 + 4)
+        tflops, gbs = flops / t_k / 1e12, nbytes / t_k / 1e9
+        if args.precision == "fp32":
+            bound, peak, kname = "fp32_fma", FP32_PEAK_TFLOPS, "is::edge_fwd_kernel<true> (fp32 SIMT)"
+        else:
+            bound, peak, kname = "tensor", tensor_peak, f"is::edge_fwd_tc_kernel<{args.precision}, true> (tcgen05 + TMEM)"
+        roofline = {"kernel": kname, "bound": bound, "achieved": tflops, "peak": peak, "unit": "TFLOP/s",
+                    "frac": tflops / peak, "traffic": None, "launch_ms": t_k * 1e3, "edges_per_launch": e,
+                    "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": nbytes,
                     "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": src},
-                    "note": "compute-bound on the FP32 pipe (SURVEY 8(d)); peak = 148 SM x 128 FMA x 2 x 1.965 GHz"}
+                    "launch_ms_by_precision": {k: v * 1e3 for k, v in t_all.items()},
+                    "note": "edge-forward kernel of one EGNN layer timed alone after an L2 flush; FLOPs = two 64x64 per-edge "
+                            "GEMMs + w4 dot (the 3xTF32 split's extra MMAs are not counted); the kernel is bound by its "
+                            "SIMT gather/SiLU/aggregation phases, not by the tensor pipe or HBM (DESIGN.md 4.2)"}
 
     # ---- CPU baseline (oracle port) on this box's host cores, rank 0 at N=1 only ------------------
     cpu_baseline = None
@@ -342,8 +384,9 @@ def main():
     if rank == 0:
         print(json.dumps({
             "metric": "pMHC graphs/sec (HybridModelv2 inference, fp32)", "value": value, "unit": "graphs/s",
+            "precision": args.precision, "other_precisions": other,
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": "IEDB HybridModelv2 inference, batch 512 per GPU, 200-node 10-NN graphs, "
                                    "283x21 sequence, fp32 (BASELINE configs[1])",
                        "batch_per_gpu": B, "nodes_per_graph": N_NODES, "edges_per_graph": N_NODES * KNN,
