@@ -69,24 +69,6 @@ __device__ __forceinline__ void store_operand8(uint8_t* __restrict__ tile, int r
     }
 }
 
-// stage a torch [64 out, 64 in] weight as the B operand (row n = output feature, K = input feature)
-template <int PREC>
-__device__ __forceinline__ void stage_weight(uint8_t* __restrict__ tile, const float* __restrict__ W, int tid) {
-    using C = TcCfg<PREC>;
-    for (int idx = tid; idx < 64 * 64; idx += IS_THREADS) {
-        const int n = idx >> 6, k = idx & 63;
-        const float w = __ldg(W + idx);
-        const uint32_t off = canon_off<C::EB>(n, k, C::KCH);
-        if (PREC == PREC_BF16) {
-            *reinterpret_cast<__nv_bfloat16*>(tile + off) = __float2bfloat16_rn(w);
-        } else {
-            const float hi = tf32_round(w);
-            *reinterpret_cast<float*>(tile + off) = hi;
-            *reinterpret_cast<float*>(tile + C::W_BYTES + off) = tf32_round(w - hi);
-        }
-    }
-}
-
 // issue one 128x64x64 GEMM: D[tmem_d] = A_tile * W_tile^T   (called by ONE thread)
 template <int PREC>
 __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr) {
@@ -106,19 +88,88 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_addr, uin
     }
 }
 
-template <int PREC, bool HAS_COORD>
-__global__ void __launch_bounds__(IS_THREADS, PREC == PREC_BF16 ? 2 : 1)
+// ---- tile walk: executed by one full warp; all lanes return the same values ------------------------
+// Longest run of consecutive destination nodes (<= 32) starting at n0 whose in-edges total <= 128.
+// tn0 >= nend means the CTA's node range is exhausted.  Nodes with more than 128 in-edges are
+// unsupported: flagged in *status and skipped.
+__device__ __forceinline__ void next_tile(const int* __restrict__ indptr, int n0, int nend, int* __restrict__ status,
+                                          int lane, int& tn0, int& tn1, int& tp0, int& tne) {
+    while (n0 < nend) {
+        const int pbase = __ldg(indptr + n0);
+        const int cand = n0 + lane + 1;
+        const bool ok = (cand <= nend) && (__ldg(indptr + (cand <= nend ? cand : nend)) - pbase <= IS_TM);
+        const int cnt = __popc(__ballot_sync(0xffffffffu, ok));
+        if (cnt == 0) {
+            if (lane == 0 && status) atomicExch(status, 1);
+            ++n0;
+            continue;
+        }
+        tn0 = n0; tn1 = n0 + cnt; tp0 = pbase; tne = __ldg(indptr + n0 + cnt) - pbase;
+        return;
+    }
+    tn0 = nend; tn1 = nend; tp0 = 0; tne = 0;
+}
+
+struct TileMeta {            // per-edge scalars of one tile, produced by the prefetch warps
+    int src[IS_TM];
+    int dst[IS_TM];
+    float r[IS_TM];
+    float a[IS_TM];
+    float dh[IS_TM * 3];
+};
+
+__device__ __forceinline__ void load_meta(const EdgeCommon& p, TileMeta& m, int j, int p0, int ne) {
+    if (j < ne) {
+        const int e = p0 + j;
+        const int s = __ldg(p.csr_src + e), d = __ldg(p.csr_dst + e);
+        const float a = __ldg(p.edge_attr + __ldg(p.csr_eid + e));
+        const float dx = __ldg(p.x + s * p.ldx + 0) - __ldg(p.x + d * p.ldx + 0);
+        const float dy = __ldg(p.x + s * p.ldx + 1) - __ldg(p.x + d * p.ldx + 1);
+        const float dz = __ldg(p.x + s * p.ldx + 2) - __ldg(p.x + d * p.ldx + 2);
+        const float r = dx * dx + dy * dy + dz * dz;
+        const float inv = 1.0f / (sqrtf(r) + 1e-30f);
+        m.src[j] = s; m.dst[j] = d; m.r[j] = r; m.a[j] = a;
+        m.dh[j * 3 + 0] = dx * inv; m.dh[j * 3 + 1] = dy * inv; m.dh[j * 3 + 2] = dz * inv;
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[N]);
+template <>
+__device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, float (&v)[32]) { tmem_ld32(taddr, v); }
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// NT threads per CTA: 256 (two CTAs per SM) for bf16, 512 (one CTA per SM, 16 warps) for 3xTF32 whose
+// hi/lo operand tiles need 147 KB of shared memory.
+template <int PREC, bool HAS_COORD, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
 edge_fwd_tc_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_out) {
     using C = TcCfg<PREC>;
+    constexpr int NW = NT / 32;                 // warps
+    constexpr int CQ = NW / 4;                  // column splits of the epilogue (TMEM lane quarter x column block)
+    constexpr int CW = 64 / CQ;                 // accumulator columns per thread
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t* sA = smem_raw;                                            // [NSPLIT][A_BYTES] t1, then m
     uint8_t* sW2 = sA + C::NSPLIT * C::A_BYTES;                        // [NSPLIT][W_BYTES]
     uint8_t* sW3 = sW2 + C::NSPLIT * C::W_BYTES;
     float* M32 = reinterpret_cast<float*>(sW3 + C::NSPLIT * C::W_BYTES);   // [128][68] fp32 m
     float* vec = M32 + IS_TM * IS_LD;                                  // b2, b3, w4, wr, wa
-    float* e_c = vec + 5 * 64;                                         // [2][128] partial c per column half
-    float* e_dh = e_c + 2 * IS_TM;                                     // [128][3]
-    __shared__ int s_tile[4];
+    float* e_c = vec + 5 * 64;                                         // [CQ][128] partial c per column block
+    TileMeta* meta = reinterpret_cast<TileMeta*>(e_c + CQ * IS_TM);    // [2]
+    __shared__ int s_tile[2][4];
     __shared__ __align__(8) uint64_t mbar[2];
     __shared__ uint32_t s_tmem;
 
@@ -126,8 +177,21 @@ edge_fwd_tc_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
     const int ldw1 = 2 * p.F + 2;
     if (warp == 0) tmem_alloc(&s_tmem, 128);
     if (tid == 32) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
-    stage_weight<PREC>(sW2, p.W2, tid);
-    if (HAS_COORD) stage_weight<PREC>(sW3, p.W3, tid);
+    for (int idx = tid; idx < 64 * 64; idx += NT) {                    // stage W2 / W3 as B operands
+        const int n = idx >> 6, k = idx & 63;
+        const uint32_t off = canon_off<C::EB>(n, k, C::KCH);
+        const float w2 = __ldg(p.W2 + idx), w3 = HAS_COORD ? __ldg(p.W3 + idx) : 0.0f;
+        if (PREC == PREC_BF16) {
+            *reinterpret_cast<__nv_bfloat16*>(sW2 + off) = __float2bfloat16_rn(w2);
+            *reinterpret_cast<__nv_bfloat16*>(sW3 + off) = __float2bfloat16_rn(w3);
+        } else {
+            const float h2 = tf32_round(w2), h3 = tf32_round(w3);
+            *reinterpret_cast<float*>(sW2 + off) = h2;
+            *reinterpret_cast<float*>(sW2 + C::W_BYTES + off) = tf32_round(w2 - h2);
+            *reinterpret_cast<float*>(sW3 + off) = h3;
+            *reinterpret_cast<float*>(sW3 + C::W_BYTES + off) = tf32_round(w3 - h3);
+        }
+    }
     if (tid < 64) {
         vec[tid] = p.b2[tid];
         vec[64 + tid] = HAS_COORD ? p.b3[tid] : 0.0f;
@@ -136,93 +200,103 @@ edge_fwd_tc_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
         vec[256 + tid] = p.W1[tid * ldw1 + 2 * p.F + 1];
     }
     const int chunk = (p.n_nodes + gridDim.x - 1) / gridDim.x;
-    int n0 = blockIdx.x * chunk;
-    const int nend = min(p.n_nodes, n0 + chunk);
+    const int nbeg = blockIdx.x * chunk;
+    const int nend = min(p.n_nodes, nbeg + chunk);
+    // prologue: first tile + its per-edge scalars (the last four warps are the prefetch warps)
+    if (warp >= NW - 4) {
+        int tn0, tn1, tp0, tne;
+        next_tile(p.indptr, nbeg, nend, p.status, lane, tn0, tn1, tp0, tne);
+        if (warp == NW - 4 && lane == 0) { s_tile[0][0] = tn0; s_tile[0][1] = tn1; s_tile[0][2] = tp0; s_tile[0][3] = tne; }
+        load_meta(p, meta[0], (warp - (NW - 4)) * 32 + lane, tp0, tne);
+    }
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem = s_tmem;
     const uint32_t a_addr = smem_u32(sA), w2_addr = smem_u32(sW2), w3_addr = smem_u32(sW3);
-    // epilogue mapping: TMEM lane quarter q = warp % 4 (rows 32q + lane), column half ch = warp / 4
-    const int q = warp & 3, ch = warp >> 2, erow = 32 * q + lane;
-    const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
+    // epilogue mapping: TMEM lane quarter q = warp % 4 (rows 32q + lane), column block cq = warp / 4
+    const int q = warp & 3, cq = warp >> 2, erow = 32 * q + lane;
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16) + CW * cq;
     // gather mapping: 4 edges per warp per pass, 8 lanes per edge, 8 features per lane
     const int esub = lane >> 3, kc8 = lane & 7;
+    const float4 wr0 = *reinterpret_cast<const float4*>(vec + 192 + 8 * kc8), wr1 = *reinterpret_cast<const float4*>(vec + 196 + 8 * kc8);
+    const float4 wa0 = *reinterpret_cast<const float4*>(vec + 256 + 8 * kc8), wa1 = *reinterpret_cast<const float4*>(vec + 260 + 8 * kc8);
     uint32_t phase = 0;
+    int cur = 0;
 
-    while (n0 < nend) {
-        select_tile(s_tile, p.indptr, n0, nend, p.status);
-        __syncthreads();
-        const int n1 = s_tile[1], p0 = s_tile[2], ne = s_tile[3];
-        if (ne < 0) { n0 = n1; __syncthreads(); continue; }
+    while (true) {
+        const int n0 = s_tile[cur][0], n1 = s_tile[cur][1], p0 = s_tile[cur][2], ne = s_tile[cur][3];
+        if (n0 >= nend) break;
+        const TileMeta& mt = meta[cur];
 
         // ---- gather -> A operand (t1) -----------------------------------------------------------
-        {
-            const float4 wr0 = *reinterpret_cast<const float4*>(vec + 192 + 8 * kc8), wr1 = *reinterpret_cast<const float4*>(vec + 196 + 8 * kc8);
-            const float4 wa0 = *reinterpret_cast<const float4*>(vec + 256 + 8 * kc8), wa1 = *reinterpret_cast<const float4*>(vec + 260 + 8 * kc8);
 #pragma unroll
-            for (int pass = 0; pass < IS_TM / 32; ++pass) {
-                const int j = pass * 32 + warp * 4 + esub;
-                float v[8];
+        for (int pass = 0; pass < IS_TM / (4 * NW); ++pass) {
+            const int j = pass * 4 * NW + warp * 4 + esub;
+            float v[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = 0.0f;
-                if (j < ne) {
-                    const int e = p0 + j;
-                    const int s = __ldg(p.csr_src + e), d = __ldg(p.csr_dst + e);
-                    const float a = __ldg(p.edge_attr + __ldg(p.csr_eid + e));
-                    const float dx = __ldg(p.x + s * p.ldx + 0) - __ldg(p.x + d * p.ldx + 0);
-                    const float dy = __ldg(p.x + s * p.ldx + 1) - __ldg(p.x + d * p.ldx + 1);
-                    const float dz = __ldg(p.x + s * p.ldx + 2) - __ldg(p.x + d * p.ldx + 2);
-                    const float r = dx * dx + dy * dy + dz * dz;
-                    const float4* pp = reinterpret_cast<const float4*>(p.PQ + (size_t)s * 128 + 8 * kc8);
-                    const float4* qp = reinterpret_cast<const float4*>(p.PQ + (size_t)d * 128 + 64 + 8 * kc8);
-                    const float4 p0v = __ldg(pp), p1v = __ldg(pp + 1), q0v = __ldg(qp), q1v = __ldg(qp + 1);
-                    v[0] = act<PREC>(p0v.x + q0v.x + wr0.x * r + wa0.x * a);
-                    v[1] = act<PREC>(p0v.y + q0v.y + wr0.y * r + wa0.y * a);
-                    v[2] = act<PREC>(p0v.z + q0v.z + wr0.z * r + wa0.z * a);
-                    v[3] = act<PREC>(p0v.w + q0v.w + wr0.w * r + wa0.w * a);
-                    v[4] = act<PREC>(p1v.x + q1v.x + wr1.x * r + wa1.x * a);
-                    v[5] = act<PREC>(p1v.y + q1v.y + wr1.y * r + wa1.y * a);
-                    v[6] = act<PREC>(p1v.z + q1v.z + wr1.z * r + wa1.z * a);
-                    v[7] = act<PREC>(p1v.w + q1v.w + wr1.w * r + wa1.w * a);
-                    if (HAS_COORD && kc8 == 0) {
-                        const float inv = 1.0f / (sqrtf(r) + 1e-30f);
-                        e_dh[j * 3 + 0] = dx * inv; e_dh[j * 3 + 1] = dy * inv; e_dh[j * 3 + 2] = dz * inv;
-                    }
-                }
-                store_operand8<PREC>(sA, j, kc8, v);
+            for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+            if (j < ne) {
+                const int s = mt.src[j], d = mt.dst[j];
+                const float r = mt.r[j], a = mt.a[j];
+                const float4* pp = reinterpret_cast<const float4*>(p.PQ + (size_t)s * 128 + 8 * kc8);
+                const float4* qp = reinterpret_cast<const float4*>(p.PQ + (size_t)d * 128 + 64 + 8 * kc8);
+                const float4 p0v = __ldg(pp), p1v = __ldg(pp + 1), q0v = __ldg(qp), q1v = __ldg(qp + 1);
+                v[0] = act<PREC>(p0v.x + q0v.x + wr0.x * r + wa0.x * a);
+                v[1] = act<PREC>(p0v.y + q0v.y + wr0.y * r + wa0.y * a);
+                v[2] = act<PREC>(p0v.z + q0v.z + wr0.z * r + wa0.z * a);
+                v[3] = act<PREC>(p0v.w + q0v.w + wr0.w * r + wa0.w * a);
+                v[4] = act<PREC>(p1v.x + q1v.x + wr1.x * r + wa1.x * a);
+                v[5] = act<PREC>(p1v.y + q1v.y + wr1.y * r + wa1.y * a);
+                v[6] = act<PREC>(p1v.z + q1v.z + wr1.z * r + wa1.z * a);
+                v[7] = act<PREC>(p1v.w + q1v.w + wr1.w * r + wa1.w * a);
             }
+            store_operand8<PREC>(sA, j, kc8, v);
         }
         fence_async_smem();
         fence_before_sync();
-        __syncthreads();
+        __syncthreads();                                                           // S1
         if (tid == 0) {
             fence_after_sync();
             issue_gemm<PREC>(tmem, a_addr, w2_addr);
             mma_commit(&mbar[0]);
         }
+        // ---- while MMA 1 runs: walk to the next tile and prefetch its per-edge scalars ------------
+        if (warp >= NW - 4) {
+            int tn0, tn1, tp0, tne;
+            next_tile(p.indptr, n1, nend, p.status, lane, tn0, tn1, tp0, tne);
+            if (warp == NW - 4 && lane == 0) {
+                s_tile[cur ^ 1][0] = tn0; s_tile[cur ^ 1][1] = tn1; s_tile[cur ^ 1][2] = tp0; s_tile[cur ^ 1][3] = tne;
+            }
+            load_meta(p, meta[cur ^ 1], (warp - (NW - 4)) * 32 + lane, tp0, tne);
+        }
+        if (tid == 0) mbar_wait(&mbar[0], phase);      // one poller; everybody else parks on the barrier
+        __syncthreads();                                                           // S2
+        fence_after_sync();
 
         // ---- epilogue 1: m = silu(acc0 + b2) -> fp32 rows (+ next A operand) ----------------------
-        mbar_wait(&mbar[0], phase);
-        fence_after_sync();
         {
-            float z[32];
-            tmem_ld32(t_lane + 32 * ch, z);
+            float z[CW];
+            tmem_ld<CW>(t_lane, z);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
+            for (int g = 0; g < CW / 8; ++g) {
+                const float4 b0 = *reinterpret_cast<const float4*>(vec + CW * cq + 8 * g);
+                const float4 b1 = *reinterpret_cast<const float4*>(vec + CW * cq + 8 * g + 4);
                 float m8[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) m8[i] = act<PREC>(z[8 * g + i] + vec[32 * ch + 8 * g + i]);
-                float* dst = M32 + erow * IS_LD + 32 * ch + 8 * g;
+                m8[0] = act<PREC>(z[8 * g + 0] + b0.x); m8[1] = act<PREC>(z[8 * g + 1] + b0.y);
+                m8[2] = act<PREC>(z[8 * g + 2] + b0.z); m8[3] = act<PREC>(z[8 * g + 3] + b0.w);
+                m8[4] = act<PREC>(z[8 * g + 4] + b1.x); m8[5] = act<PREC>(z[8 * g + 5] + b1.y);
+                m8[6] = act<PREC>(z[8 * g + 6] + b1.z); m8[7] = act<PREC>(z[8 * g + 7] + b1.w);
+                float* dst = M32 + erow * IS_LD + CW * cq + 8 * g;
                 *reinterpret_cast<float4*>(dst) = make_float4(m8[0], m8[1], m8[2], m8[3]);
                 *reinterpret_cast<float4*>(dst + 4) = make_float4(m8[4], m8[5], m8[6], m8[7]);
-                if (HAS_COORD) store_operand8<PREC>(sA, erow, 4 * ch + g, m8);     // MMA 1 has finished reading sA
+                if (HAS_COORD) store_operand8<PREC>(sA, erow, (CW / 8) * cq + g, m8);   // MMA 1 is done with sA
             }
         }
         fence_async_smem();
         fence_before_sync();
-        __syncthreads();
+        __syncthreads();                                                           // S3
         if (HAS_COORD && tid == 0) {
             fence_after_sync();
             issue_gemm<PREC>(tmem + 64, a_addr, w3_addr);
@@ -230,7 +304,7 @@ edge_fwd_tc_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
         }
 
         // ---- hn aggregation (overlaps MMA 2): one warp per destination node -----------------------
-        for (int node = n0 + warp; node < n1; node += IS_THREADS / 32) {
+        for (int node = n0 + warp; node < n1; node += NW) {
             const int jb = __ldg(p.indptr + node) - p0, je = __ldg(p.indptr + node + 1) - p0;
             float2 s = make_float2(0.0f, 0.0f);
             for (int j = jb; j < je; ++j) {
@@ -241,49 +315,64 @@ edge_fwd_tc_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
         }
 
         if (HAS_COORD) {
-            // ---- epilogue 2: c = w4 . silu(acc1 + b3) (each thread: one row, 32 columns) ----------
-            mbar_wait(&mbar[1], phase);
+            // ---- epilogue 2: c = w4 . silu(acc1 + b3) (each thread: one row, CW columns) ----------
+            if (tid == 0) mbar_wait(&mbar[1], phase);
+            __syncthreads();                                                       // S4
             fence_after_sync();
-            float z[32];
-            tmem_ld32(t_lane + 64 + 32 * ch, z);
+            float z[CW];
+            tmem_ld<CW>(t_lane + 64, z);
             float c = 0.0f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) c = fmaf(vec[128 + 32 * ch + i], act<PREC>(z[i] + vec[64 + 32 * ch + i]), c);
-            e_c[ch * IS_TM + erow] = c;
+            for (int g = 0; g < CW / 4; ++g) {
+                const float4 b = *reinterpret_cast<const float4*>(vec + 64 + CW * cq + 4 * g);
+                const float4 w = *reinterpret_cast<const float4*>(vec + 128 + CW * cq + 4 * g);
+                c = fmaf(w.x, act<PREC>(z[4 * g + 0] + b.x), c);
+                c = fmaf(w.y, act<PREC>(z[4 * g + 1] + b.y), c);
+                c = fmaf(w.z, act<PREC>(z[4 * g + 2] + b.z), c);
+                c = fmaf(w.w, act<PREC>(z[4 * g + 3] + b.w), c);
+            }
+            e_c[cq * IS_TM + erow] = c;
             fence_before_sync();
-            __syncthreads();
-            for (int node = n0 + warp; node < n1; node += IS_THREADS / 32) {
+            __syncthreads();                                                       // S5
+            for (int node = n0 + warp; node < n1; node += NW) {
                 if (lane < 3) {
                     const int jb = __ldg(p.indptr + node) - p0, je = __ldg(p.indptr + node + 1) - p0;
                     float sx = 0.0f;
-                    for (int j = jb; j < je; ++j) sx += (e_c[j] + e_c[IS_TM + j]) * e_dh[j * 3 + lane];
+                    for (int j = jb; j < je; ++j) {
+                        float cj = e_c[j];
+#pragma unroll
+                        for (int t = 1; t < CQ; ++t) cj += e_c[t * IS_TM + j];
+                        sx += cj * mt.dh[j * 3 + lane];
+                    }
                     const int deg = je - jb;
                     x_out[(size_t)node * 3 + lane] = __ldg(p.x + node * p.ldx + lane) + sx / (float)max(deg, 1);
                 }
             }
         }
+        // No barrier here: the next tile's gather only writes sA (both MMAs of this tile have been
+        // waited for) and reads meta[cur ^ 1]; M32 / e_c / meta[cur] / TMEM are next written after
+        // the barriers S1..S4 of the next iteration.
         phase ^= 1;
-        n0 = n1;
-        fence_before_sync();
-        __syncthreads();
+        cur ^= 1;
     }
     fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
-template <int PREC>
+template <int PREC, int NT>
 static size_t tc_smem_bytes() {
     using C = TcCfg<PREC>;
-    return (size_t)C::NSPLIT * (C::A_BYTES + 2 * C::W_BYTES) + sizeof(float) * (IS_TM * IS_LD + 5 * 64 + 2 * IS_TM + 3 * IS_TM) + 128;
+    return (size_t)C::NSPLIT * (C::A_BYTES + 2 * C::W_BYTES) +
+           sizeof(float) * (IS_TM * IS_LD + 5 * 64 + (NT / 128) * IS_TM) + 2 * sizeof(TileMeta) + 128;
 }
 
-template <int PREC, bool HAS_COORD>
+template <int PREC, bool HAS_COORD, int NT>
 static int launch_tc(const EdgeCommon& c, float* hn, float* x_out, int grid, cudaStream_t st) {
-    const size_t smem = tc_smem_bytes<PREC>();
-    cudaError_t e = cudaFuncSetAttribute(edge_fwd_tc_kernel<PREC, HAS_COORD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = tc_smem_bytes<PREC, NT>();
+    cudaError_t e = cudaFuncSetAttribute(edge_fwd_tc_kernel<PREC, HAS_COORD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    edge_fwd_tc_kernel<PREC, HAS_COORD><<<grid, IS_THREADS, smem, st>>>(c, hn, x_out);
+    edge_fwd_tc_kernel<PREC, HAS_COORD, NT><<<grid, NT, smem, st>>>(c, hn, x_out);
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
@@ -314,8 +403,8 @@ int is_egnn_edge_fwd_tc(const int* indptr, const int* csr_src, const int* csr_ds
     const int grid = (int)(g < 1 ? 1 : g);
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == PREC_BF16)
-        return update_coords ? launch_tc<PREC_BF16, true>(c, hn, x_out, grid, st) : launch_tc<PREC_BF16, false>(c, hn, x_out, grid, st);
-    return update_coords ? launch_tc<PREC_TF32X3, true>(c, hn, x_out, grid, st) : launch_tc<PREC_TF32X3, false>(c, hn, x_out, grid, st);
+        return update_coords ? launch_tc<PREC_BF16, true, 256>(c, hn, x_out, grid, st) : launch_tc<PREC_BF16, false, 256>(c, hn, x_out, grid, st);
+    return update_coords ? launch_tc<PREC_TF32X3, true, 512>(c, hn, x_out, grid, st) : launch_tc<PREC_TF32X3, false, 512>(c, hn, x_out, grid, st);
 }
 
 }  // extern "C"
