@@ -39,7 +39,7 @@ def exported_symbols():
             "is_loss_num_partials", "is_collate_csr", "is_egnn_node_pre_fwd", "is_egnn_edge_fwd",
             "is_egnn_node_post_fwd", "is_egnn_node_post_bwd", "is_egnn_edge_bwd", "is_egnn_node_pre_bwd",
             "is_reduce_partials", "is_attn_pool_fwd", "is_attn_pool_bwd", "is_fusion_attn_fwd",
-            "is_fusion_attn_bwd", "is_loss_fwd", "is_loss_bwd", "is_umma_selftest", "is_egnn_edge_fwd_tc"]
+            "is_fusion_attn_bwd", "is_loss_fwd", "is_loss_bwd", "is_umma_selftest", "is_egnn_edge_fwd_tc", "is_attn_pool_infer"]
 
 
 def _check(rc: int, name: str):
@@ -206,6 +206,12 @@ def attn_pool_fwd(QKV, node_off, n_head, max_nodes, O, LSE, pooled, attn=None, a
     _call("is_attn_pool_fwd", _t(QKV, f32, "QKV"), _t(node_off, i64, "node_off"), _i32(node_off.numel() - 1),
           _i32(n_head), _i32(max_nodes), _t(O, f32, "O"), _t(LSE, f32, "LSE"), _t(pooled, f32, "pooled"),
           _t(attn, f32, "attn"), _t(attn_off, i64, "attn_off"), _stream())
+
+
+def attn_pool_infer(QKV, node_off, n_head, max_nodes, pooled):
+    f32, i64 = torch.float32, torch.int64
+    _call("is_attn_pool_infer", _t(QKV, f32, "QKV"), _t(node_off, i64, "node_off"), _i32(node_off.numel() - 1),
+          _i32(n_head), _i32(max_nodes), _t(pooled, f32, "pooled"), _stream())
 
 
 def attn_pool_bwd(QKV, O, LSE, node_off, n_head, max_nodes, g_pooled, gO_full, gQKV):

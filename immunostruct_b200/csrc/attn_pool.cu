@@ -226,6 +226,118 @@ attn_bwd_kernel(const float* __restrict__ QKV, const float* __restrict__ O, cons
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Inference fast path: only the pooled output is needed (no_grad, no attention weights).  Because the
+// mean over rows commutes with the P V product,
+//     pooled[h*dh + c] = sum_j w^h_j V[j][h*dh + c],   w^h_j = (1/n) sum_i softmax_j(q_i . k_j / sqrt(dh)),
+// so only the column sums of the attention matrix are accumulated (in registers, per warp, fixed order)
+// and the P V product disappears.  Q K^T is register blocked: each warp handles 4 query rows at a time,
+// each lane up to 8 key columns -> 128 FMAs per 12 shared-memory loads.
+#define IS_ATT_LD4 68
+__global__ void __launch_bounds__(IS_THREADS, 2)
+attn_pool_infer_kernel(const float* __restrict__ QKV, const int64_t* __restrict__ node_off, int H, float scale,
+                       float* __restrict__ pooled) {
+    extern __shared__ __align__(16) float smem[];
+    const int g = blockIdx.x;
+    const int64_t n0 = node_off[g];
+    const int n = (int)(node_off[g + 1] - n0);
+    float* Ks = smem;                               // [NMAX][68]
+    float* qs = Ks + IS_ATT_NMAX * IS_ATT_LD4;      // [8 warps][4][64]
+    float* part = qs + 8 * 4 * 64;                  // [8 warps][NMAX] column-sum partials
+    float* wcol = part + 8 * IS_ATT_NMAX;           // [NMAX]
+    float* red = wcol + IS_ATT_NMAX;                // [4][64]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int dh = 64 / H;
+    for (int idx = tid; idx < n * 16; idx += IS_THREADS) {
+        const int r = idx >> 4, c4 = idx & 15;
+        *reinterpret_cast<float4*>(Ks + r * IS_ATT_LD4 + 4 * c4) =
+            __ldg(reinterpret_cast<const float4*>(QKV + (n0 + r) * 192 + 64) + c4);
+    }
+    __syncthreads();
+    float* q = qs + warp * 256;
+    const float inv_n = 1.0f / (float)max(n, 1);
+    for (int h = 0; h < H; ++h) {
+        float colacc[IS_ATT_NMAX / 32];
+#pragma unroll
+        for (int jj = 0; jj < IS_ATT_NMAX / 32; ++jj) colacc[jj] = 0.0f;
+        for (int i0 = 4 * warp; i0 < n; i0 += 4 * (IS_THREADS / 32)) {
+            __syncwarp();
+            // stage this warp's 4 query rows (this head's dh channels), zero beyond n
+            for (int t = lane; t < 4 * dh; t += 32) {
+                const int r = t / dh, c = t - r * dh;
+                q[r * 64 + c] = (i0 + r < n) ? __ldg(QKV + (n0 + i0 + r) * 192 + h * dh + c) : 0.0f;
+            }
+            __syncwarp();
+            float acc[4][IS_ATT_NMAX / 32];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int jj = 0; jj < IS_ATT_NMAX / 32; ++jj) acc[r][jj] = 0.0f;
+            for (int k = 0; k < dh; k += 4) {
+                float4 q4[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) q4[r] = *reinterpret_cast<const float4*>(q + r * 64 + k);
+#pragma unroll
+                for (int jj = 0; jj < IS_ATT_NMAX / 32; ++jj) {
+                    const int j = jj * 32 + lane;
+                    if (jj * 32 < n) {      // warp-uniform skip of empty column blocks
+                        const float4 kv = *reinterpret_cast<const float4*>(Ks + (j < n ? j : 0) * IS_ATT_LD4 + h * dh + k);
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+                            acc[r][jj] = fmaf(q4[r].x, kv.x, fmaf(q4[r].y, kv.y, fmaf(q4[r].z, kv.z, fmaf(q4[r].w, kv.w, acc[r][jj]))));
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                float mx = -INFINITY;
+#pragma unroll
+                for (int jj = 0; jj < IS_ATT_NMAX / 32; ++jj) {
+                    const float a = (jj * 32 + lane < n) ? acc[r][jj] * scale : -INFINITY;
+                    acc[r][jj] = a;
+                    mx = fmaxf(mx, a);
+                }
+                mx = warp_max(mx);
+                float z = 0.0f;
+#pragma unroll
+                for (int jj = 0; jj < IS_ATT_NMAX / 32; ++jj) {
+                    const float e = (jj * 32 + lane < n) ? expf(acc[r][jj] - mx) : 0.0f;
+                    acc[r][jj] = e;
+                    z += e;
+                }
+                z = warp_sum(z);
+                const float rz = (i0 + r < n) ? 1.0f / z : 0.0f;      // rows beyond n contribute nothing
+#pragma unroll
+                for (int jj = 0; jj < IS_ATT_NMAX / 32; ++jj) colacc[jj] = fmaf(acc[r][jj], rz, colacc[jj]);
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < IS_ATT_NMAX / 32; ++jj) part[warp * IS_ATT_NMAX + jj * 32 + lane] = colacc[jj];
+        __syncthreads();
+        for (int j = tid; j < n; j += IS_THREADS) {
+            float s = 0.0f;
+#pragma unroll
+            for (int w = 0; w < IS_THREADS / 32; ++w) s += part[w * IS_ATT_NMAX + j];
+            wcol[j] = s * inv_n;
+        }
+        __syncthreads();
+        // pooled[h*dh + c] = sum_j wcol[j] V[j][h*dh + c]: 4 row quarters x dh channels, fixed order
+        {
+            const int c = tid & 63, quarter = tid >> 6;
+            float sacc = 0.0f;
+            if (c < dh) {
+                const int per = (n + 3) / 4, j0 = min(n, quarter * per), j1 = min(n, j0 + per);
+                for (int j = j0; j < j1; ++j) sacc = fmaf(wcol[j], __ldg(QKV + (n0 + j) * 192 + 128 + h * dh + c), sacc);
+            }
+            red[quarter * 64 + c] = sacc;
+        }
+        __syncthreads();
+        if (tid < dh) pooled[(int64_t)g * 64 + h * dh + tid] = red[tid] + red[64 + tid] + red[128 + tid] + red[192 + tid];
+        __syncthreads();
+    }
+}
+
 }  // namespace is
 
 using namespace is;
@@ -244,6 +356,20 @@ int is_attn_pool_fwd(const float* QKV, const int64_t* node_off, int n_graphs, in
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     attn_fwd_kernel<<<n_graphs, IS_THREADS, smem, (cudaStream_t)stream>>>(QKV, node_off, n_head, scale, O, LSE, pooled, attn, attn_off);
+    IS_LAUNCH_CHECK();
+    return IS_OK;
+}
+
+// Inference-only variant: pooled [B,64] only (nothing saved for a backward pass, no weights output).
+int is_attn_pool_infer(const float* QKV, const int64_t* node_off, int n_graphs, int n_head, int max_nodes,
+                       float* pooled, void* stream) {
+    if (n_graphs <= 0 || !(n_head == 1 || n_head == 2 || n_head == 4 || n_head == 8)) return IS_ERR_ARG;
+    if (max_nodes > IS_ATT_NMAX) return IS_ERR_UNSUPPORTED;
+    const float scale = 1.0f / sqrtf((float)(64 / n_head));
+    size_t smem = sizeof(float) * (IS_ATT_NMAX * IS_ATT_LD4 + 8 * 4 * 64 + 8 * IS_ATT_NMAX + IS_ATT_NMAX + 4 * 64);
+    cudaError_t e = cudaFuncSetAttribute(attn_pool_infer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attn_pool_infer_kernel<<<n_graphs, IS_THREADS, smem, (cudaStream_t)stream>>>(QKV, node_off, n_head, scale, pooled);
     IS_LAUNCH_CHECK();
     return IS_OK;
 }

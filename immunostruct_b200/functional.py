@@ -180,7 +180,14 @@ class _AttnPool(torch.autograd.Function):
         return None, None, None, gQKV
 
 
-def attention_pool(graph, QKV, n_head=1, want_attn=False):
+def attention_pool(graph, QKV, n_head=1, want_attn=False, want_nodes=False):
+    """-> (O [N,64] or None, pooled [B,64], attention weights or None).  Without autograd and when only
+    the pooled rows are wanted, the inference kernel (column sums of P, no P V product) is used."""
+    if not want_attn and not want_nodes and not (torch.is_grad_enabled() and QKV.requires_grad):
+        QKV = QKV.contiguous()
+        pooled = _new(QKV, graph.n_graphs, H)
+        _C.attn_pool_infer(QKV, graph.node_off, n_head, graph.max_nodes, pooled)
+        return None, pooled, None
     return _AttnPool.apply(graph, n_head, want_attn, QKV)
 
 

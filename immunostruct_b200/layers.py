@@ -77,7 +77,7 @@ class SelfAttention(nn.Module):
 
     def pooled(self, graph, h, want_attn=False, want_nodes=False):
         """h [N_total,64] -> (per-graph mean of the attention output [B,64], weights|None, per-node out|None)."""
-        O, pooled, attn = IF.attention_pool(graph, self._qkv(h), 1, want_attn)
+        O, pooled, attn = IF.attention_pool(graph, self._qkv(h), 1, want_attn, want_nodes)
         if want_attn:
             attn = attn.squeeze(1)         # SelfAttention returns [B, n, n]
         return pooled, attn, (O if want_nodes else None)
@@ -124,7 +124,7 @@ class MultiHeadAttention(nn.Module):
         affine ``w_concat``, so the projection is applied to the pooled [B,64] rows."""
         if self.feature_dim != 64 or self.input_dim != 64:
             raise NotImplementedError("fused per-graph attention is specialised for 64 channels")
-        O, pooled, attn = IF.attention_pool(graph, self._qkv(h), self.n_head, want_attn)
+        O, pooled, attn = IF.attention_pool(graph, self._qkv(h), self.n_head, want_attn, want_nodes)
         nodes = self.w_concat(O) if want_nodes else None
         return self.w_concat(pooled), attn, nodes
 

@@ -81,6 +81,9 @@ int is_attn_pool_fwd(const float* QKV, const int64_t* node_off, int n_graphs, in
                      float* O, float* LSE, float* pooled, float* attn, const int64_t* attn_off, void* stream);
 int is_attn_pool_bwd(const float* QKV, const float* O, const float* LSE, const int64_t* node_off, int n_graphs,
                      int n_head, int max_nodes, const float* g_pooled, const float* gO_full, float* gQKV, void* stream);
+/* inference-only: pooled [B,64] from column sums of the attention matrix (no O / LSE / weights) */
+int is_attn_pool_infer(const float* QKV, const int64_t* node_off, int n_graphs, int n_head, int max_nodes,
+                       float* pooled, void* stream);
 
 /* ---- fusion attention over the fused scalars + mean(dim=2) (models/hybrid_models.py:275,344-347;
  * comparative_models.py:392,484-486).  coef: [A(H) | C(H) | alpha(H) | beta(H) | btilde]. */

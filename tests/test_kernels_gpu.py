@@ -296,6 +296,9 @@ def test_attention_pool_kernels(case, n_head):
     _C.attn_pool_fwd(QKV.to(DEV), gb.node_off, n_head, gb.max_nodes, O_d, LSE_d, pooled_d)
     KC.attn_pool_fwd(QKV, cg.node_off, n_head, gb.max_nodes, O, LSE, pooled)
     close(O_d, O, what="O"); close(LSE_d, LSE, what="LSE"); close(pooled_d, pooled, what="pooled")
+    pooled_i = torch.full((b, 64), float("nan"), device=DEV)
+    _C.attn_pool_infer(QKV.to(DEV), gb.node_off, n_head, gb.max_nodes, pooled_i)
+    close(pooled_i, pooled, what="pooled (inference kernel)")
     g_pooled, gO = rnd(gen, b, 64), rnd(gen, n, 64)
     for gp, go in ((g_pooled, None), (g_pooled, gO), (None, gO)):
         gQKV, gQKV_d = torch.empty(n, 192), torch.empty(n, 192, device=DEV)
