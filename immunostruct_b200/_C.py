@@ -39,7 +39,7 @@ def exported_symbols():
             "is_loss_num_partials", "is_collate_csr", "is_egnn_node_pre_fwd", "is_egnn_edge_fwd",
             "is_egnn_node_post_fwd", "is_egnn_node_post_bwd", "is_egnn_edge_bwd", "is_egnn_node_pre_bwd",
             "is_reduce_partials", "is_attn_pool_fwd", "is_attn_pool_bwd", "is_fusion_attn_fwd",
-            "is_fusion_attn_bwd", "is_loss_fwd", "is_loss_bwd", "is_umma_selftest", "is_egnn_edge_fwd_tc", "is_attn_pool_infer"]
+            "is_fusion_attn_bwd", "is_loss_fwd", "is_loss_bwd", "is_umma_selftest", "is_egnn_edge_fwd_tc", "is_attn_pool_infer", "is_egnn_node_post_pre_tc"]
 
 
 def _check(rc: int, name: str):
@@ -145,7 +145,16 @@ def egnn_edge_fwd(g, PQ, x, edge_attr, F, W1, W2, b2, W3, b3, w4, update_coords,
           _t(x_out, f32, "x_out"), _i64(PQ.shape[0]), _t(g.status, torch.int32, "status"), _stream())
 
 
-PREC_BF16, PREC_TF32X3 = 0, 2
+PREC_BF16, PREC_TF32X3, PREC_BF16X3 = 0, 2, 3
+
+
+def egnn_node_post_pre_tc(h, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, precision):
+    """node_post(l) + node_pre(l+1) on the tensor cores (csrc/egnn_node_tc.cu); W1n/b1n/PQn None for the last layer."""
+    f32 = torch.float32
+    hp, ldh = _rows(h, "h")
+    _call("is_egnn_node_post_pre_tc", hp, ldh, _i32(h.shape[1]), _t(hn, f32, "hn"), _t(W5, f32, "W5"),
+          _t(b5, f32, "b5"), _t(W6, f32, "W6"), _t(b6, f32, "b6"), _t(h_out, f32, "h_out"), _t(W1n, f32, "W1n"),
+          _t(b1n, f32, "b1n"), _t(PQn, f32, "PQn"), _i64(h.shape[0]), _i32(precision), _stream())
 
 
 def egnn_edge_fwd_tc(g, PQ, x, edge_attr, F, W1, W2, b2, W3, b3, w4, update_coords, precision, hn, x_out):

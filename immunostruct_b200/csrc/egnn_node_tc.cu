@@ -1,0 +1,205 @@
+// Node-side half of an EGNN layer on the tensor cores, fused across the layer boundary:
+//
+//   node_post(l) :  h' = W6 silu(W5 [h | hn] + b5) + b6              (reference: EGNNConv node_mlp)
+//   node_pre(l+1):  P' = h' Ws'^T ,  Q' = h' Wd'^T + b1'              (first edge-MLP layer of layer l+1,
+//                                                                      split per node, see egnn.cu)
+// Per tile of 128 nodes four chained tcgen05 GEMM groups run against weight blocks that stay resident
+// in shared memory for the CTA's lifetime; the activations never leave the SM between them:
+//   D1 = h W5h^T + hn W5n^T  -> +b5, SiLU -> D2 = t5 W6^T -> +b6 = h' (stored) -> D3 = h' [Ws'; Wd']^T (+b1')
+// A single A-operand buffer (one 64-wide K block) is re-staged between the groups.  Used by the
+// no-grad inference path (immunostruct_b200.functional.egnn_stack_infer); the training path keeps the
+// SIMT node kernels.  PREC_BF16 (bf16 mode) or PREC_BF16X3 (fp32 parity; the hi/lo tf32 form of the five
+// resident weight blocks would not fit in shared memory, the three-term bf16 form does: 138 KB).
+#include "tc_common.cuh"
+
+namespace is {
+
+template <int PREC, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
+node_post_pre_tc_kernel(const float* __restrict__ h, int64_t ldh, int F, const float* __restrict__ hn,
+                        const float* __restrict__ W5, const float* __restrict__ b5,
+                        const float* __restrict__ W6, const float* __restrict__ b6, float* __restrict__ h_out,
+                        const float* __restrict__ W1n /* next layer edge_mlp.0.weight [64,130] or null */,
+                        const float* __restrict__ b1n, float* __restrict__ PQn, int64_t M) {
+    using C = TcCfg<PREC>;
+    constexpr int NW = NT / 32, CQ = NW / 4, CW = 64 / CQ;
+    constexpr uint32_t ASPL = C::A_BYTES, WSPL = 5 * C::W_BYTES;          // split-term strides
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t* sA = smem_raw;                                   // [NSPLIT][A_BYTES]
+    uint8_t* sW = sA + C::NSPLIT * ASPL;                      // [NSPLIT][5 blocks][W_BYTES]: W5h W5n W6 Ws' Wd'
+    float* vec = reinterpret_cast<float*>(sW + C::NSPLIT * WSPL);   // b5, b6, b1'
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool has_next = W1n != nullptr;
+    const int K5 = F + 64;
+
+    if (warp == 0) tmem_alloc(&s_tmem, 256);
+    if (tid == 32) mbar_init(&mbar, 1);
+    for (int idx = tid; idx < 64 * 64; idx += NT) {
+        const int n = idx >> 6, k = idx & 63;
+        store_weight1<PREC>(sW + 0 * C::W_BYTES, WSPL, n, k, k < F ? __ldg(W5 + n * K5 + k) : 0.0f);
+        store_weight1<PREC>(sW + 1 * C::W_BYTES, WSPL, n, k, __ldg(W5 + n * K5 + F + k));
+        store_weight1<PREC>(sW + 2 * C::W_BYTES, WSPL, n, k, __ldg(W6 + idx));
+        store_weight1<PREC>(sW + 3 * C::W_BYTES, WSPL, n, k, has_next ? __ldg(W1n + n * 130 + k) : 0.0f);
+        store_weight1<PREC>(sW + 4 * C::W_BYTES, WSPL, n, k, has_next ? __ldg(W1n + n * 130 + 64 + k) : 0.0f);
+    }
+    if (tid < 64) {
+        vec[tid] = b5[tid];
+        vec[64 + tid] = b6[tid];
+        vec[128 + tid] = has_next ? b1n[tid] : 0.0f;
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = s_tmem;
+    const uint32_t a_addr = smem_u32(sA), w_addr = smem_u32(sW);
+    const int q = warp & 3, cq = warp >> 2, erow = 32 * q + lane;
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
+    const int rsub = lane >> 3, kc8 = lane & 7;
+    uint32_t phase = 0;
+
+    // stage a [128 x 64] fp32 tile (rows m0.., `ncols` valid columns, row stride ld) as the A operand
+    auto stage_rows = [&](const float* __restrict__ src, int64_t ld, int ncols, int64_t m0) {
+#pragma unroll
+        for (int pass = 0; pass < IS_TM / (4 * NW); ++pass) {
+            const int r = pass * 4 * NW + warp * 4 + rsub;
+            const int64_t m = m0 + r;
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+            if (m < M) {
+                const float* rp = src + m * ld + 8 * kc8;
+                if (ncols == 64 && (ld & 3) == 0) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(rp)), b = __ldg(reinterpret_cast<const float4*>(rp) + 1);
+                    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = (8 * kc8 + i < ncols) ? __ldg(rp + i) : 0.0f;
+                }
+            }
+            store_operand8<PREC>(sA, ASPL, r, kc8, v);
+        }
+    };
+    auto run_gemm = [&](uint32_t tmem_d, int wblock, uint32_t ncols, uint32_t accumulate) {
+        fence_async_smem();
+        fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            fence_after_sync();
+            issue_gemm<PREC>(tmem_d, a_addr, ASPL, w_addr + wblock * C::W_BYTES, WSPL, ncols, accumulate);
+            mma_commit(&mbar);
+            mbar_wait(&mbar, phase);
+        }
+        phase ^= 1;
+        __syncthreads();
+        fence_after_sync();
+    };
+
+    const int64_t ntiles = (M + IS_TM - 1) / IS_TM;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t m0 = t * IS_TM;
+        // ---- D1 = h W5h^T + hn W5n^T ---------------------------------------------------------------
+        stage_rows(h, ldh, F, m0);
+        run_gemm(tmem, 0, 64, 0);
+        stage_rows(hn, 64, 64, m0);
+        run_gemm(tmem, 1, 64, 1);
+        // ---- t5 = silu(D1 + b5) -> A operand ; D2 = t5 W6^T -------------------------------------------
+        {
+            float z[CW];
+            tmem_ld<CW>(t_lane + CW * cq, z);
+#pragma unroll
+            for (int g = 0; g < CW / 8; ++g) {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = act<PREC>(z[8 * g + i] + vec[CW * cq + 8 * g + i]);
+                store_operand8<PREC>(sA, ASPL, erow, (CW / 8) * cq + g, v);
+            }
+        }
+        run_gemm(tmem + 64, 2, 64, 0);
+        // ---- h' = D2 + b6 -> global (+ A operand for the next layer's P/Q) ------------------------------
+        {
+            float z[CW];
+            tmem_ld<CW>(t_lane + 64 + CW * cq, z);
+            const int64_t m = m0 + erow;
+#pragma unroll
+            for (int g = 0; g < CW / 8; ++g) {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = z[8 * g + i] + vec[64 + CW * cq + 8 * g + i];
+                if (m < M) {
+                    float* dst = h_out + m * 64 + CW * cq + 8 * g;
+                    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                }
+                if (has_next) store_operand8<PREC>(sA, ASPL, erow, (CW / 8) * cq + g, v);
+            }
+        }
+        if (has_next) {
+            // ---- D3 = h' [Ws'; Wd']^T (N = 128: weight blocks 3 and 4 are contiguous row groups) -------
+            run_gemm(tmem + 128, 3, 128, 0);
+            const int64_t m = m0 + erow;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float z[CW];
+                tmem_ld<CW>(t_lane + 128 + 64 * half + CW * cq, z);
+                if (m < M) {
+#pragma unroll
+                    for (int g = 0; g < CW / 4; ++g) {
+                        const int c = CW * cq + 4 * g;
+                        float4 o = make_float4(z[4 * g], z[4 * g + 1], z[4 * g + 2], z[4 * g + 3]);
+                        if (half) { o.x += vec[128 + c]; o.y += vec[128 + c + 1]; o.z += vec[128 + c + 2]; o.w += vec[128 + c + 3]; }
+                        *reinterpret_cast<float4*>(PQn + m * 128 + 64 * half + c) = o;
+                    }
+                }
+            }
+        }
+        fence_before_sync();      // TMEM reads of this tile are ordered before the next tile's MMAs
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+template <int PREC, int NT>
+static int launch_node_tc(const float* h, int64_t ldh, int F, const float* hn, const float* W5, const float* b5,
+                          const float* W6, const float* b6, float* h_out, const float* W1n, const float* b1n,
+                          float* PQn, int64_t M, cudaStream_t st) {
+    using C = TcCfg<PREC>;
+    const size_t smem = (size_t)C::NSPLIT * (C::A_BYTES + 5 * C::W_BYTES) + 3 * 64 * sizeof(float) + 128;
+    cudaError_t e = cudaFuncSetAttribute(node_post_pre_tc_kernel<PREC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    int64_t tiles = (M + IS_TM - 1) / IS_TM;
+    int64_t cap = (int64_t)sms * (NT == 256 ? 2 : 1);
+    int grid = (int)(tiles < cap ? tiles : cap);
+    node_post_pre_tc_kernel<PREC, NT><<<grid < 1 ? 1 : grid, NT, smem, st>>>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, M);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+}  // namespace is
+
+using namespace is;
+
+extern "C" {
+
+// node_mlp of layer l fused with the per-node half of layer l+1's first edge-MLP layer (W1n / b1n / PQn
+// may be NULL for the last layer).  precision: 0 = bf16, 3 = bf16x3 (fp32-accurate).  W1n must be the
+// [64, 130] weight of a 64-wide layer.
+int is_egnn_node_post_pre_tc(const float* h, int64_t ldh, int F, const float* hn, const float* W5, const float* b5,
+                             const float* W6, const float* b6, float* h_out, const float* W1n, const float* b1n,
+                             float* PQn, int64_t n_nodes, int precision, void* stream) {
+    if (!(F == 20 || F == 64) || n_nodes <= 0) return IS_ERR_ARG;
+    if ((W1n == nullptr) != (PQn == nullptr)) return IS_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == PREC_BF16)
+        return launch_node_tc<PREC_BF16, 256>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, n_nodes, st);
+    if (precision == PREC_BF16X3)
+        return launch_node_tc<PREC_BF16X3, 512>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, n_nodes, st);
+    return IS_ERR_ARG;
+}
+
+}  // extern "C"

@@ -21,82 +21,10 @@
 // SIMT phases.
 #include "common.cuh"
 #include "egnn_common.cuh"
-#include "umma.cuh"
 
-#define PREC_BF16 0
-#define PREC_TF32X3 2
+#include "tc_common.cuh"
 
 namespace is {
-
-using namespace umma;
-
-template <int PREC>
-struct TcCfg {
-    static constexpr int EB = PREC == PREC_BF16 ? 2 : 4;              // operand element bytes
-    static constexpr int KCH = 64 * EB / 16;                          // 16-byte chunks per 64-wide row
-    static constexpr uint32_t SBO = KCH * kLBO;                       // bytes between 8-row groups
-    static constexpr uint32_t A_BYTES = 16 * SBO;                     // 128-row operand tile
-    static constexpr uint32_t W_BYTES = 8 * SBO;                      // 64-row operand tile
-    static constexpr int NSPLIT = PREC == PREC_BF16 ? 1 : 2;          // hi (+ lo)
-    static constexpr uint32_t FMT = PREC == PREC_BF16 ? 1u : 2u;
-};
-
-// SiLU.  bf16 mode: z*sigmoid(z) = h + h*tanh(h), h = z/2, with the hardware tanh (one MUFU, three
-// instructions, 2^-11 relative error -- below the bf16 operand rounding that follows).  3xTF32 mode:
-// accurate expf and an approximate reciprocal (1 ulp), 2^-22-level error, fp32 parity.
-template <int PREC>
-__device__ __forceinline__ float act(float z) {
-    if (PREC == PREC_BF16) {
-        const float h = 0.5f * z;
-        float t;
-        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-        return fmaf(h, t, h);
-    }
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + expf(-z)));
-    return z * r;
-}
-
-// store 8 consecutive K values (features 8*kc8 .. 8*kc8+7) of operand row `row`
-template <int PREC>
-__device__ __forceinline__ void store_operand8(uint8_t* __restrict__ tile, int row, int kc8, const float (&v)[8]) {
-    using C = TcCfg<PREC>;
-    const uint32_t rbase = (uint32_t)((row >> 3) * C::SBO + (row & 7) * 16);
-    if (PREC == PREC_BF16) {
-        uint4 q;
-        q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
-        q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
-        *reinterpret_cast<uint4*>(tile + rbase + kc8 * kLBO) = q;
-    } else {
-        float hi[8], lo[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { hi[i] = tf32_round(v[i]); lo[i] = tf32_round(v[i] - hi[i]); }
-        uint8_t* p0 = tile + rbase + (2 * kc8) * kLBO;
-        *reinterpret_cast<float4*>(p0) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(p0 + kLBO) = make_float4(hi[4], hi[5], hi[6], hi[7]);
-        *reinterpret_cast<float4*>(p0 + C::A_BYTES) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-        *reinterpret_cast<float4*>(p0 + C::A_BYTES + kLBO) = make_float4(lo[4], lo[5], lo[6], lo[7]);
-    }
-}
-
-// issue one 128x64x64 GEMM: D[tmem_d] = A_tile * W_tile^T   (called by ONE thread)
-template <int PREC>
-__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr) {
-    using C = TcCfg<PREC>;
-    const uint32_t idesc = make_instr_desc(C::FMT, 128, 64);
-    uint32_t acc = 0;
-#pragma unroll
-    for (int term = (PREC == PREC_BF16 ? 2 : 0); term < 3; ++term) {        // lo*hi, hi*lo, hi*hi
-        const uint32_t aoff = (term == 0) ? C::A_BYTES : 0, woff = (term == 1) ? C::W_BYTES : 0;
-#pragma unroll
-        for (int ks = 0; ks < C::KCH / 2; ++ks) {
-            const uint64_t da = make_smem_desc(a_addr + aoff + ks * 2 * kLBO, kLBO, C::SBO);
-            const uint64_t db = make_smem_desc(w_addr + woff + ks * 2 * kLBO, kLBO, C::SBO);
-            if (PREC == PREC_BF16) mma_bf16(tmem_d, da, db, idesc, acc); else mma_tf32(tmem_d, da, db, idesc, acc);
-            acc = 1;
-        }
-    }
-}
 
 // ---- tile walk: executed by one full warp; all lanes return the same values ------------------------
 // Longest run of consecutive destination nodes (<= 32) starting at n0 whose in-edges total <= 128.
@@ -143,25 +71,6 @@ __device__ __forceinline__ void load_meta(const EdgeCommon& p, TileMeta& m, int 
     }
 }
 
-template <int N>
-__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[N]);
-template <>
-__device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, float (&v)[32]) { tmem_ld32(taddr, v); }
-template <>
-__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
 // NT threads per CTA: 256 (two CTAs per SM) for bf16, 512 (one CTA per SM, 16 warps) for 3xTF32 whose
 // hi/lo operand tiles need 147 KB of shared memory.
 template <int PREC, bool HAS_COORD, int NT>
@@ -189,18 +98,8 @@ edge_fwd_tc_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
     if (tid == 32) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
     for (int idx = tid; idx < 64 * 64; idx += NT) {                    // stage W2 / W3 as B operands
         const int n = idx >> 6, k = idx & 63;
-        const uint32_t off = canon_off<C::EB>(n, k, C::KCH);
-        const float w2 = __ldg(p.W2 + idx), w3 = HAS_COORD ? __ldg(p.W3 + idx) : 0.0f;
-        if (PREC == PREC_BF16) {
-            *reinterpret_cast<__nv_bfloat16*>(sW2 + off) = __float2bfloat16_rn(w2);
-            *reinterpret_cast<__nv_bfloat16*>(sW3 + off) = __float2bfloat16_rn(w3);
-        } else {
-            const float h2 = tf32_round(w2), h3 = tf32_round(w3);
-            *reinterpret_cast<float*>(sW2 + off) = h2;
-            *reinterpret_cast<float*>(sW2 + C::W_BYTES + off) = tf32_round(w2 - h2);
-            *reinterpret_cast<float*>(sW3 + off) = h3;
-            *reinterpret_cast<float*>(sW3 + C::W_BYTES + off) = tf32_round(w3 - h3);
-        }
+        store_weight1<PREC>(sW2, C::W_BYTES, n, k, __ldg(p.W2 + idx));
+        store_weight1<PREC>(sW3, C::W_BYTES, n, k, HAS_COORD ? __ldg(p.W3 + idx) : 0.0f);
     }
     if (tid < 64) {
         vec[tid] = p.b2[tid];
@@ -273,7 +172,7 @@ edge_fwd_tc_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
                     v[6] = act<PREC>(pv[u][1].z + qv[u][1].z + wr1.z * r + wa1.z * a);
                     v[7] = act<PREC>(pv[u][1].w + qv[u][1].w + wr1.w * r + wa1.w * a);
                     // rows beyond the tile's edges hold finite garbage: they are never aggregated
-                    store_operand8<PREC>(sA, j, kc8, v);
+                    store_operand8<PREC>(sA, C::A_BYTES, j, kc8, v);
                 }
             }
         }
@@ -282,7 +181,7 @@ edge_fwd_tc_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
         __syncthreads();                                                           // S1
         if (tid == 0) {
             fence_after_sync();
-            issue_gemm<PREC>(tmem, a_addr, w2_addr);
+            issue_gemm<PREC>(tmem, a_addr, C::A_BYTES, w2_addr, C::W_BYTES, 64, 0);
             mma_commit(&mbar[0]);
         }
         // ---- while MMA 1 runs: walk to the next tile and prefetch its per-edge scalars ------------
@@ -314,7 +213,7 @@ edge_fwd_tc_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
                 float* dst = M32 + erow * IS_LD + CW * cq + 8 * g;
                 *reinterpret_cast<float4*>(dst) = make_float4(m8[0], m8[1], m8[2], m8[3]);
                 *reinterpret_cast<float4*>(dst + 4) = make_float4(m8[4], m8[5], m8[6], m8[7]);
-                if (HAS_COORD) store_operand8<PREC>(sA, erow, (CW / 8) * cq + g, m8);   // MMA 1 is done with sA
+                if (HAS_COORD) store_operand8<PREC>(sA, C::A_BYTES, erow, (CW / 8) * cq + g, m8);   // MMA 1 is done with sA
             }
         }
         fence_async_smem();
@@ -322,7 +221,7 @@ edge_fwd_tc_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
         __syncthreads();                                                           // S3
         if (HAS_COORD && tid == 0) {
             fence_after_sync();
-            issue_gemm<PREC>(tmem + 64, a_addr, w3_addr);
+            issue_gemm<PREC>(tmem + 64, a_addr, C::A_BYTES, w3_addr, C::W_BYTES, 64, 0);
             mma_commit(&mbar[1]);
         }
 

@@ -1,0 +1,163 @@
+// Helpers shared by the tcgen05 kernels (egnn_tc.cu, egnn_node_tc.cu): precision configurations,
+// SiLU variants, operand staging in the canonical K-major layout, GEMM issue, TMEM loads.
+//
+// Precisions
+//   PREC_BF16   (0): bf16 operands, fp32 accumulate, hardware-tanh SiLU        -- bf16 mode (1e-2)
+//   PREC_TF32X3 (2): a = hi + lo in tf32, D = lo*Bhi + hi*Blo + hi*Bhi          -- fp32 parity, 8 B/element
+//   PREC_BF16X3 (3): a = a1 + a2 + a3 in bf16, six partial products             -- fp32 parity, 6 B/element
+#pragma once
+#include "common.cuh"
+#include "umma.cuh"
+
+#define PREC_BF16 0
+#define PREC_TF32X3 2
+#define PREC_BF16X3 3
+
+namespace is {
+
+using namespace umma;
+
+template <int PREC>
+struct TcCfg {
+    static constexpr int EB = PREC == PREC_TF32X3 ? 4 : 2;             // operand element bytes
+    static constexpr int KCH = 64 * EB / 16;                          // 16-byte chunks per 64-wide K block
+    static constexpr uint32_t SBO = KCH * kLBO;                       // bytes between 8-row groups
+    static constexpr uint32_t A_BYTES = 16 * SBO;                     // 128-row operand tile (one split term)
+    static constexpr uint32_t W_BYTES = 8 * SBO;                      // 64-row operand tile (one split term)
+    static constexpr int NSPLIT = PREC == PREC_BF16 ? 1 : PREC == PREC_TF32X3 ? 2 : 3;
+    static constexpr uint32_t FMT = PREC == PREC_TF32X3 ? 2u : 1u;
+    static constexpr bool ACCURATE = PREC != PREC_BF16;
+};
+
+// SiLU.  bf16 mode: z*sigmoid(z) = h + h*tanh(h), h = z/2, with the hardware tanh (one MUFU, three
+// instructions, 2^-11 relative error -- below the bf16 operand rounding that follows).  fp32-parity
+// modes: accurate expf and an approximate reciprocal (1 ulp), 2^-22-level error.
+template <int PREC>
+__device__ __forceinline__ float act(float z) {
+    if (!TcCfg<PREC>::ACCURATE) {
+        const float h = 0.5f * z;
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+        return fmaf(h, t, h);
+    }
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + expf(-z)));
+    return z * r;
+}
+
+__device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
+    uint4 q;
+    q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
+    q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
+    return q;
+}
+
+// store 8 consecutive K values (k = 8*kc8 .. 8*kc8+7 of a 64-wide K block) of operand row `row`;
+// `split_bytes` = distance between the split-term copies of the tile
+template <int PREC>
+__device__ __forceinline__ void store_operand8(uint8_t* __restrict__ tile, uint32_t split_bytes, int row, int kc8,
+                                               const float (&v)[8]) {
+    using C = TcCfg<PREC>;
+    const uint32_t rbase = (uint32_t)((row >> 3) * C::SBO + (row & 7) * 16);
+    if (PREC == PREC_BF16) {
+        *reinterpret_cast<uint4*>(tile + rbase + kc8 * kLBO) = pack8_bf16(v);
+    } else if (PREC == PREC_BF16X3) {
+        float t1[8], t2[8], t3[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            t1[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
+            const float r1 = v[i] - t1[i];
+            t2[i] = __bfloat162float(__float2bfloat16_rn(r1));
+            t3[i] = r1 - t2[i];
+        }
+        uint8_t* p0 = tile + rbase + kc8 * kLBO;
+        *reinterpret_cast<uint4*>(p0) = pack8_bf16(t1);
+        *reinterpret_cast<uint4*>(p0 + split_bytes) = pack8_bf16(t2);
+        *reinterpret_cast<uint4*>(p0 + 2 * split_bytes) = pack8_bf16(t3);
+    } else {
+        float hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { hi[i] = tf32_round(v[i]); lo[i] = tf32_round(v[i] - hi[i]); }
+        uint8_t* p0 = tile + rbase + (2 * kc8) * kLBO;
+        *reinterpret_cast<float4*>(p0) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(p0 + kLBO) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+        *reinterpret_cast<float4*>(p0 + split_bytes) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<float4*>(p0 + split_bytes + kLBO) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+    }
+}
+
+// stage one element of a weight block (row n = output feature, k = input feature within a 64-wide K block)
+template <int PREC>
+__device__ __forceinline__ void store_weight1(uint8_t* __restrict__ tile, uint32_t split_bytes, int n, int k, float w) {
+    using C = TcCfg<PREC>;
+    const uint32_t off = canon_off<C::EB>(n, k, C::KCH);
+    if (PREC == PREC_BF16) {
+        *reinterpret_cast<__nv_bfloat16*>(tile + off) = __float2bfloat16_rn(w);
+    } else if (PREC == PREC_BF16X3) {
+        const __nv_bfloat16 w1 = __float2bfloat16_rn(w);
+        const float r1 = w - __bfloat162float(w1);
+        const __nv_bfloat16 w2 = __float2bfloat16_rn(r1);
+        *reinterpret_cast<__nv_bfloat16*>(tile + off) = w1;
+        *reinterpret_cast<__nv_bfloat16*>(tile + split_bytes + off) = w2;
+        *reinterpret_cast<__nv_bfloat16*>(tile + 2 * split_bytes + off) = __float2bfloat16_rn(r1 - __bfloat162float(w2));
+    } else {
+        const float hi = tf32_round(w);
+        *reinterpret_cast<float*>(tile + off) = hi;
+        *reinterpret_cast<float*>(tile + split_bytes + off) = tf32_round(w - hi);
+    }
+}
+
+// issue D[tmem_d] (+)= A * W^T over one 64-wide K block (called by ONE thread); N = 64 or 128 output
+// columns (W tile rows); a_split / w_split = byte distance between split-term copies.
+template <int PREC>
+__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_addr, uint32_t a_split, uint32_t w_addr,
+                                           uint32_t w_split, uint32_t n_cols, uint32_t accumulate) {
+    using C = TcCfg<PREC>;
+    const uint32_t idesc = make_instr_desc(C::FMT, 128, n_cols);
+    uint32_t acc = accumulate;
+    if (PREC == PREC_BF16X3) {
+        // (a-term, w-term), smallest products first: a3w1 a1w3 a2w2 a2w1 a1w2 a1w1
+        const uint32_t ta[6] = {2, 0, 1, 1, 0, 0}, tw[6] = {0, 2, 1, 0, 1, 0};
+#pragma unroll
+        for (int t = 0; t < 6; ++t)
+#pragma unroll
+            for (int ks = 0; ks < C::KCH / 2; ++ks) {
+                mma_bf16(tmem_d, make_smem_desc(a_addr + ta[t] * a_split + ks * 2 * kLBO, kLBO, C::SBO),
+                         make_smem_desc(w_addr + tw[t] * w_split + ks * 2 * kLBO, kLBO, C::SBO), idesc, acc);
+                acc = 1;
+            }
+    } else {
+#pragma unroll
+        for (int term = (PREC == PREC_BF16 ? 2 : 0); term < 3; ++term) {        // lo*hi, hi*lo, hi*hi
+            const uint32_t aoff = (term == 0) ? a_split : 0, woff = (term == 1) ? w_split : 0;
+#pragma unroll
+            for (int ks = 0; ks < C::KCH / 2; ++ks) {
+                const uint64_t da = make_smem_desc(a_addr + aoff + ks * 2 * kLBO, kLBO, C::SBO);
+                const uint64_t db = make_smem_desc(w_addr + woff + ks * 2 * kLBO, kLBO, C::SBO);
+                if (PREC == PREC_BF16) mma_bf16(tmem_d, da, db, idesc, acc); else mma_tf32(tmem_d, da, db, idesc, acc);
+                acc = 1;
+            }
+        }
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[N]);
+template <>
+__device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, float (&v)[32]) { tmem_ld32(taddr, v); }
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+}  // namespace is

@@ -1,6 +1,7 @@
 // Self-test of the hand-written tcgen05 path: D[128,64] = A[128,64] * B[64,64]^T for one tile, with the
 // exact device helpers (canonical layout, descriptors, MMA issue, commit, TMEM load) that the fused
-// EGNN tensor-core kernels use.  mode 0: bf16 operands; 1: tf32; 2: 3xTF32 split (fp32-accurate).
+// EGNN tensor-core kernels use.  mode 0: bf16 operands; 1: tf32; 2: 3xTF32 split (fp32-accurate);
+// 3: bf16x3 split (a = a1 + a2 + a3 in bf16, six partial products, fp32-accurate, 6 bytes / element).
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -10,11 +11,11 @@ template <int MODE>
 __global__ void __launch_bounds__(128)
 umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D) {
     using namespace umma;
-    constexpr int EB = MODE == 0 ? 2 : 4;                 // operand element bytes
+    constexpr int EB = (MODE == 0 || MODE == 3) ? 2 : 4;  // operand element bytes
     constexpr int KCH = 64 * EB / 16;                     // 16-byte chunks per row (8 for bf16, 16 for tf32)
     constexpr uint32_t SBO = KCH * kLBO;
     constexpr uint32_t A_BYTES = 16 * SBO, B_BYTES = 8 * SBO;
-    constexpr int NSPLIT = MODE == 2 ? 2 : 1;             // hi (+ lo) copies
+    constexpr int NSPLIT = MODE == 2 ? 2 : MODE == 3 ? 3 : 1;   // operand copies (split terms)
     extern __shared__ __align__(128) uint8_t sm[];
     uint8_t* sA = sm;                                     // [NSPLIT][A_BYTES]
     uint8_t* sB = sm + NSPLIT * A_BYTES;                  // [NSPLIT][B_BYTES]
@@ -31,6 +32,14 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, f
         const uint32_t off = canon_off<EB>(r, k, KCH);
         if (MODE == 0) {
             *reinterpret_cast<__nv_bfloat16*>(sA + off) = __float2bfloat16_rn(a);
+        } else if (MODE == 3) {
+            const __nv_bfloat16 a1 = __float2bfloat16_rn(a);
+            const float r1 = a - __bfloat162float(a1);
+            const __nv_bfloat16 a2 = __float2bfloat16_rn(r1);
+            const __nv_bfloat16 a3 = __float2bfloat16_rn(r1 - __bfloat162float(a2));
+            *reinterpret_cast<__nv_bfloat16*>(sA + off) = a1;
+            *reinterpret_cast<__nv_bfloat16*>(sA + A_BYTES + off) = a2;
+            *reinterpret_cast<__nv_bfloat16*>(sA + 2 * A_BYTES + off) = a3;
         } else {
             const float hi = tf32_round(a);
             *reinterpret_cast<float*>(sA + off) = hi;
@@ -43,6 +52,14 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, f
         const uint32_t off = canon_off<EB>(r, k, KCH);
         if (MODE == 0) {
             *reinterpret_cast<__nv_bfloat16*>(sB + off) = __float2bfloat16_rn(b);
+        } else if (MODE == 3) {
+            const __nv_bfloat16 b1 = __float2bfloat16_rn(b);
+            const float r1 = b - __bfloat162float(b1);
+            const __nv_bfloat16 b2 = __float2bfloat16_rn(r1);
+            const __nv_bfloat16 b3 = __float2bfloat16_rn(r1 - __bfloat162float(b2));
+            *reinterpret_cast<__nv_bfloat16*>(sB + off) = b1;
+            *reinterpret_cast<__nv_bfloat16*>(sB + B_BYTES + off) = b2;
+            *reinterpret_cast<__nv_bfloat16*>(sB + 2 * B_BYTES + off) = b3;
         } else {
             const float hi = tf32_round(b);
             *reinterpret_cast<float*>(sB + off) = hi;
@@ -55,9 +72,20 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, f
     fence_after_sync();
     const uint32_t tbase = tmem_base;
     if (tid == 0) {
-        const uint32_t idesc = make_instr_desc(MODE == 0 ? 1u : 2u, 128, 64);
+        const uint32_t idesc = make_instr_desc((MODE == 0 || MODE == 3) ? 1u : 2u, 128, 64);
         const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
         uint32_t acc = 0;
+        if (MODE == 3) {
+            // (a-term, b-term) pairs, smallest products first: a3b1 a1b3 a2b2 a2b1 a1b2 a1b1
+            const int ta[6] = {2, 0, 1, 1, 0, 0}, tb[6] = {0, 2, 1, 0, 1, 0};
+            for (int t = 0; t < 6; ++t)
+                for (int ks = 0; ks < KCH / 2; ++ks) {
+                    const uint64_t da = make_smem_desc(a0 + ta[t] * A_BYTES + ks * 2 * kLBO, kLBO, SBO);
+                    const uint64_t db = make_smem_desc(b0 + tb[t] * B_BYTES + ks * 2 * kLBO, kLBO, SBO);
+                    mma_bf16(tbase, da, db, idesc, acc);
+                    acc = 1;
+                }
+        } else {
         // small terms first: A_lo*B_hi, A_hi*B_lo, then A_hi*B_hi
         for (int term = (MODE == 2 ? 0 : 2); term < 3; ++term) {
             const uint32_t aoff = (term == 0) ? A_BYTES : 0, boff = (term == 1) ? B_BYTES : 0;
@@ -67,6 +95,7 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, f
                 if (MODE == 0) mma_bf16(tbase, da, db, idesc, acc); else mma_tf32(tbase, da, db, idesc, acc);
                 acc = 1;
             }
+        }
         }
         mma_commit(&mbar);
     }
@@ -106,6 +135,11 @@ extern "C" int is_umma_selftest(const float* A, const float* B, float* D, int mo
         e = cudaFuncSetAttribute(umma_selftest_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         umma_selftest_kernel<2><<<1, 128, smem, st>>>(A, B, D);
+    } else if (mode == 3) {
+        size_t smem = 3 * 24 * 8 * umma::kLBO + 128;
+        e = cudaFuncSetAttribute(umma_selftest_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        umma_selftest_kernel<3><<<1, 128, smem, st>>>(A, B, D);
     } else {
         return IS_ERR_ARG;
     }

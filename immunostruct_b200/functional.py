@@ -131,6 +131,44 @@ class _EGNNLayer(torch.autograd.Function):
         return (None, None, gh, gx, None, gW1, gb1, gW2, gb2, gW3, gb3, gw4, gW5, gb5, gW6, gb6)
 
 
+def egnn_stack_infer(graph, x23, edge_attr, layer_params):
+    """No-grad EGNN stack (models/hybrid_models.py:82,89-90): node_pre(0) -> [edge(l) -> node_post(l) +
+    node_pre(l+1)]; the last layer's coordinate branch is skipped (its output is never consumed).  In the
+    tensor-core precisions the node side runs fused across the layer boundary (csrc/egnn_node_tc.cu).
+    ``layer_params``: list of the 11-tuples of EGNNConv.kernel_params().  Returns the final h [N,64]."""
+    h, x = x23[:, :20], x23[:, 20:]
+    n = h.shape[0]
+    edge_attr = edge_attr.contiguous()
+    prec = _PRECISIONS[_precision]
+    node_prec = {None: None, _C.PREC_BF16: _C.PREC_BF16, _C.PREC_TF32X3: _C.PREC_BF16X3}[prec]
+    params = [[t.detach().contiguous() for t in lp] for lp in layer_params]
+    PQ = _new(h, n, 2 * H)
+    _C.egnn_node_pre_fwd(h, params[0][0], params[0][1], PQ)
+    last = len(params) - 1
+    for l, (W1, b1, W2, b2, W3, b3, w4, W5, b5, W6, b6) in enumerate(params):
+        f = h.shape[1]
+        upd = l != last
+        hn, h_out = _new(h, n, H), _new(h, n, H)
+        x_out = _new(h, n, 3) if upd else None
+        if prec is None:
+            _C.egnn_edge_fwd(graph, PQ, x, edge_attr, f, W1, W2, b2, W3, b3, w4, upd, hn, x_out)
+        else:
+            _C.egnn_edge_fwd_tc(graph, PQ, x, edge_attr, f, W1, W2, b2, W3, b3, w4, upd, prec, hn, x_out)
+        nxt = params[l + 1] if upd else None
+        PQ_next = _new(h, n, 2 * H) if upd else None
+        if node_prec is None:
+            _C.egnn_node_post_fwd(h, hn, W5, b5, W6, b6, h_out)
+            if upd:
+                _C.egnn_node_pre_fwd(h_out, nxt[0], nxt[1], PQ_next)
+        else:
+            _C.egnn_node_post_pre_tc(h, hn, W5, b5, W6, b6, h_out, nxt[0] if upd else None,
+                                     nxt[1] if upd else None, PQ_next, node_prec)
+        h, PQ = h_out, PQ_next
+        if upd:
+            x = x_out
+    return h
+
+
 def egnn_layer(graph, h, x, edge_attr, params, update_coords=True):
     """params = (W1, b1, W2, b2, W3, b3, w4, W5, b5, W6, b6); returns (h_out, x_out|None)."""
     return _EGNNLayer.apply(graph, update_coords, h, x, edge_attr, *params)

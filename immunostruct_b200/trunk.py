@@ -11,6 +11,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import functional as IF
 from .graph import GraphBatch
 from .layers import EGNNConv, MultiHeadAttention, SelfAttention
 
@@ -41,6 +42,10 @@ class StructureTrunk:
         _require_device_batch(graph_data)
         xin = graph_data.ndata["x"]
         node_feat, coord_feat, edge_feat = xin[:, :20], xin[:, 20:], graph_data.edata["edge_attr"]
+        if not torch.is_grad_enabled():
+            # inference: the whole stack through the fused kernels, nothing saved for a backward pass
+            node_feat = IF.egnn_stack_infer(graph_data, xin, edge_feat, [l.kernel_params() for l in self.GCN_layers])
+            return self.self_attention.pooled(graph_data, node_feat, want_attn=want_attn, want_nodes=want_nodes)
         last = len(self.GCN_layers) - 1
         for i, layer in enumerate(self.GCN_layers):
             # the last layer's coordinates are never consumed (hybrid_models.py:323-326)

@@ -116,6 +116,12 @@ def egnn_node_post_fwd(h, hn, W5, b5, W6, b6, h_out):
     h_out.copy_(F.linear(_silu(F.linear(torch.cat([h, hn], 1), W5, b5)), W6, b6))
 
 
+def egnn_node_post_pre_tc(h, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, precision):
+    egnn_node_post_fwd(h, hn, W5, b5, W6, b6, h_out)
+    if W1n is not None:
+        egnn_node_pre_fwd(h_out, W1n, b1n, PQn)
+
+
 # ---- EGNN backward (autograd = independent derivation) -------------------------------------------
 def _partials(rows, *tensors):
     flat = torch.cat([t.reshape(-1) for t in tensors])
@@ -288,6 +294,6 @@ def loss_bwd(recon, seq, mu, logvar, logits, y, mode, pos_weight, w_pred, w_mse,
 
 
 ALL = ["num_sms", "egnn_node_grid", "egnn_edge_bwd_grid", "attn_max_nodes", "loss_num_partials", "collate_csr",
-       "egnn_node_pre_fwd", "egnn_edge_fwd", "egnn_edge_fwd_tc", "egnn_node_post_fwd", "egnn_node_post_bwd", "egnn_edge_bwd",
+       "egnn_node_pre_fwd", "egnn_edge_fwd", "egnn_edge_fwd_tc", "egnn_node_post_pre_tc", "egnn_node_post_fwd", "egnn_node_post_bwd", "egnn_edge_bwd",
        "egnn_node_pre_bwd", "reduce_partials", "attn_pool_fwd", "attn_pool_infer", "attn_pool_bwd", "fusion_attn_fwd",
        "fusion_attn_bwd", "loss_fwd", "loss_bwd"]

@@ -45,6 +45,10 @@ def test_hybrid_model_matches_reference_golden(cpu_backend, name, cls):
                    o["loss_reg"]) < TOL
     loss.backward()
     assert_grads_close(named_grads(model), gd["grads"], 1e-4)
+    inject_eps(model, d["eps"], d["eps"], d["eps"])
+    with torch.no_grad():                         # inference path: fused stack + pooled-only attention
+        r_ng = model(g, d["seq"], d["prop"])
+    assert rel_err(r_ng[3], o["logits"]) < TOL and rel_err(r_ng[0], o["recon"]) < TOL
     emb = model(g, d["seq"], d["prop"], return_embedding=True)[0]
     att = model(g, d["seq"], d["prop"], return_attention=True)[0]
     assert rel_err(emb, o["embedding"]) < TOL

@@ -186,6 +186,29 @@ def test_egnn_edge_forward_tensor_core(case, f, prec, tol):
     assert int(gb.status.item()) == 0
 
 
+@pytest.mark.parametrize("prec,tol", [(_C.PREC_BF16X3, 1e-5), (_C.PREC_BF16, 2e-2)])
+@pytest.mark.parametrize("f,with_next", [(20, True), (64, True), (64, False)])
+def test_egnn_node_post_pre_tensor_core(case, f, with_next, prec, tol):
+    """Fused node_post(l) + node_pre(l+1) tcgen05 kernel vs the CPU contracts of the two SIMT kernels."""
+    arrays, gb, _ = case
+    gen = torch.Generator().manual_seed(41)
+    n = gb.n_nodes
+    w, wn = egnn_weights(gen, f), egnn_weights(gen, 64)
+    h = arrays["x"][:, :20].clone() if f == 20 else rnd(gen, n, 64)
+    hn = rnd(gen, n, 64, scale=3.0)
+    h_d = arrays["x"].to(DEV)[:, :20] if f == 20 else h.to(DEV)
+    ho, PQn = torch.empty(n, 64), torch.empty(n, 128)
+    ho_d, PQn_d = torch.full((n, 64), float("nan"), device=DEV), torch.full((n, 128), float("nan"), device=DEV)
+    KC.egnn_node_post_pre_tc(h, hn, w["W5"], w["b5"], w["W6"], w["b6"], ho, wn["W1"] if with_next else None,
+                             wn["b1"] if with_next else None, PQn if with_next else None, prec)
+    _C.egnn_node_post_pre_tc(h_d, hn.to(DEV), *dev(w["W5"], w["b5"], w["W6"], w["b6"]), ho_d,
+                             *(dev(wn["W1"], wn["b1"]) if with_next else (None, None)),
+                             PQn_d if with_next else None, prec)
+    close(ho_d, ho, tol, what=f"node tc h' prec={prec} f={f}")
+    if with_next:
+        close(PQn_d, PQn, tol, what=f"node tc PQ' prec={prec} f={f}")
+
+
 # ---- EGNN backward -----------------------------------------------------------------------------
 @pytest.mark.parametrize("f,coord", [(64, True), (64, False), (20, True)])
 def test_egnn_backward_kernels(case, f, coord):

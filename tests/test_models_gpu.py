@@ -41,6 +41,10 @@ def test_hybrid_golden(name, cls):
                    o["loss_reg"]) < TOL
     loss.backward()
     assert_grads_close(named_grads(model), gd["grads"], TOL, truth=gd["grads64"])
+    inject_eps(model, d["eps"], d["eps"], d["eps"])
+    with torch.no_grad():                         # inference path: fused stack + pooled-only attention
+        r_ng = model(g, _d(d["seq"]), _d(d["prop"]))
+    assert rel_err(r_ng[3], o["logits"]) < TOL and rel_err(r_ng[0], o["recon"]) < TOL
     emb = model(g, _d(d["seq"]), _d(d["prop"]), return_embedding=True)[0]
     att = model(g, _d(d["seq"]), _d(d["prop"]), return_attention=True)[0]
     assert rel_err(emb, o["embedding"]) < TOL
