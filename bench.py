@@ -39,7 +39,13 @@ N_NODES, KNN = 200, 10
 VAE_IN = 5943
 POOL = 8                    # resident input batches cycled through (8 x 42 MB > 126 MB of L2)
 FLOP_PER_EDGE_EDGE_KERNEL = 2 * 64 * 64 * 2 + 2 * 64      # two 64x64 per-edge GEMMs + the w4 dot
-BYTES_PER_EDGE_EDGE_KERNEL = 2 * 256 + 3 * 4 + 4           # P[src] + Q[dst] rows (L2-resident gathers) + ids + attr
+# algorithmic (compulsory, each byte once) traffic of one edge-forward launch -- DESIGN.md 4.2:
+BYTES_PER_NODE_EDGE_KERNEL = 512 + 12 + 4 + 256 + 12       # read PQ row, x, indptr ; write hn row, x'
+BYTES_PER_EDGE_EDGE_KERNEL = 3 * 4 + 4                     # read csr_src/dst/eid + edge_attr
+GATHER_BYTES_PER_EDGE = 2 * 256                            # P[src] + Q[dst] rows (served by L2)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
+# (profiles/r01_tc_*_edge_fwd_full.md, profiles/r01_simt_edge_fwd_full.md), batch 512
+NCU_TRAFFIC_BYTES = {"bf16": 79.72e6 + 8.99e6, "tf32x3": 82.36e6 + 10.82e6, "fp32": 80.64e6 + 8.85e6}
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12          # 74.4
 
 
@@ -52,6 +58,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "bf16"],
                     help="EGNN edge-GEMM arithmetic of the headline run (tf32x3 = fp32-accurate tensor cores)")
+    ap.add_argument("--profile", action="store_true",
+                    help="bracket the timed inference region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -219,11 +227,15 @@ def main():
         launches0 = _C.LAUNCHES
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local) as clk:
+            if args.profile:
+                torch.cuda.profiler.start()
             e0.record()
             for i in range(K):
                 probs = infer_step(*pool[i % POOL])
             e1.record()
             barrier()
+            if args.profile:
+                torch.cuda.profiler.stop()
         ms = max_over_ranks(e0.elapsed_time(e1))
     launches = _C.LAUNCHES - launches0
     value = world * B * K / (ms / 1e3)
@@ -347,20 +359,27 @@ def main():
         t_all = {k: time_kernel(fn) for k, fn in variants.items()}
         t_k = t_all[args.precision]
         flops = e * FLOP_PER_EDGE_EDGE_KERNEL
-        nbytes = e * BYTES_PER_EDGE_EDGE_KERNEL + n * (256 + 12 + 12 + 4)
-        tflops, gbs = flops / t_k / 1e12, nbytes / t_k / 1e9
-        if args.precision == "fp32":
-            bound, peak, kname = "fp32_fma", FP32_PEAK_TFLOPS, "is::edge_fwd_kernel<true> (fp32 SIMT)"
-        else:
-            bound, peak, kname = "tensor", tensor_peak, f"is::edge_fwd_tc_kernel<{args.precision}, true> (tcgen05 + TMEM)"
-        roofline = {"kernel": kname, "bound": bound, "achieved": tflops, "peak": peak, "unit": "TFLOP/s",
-                    "frac": tflops / peak, "traffic": None, "launch_ms": t_k * 1e3, "edges_per_launch": e,
-                    "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": nbytes,
-                    "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": src},
+        nbytes = e * BYTES_PER_EDGE_EDGE_KERNEL + n * BYTES_PER_NODE_EDGE_KERNEL
+        gbs = nbytes / t_k / 1e9
+        kname = ("is::edge_fwd_kernel<true> (fp32 SIMT)" if args.precision == "fp32" else
+                 f"is::edge_fwd_tc_kernel<{args.precision}, true> (tcgen05 + TMEM)")
+        # The fused kernel's two roofline terms: compulsory bytes / HBM peak and GEMM flops / tensor peak.
+        # The byte term is the larger one, so "hbm" is the bound the schema asks for; in practice the
+        # kernel is limited by instruction issue / latency of its SIMT gather, SiLU and aggregation phases
+        # (issue slots 38 % busy, tensor pipe 4-11 %, DRAM 2 %: profiles/r01_tc_*_edge_fwd_full.md).
+        roofline = {"kernel": kname, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": gbs / hbm_peak, "traffic": NCU_TRAFFIC_BYTES.get(args.precision) if B == BATCH else None,
+                    "peak_source": src, "launch_ms": t_k * 1e3, "edges_per_launch": e,
+                    "algorithmic_bytes_per_launch": nbytes, "algorithmic_flops_per_launch": flops,
+                    "tensor": {"achieved": flops / t_k / 1e12, "peak": tensor_peak, "unit": "TFLOP/s",
+                               "frac": flops / t_k / 1e12 / tensor_peak},
+                    "l2_gather_gbs": e * GATHER_BYTES_PER_EDGE / t_k / 1e9,
+                    "roofline_time_ms": {"hbm": nbytes / hbm_peak / 1e6, "tensor": flops / tensor_peak / 1e9},
                     "launch_ms_by_precision": {k: v * 1e3 for k, v in t_all.items()},
-                    "note": "edge-forward kernel of one EGNN layer timed alone after an L2 flush; FLOPs = two 64x64 per-edge "
-                            "GEMMs + w4 dot (the 3xTF32 split's extra MMAs are not counted); the kernel is bound by its "
-                            "SIMT gather/SiLU/aggregation phases, not by the tensor pipe or HBM (DESIGN.md 4.2)"}
+                    "note": "edge-forward kernel of one EGNN layer (batch 512) timed alone with CUDA events after an "
+                            "L2 flush; bytes = each input/output byte once (PQ rows, coordinates, CSR ids, edge_attr, hn, "
+                            "x'); FLOPs = two 64x64 per-edge GEMMs + w4 dot (split-precision extra MMAs not counted); "
+                            "traffic = ncu dram bytes of the same launch"}
 
     # ---- CPU baseline (oracle port) on this box's host cores, rank 0 at N=1 only ------------------
     cpu_baseline = None

@@ -136,6 +136,39 @@ def test_benchmark_shape_against_full_model_oracle():
     assert_grads_close(named_grads(model), grads32, TOL, truth=grads64)
 
 
+def test_bf16_mode_within_1e_2_of_fp32_reference():
+    """bf16 tensor-core mode (north star: 1e-2 relative): logits and loss at the benchmark shape against
+    the fp32 CPU oracle, inference path and training-forward path; gradients against the fp32-accurate
+    product run (the backward always recomputes in fp32, so only the forward activations differ)."""
+    b = 8
+    arr, dense, model, eps = _bench_shape_case(b, seed=21)
+    state = {k: v.cpu() for k, v in model.state_dict().items()}
+    recon, out, loss_ref, _ = _oracle_run(state, arr, dense, eps, torch.float32)
+    model = model.to(DEV).eval()
+    gb = graph_batch(arr, DEV)
+    losses = I.Losses(5943, [4.25, 1.0], sequence=True)
+    grads = {}
+    try:
+        for prec in ("tf32x3", "bf16"):
+            I.set_precision(prec)
+            inject_eps(model, eps, eps)
+            with torch.no_grad():
+                o_inf = model(gb, _d(dense["seq"]), _d(dense["prop"]))[3]
+            model.zero_grad()
+            r2, m2, lv2, o2 = model(gb, _d(dense["seq"]), _d(dense["prop"]))
+            loss = losses.BCE_loss(r2, _d(dense["seq"]), m2, lv2, o2, _d(dense["target"]))
+            loss.backward()
+            grads[prec] = {k: v.clone() for k, v in named_grads(model).items() if v is not None}
+            tol = 1e-2 if prec == "bf16" else TOL
+            assert rel_err(o_inf, out) < tol and rel_err(o2, out) < tol and rel_err(loss, loss_ref) < tol, prec
+    finally:
+        I.set_precision("tf32x3")
+    gmax = max(float(v.abs().max()) for v in grads["tf32x3"].values())
+    for k, ref in grads["tf32x3"].items():
+        err = float((grads["bf16"][k] - ref).abs().max())
+        assert err <= 5e-2 * max(float(ref.abs().max()), 1e-2 * gmax), (k, err)
+
+
 def test_full_batch_properties():
     """Batch 512 (BASELINE inference batch): bit-determinism, edge-order invariance within tolerance,
     per-graph independence (a graph's output does not depend on its batch neighbours)."""
