@@ -45,7 +45,7 @@ BYTES_PER_EDGE_EDGE_KERNEL = 3 * 4 + 4                     # read csr_src/dst/ei
 GATHER_BYTES_PER_EDGE = 2 * 256                            # P[src] + Q[dst] rows (served by L2)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
 # (profiles/r01_tc_*_edge_fwd_full.md, profiles/r01_simt_edge_fwd_full.md), batch 512
-NCU_TRAFFIC_BYTES = {"bf16": 79.72e6 + 8.99e6, "tf32x3": 82.36e6 + 10.82e6, "fp32": 80.64e6 + 8.85e6}
+NCU_TRAFFIC_BYTES = {"bf16": 79.72e6 + 8.99e6, "tf32x3": 82.36e6 + 10.82e6, "fp32": 80.64e6 + 8.85e6}   # bf16x3: see profiles/
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12          # 74.4
 
 
@@ -56,8 +56,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "bf16"],
-                    help="EGNN edge-GEMM arithmetic of the headline run (tf32x3 = fp32-accurate tensor cores)")
+    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "tf32x3", "bf16"],
+                    help="EGNN GEMM arithmetic of the headline run (bf16x3 / tf32x3 = fp32-accurate tensor cores)")
     ap.add_argument("--profile", action="store_true",
                     help="bracket the timed inference region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     ap.add_argument("--no-train", action="store_true")
@@ -272,7 +272,7 @@ def main():
     # ---- the same device-resident step in the other arithmetic modes (short runs) -----------------
     other = {}
     with torch.no_grad():
-        for prec in ("fp32", "tf32x3", "bf16"):
+        for prec in ("fp32", "bf16x3", "tf32x3", "bf16"):
             if prec == args.precision:
                 continue
             I.set_precision(prec)
@@ -353,6 +353,7 @@ def main():
 
         variants = {
             "fp32": lambda: _C.egnn_edge_fwd(gb, PQ, x, arr["edge_attr"], 64, W1, W2, b2, W3, b3, w4, True, hn, xo),
+            "bf16x3": lambda: _C.egnn_edge_fwd_tc(gb, PQ, x, arr["edge_attr"], 64, W1, W2, b2, W3, b3, w4, True, _C.PREC_BF16X3, hn, xo),
             "tf32x3": lambda: _C.egnn_edge_fwd_tc(gb, PQ, x, arr["edge_attr"], 64, W1, W2, b2, W3, b3, w4, True, _C.PREC_TF32X3, hn, xo),
             "bf16": lambda: _C.egnn_edge_fwd_tc(gb, PQ, x, arr["edge_attr"], 64, W1, W2, b2, W3, b3, w4, True, _C.PREC_BF16, hn, xo),
         }

@@ -74,7 +74,7 @@ __device__ __forceinline__ void load_meta(const EdgeCommon& p, TileMeta& m, int 
 // NT threads per CTA: 256 (two CTAs per SM) for bf16, 512 (one CTA per SM, 16 warps) for 3xTF32 whose
 // hi/lo operand tiles need 147 KB of shared memory.
 template <int PREC, bool HAS_COORD, int NT>
-__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
+__global__ void __launch_bounds__(NT, NT == 256 ? (PREC == PREC_BF16 ? 3 : 2) : 1)
 edge_fwd_tc_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_out) {
     using C = TcCfg<PREC>;
     constexpr int NW = NT / 32;                 // warps
@@ -84,8 +84,11 @@ edge_fwd_tc_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
     uint8_t* sA = smem_raw;                                            // [NSPLIT][A_BYTES] t1, then m
     uint8_t* sW2 = sA + C::NSPLIT * C::A_BYTES;                        // [NSPLIT][W_BYTES]
     uint8_t* sW3 = sW2 + C::NSPLIT * C::W_BYTES;
+    // fp32 copy of m for the hn aggregation: only the tf32 variant needs it; the bf16 variants
+    // re-read the (split) bf16 operand tile, which is bank-conflict free thanks to the 144-byte LBO
+    constexpr bool USE_M32 = PREC == PREC_TF32X3;
     float* M32 = reinterpret_cast<float*>(sW3 + C::NSPLIT * C::W_BYTES);   // [128][68] fp32 m
-    float* vec = M32 + IS_TM * IS_LD;                                  // b2, b3, w4, wr, wa
+    float* vec = M32 + (USE_M32 ? IS_TM * IS_LD : 0);                  // b2, b3, w4, wr, wa
     float* e_c = vec + 5 * 64;                                         // [CQ][128] partial c per column block
     TileMeta* meta = reinterpret_cast<TileMeta*>(e_c + CQ * IS_TM);    // [2]
     __shared__ int s_tile[2][4];
@@ -210,10 +213,12 @@ edge_fwd_tc_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
                 m8[2] = act<PREC>(z[8 * g + 2] + b0.z); m8[3] = act<PREC>(z[8 * g + 3] + b0.w);
                 m8[4] = act<PREC>(z[8 * g + 4] + b1.x); m8[5] = act<PREC>(z[8 * g + 5] + b1.y);
                 m8[6] = act<PREC>(z[8 * g + 6] + b1.z); m8[7] = act<PREC>(z[8 * g + 7] + b1.w);
-                float* dst = M32 + erow * IS_LD + CW * cq + 8 * g;
-                *reinterpret_cast<float4*>(dst) = make_float4(m8[0], m8[1], m8[2], m8[3]);
-                *reinterpret_cast<float4*>(dst + 4) = make_float4(m8[4], m8[5], m8[6], m8[7]);
-                if (HAS_COORD) store_operand8<PREC>(sA, C::A_BYTES, erow, (CW / 8) * cq + g, m8);   // MMA 1 is done with sA
+                if (USE_M32) {
+                    float* dst = M32 + erow * IS_LD + CW * cq + 8 * g;
+                    *reinterpret_cast<float4*>(dst) = make_float4(m8[0], m8[1], m8[2], m8[3]);
+                    *reinterpret_cast<float4*>(dst + 4) = make_float4(m8[4], m8[5], m8[6], m8[7]);
+                }
+                if (HAS_COORD || !USE_M32) store_operand8<PREC>(sA, C::A_BYTES, erow, (CW / 8) * cq + g, m8);   // MMA 1 is done with sA
             }
         }
         fence_async_smem();
@@ -230,7 +235,9 @@ edge_fwd_tc_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
             const int jb = __ldg(p.indptr + node) - p0, je = __ldg(p.indptr + node + 1) - p0;
             float2 s = make_float2(0.0f, 0.0f);
             for (int j = jb; j < je; ++j) {
-                const float2 v = *reinterpret_cast<const float2*>(M32 + j * IS_LD + 2 * lane);
+                float2 v;
+                if constexpr (USE_M32) v = *reinterpret_cast<const float2*>(M32 + j * IS_LD + 2 * lane);
+                else v = load_operand2<PREC>(sA, C::A_BYTES, j, lane);
                 s.x += v.x; s.y += v.y;
             }
             *reinterpret_cast<float2*>(hn + (size_t)node * 64 + 2 * lane) = s;
@@ -271,9 +278,11 @@ edge_fwd_tc_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
                 }
             }
         }
-        // No barrier here: the next tile's gather only writes sA (both MMAs of this tile have been
-        // waited for) and reads meta[cur ^ 1]; M32 / e_c / meta[cur] / TMEM are next written after
-        // the barriers S1..S4 of the next iteration.
+        // No barrier here when the coordinate branch ran: the next tile's gather only writes sA (both
+        // MMAs of this tile have been waited for; the hn aggregation, which reads sA in the bf16
+        // variants, finished before S4) and reads meta[cur ^ 1]; M32 / e_c / meta[cur] / TMEM are next
+        // written after the barriers S1..S4 of the next iteration.
+        if (!HAS_COORD && !USE_M32) __syncthreads();   // hn aggregation reads sA: finish before the next gather
         phase ^= 1;
         cur ^= 1;
     }
@@ -286,7 +295,7 @@ template <int PREC, int NT>
 static size_t tc_smem_bytes() {
     using C = TcCfg<PREC>;
     return (size_t)C::NSPLIT * (C::A_BYTES + 2 * C::W_BYTES) +
-           sizeof(float) * (IS_TM * IS_LD + 5 * 64 + (NT / 128) * IS_TM) + 2 * sizeof(TileMeta) + 128;
+           sizeof(float) * ((PREC == PREC_TF32X3 ? IS_TM * IS_LD : 0) + 5 * 64 + (NT / 128) * IS_TM) + 2 * sizeof(TileMeta) + 128;
 }
 
 template <int PREC, bool HAS_COORD, int NT>
@@ -305,27 +314,29 @@ using namespace is;
 
 extern "C" {
 
-// Tensor-core variant of is_egnn_edge_fwd.  precision: 0 = bf16 operands, 2 = 3xTF32 (fp32-accurate).
+// Tensor-core variant of is_egnn_edge_fwd.  precision: 0 = bf16 operands, 2 = 3xTF32, 3 = bf16x3 (both fp32-accurate).
 int is_egnn_edge_fwd_tc(const int* indptr, const int* csr_src, const int* csr_dst, const int* csr_eid,
                         const float* PQ, const float* x, int64_t ldx, const float* edge_attr,
                         const float* W1, int F, const float* W2, const float* b2,
                         const float* W3, const float* b3, const float* w4, int update_coords, int precision,
                         float* hn, float* x_out, int64_t n_nodes, int* status, void* stream) {
     if (!(F == 20 || F == 64) || n_nodes <= 0 || n_nodes > 0x7fffffff) return IS_ERR_ARG;
-    if (precision != PREC_BF16 && precision != PREC_TF32X3) return IS_ERR_ARG;
+    if (precision != PREC_BF16 && precision != PREC_TF32X3 && precision != PREC_BF16X3) return IS_ERR_ARG;
     EdgeCommon c;
     c.indptr = indptr; c.csr_src = csr_src; c.csr_dst = csr_dst; c.csr_eid = csr_eid;
     c.PQ = PQ; c.x = x; c.ldx = ldx; c.edge_attr = edge_attr; c.W1 = W1; c.F = F;
     c.W2 = W2; c.b2 = b2; c.W3 = W3; c.b3 = b3; c.w4 = w4; c.n_nodes = (int)n_nodes; c.status = status;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    const int per_sm = precision == PREC_BF16 ? 2 : 1;
+    const int per_sm = precision == PREC_BF16 ? 3 : precision == PREC_BF16X3 ? 2 : 1;
     int64_t g = (n_nodes + 31) / 32;
     if (g > (int64_t)sms * per_sm) g = (int64_t)sms * per_sm;
     const int grid = (int)(g < 1 ? 1 : g);
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == PREC_BF16)
         return update_coords ? launch_tc<PREC_BF16, true, 256>(c, hn, x_out, grid, st) : launch_tc<PREC_BF16, false, 256>(c, hn, x_out, grid, st);
+    if (precision == PREC_BF16X3)
+        return update_coords ? launch_tc<PREC_BF16X3, true, 256>(c, hn, x_out, grid, st) : launch_tc<PREC_BF16X3, false, 256>(c, hn, x_out, grid, st);
     return update_coords ? launch_tc<PREC_TF32X3, true, 512>(c, hn, x_out, grid, st) : launch_tc<PREC_TF32X3, false, 512>(c, hn, x_out, grid, st);
 }
 

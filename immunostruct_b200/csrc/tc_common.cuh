@@ -21,9 +21,10 @@ template <int PREC>
 struct TcCfg {
     static constexpr int EB = PREC == PREC_TF32X3 ? 4 : 2;             // operand element bytes
     static constexpr int KCH = 64 * EB / 16;                          // 16-byte chunks per 64-wide K block
-    static constexpr uint32_t SBO = KCH * kLBO;                       // bytes between 8-row groups
+    static constexpr uint32_t SBO = KCH * kLBO;                       // activation tiles: bytes between 8-row groups
+    static constexpr uint32_t SBO_W = KCH * kLBO_W;                   // weight tiles (unpadded)
     static constexpr uint32_t A_BYTES = 16 * SBO;                     // 128-row operand tile (one split term)
-    static constexpr uint32_t W_BYTES = 8 * SBO;                      // 64-row operand tile (one split term)
+    static constexpr uint32_t W_BYTES = 8 * SBO_W;                    // 64-row operand tile (one split term)
     static constexpr int NSPLIT = PREC == PREC_BF16 ? 1 : PREC == PREC_TF32X3 ? 2 : 3;
     static constexpr uint32_t FMT = PREC == PREC_TF32X3 ? 2u : 1u;
     static constexpr bool ACCURATE = PREC != PREC_BF16;
@@ -86,11 +87,27 @@ __device__ __forceinline__ void store_operand8(uint8_t* __restrict__ tile, uint3
     }
 }
 
+// features (2*lane, 2*lane+1) of operand row `row`, reconstructed from the (split) bf16 operand tile:
+// with LBO = 144 the 32 lanes of a warp hit 32 different banks
+template <int PREC>
+__device__ __forceinline__ float2 load_operand2(const uint8_t* __restrict__ tile, uint32_t split_bytes, int row, int lane) {
+    using C = TcCfg<PREC>;
+    static_assert(C::EB == 2, "bf16 operand tiles only");
+    const uint8_t* p = tile + (uint32_t)((row >> 3) * C::SBO + (row & 7) * 16) + (lane >> 2) * kLBO + (lane & 3) * 4;
+    float2 r = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+    if (PREC == PREC_BF16X3) {
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p + split_bytes));
+        const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p + 2 * split_bytes));
+        r.x += b.x + c.x; r.y += b.y + c.y;
+    }
+    return r;
+}
+
 // stage one element of a weight block (row n = output feature, k = input feature within a 64-wide K block)
 template <int PREC>
 __device__ __forceinline__ void store_weight1(uint8_t* __restrict__ tile, uint32_t split_bytes, int n, int k, float w) {
     using C = TcCfg<PREC>;
-    const uint32_t off = canon_off<C::EB>(n, k, C::KCH);
+    const uint32_t off = canon_off<C::EB>(n, k, C::KCH, kLBO_W);
     if (PREC == PREC_BF16) {
         *reinterpret_cast<__nv_bfloat16*>(tile + off) = __float2bfloat16_rn(w);
     } else if (PREC == PREC_BF16X3) {
@@ -123,7 +140,7 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_addr, uin
 #pragma unroll
             for (int ks = 0; ks < C::KCH / 2; ++ks) {
                 mma_bf16(tmem_d, make_smem_desc(a_addr + ta[t] * a_split + ks * 2 * kLBO, kLBO, C::SBO),
-                         make_smem_desc(w_addr + tw[t] * w_split + ks * 2 * kLBO, kLBO, C::SBO), idesc, acc);
+                         make_smem_desc(w_addr + tw[t] * w_split + ks * 2 * kLBO_W, kLBO_W, C::SBO_W), idesc, acc);
                 acc = 1;
             }
     } else {
@@ -133,7 +150,7 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_addr, uin
 #pragma unroll
             for (int ks = 0; ks < C::KCH / 2; ++ks) {
                 const uint64_t da = make_smem_desc(a_addr + aoff + ks * 2 * kLBO, kLBO, C::SBO);
-                const uint64_t db = make_smem_desc(w_addr + woff + ks * 2 * kLBO, kLBO, C::SBO);
+                const uint64_t db = make_smem_desc(w_addr + woff + ks * 2 * kLBO_W, kLBO_W, C::SBO_W);
                 if (PREC == PREC_BF16) mma_bf16(tmem_d, da, db, idesc, acc); else mma_tf32(tmem_d, da, db, idesc, acc);
                 acc = 1;
             }

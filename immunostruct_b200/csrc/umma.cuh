@@ -21,7 +21,8 @@
 namespace is {
 namespace umma {
 
-constexpr uint32_t kLBO = 144;                       // bytes between K-adjacent core matrices
+constexpr uint32_t kLBO = 144;                       // bytes between K-adjacent core matrices (activation tiles)
+constexpr uint32_t kLBO_W = 128;                     // weight tiles are staged once: no padding needed
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -128,9 +129,9 @@ __device__ __forceinline__ float tf32_round(float x) {
 
 // byte offset of element (row, k) inside a canonical K-major tile with `kchunks` 16-byte chunks per row
 template <int ELEM_BYTES>
-__device__ __forceinline__ uint32_t canon_off(int row, int k, int kchunks) {
+__device__ __forceinline__ uint32_t canon_off(int row, int k, int kchunks, uint32_t lbo = kLBO) {
     constexpr int per = 16 / ELEM_BYTES;
-    return (uint32_t)((row >> 3) * (kchunks * kLBO) + (k / per) * kLBO + (row & 7) * 16 + (k % per) * ELEM_BYTES);
+    return (uint32_t)((row >> 3) * (kchunks * lbo) + (k / per) * lbo + (row & 7) * 16 + (k % per) * ELEM_BYTES);
 }
 
 }  // namespace umma

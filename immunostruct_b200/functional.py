@@ -15,10 +15,12 @@ H = 64   # hidden width of the EGNN MLPs and of the node embedding (hybrid_model
 
 # Arithmetic of the EGNN edge GEMMs in the FORWARD pass (the backward always recomputes in fp32 SIMT):
 #   "fp32"   : fp32 SIMT FMA kernels (csrc/egnn.cu)
-#   "tf32x3" : tcgen05 tensor cores with the 3xTF32 split -- fp32-accurate (csrc/egnn_tc.cu)
+#   "bf16x3" : tcgen05 tensor cores, operands split into three bf16 terms, six partial products --
+#              fp32-accurate, two CTAs per SM (csrc/egnn_tc.cu); the default
+#   "tf32x3" : tcgen05 tensor cores with the 3xTF32 split -- fp32-accurate, one 512-thread CTA per SM
 #   "bf16"   : tcgen05 tensor cores, bf16 operands, fp32 accumulate, fast SiLU (1e-2 tolerance mode)
-_PRECISIONS = {"fp32": None, "tf32x3": _C.PREC_TF32X3, "bf16": _C.PREC_BF16}
-_precision = "tf32x3"
+_PRECISIONS = {"fp32": None, "bf16x3": _C.PREC_BF16X3, "tf32x3": _C.PREC_TF32X3, "bf16": _C.PREC_BF16}
+_precision = "bf16x3"
 
 
 def set_precision(name: str) -> None:
@@ -140,7 +142,7 @@ def egnn_stack_infer(graph, x23, edge_attr, layer_params):
     n = h.shape[0]
     edge_attr = edge_attr.contiguous()
     prec = _PRECISIONS[_precision]
-    node_prec = {None: None, _C.PREC_BF16: _C.PREC_BF16, _C.PREC_TF32X3: _C.PREC_BF16X3}[prec]
+    node_prec = {None: None, _C.PREC_BF16: _C.PREC_BF16, _C.PREC_TF32X3: _C.PREC_BF16X3, _C.PREC_BF16X3: _C.PREC_BF16X3}[prec]
     params = [[t.detach().contiguous() for t in lp] for lp in layer_params]
     PQ = _new(h, n, 2 * H)
     _C.egnn_node_pre_fwd(h, params[0][0], params[0][1], PQ)

@@ -161,7 +161,7 @@ def test_egnn_forward_kernels(case, f):
     assert int(gb.status.item()) == 0
 
 
-@pytest.mark.parametrize("prec,tol", [(_C.PREC_TF32X3, 1e-5), (_C.PREC_BF16, 2e-2)])
+@pytest.mark.parametrize("prec,tol", [(_C.PREC_BF16X3, 1e-5), (_C.PREC_TF32X3, 1e-5), (_C.PREC_BF16, 2e-2)])
 @pytest.mark.parametrize("f", [20, 64])
 def test_egnn_edge_forward_tensor_core(case, f, prec, tol):
     """tcgen05 edge kernel vs the same CPU contract: 3xTF32 at the fp32 tolerance, bf16 at 2e-2."""
