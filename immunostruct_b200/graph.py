@@ -70,7 +70,7 @@ class GraphBatch:
                    "outptr", "csc_pos", "stats")
 
     def __init__(self, x, src_local, dst_local, edge_attr, node_counts, edge_counts,
-                 max_nodes: Optional[int] = None):
+                 max_nodes: Optional[int] = None, collate_now: bool = True):
         self.ndata = {"x": x}
         self.edata = {"edge_attr": edge_attr}
         self._src_local = src_local
@@ -84,7 +84,7 @@ class GraphBatch:
         self.status = None
         for f in self._CSR_FIELDS:
             setattr(self, self._attr(f), None)
-        if x.is_cuda:
+        if x.is_cuda and collate_now:
             self._collate()
 
     @staticmethod
@@ -138,7 +138,7 @@ class GraphBatch:
 
     def to(self, device, non_blocking: bool = False):
         device = torch.device(device)
-        if device == self.device:
+        if device.type == self.device.type and (device.index is None or device.index == self.device.index):
             return self
         mv = lambda t: t.to(device, non_blocking=non_blocking)
         return GraphBatch(mv(self.ndata["x"]), mv(self._src_local), mv(self._dst_local),

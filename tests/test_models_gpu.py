@@ -232,3 +232,33 @@ def test_contrastive_gate_on_device():
     e1, e2 = torch.randn(8, 104, device=DEV), torch.randn(8, 104, device=DEV)
     assert float(pcl(e1, e2, torch.ones(8, device=DEV))) == 0.0
     assert float(pcl(e1, e2, torch.tensor([0., 1, 0, 1, 1, 0, 0, 1], device=DEV))) > 0.0
+
+
+def test_device_prefetcher_matches_direct_path():
+    """Overlapped H2D + collation (DevicePrefetcher) yields the same batches / logits as `.to(device)`."""
+    from immunostruct_b200.graph import GraphBatch
+    arr, dense, model, eps = _bench_shape_case(12, seed=17)
+    model = model.to(DEV).eval()
+    keys = ("x", "src", "dst", "edge_attr", "node_counts", "edge_counts")
+
+    def host_batches():
+        for lo in (0, 4, 8):
+            n0, e0 = lo * 200, lo * 2000
+            sub = {"x": arr["x"][n0:n0 + 800], "src": arr["src"][e0:e0 + 8000], "dst": arr["dst"][e0:e0 + 8000],
+                   "edge_attr": arr["edge_attr"][e0:e0 + 8000], "node_counts": arr["node_counts"][lo:lo + 4],
+                   "edge_counts": arr["edge_counts"][lo:lo + 4]}
+            yield (GraphBatch.from_arrays(*(sub[k] for k in keys), max_nodes=200), dense["seq"][lo:lo + 4],
+                   dense["target"][lo:lo + 4], dense["prop"][lo:lo + 4])
+
+    direct, fetched = [], []
+    with torch.no_grad():
+        for i, (g, seq, y, prop) in enumerate(host_batches()):
+            inject_eps(model, eps[4 * i:4 * i + 4])
+            direct.append(model(g.to(DEV), seq.to(DEV), prop.to(DEV))[3])
+        for i, (g, seq, y, prop) in enumerate(I.DevicePrefetcher(host_batches(), DEV)):
+            assert g.device.type == "cuda" and seq.is_cuda and y.is_cuda and g.to(DEV) is g
+            inject_eps(model, eps[4 * i:4 * i + 4])
+            fetched.append(model(g, seq, prop)[3])
+    assert len(fetched) == 3
+    for a, b in zip(direct, fetched):
+        assert torch.equal(a, b)
