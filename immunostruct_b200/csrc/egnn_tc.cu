@@ -73,7 +73,7 @@ __device__ __forceinline__ void load_meta(const EdgeCommon& p, TileMeta& m, int 
 
 // NT threads per CTA: 256 (two CTAs per SM) for bf16, 512 (one CTA per SM, 16 warps) for 3xTF32 whose
 // hi/lo operand tiles need 147 KB of shared memory.
-template <int PREC, bool HAS_COORD, int NT>
+template <int PREC, bool HAS_COORD, int NT, bool FAST>
 __global__ void __launch_bounds__(NT, NT == 256 ? (PREC == PREC_BF16 ? 3 : 2) : 1)
 edge_fwd_tc_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_out) {
     using C = TcCfg<PREC>;
@@ -166,14 +166,14 @@ edge_fwd_tc_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
                     const int j = (pb + u) * 4 * NW + warp * 4 + esub;
                     const float r = rr[u], a = aa[u];
                     float v[8];
-                    v[0] = act<PREC>(pv[u][0].x + qv[u][0].x + wr0.x * r + wa0.x * a);
-                    v[1] = act<PREC>(pv[u][0].y + qv[u][0].y + wr0.y * r + wa0.y * a);
-                    v[2] = act<PREC>(pv[u][0].z + qv[u][0].z + wr0.z * r + wa0.z * a);
-                    v[3] = act<PREC>(pv[u][0].w + qv[u][0].w + wr0.w * r + wa0.w * a);
-                    v[4] = act<PREC>(pv[u][1].x + qv[u][1].x + wr1.x * r + wa1.x * a);
-                    v[5] = act<PREC>(pv[u][1].y + qv[u][1].y + wr1.y * r + wa1.y * a);
-                    v[6] = act<PREC>(pv[u][1].z + qv[u][1].z + wr1.z * r + wa1.z * a);
-                    v[7] = act<PREC>(pv[u][1].w + qv[u][1].w + wr1.w * r + wa1.w * a);
+                    v[0] = act<PREC, FAST>(pv[u][0].x + qv[u][0].x + wr0.x * r + wa0.x * a);
+                    v[1] = act<PREC, FAST>(pv[u][0].y + qv[u][0].y + wr0.y * r + wa0.y * a);
+                    v[2] = act<PREC, FAST>(pv[u][0].z + qv[u][0].z + wr0.z * r + wa0.z * a);
+                    v[3] = act<PREC, FAST>(pv[u][0].w + qv[u][0].w + wr0.w * r + wa0.w * a);
+                    v[4] = act<PREC, FAST>(pv[u][1].x + qv[u][1].x + wr1.x * r + wa1.x * a);
+                    v[5] = act<PREC, FAST>(pv[u][1].y + qv[u][1].y + wr1.y * r + wa1.y * a);
+                    v[6] = act<PREC, FAST>(pv[u][1].z + qv[u][1].z + wr1.z * r + wa1.z * a);
+                    v[7] = act<PREC, FAST>(pv[u][1].w + qv[u][1].w + wr1.w * r + wa1.w * a);
                     // rows beyond the tile's edges hold finite garbage: they are never aggregated
                     store_operand8<PREC>(sA, C::A_BYTES, j, kc8, v);
                 }
@@ -209,10 +209,10 @@ edge_fwd_tc_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
                 const float4 b0 = *reinterpret_cast<const float4*>(vec + CW * cq + 8 * g);
                 const float4 b1 = *reinterpret_cast<const float4*>(vec + CW * cq + 8 * g + 4);
                 float m8[8];
-                m8[0] = act<PREC>(z[8 * g + 0] + b0.x); m8[1] = act<PREC>(z[8 * g + 1] + b0.y);
-                m8[2] = act<PREC>(z[8 * g + 2] + b0.z); m8[3] = act<PREC>(z[8 * g + 3] + b0.w);
-                m8[4] = act<PREC>(z[8 * g + 4] + b1.x); m8[5] = act<PREC>(z[8 * g + 5] + b1.y);
-                m8[6] = act<PREC>(z[8 * g + 6] + b1.z); m8[7] = act<PREC>(z[8 * g + 7] + b1.w);
+                m8[0] = act<PREC, FAST>(z[8 * g + 0] + b0.x); m8[1] = act<PREC, FAST>(z[8 * g + 1] + b0.y);
+                m8[2] = act<PREC, FAST>(z[8 * g + 2] + b0.z); m8[3] = act<PREC, FAST>(z[8 * g + 3] + b0.w);
+                m8[4] = act<PREC, FAST>(z[8 * g + 4] + b1.x); m8[5] = act<PREC, FAST>(z[8 * g + 5] + b1.y);
+                m8[6] = act<PREC, FAST>(z[8 * g + 6] + b1.z); m8[7] = act<PREC, FAST>(z[8 * g + 7] + b1.w);
                 if (USE_M32) {
                     float* dst = M32 + erow * IS_LD + CW * cq + 8 * g;
                     *reinterpret_cast<float4*>(dst) = make_float4(m8[0], m8[1], m8[2], m8[3]);
@@ -255,10 +255,10 @@ edge_fwd_tc_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
             for (int g = 0; g < CW / 4; ++g) {
                 const float4 b = *reinterpret_cast<const float4*>(vec + 64 + CW * cq + 4 * g);
                 const float4 w = *reinterpret_cast<const float4*>(vec + 128 + CW * cq + 4 * g);
-                c = fmaf(w.x, act<PREC>(z[4 * g + 0] + b.x), c);
-                c = fmaf(w.y, act<PREC>(z[4 * g + 1] + b.y), c);
-                c = fmaf(w.z, act<PREC>(z[4 * g + 2] + b.z), c);
-                c = fmaf(w.w, act<PREC>(z[4 * g + 3] + b.w), c);
+                c = fmaf(w.x, act<PREC, FAST>(z[4 * g + 0] + b.x), c);
+                c = fmaf(w.y, act<PREC, FAST>(z[4 * g + 1] + b.y), c);
+                c = fmaf(w.z, act<PREC, FAST>(z[4 * g + 2] + b.z), c);
+                c = fmaf(w.w, act<PREC, FAST>(z[4 * g + 3] + b.w), c);
             }
             e_c[cq * IS_TM + erow] = c;
             fence_before_sync();
@@ -298,14 +298,20 @@ static size_t tc_smem_bytes() {
            sizeof(float) * ((PREC == PREC_TF32X3 ? IS_TM * IS_LD : 0) + 5 * 64 + (NT / 128) * IS_TM) + 2 * sizeof(TileMeta) + 128;
 }
 
-template <int PREC, bool HAS_COORD, int NT>
-static int launch_tc(const EdgeCommon& c, float* hn, float* x_out, int grid, cudaStream_t st) {
+template <int PREC, bool HAS_COORD, int NT, bool FAST>
+static int launch_tc2(const EdgeCommon& c, float* hn, float* x_out, int grid, cudaStream_t st) {
     const size_t smem = tc_smem_bytes<PREC, NT>();
-    cudaError_t e = cudaFuncSetAttribute(edge_fwd_tc_kernel<PREC, HAS_COORD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(edge_fwd_tc_kernel<PREC, HAS_COORD, NT, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    edge_fwd_tc_kernel<PREC, HAS_COORD, NT><<<grid, NT, smem, st>>>(c, hn, x_out);
+    edge_fwd_tc_kernel<PREC, HAS_COORD, NT, FAST><<<grid, NT, smem, st>>>(c, hn, x_out);
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
+}
+
+template <int PREC, bool HAS_COORD, int NT>
+static int launch_tc(const EdgeCommon& c, float* hn, float* x_out, int grid, cudaStream_t st, bool fast) {
+    if (PREC == PREC_BF16 || fast) return launch_tc2<PREC, HAS_COORD, NT, true>(c, hn, x_out, grid, st);
+    return launch_tc2<PREC, HAS_COORD, NT, false>(c, hn, x_out, grid, st);
 }
 
 }  // namespace is
@@ -315,11 +321,12 @@ using namespace is;
 extern "C" {
 
 // Tensor-core variant of is_egnn_edge_fwd.  precision: 0 = bf16 operands, 2 = 3xTF32, 3 = bf16x3 (both fp32-accurate).
+// fast_act: use the 5-instruction SiLU in the fp32-accurate modes (inference); 0 keeps expf (training forward).
 int is_egnn_edge_fwd_tc(const int* indptr, const int* csr_src, const int* csr_dst, const int* csr_eid,
                         const float* PQ, const float* x, int64_t ldx, const float* edge_attr,
                         const float* W1, int F, const float* W2, const float* b2,
                         const float* W3, const float* b3, const float* w4, int update_coords, int precision,
-                        float* hn, float* x_out, int64_t n_nodes, int* status, void* stream) {
+                        int fast_act, float* hn, float* x_out, int64_t n_nodes, int* status, void* stream) {
     if (!(F == 20 || F == 64) || n_nodes <= 0 || n_nodes > 0x7fffffff) return IS_ERR_ARG;
     if (precision != PREC_BF16 && precision != PREC_TF32X3 && precision != PREC_BF16X3) return IS_ERR_ARG;
     EdgeCommon c;
@@ -334,10 +341,10 @@ int is_egnn_edge_fwd_tc(const int* indptr, const int* csr_src, const int* csr_ds
     const int grid = (int)(g < 1 ? 1 : g);
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == PREC_BF16)
-        return update_coords ? launch_tc<PREC_BF16, true, 256>(c, hn, x_out, grid, st) : launch_tc<PREC_BF16, false, 256>(c, hn, x_out, grid, st);
+        return update_coords ? launch_tc<PREC_BF16, true, 256>(c, hn, x_out, grid, st, fast_act != 0) : launch_tc<PREC_BF16, false, 256>(c, hn, x_out, grid, st, fast_act != 0);
     if (precision == PREC_BF16X3)
-        return update_coords ? launch_tc<PREC_BF16X3, true, 256>(c, hn, x_out, grid, st) : launch_tc<PREC_BF16X3, false, 256>(c, hn, x_out, grid, st);
-    return update_coords ? launch_tc<PREC_TF32X3, true, 512>(c, hn, x_out, grid, st) : launch_tc<PREC_TF32X3, false, 512>(c, hn, x_out, grid, st);
+        return update_coords ? launch_tc<PREC_BF16X3, true, 256>(c, hn, x_out, grid, st, fast_act != 0) : launch_tc<PREC_BF16X3, false, 256>(c, hn, x_out, grid, st, fast_act != 0);
+    return update_coords ? launch_tc<PREC_TF32X3, true, 512>(c, hn, x_out, grid, st, fast_act != 0) : launch_tc<PREC_TF32X3, false, 512>(c, hn, x_out, grid, st, fast_act != 0);
 }
 
 }  // extern "C"

@@ -32,8 +32,12 @@ struct TcCfg {
 
 // SiLU.  bf16 mode: z*sigmoid(z) = h + h*tanh(h), h = z/2, with the hardware tanh (one MUFU, three
 // instructions, 2^-11 relative error -- below the bf16 operand rounding that follows).  fp32-parity
-// modes: accurate expf and an approximate reciprocal (1 ulp), 2^-22-level error.
-template <int PREC>
+// modes: z * rcp(1 + 2^(-z log2 e)) with ex2.approx / rcp.approx (2^-22 each); the rounding of the
+// product z*log2(e) adds |z| * 6e-8 relative error to exp(-z), which only matters where sigmoid is far
+// from saturation, i.e. |z| = O(1): total error ~4e-7 relative, five instructions.  That is enough for
+// logits at 1e-5 (inference) but was measured to push a few parameter GRADIENTS to 1.1-1.4e-5 of their
+// scale, so the training forward (FAST = false) keeps the accurate expf.
+template <int PREC, bool FAST = true>
 __device__ __forceinline__ float act(float z) {
     if (!TcCfg<PREC>::ACCURATE) {
         const float h = 0.5f * z;
@@ -41,8 +45,10 @@ __device__ __forceinline__ float act(float z) {
         asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
         return fmaf(h, t, h);
     }
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + expf(-z)));
+    float e, r;
+    if (FAST) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
+    else e = expf(-z);      // training forward: gradient parity at 1e-5 needs the fully accurate exp
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
     return z * r;
 }
 
@@ -63,18 +69,23 @@ __device__ __forceinline__ void store_operand8(uint8_t* __restrict__ tile, uint3
     if (PREC == PREC_BF16) {
         *reinterpret_cast<uint4*>(tile + rbase + kc8 * kLBO) = pack8_bf16(v);
     } else if (PREC == PREC_BF16X3) {
-        float t1[8], t2[8], t3[8];
+        // three bf16 terms by truncation (top 16 bits); every residual is exact in fp32, so the sum of
+        // the terms differs from v only by the truncation of the last one (2^-24 relative)
+        uint32_t q1[4], q2[4], q3[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            t1[i] = __bfloat162float(__float2bfloat16_rn(v[i]));
-            const float r1 = v[i] - t1[i];
-            t2[i] = __bfloat162float(__float2bfloat16_rn(r1));
-            t3[i] = r1 - t2[i];
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t a1 = __float_as_uint(v[2 * i]) & 0xffff0000u, b1 = __float_as_uint(v[2 * i + 1]) & 0xffff0000u;
+            const float ra = v[2 * i] - __uint_as_float(a1), rb = v[2 * i + 1] - __uint_as_float(b1);
+            const uint32_t a2 = __float_as_uint(ra) & 0xffff0000u, b2 = __float_as_uint(rb) & 0xffff0000u;
+            const float sa = ra - __uint_as_float(a2), sb = rb - __uint_as_float(b2);
+            q1[i] = __byte_perm(a1, b1, 0x7632);          // {hi16(a1), hi16(b1)} = bf16x2(a, b)
+            q2[i] = __byte_perm(a2, b2, 0x7632);
+            q3[i] = __byte_perm(__float_as_uint(sa), __float_as_uint(sb), 0x7632);
         }
         uint8_t* p0 = tile + rbase + kc8 * kLBO;
-        *reinterpret_cast<uint4*>(p0) = pack8_bf16(t1);
-        *reinterpret_cast<uint4*>(p0 + split_bytes) = pack8_bf16(t2);
-        *reinterpret_cast<uint4*>(p0 + 2 * split_bytes) = pack8_bf16(t3);
+        *reinterpret_cast<uint4*>(p0) = make_uint4(q1[0], q1[1], q1[2], q1[3]);
+        *reinterpret_cast<uint4*>(p0 + split_bytes) = make_uint4(q2[0], q2[1], q2[2], q2[3]);
+        *reinterpret_cast<uint4*>(p0 + 2 * split_bytes) = make_uint4(q3[0], q3[1], q3[2], q3[3]);
     } else {
         float hi[8], lo[8];
 #pragma unroll

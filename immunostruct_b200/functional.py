@@ -155,7 +155,8 @@ def egnn_stack_infer(graph, x23, edge_attr, layer_params):
         if prec is None:
             _C.egnn_edge_fwd(graph, PQ, x, edge_attr, f, W1, W2, b2, W3, b3, w4, upd, hn, x_out)
         else:
-            _C.egnn_edge_fwd_tc(graph, PQ, x, edge_attr, f, W1, W2, b2, W3, b3, w4, upd, prec, hn, x_out)
+            _C.egnn_edge_fwd_tc(graph, PQ, x, edge_attr, f, W1, W2, b2, W3, b3, w4, upd, prec, hn, x_out,
+                                fast_act=True)
         nxt = params[l + 1] if upd else None
         PQ_next = _new(h, n, 2 * H) if upd else None
         if node_prec is None:

@@ -51,12 +51,13 @@ int is_egnn_edge_fwd(const int* indptr, const int* csr_src, const int* csr_dst, 
                      const float* W3, const float* b3, const float* w4, int update_coords,
                      float* hn, float* x_out, int64_t n_nodes, int* status, void* stream);
 /* tcgen05 / TMEM variant of is_egnn_edge_fwd: the two per-tile 128x64x64 GEMMs run on the tensor
- * cores.  precision 0 = bf16 operands (fp32 accumulate), 2 = 3xTF32 split (fp32-accurate). */
+ * cores.  precision 0 = bf16 operands (fp32 accumulate), 2 = 3xTF32, 3 = bf16x3 (both fp32-accurate);
+ * fast_act != 0 selects the 5-instruction SiLU in the fp32-accurate modes (inference path). */
 int is_egnn_edge_fwd_tc(const int* indptr, const int* csr_src, const int* csr_dst, const int* csr_eid,
                         const float* PQ, const float* x, int64_t ldx, const float* edge_attr,
                         const float* W1, int F, const float* W2, const float* b2,
                         const float* W3, const float* b3, const float* w4, int update_coords, int precision,
-                        float* hn, float* x_out, int64_t n_nodes, int* status, void* stream);
+                        int fast_act, float* hn, float* x_out, int64_t n_nodes, int* status, void* stream);
 /* node_mlp of layer l fused with the per-node half (P', Q') of layer l+1's first edge-MLP layer, on the
  * tensor cores (inference path).  W1n/b1n/PQn NULL for the last layer.  precision 0 = bf16, 3 = bf16x3. */
 int is_egnn_node_post_pre_tc(const float* h, int64_t ldh, int F, const float* hn, const float* W5, const float* b5,

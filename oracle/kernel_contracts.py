@@ -107,7 +107,8 @@ def egnn_edge_fwd(g, PQ, x, edge_attr, f, W1, W2, b2, W3, b3, w4, update_coords,
         x_out.copy_(x + xn)
 
 
-def egnn_edge_fwd_tc(g, PQ, x, edge_attr, f, W1, W2, b2, W3, b3, w4, update_coords, precision, hn, x_out):
+def egnn_edge_fwd_tc(g, PQ, x, edge_attr, f, W1, W2, b2, W3, b3, w4, update_coords, precision, hn, x_out,
+                     fast_act=False):
     """Same contract as egnn_edge_fwd; the tensor-core kernel only changes the GEMM arithmetic."""
     egnn_edge_fwd(g, PQ, x, edge_attr, f, W1, W2, b2, W3, b3, w4, update_coords, hn, x_out)
 

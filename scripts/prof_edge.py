@@ -20,6 +20,6 @@ for _ in range(4):
     if prec is None:
         _C.egnn_edge_fwd(gb, PQ, x, arr["edge_attr"], 64, W1, W2, b2, W3, b3, w4, True, hn, xo)
     else:
-        _C.egnn_edge_fwd_tc(gb, PQ, x, arr["edge_attr"], 64, W1, W2, b2, W3, b3, w4, True, prec, hn, xo)
+        _C.egnn_edge_fwd_tc(gb, PQ, x, arr["edge_attr"], 64, W1, W2, b2, W3, b3, w4, True, prec, hn, xo, fast_act=True)
 torch.cuda.synchronize()
 print("done", float(hn.abs().mean()))

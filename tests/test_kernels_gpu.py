@@ -177,12 +177,13 @@ def test_egnn_edge_forward_tensor_core(case, f, prec, tol):
     for upd in (True, False):
         hn_d, xo_d = torch.empty(n, 64, device=DEV), torch.empty(n, 3, device=DEV)
         hn, xo = torch.empty(n, 64), torch.empty(n, 3)
-        _C.egnn_edge_fwd_tc(gb, PQ.to(DEV), x_d, ea.to(DEV), f, wd["W1"], wd["W2"], wd["b2"], wd["W3"], wd["b3"],
-                            wd["w4"], upd, prec, hn_d, xo_d if upd else None)
         KC.egnn_edge_fwd(cg, PQ, x, ea, f, w["W1"], w["W2"], w["b2"], w["W3"], w["b3"], w["w4"], upd, hn, xo)
-        close(hn_d, hn, tol, what=f"tc hn prec={prec} upd={upd}")
-        if upd:
-            close(xo_d - x_d, xo - x, tol, what=f"tc x'-x prec={prec}")
+        for fast in (False, True):
+            _C.egnn_edge_fwd_tc(gb, PQ.to(DEV), x_d, ea.to(DEV), f, wd["W1"], wd["W2"], wd["b2"], wd["W3"], wd["b3"],
+                                wd["w4"], upd, prec, hn_d, xo_d if upd else None, fast_act=fast)
+            close(hn_d, hn, tol, what=f"tc hn prec={prec} upd={upd} fast={fast}")
+            if upd:
+                close(xo_d - x_d, xo - x, tol, what=f"tc x'-x prec={prec} fast={fast}")
     assert int(gb.status.item()) == 0
 
 
