@@ -21,6 +21,81 @@
 
 namespace is {
 
+#define IS_ATT_LD4 68
+#define IS_ATT_JB (IS_ATT_NMAX / 32)
+
+// ---- register-blocked building blocks (one warp, 4 rows at a time) ------------------------------------
+// acc[r][jj] = sum_{k < dh} rows[r*64 + c0 + k] * Mat[(jj*32 + lane) * 68 + c0 + k]
+// rows: this warp's [4][64] staging area; Mat: [n][68] in shared memory.  128 FMAs per 12 LDS.128.
+__device__ __forceinline__ void blocked_dots(float (&acc)[4][IS_ATT_JB], const float* __restrict__ rows,
+                                             const float* __restrict__ Mat, int c0, int dh, int n, int lane) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int jj = 0; jj < IS_ATT_JB; ++jj) acc[r][jj] = 0.0f;
+    for (int k = 0; k < dh; k += 4) {
+        float4 q4[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) q4[r] = *reinterpret_cast<const float4*>(rows + r * 64 + c0 + k);
+#pragma unroll
+        for (int jj = 0; jj < IS_ATT_JB; ++jj) {
+            if (jj * 32 < n) {          // warp-uniform
+                const int j = jj * 32 + lane;
+                const float4 kv = *reinterpret_cast<const float4*>(Mat + (j < n ? j : 0) * IS_ATT_LD4 + c0 + k);
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    acc[r][jj] = fmaf(q4[r].x, kv.x, fmaf(q4[r].y, kv.y, fmaf(q4[r].z, kv.z, fmaf(q4[r].w, kv.w, acc[r][jj]))));
+            }
+        }
+    }
+}
+
+// out[r] (float2: channels c0 + 2*lane, +1; lanes with 2*lane >= dh idle) = sum_j W[r*NMAX + j] * Mat[j*68 + c0 + 2*lane ..]
+__device__ __forceinline__ void blocked_wsum(float2 (&out)[4], const float* __restrict__ W, const float* __restrict__ Mat,
+                                             int c0, int dh, int n, int lane) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) out[r] = make_float2(0.0f, 0.0f);
+    if (2 * lane < dh) {
+        const float* mc = Mat + c0 + 2 * lane;
+        int j = 0;
+        for (; j + 4 <= n; j += 4) {
+            float4 w4[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) w4[r] = *reinterpret_cast<const float4*>(W + r * IS_ATT_NMAX + j);
+            const float2 v0 = *reinterpret_cast<const float2*>(mc + (j + 0) * IS_ATT_LD4);
+            const float2 v1 = *reinterpret_cast<const float2*>(mc + (j + 1) * IS_ATT_LD4);
+            const float2 v2 = *reinterpret_cast<const float2*>(mc + (j + 2) * IS_ATT_LD4);
+            const float2 v3 = *reinterpret_cast<const float2*>(mc + (j + 3) * IS_ATT_LD4);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                out[r].x = fmaf(w4[r].x, v0.x, fmaf(w4[r].y, v1.x, fmaf(w4[r].z, v2.x, fmaf(w4[r].w, v3.x, out[r].x))));
+                out[r].y = fmaf(w4[r].x, v0.y, fmaf(w4[r].y, v1.y, fmaf(w4[r].z, v2.y, fmaf(w4[r].w, v3.y, out[r].y))));
+            }
+        }
+        for (; j < n; ++j) {
+            const float2 v = *reinterpret_cast<const float2*>(mc + j * IS_ATT_LD4);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { out[r].x = fmaf(W[r * IS_ATT_NMAX + j], v.x, out[r].x); out[r].y = fmaf(W[r * IS_ATT_NMAX + j], v.y, out[r].y); }
+        }
+    }
+}
+
+// stage rows [i0, i0+4) x 64 channels of a [N,ld] global matrix (+ optional per-graph row `add`, scaled)
+// into this warp's [4][64] area; rows >= n are zero
+__device__ __forceinline__ void stage4(float* __restrict__ dst, const float* __restrict__ src, int64_t ld, int64_t n0,
+                                       int i0, int n, int lane, const float* __restrict__ add = nullptr, float add_scale = 0.0f) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const int idx = t * 32 + lane, r = idx >> 6, c = idx & 63;
+        float v = 0.0f;
+        if (i0 + r < n) {
+            v = src ? __ldg(src + (n0 + i0 + r) * ld + c) : 0.0f;
+            if (add) v = fmaf(__ldg(add + c), add_scale, v);
+        }
+        dst[idx] = v;
+    }
+}
+
 __global__ void __launch_bounds__(IS_THREADS)
 attn_fwd_kernel(const float* __restrict__ QKV, const int64_t* __restrict__ node_off, int H, float scale,
                 float* __restrict__ O, float* __restrict__ LSE, float* __restrict__ pooled,
@@ -29,72 +104,67 @@ attn_fwd_kernel(const float* __restrict__ QKV, const int64_t* __restrict__ node_
     const int g = blockIdx.x;
     const int64_t n0 = node_off[g];
     const int n = (int)(node_off[g + 1] - n0);
-    float* Ks = smem;                               // [n][65]
-    float* Vs = Ks + IS_ATT_NMAX * IS_ATT_LD;       // [n][65]
-    float* qrow = Vs + IS_ATT_NMAX * IS_ATT_LD;     // [8 warps][64]
-    float* prow = qrow + 8 * 64;                    // [8 warps][NMAX]
-    float* red = prow + 8 * IS_ATT_NMAX;            // [4][64]
+    float* Ks = smem;                               // [NMAX][68]
+    float* Vs = Ks + IS_ATT_NMAX * IS_ATT_LD4;      // [NMAX][68]
+    float* qs = Vs + IS_ATT_NMAX * IS_ATT_LD4;      // [8 warps][4][64]
+    float* prow = qs + 8 * 256;                     // [8 warps][4][NMAX]
+    float* red = prow + 8 * 4 * IS_ATT_NMAX;        // [4][64]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dh = 64 / H;
-    for (int idx = tid; idx < n * 64; idx += IS_THREADS) {
-        const int r = idx >> 6, c = idx & 63;
-        Ks[r * IS_ATT_LD + c] = __ldg(QKV + (n0 + r) * 192 + 64 + c);
-        Vs[r * IS_ATT_LD + c] = __ldg(QKV + (n0 + r) * 192 + 128 + c);
+    for (int idx = tid; idx < n * 16; idx += IS_THREADS) {
+        const int r = idx >> 4, c4 = idx & 15;
+        *reinterpret_cast<float4*>(Ks + r * IS_ATT_LD4 + 4 * c4) = __ldg(reinterpret_cast<const float4*>(QKV + (n0 + r) * 192 + 64) + c4);
+        *reinterpret_cast<float4*>(Vs + r * IS_ATT_LD4 + 4 * c4) = __ldg(reinterpret_cast<const float4*>(QKV + (n0 + r) * 192 + 128) + c4);
     }
     __syncthreads();
-    float* q = qrow + warp * 64;
-    float* pr = prow + warp * IS_ATT_NMAX;
-    for (int i = warp; i < n; i += IS_THREADS / 32) {
+    float* q = qs + warp * 256;
+    float* pr = prow + warp * 4 * IS_ATT_NMAX;
+    for (int i0 = 4 * warp; i0 < n; i0 += 4 * (IS_THREADS / 32)) {
         __syncwarp();
-        q[lane] = __ldg(QKV + (n0 + i) * 192 + lane);
-        q[lane + 32] = __ldg(QKV + (n0 + i) * 192 + 32 + lane);
+        stage4(q, QKV, 192, n0, i0, n, lane);
         __syncwarp();
         for (int h = 0; h < H; ++h) {
-            float s[IS_ATT_NMAX / 32];
-            float mx = -INFINITY;
+            float acc[4][IS_ATT_JB];
+            blocked_dots(acc, q, Ks, h * dh, dh, n, lane);
+            __syncwarp();                              // previous head's prow reads are complete
 #pragma unroll
-            for (int jj = 0; jj < IS_ATT_NMAX / 32; ++jj) {
-                const int j = jj * 32 + lane;
-                float a = -INFINITY;
-                if (j < n) {
-                    a = 0.0f;
-                    const float* kr = Ks + j * IS_ATT_LD + h * dh;
-                    const float* qh = q + h * dh;
-                    for (int k = 0; k < dh; ++k) a = fmaf(qh[k], kr[k], a);
-                    a *= scale;
+            for (int r = 0; r < 4; ++r) {
+                float mx = -INFINITY;
+#pragma unroll
+                for (int jj = 0; jj < IS_ATT_JB; ++jj) {
+                    const float a = (jj * 32 + lane < n) ? acc[r][jj] * scale : -INFINITY;
+                    acc[r][jj] = a;
+                    mx = fmaxf(mx, a);
                 }
-                s[jj] = a;
-                mx = fmaxf(mx, a);
-            }
-            mx = warp_max(mx);
-            float z = 0.0f;
+                mx = warp_max(mx);
+                float z = 0.0f;
 #pragma unroll
-            for (int jj = 0; jj < IS_ATT_NMAX / 32; ++jj) {
-                const int j = jj * 32 + lane;
-                const float e = (j < n) ? expf(s[jj] - mx) : 0.0f;
-                s[jj] = e;
-                z += e;
-            }
-            z = warp_sum(z);
-            const float rz = 1.0f / z;
-            __syncwarp();
-#pragma unroll
-            for (int jj = 0; jj < IS_ATT_NMAX / 32; ++jj) {
-                const int j = jj * 32 + lane;
-                if (j < n) {
-                    const float pj = s[jj] * rz;
-                    pr[j] = pj;
-                    if (attn) attn[attn_off[g] + ((int64_t)h * n + i) * n + j] = pj;
+                for (int jj = 0; jj < IS_ATT_JB; ++jj) {
+                    const float e = (jj * 32 + lane < n) ? expf(acc[r][jj] - mx) : 0.0f;
+                    acc[r][jj] = e;
+                    z += e;
                 }
+                z = warp_sum(z);
+                const float rz = 1.0f / z;
+                const int i = i0 + r;
+#pragma unroll
+                for (int jj = 0; jj < IS_ATT_JB; ++jj) {
+                    const int j = jj * 32 + lane;
+                    if (jj * 32 < n) {
+                        const float pj = acc[r][jj] * rz;
+                        pr[r * IS_ATT_NMAX + j] = (j < n) ? pj : 0.0f;
+                        if (attn && i < n && j < n) attn[attn_off[g] + ((int64_t)h * n + i) * n + j] = pj;
+                    }
+                }
+                if (lane == 0 && i < n) LSE[(n0 + i) * H + h] = mx + logf(z);
             }
             __syncwarp();
-            if (lane == 0) LSE[(n0 + i) * H + h] = mx + logf(z);
-            // O[i][h*dh + k] = sum_j p_j V[j][h*dh + k]; lanes over k (two k per lane when dh = 64)
-            for (int k = lane; k < dh; k += 32) {
-                float o = 0.0f;
-                const float* vc = Vs + h * dh + k;
-                for (int j = 0; j < n; ++j) o = fmaf(pr[j], vc[j * IS_ATT_LD], o);
-                O[(n0 + i) * 64 + h * dh + k] = o;
+            float2 o[4];
+            blocked_wsum(o, pr, Vs, h * dh, dh, n, lane);
+            if (2 * lane < dh) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    if (i0 + r < n) *reinterpret_cast<float2*>(O + (n0 + i0 + r) * 64 + h * dh + 2 * lane) = o[r];
             }
         }
     }
@@ -111,8 +181,8 @@ attn_fwd_kernel(const float* __restrict__ QKV, const int64_t* __restrict__ node_
     if (tid < 64) pooled[(int64_t)g * 64 + tid] = (red[tid] + red[64 + tid] + red[128 + tid] + red[192 + tid]) / (float)max(n, 1);
 }
 
-// Backward.  gO[i] = gO_full[i] (optional) + g_pooled[g] / n.  Two passes with recomputed scores:
-// rows (gQ) then columns (gK, gV), both in fixed summation order.
+// Backward.  gO[i] = gO_full[i] (optional) + g_pooled[g] / n.  Two register-blocked passes with
+// recomputed scores: row blocks (gQ) then column blocks (gK, gV), fixed summation order.
 __global__ void __launch_bounds__(IS_THREADS)
 attn_bwd_kernel(const float* __restrict__ QKV, const float* __restrict__ O, const float* __restrict__ LSE,
                 const int64_t* __restrict__ node_off, int H, float scale,
@@ -122,110 +192,120 @@ attn_bwd_kernel(const float* __restrict__ QKV, const float* __restrict__ O, cons
     const int g = blockIdx.x;
     const int64_t n0 = node_off[g];
     const int n = (int)(node_off[g + 1] - n0);
-    float* S0 = smem;                               // pass A: K   ; pass B: Q
-    float* S1 = S0 + IS_ATT_NMAX * IS_ATT_LD;       // pass A: V   ; pass B: gO
-    float* row0 = S1 + IS_ATT_NMAX * IS_ATT_LD;     // [8][64]  pass A: q row  ; pass B: k row
-    float* row1 = row0 + 8 * 64;                    // [8][64]  pass A: gO row ; pass B: v row
-    float* prow = row1 + 8 * 64;                    // [8][NMAX] gs row / column
-    float* prow2 = prow + 8 * IS_ATT_NMAX;          // [8][NMAX] p column (pass B)
-    float* Dn = prow2 + 8 * IS_ATT_NMAX;            // [NMAX][8] D[i][h] = gO_i . O_i per head
+    float* S0 = smem;                               // pass A: K   ; pass B: Q      [NMAX][68]
+    float* S1 = S0 + IS_ATT_NMAX * IS_ATT_LD4;      // pass A: V   ; pass B: gO     [NMAX][68]
+    float* ra = S1 + IS_ATT_NMAX * IS_ATT_LD4;      // [8][4][64] pass A: q rows  ; pass B: k rows
+    float* rb = ra + 8 * 256;                       // [8][4][64] pass A: gO rows ; pass B: v rows
+    float* wa = rb + 8 * 256;                       // [8][4][NMAX] gs
+    float* wb = wa + 8 * 4 * IS_ATT_NMAX;           // [8][4][NMAX] p (pass B)
+    float* Dn = wb + 8 * 4 * IS_ATT_NMAX;           // [NMAX][8]   D[i][h] = gO_i . O_i per head
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int dh = 64 / H;
     const float inv_n = 1.0f / (float)max(n, 1);
+    const float* gp_row = g_pooled ? g_pooled + (int64_t)g * 64 : nullptr;
+    float* A = ra + warp * 256;
+    float* Bv = rb + warp * 256;
+    float* WA = wa + warp * 4 * IS_ATT_NMAX;
+    float* WB = wb + warp * 4 * IS_ATT_NMAX;
 
-    // ---------------- pass A: rows ----------------
-    for (int idx = tid; idx < n * 64; idx += IS_THREADS) {
-        const int r = idx >> 6, c = idx & 63;
-        S0[r * IS_ATT_LD + c] = __ldg(QKV + (n0 + r) * 192 + 64 + c);
-        S1[r * IS_ATT_LD + c] = __ldg(QKV + (n0 + r) * 192 + 128 + c);
+    // ---------------- pass A: row blocks ----------------
+    for (int idx = tid; idx < n * 16; idx += IS_THREADS) {
+        const int r = idx >> 4, c4 = idx & 15;
+        *reinterpret_cast<float4*>(S0 + r * IS_ATT_LD4 + 4 * c4) = __ldg(reinterpret_cast<const float4*>(QKV + (n0 + r) * 192 + 64) + c4);
+        *reinterpret_cast<float4*>(S1 + r * IS_ATT_LD4 + 4 * c4) = __ldg(reinterpret_cast<const float4*>(QKV + (n0 + r) * 192 + 128) + c4);
     }
     __syncthreads();
-    float* q = row0 + warp * 64;
-    float* go = row1 + warp * 64;
-    float* pr = prow + warp * IS_ATT_NMAX;
-    for (int i = warp; i < n; i += IS_THREADS / 32) {
+    for (int i0 = 4 * warp; i0 < n; i0 += 4 * (IS_THREADS / 32)) {
         __syncwarp();
+        stage4(A, QKV, 192, n0, i0, n, lane);
+        stage4(Bv, gO_full, 64, n0, i0, n, lane, gp_row, inv_n);
+        __syncwarp();
+        for (int h = 0; h < H; ++h) {
+            // D[r] = sum over this head's channels of gO[r][c] * O[r][c]
+            float D[4];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int c = lane + 32 * half;
-            q[c] = __ldg(QKV + (n0 + i) * 192 + c);
-            float v = g_pooled ? __ldg(g_pooled + (int64_t)g * 64 + c) * inv_n : 0.0f;
-            if (gO_full) v += __ldg(gO_full + (n0 + i) * 64 + c);
-            go[c] = v;
-        }
-        __syncwarp();
-        for (int h = 0; h < H; ++h) {
-            // D = sum_k gO[i][k] O[i][k] over this head's channels
-            float dpart = 0.0f;
-            for (int k = lane; k < dh; k += 32) dpart += go[h * dh + k] * __ldg(O + (n0 + i) * 64 + h * dh + k);
-            const float D = warp_sum(dpart);
-            if (lane == 0) Dn[i * 8 + h] = D;
-            const float lse = __ldg(LSE + (n0 + i) * H + h);
+            for (int r = 0; r < 4; ++r) {
+                float dpart = 0.0f;
+                if (i0 + r < n)
+                    for (int k = lane; k < dh; k += 32) dpart += Bv[r * 64 + h * dh + k] * __ldg(O + (n0 + i0 + r) * 64 + h * dh + k);
+                D[r] = warp_sum(dpart);
+                if (lane == 0 && i0 + r < n) Dn[(i0 + r) * 8 + h] = D[r];
+            }
+            float s[4][IS_ATT_JB], gp[4][IS_ATT_JB];
+            blocked_dots(s, A, S0, h * dh, dh, n, lane);
+            blocked_dots(gp, Bv, S1, h * dh, dh, n, lane);
             __syncwarp();
-            for (int j = lane; j < n; j += 32) {
-                const float* kr = S0 + j * IS_ATT_LD + h * dh;
-                const float* vr = S1 + j * IS_ATT_LD + h * dh;
-                float a = 0.0f, gp = 0.0f;
-                for (int k = 0; k < dh; ++k) { a = fmaf(q[h * dh + k], kr[k], a); gp = fmaf(go[h * dh + k], vr[k], gp); }
-                const float pj = expf(a * scale - lse);
-                pr[j] = pj * (gp - D);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float lse = (i0 + r < n) ? __ldg(LSE + (n0 + i0 + r) * H + h) : 0.0f;
+#pragma unroll
+                for (int jj = 0; jj < IS_ATT_JB; ++jj) {
+                    const int j = jj * 32 + lane;
+                    if (jj * 32 < n) WA[r * IS_ATT_NMAX + j] = (j < n && i0 + r < n) ? expf(s[r][jj] * scale - lse) * (gp[r][jj] - D[r]) : 0.0f;
+                }
             }
             __syncwarp();
-            for (int k = lane; k < dh; k += 32) {
-                float acc = 0.0f;
-                const float* kc = S0 + h * dh + k;
-                for (int j = 0; j < n; ++j) acc = fmaf(pr[j], kc[j * IS_ATT_LD], acc);
-                gQKV[(n0 + i) * 192 + h * dh + k] = acc * scale;
+            float2 o[4];
+            blocked_wsum(o, WA, S0, h * dh, dh, n, lane);
+            if (2 * lane < dh) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    if (i0 + r < n)
+                        *reinterpret_cast<float2*>(gQKV + (n0 + i0 + r) * 192 + h * dh + 2 * lane) = make_float2(o[r].x * scale, o[r].y * scale);
             }
         }
     }
     __syncthreads();
-    // ---------------- pass B: columns ----------------
+    // ---------------- pass B: column blocks ----------------
     for (int idx = tid; idx < n * 64; idx += IS_THREADS) {
         const int r = idx >> 6, c = idx & 63;
-        S0[r * IS_ATT_LD + c] = __ldg(QKV + (n0 + r) * 192 + c);
-        float v = g_pooled ? __ldg(g_pooled + (int64_t)g * 64 + c) * inv_n : 0.0f;
+        S0[r * IS_ATT_LD4 + c] = __ldg(QKV + (n0 + r) * 192 + c);
+        float v = gp_row ? __ldg(gp_row + c) * inv_n : 0.0f;
         if (gO_full) v += __ldg(gO_full + (n0 + r) * 64 + c);
-        S1[r * IS_ATT_LD + c] = v;
+        S1[r * IS_ATT_LD4 + c] = v;
     }
     __syncthreads();
-    float* kk = row0 + warp * 64;
-    float* vv = row1 + warp * 64;
-    float* pc = prow2 + warp * IS_ATT_NMAX;
-    for (int j = warp; j < n; j += IS_THREADS / 32) {
+    for (int j0 = 4 * warp; j0 < n; j0 += 4 * (IS_THREADS / 32)) {
         __syncwarp();
-        kk[lane] = __ldg(QKV + (n0 + j) * 192 + 64 + lane);
-        kk[lane + 32] = __ldg(QKV + (n0 + j) * 192 + 96 + lane);
-        vv[lane] = __ldg(QKV + (n0 + j) * 192 + 128 + lane);
-        vv[lane + 32] = __ldg(QKV + (n0 + j) * 192 + 160 + lane);
+        stage4(A, QKV + 64, 192, n0, j0, n, lane);       // K rows of the 4 columns
+        stage4(Bv, QKV + 128, 192, n0, j0, n, lane);     // V rows
         __syncwarp();
         for (int h = 0; h < H; ++h) {
-            for (int i = lane; i < n; i += 32) {
-                const float* qr = S0 + i * IS_ATT_LD + h * dh;
-                const float* gr = S1 + i * IS_ATT_LD + h * dh;
-                float a = 0.0f, gp = 0.0f;
-                for (int k = 0; k < dh; ++k) { a = fmaf(qr[k], kk[h * dh + k], a); gp = fmaf(gr[k], vv[h * dh + k], gp); }
-                const float pij = expf(a * scale - __ldg(LSE + (n0 + i) * H + h));
-                pc[i] = pij;
-                pr[i] = pij * (gp - Dn[i * 8 + h]);
+            float s[4][IS_ATT_JB], gp[4][IS_ATT_JB];
+            blocked_dots(s, A, S0, h * dh, dh, n, lane);       // s[c][i] = k_c . q_i
+            blocked_dots(gp, Bv, S1, h * dh, dh, n, lane);     // gp[c][i] = v_c . gO_i
+            __syncwarp();
+#pragma unroll
+            for (int jj = 0; jj < IS_ATT_JB; ++jj) {
+                const int i = jj * 32 + lane;
+                if (jj * 32 < n) {
+                    const bool vi = i < n;
+                    const float lse = vi ? __ldg(LSE + (n0 + i) * H + h) : 0.0f;
+                    const float Di = vi ? Dn[i * 8 + h] : 0.0f;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float pij = (vi && j0 + c < n) ? expf(s[c][jj] * scale - lse) : 0.0f;
+                        WB[c * IS_ATT_NMAX + i] = pij;
+                        WA[c * IS_ATT_NMAX + i] = pij * (gp[c][jj] - Di);
+                    }
+                }
             }
             __syncwarp();
-            for (int k = lane; k < dh; k += 32) {
-                float gk = 0.0f, gv = 0.0f;
-                const float* qc = S0 + h * dh + k;
-                const float* gc = S1 + h * dh + k;
-                for (int i = 0; i < n; ++i) {
-                    gk = fmaf(pr[i], qc[i * IS_ATT_LD], gk);
-                    gv = fmaf(pc[i], gc[i * IS_ATT_LD], gv);
-                }
-                gQKV[(n0 + j) * 192 + 64 + h * dh + k] = gk * scale;
-                gQKV[(n0 + j) * 192 + 128 + h * dh + k] = gv;
+            float2 gk[4], gv[4];
+            blocked_wsum(gk, WA, S0, h * dh, dh, n, lane);
+            blocked_wsum(gv, WB, S1, h * dh, dh, n, lane);
+            if (2 * lane < dh) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (j0 + c < n) {
+                        *reinterpret_cast<float2*>(gQKV + (n0 + j0 + c) * 192 + 64 + h * dh + 2 * lane) = make_float2(gk[c].x * scale, gk[c].y * scale);
+                        *reinterpret_cast<float2*>(gQKV + (n0 + j0 + c) * 192 + 128 + h * dh + 2 * lane) = gv[c];
+                    }
             }
             __syncwarp();
         }
     }
 }
-
 
 // ---------------------------------------------------------------------------------------------------
 // Inference fast path: only the pooled output is needed (no_grad, no attention weights).  Because the
@@ -352,7 +432,7 @@ int is_attn_pool_fwd(const float* QKV, const int64_t* node_off, int n_graphs, in
     if (n_graphs <= 0 || !(n_head == 1 || n_head == 2 || n_head == 4 || n_head == 8)) return IS_ERR_ARG;
     if (max_nodes > IS_ATT_NMAX) return IS_ERR_UNSUPPORTED;
     const float scale = 1.0f / sqrtf((float)(64 / n_head));
-    size_t smem = sizeof(float) * (2 * IS_ATT_NMAX * IS_ATT_LD + 8 * 64 + 8 * IS_ATT_NMAX + 4 * 64);
+    size_t smem = sizeof(float) * (2 * IS_ATT_NMAX * IS_ATT_LD4 + 8 * 256 + 8 * 4 * IS_ATT_NMAX + 4 * 64);
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     attn_fwd_kernel<<<n_graphs, IS_THREADS, smem, (cudaStream_t)stream>>>(QKV, node_off, n_head, scale, O, LSE, pooled, attn, attn_off);
@@ -379,7 +459,7 @@ int is_attn_pool_bwd(const float* QKV, const float* O, const float* LSE, const i
     if (n_graphs <= 0 || !(n_head == 1 || n_head == 2 || n_head == 4 || n_head == 8)) return IS_ERR_ARG;
     if (max_nodes > IS_ATT_NMAX) return IS_ERR_UNSUPPORTED;
     const float scale = 1.0f / sqrtf((float)(64 / n_head));
-    size_t smem = sizeof(float) * (2 * IS_ATT_NMAX * IS_ATT_LD + 2 * 8 * 64 + 2 * 8 * IS_ATT_NMAX + IS_ATT_NMAX * 8);
+    size_t smem = sizeof(float) * (2 * IS_ATT_NMAX * IS_ATT_LD4 + 2 * 8 * 256 + 2 * 8 * 4 * IS_ATT_NMAX + IS_ATT_NMAX * 8);
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     attn_bwd_kernel<<<n_graphs, IS_THREADS, smem, (cudaStream_t)stream>>>(QKV, O, LSE, node_off, n_head, scale, g_pooled, gO_full, gQKV);
