@@ -26,28 +26,6 @@
 
 namespace is {
 
-// ---- tile walk: executed by one full warp; all lanes return the same values ------------------------
-// Longest run of consecutive destination nodes (<= 32) starting at n0 whose in-edges total <= 128.
-// tn0 >= nend means the CTA's node range is exhausted.  Nodes with more than 128 in-edges are
-// unsupported: flagged in *status and skipped.
-__device__ __forceinline__ void next_tile(const int* __restrict__ indptr, int n0, int nend, int* __restrict__ status,
-                                          int lane, int& tn0, int& tn1, int& tp0, int& tne) {
-    while (n0 < nend) {
-        const int pbase = __ldg(indptr + n0);
-        const int cand = n0 + lane + 1;
-        const bool ok = (cand <= nend) && (__ldg(indptr + (cand <= nend ? cand : nend)) - pbase <= IS_TM);
-        const int cnt = __popc(__ballot_sync(0xffffffffu, ok));
-        if (cnt == 0) {
-            if (lane == 0 && status) atomicExch(status, 1);
-            ++n0;
-            continue;
-        }
-        tn0 = n0; tn1 = n0 + cnt; tp0 = pbase; tne = __ldg(indptr + n0 + cnt) - pbase;
-        return;
-    }
-    tn0 = nend; tn1 = nend; tp0 = 0; tne = 0;
-}
-
 struct TileMeta {            // per-edge scalars of one tile, produced by the prefetch warps
     int src[IS_TM];
     int dst[IS_TM];

@@ -36,9 +36,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     return d;                                                // base_offset = 0, lbo_mode = 0, layout = SWIZZLE_NONE
 }
 
-// 32-bit instruction descriptor: D fp32, A/B both `fmt` (1 = bf16, 2 = tf32), K-major A and B, dense
-__device__ __forceinline__ constexpr uint32_t make_instr_desc(uint32_t fmt, uint32_t M, uint32_t N) {
-    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+// 32-bit instruction descriptor: D fp32, A/B both `fmt` (1 = bf16, 2 = tf32), dense; a_mn / b_mn = 1 selects
+// an MN-major operand (bits 15 / 16), 0 = K-major
+__device__ __forceinline__ constexpr uint32_t make_instr_desc(uint32_t fmt, uint32_t M, uint32_t N,
+                                                              uint32_t a_mn = 0, uint32_t b_mn = 0) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 // ---- TMEM allocation (one full warp executes these) ------------------------------------------------

@@ -113,6 +113,75 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, f
     if (warp == 0) tmem_dealloc(tbase, 64);
 }
 
+
+// Layout experiments for the tensor-core backward (weight gradients need transposed operands):
+//  mode 4: B operand MN-major  -- B^T is staged as a K-major tile (rows = k, cols = n) and read through an
+//          MN-major descriptor (SBO <- LBO, LBO <- SBO, b_major = 1): D must still equal A B^T.
+//  mode 5: A operand MN-major  -- same trick for A (tile rows = k, cols = m).
+//  mode 6: M = 64 accumulator  -- D[64,64] = A[0:64] B^T with an M = 64 instruction; all 128 TMEM lanes are
+//          dumped so the lane mapping of the 64 rows can be read off.
+template <int MODE>
+__global__ void __launch_bounds__(128)
+umma_layout_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D) {
+    using namespace umma;
+    constexpr int KCH8 = 8;                                  // 64 bf16 columns = 8 chunks
+    constexpr int KCH16 = 16;                                // 128 bf16 columns
+    extern __shared__ __align__(128) uint8_t sm[];
+    uint8_t* sA = sm;                                        // up to 128 rows x 64 cols or 64 rows x 128 cols
+    uint8_t* sB = sm + 16 * KCH16 * kLBO;
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tmem_alloc(&tmem_base, 64);
+    if (tid == 32) mbar_init(&mbar, 1);
+    for (int idx = tid; idx < 128 * 64; idx += 128) {
+        const int m = idx >> 6, k = idx & 63;
+        const __nv_bfloat16 v = __float2bfloat16_rn(A[idx]);
+        if (MODE == 5) *reinterpret_cast<__nv_bfloat16*>(sA + canon_off<2>(k, m, KCH16)) = v;     // tile rows = k, cols = m
+        else *reinterpret_cast<__nv_bfloat16*>(sA + canon_off<2>(m, k, KCH8)) = v;
+    }
+    for (int idx = tid; idx < 64 * 64; idx += 128) {
+        const int n = idx >> 6, k = idx & 63;
+        const __nv_bfloat16 v = __float2bfloat16_rn(B[idx]);
+        if (MODE == 4) *reinterpret_cast<__nv_bfloat16*>(sB + canon_off<2>(k, n, KCH8)) = v;      // tile rows = k, cols = n
+        else *reinterpret_cast<__nv_bfloat16*>(sB + canon_off<2>(n, k, KCH8)) = v;
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tbase = tmem_base;
+    if (tid == 0) {
+        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+        const uint32_t idesc = make_instr_desc(1u, MODE == 6 ? 64 : 128, 64, MODE == 5 ? 1u : 0u, MODE == 4 ? 1u : 0u);
+        for (int ks = 0; ks < 4; ++ks) {                     // K = 64 = 4 steps of 16
+            uint64_t da, db;
+            if (MODE == 5)   // MN-major A: MN-block stride = kLBO, K-group stride = row-group stride of the tile
+                da = make_smem_desc(a0 + ks * 2 * (KCH16 * kLBO), KCH16 * kLBO, kLBO);
+            else
+                da = make_smem_desc(a0 + ks * 2 * kLBO, kLBO, KCH8 * kLBO);
+            if (MODE == 4)
+                db = make_smem_desc(b0 + ks * 2 * (KCH8 * kLBO), KCH8 * kLBO, kLBO);
+            else
+                db = make_smem_desc(b0 + ks * 2 * kLBO, kLBO, KCH8 * kLBO);
+            mma_bf16(tbase, da, db, idesc, ks > 0);
+        }
+        mma_commit(&mbar);
+    }
+    mbar_wait(&mbar, 0);
+    fence_after_sync();
+    float v[32];
+    for (int half = 0; half < 2; ++half) {
+        tmem_ld32(tbase + ((uint32_t)(warp * 32) << 16) + half * 32, v);
+        const int row = warp * 32 + lane;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) D[row * 64 + half * 32 + c] = v[c];
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 64);
+}
+
 }  // namespace is
 
 using namespace is;
@@ -140,6 +209,11 @@ extern "C" int is_umma_selftest(const float* A, const float* B, float* D, int mo
         e = cudaFuncSetAttribute(umma_selftest_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         umma_selftest_kernel<3><<<1, 128, smem, st>>>(A, B, D);
+    } else if (mode >= 4 && mode <= 6) {
+        size_t smem = (16 * 16 + 8 * 16) * umma::kLBO + 128;
+        if (mode == 4) { cudaFuncSetAttribute(umma_layout_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); umma_layout_kernel<4><<<1, 128, smem, st>>>(A, B, D); }
+        if (mode == 5) { cudaFuncSetAttribute(umma_layout_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); umma_layout_kernel<5><<<1, 128, smem, st>>>(A, B, D); }
+        if (mode == 6) { cudaFuncSetAttribute(umma_layout_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); umma_layout_kernel<6><<<1, 128, smem, st>>>(A, B, D); }
     } else {
         return IS_ERR_ARG;
     }

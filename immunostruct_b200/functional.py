@@ -13,7 +13,8 @@ from . import _C
 H = 64   # hidden width of the EGNN MLPs and of the node embedding (hybrid_models.py:247)
 
 
-# Arithmetic of the EGNN edge GEMMs in the FORWARD pass (the backward always recomputes in fp32 SIMT):
+# Arithmetic of the EGNN GEMMs.  Forward modes below; the edge BACKWARD runs on the tensor cores with the
+# fp32-accurate bf16x3 split in every mode except "fp32" (which keeps the fp32 SIMT backward):
 #   "fp32"   : fp32 SIMT FMA kernels (csrc/egnn.cu)
 #   "bf16x3" : tcgen05 tensor cores, operands split into three bf16 terms, six partial products --
 #              fp32-accurate, two CTAs per SM (csrc/egnn_tc.cu); the default
@@ -100,7 +101,8 @@ class _EGNNLayer(torch.autograd.Function):
         # edge backward
         gz1, gQ, gD, gxd = _new(h, e, H), _new(h, n, H), _new(h, e, 3), _new(h, n, 3)
         p_edge = _new(h, grid_e, 2 * H * H + 5 * H)
-        _C.egnn_edge_bwd(g, PQ, x, edge_attr, f, W1, W2, b2, W3, b3, w4, ghn, gx_out, gz1, gQ, gD, gxd, p_edge)
+        bwd = _C.egnn_edge_bwd if _PRECISIONS[_precision] is None else _C.egnn_edge_bwd_tc
+        bwd(g, PQ, x, edge_attr, f, W1, W2, b2, W3, b3, w4, ghn, gx_out, gz1, gQ, gD, gxd, p_edge)
         # node_pre backward (source-side reduction through the CSC transpose)
         gh = _new(h, n, H) if need_gh else None
         gx = _new(h, n, 3) if need_gx else None

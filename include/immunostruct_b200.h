@@ -75,6 +75,14 @@ int is_egnn_edge_bwd(const int* indptr, const int* csr_src, const int* csr_dst, 
                      const float* ghn, const float* gx_out,
                      float* gz1, float* gQ, float* gD, float* gxd, float* partials,
                      int64_t n_nodes, int* status, void* stream);
+/* tcgen05 / TMEM variant of is_egnn_edge_bwd (bf16x3 operands, fp32-accurate; same outputs and partial layout) */
+int is_egnn_edge_bwd_tc(const int* indptr, const int* csr_src, const int* csr_dst, const int* csr_eid,
+                        const float* PQ, const float* x, int64_t ldx, const float* edge_attr,
+                        const float* W1, int F, const float* W2, const float* b2,
+                        const float* W3, const float* b3, const float* w4,
+                        const float* ghn, const float* gx_out,
+                        float* gz1, float* gQ, float* gD, float* gxd, float* partials,
+                        int64_t n_nodes, int* status, void* stream);
 int is_egnn_node_pre_bwd(const float* gz1, const float* gQ, const float* gD, const float* gxd,
                          const float* gx_out, const float* gh_direct,
                          const int* outptr, const int* csc_pos, const float* h, int64_t ldh, int F,

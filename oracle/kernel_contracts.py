@@ -174,6 +174,11 @@ def egnn_edge_bwd(g, PQ, x, edge_attr, f, W1, W2, b2, W3, b3, w4, ghn, gx_out, g
     partials.copy_(_partials(partials.shape[0], gW2, gW3, gb2, gb3, gw4, grads[2], grads[3]))
 
 
+def egnn_edge_bwd_tc(*args):
+    """Same contract as egnn_edge_bwd; the tensor-core kernel only changes the GEMM arithmetic."""
+    egnn_edge_bwd(*args)
+
+
 def egnn_node_pre_bwd(gz1, gQ, gD, gxd, gx_out, gh_direct, g, h, W1, gh, gx, partials):
     f = h.shape[1]
     n = h.shape[0]
@@ -295,6 +300,6 @@ def loss_bwd(recon, seq, mu, logvar, logits, y, mode, pos_weight, w_pred, w_mse,
 
 
 ALL = ["num_sms", "egnn_node_grid", "egnn_edge_bwd_grid", "attn_max_nodes", "loss_num_partials", "collate_csr",
-       "egnn_node_pre_fwd", "egnn_edge_fwd", "egnn_edge_fwd_tc", "egnn_node_post_pre_tc", "egnn_node_post_fwd", "egnn_node_post_bwd", "egnn_edge_bwd",
+       "egnn_node_pre_fwd", "egnn_edge_fwd", "egnn_edge_fwd_tc", "egnn_node_post_pre_tc", "egnn_node_post_fwd", "egnn_node_post_bwd", "egnn_edge_bwd", "egnn_edge_bwd_tc",
        "egnn_node_pre_bwd", "reduce_partials", "attn_pool_fwd", "attn_pool_infer", "attn_pool_bwd", "fusion_attn_fwd",
        "fusion_attn_bwd", "loss_fwd", "loss_bwd"]

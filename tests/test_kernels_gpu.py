@@ -211,9 +211,12 @@ def test_egnn_node_post_pre_tensor_core(case, f, with_next, prec, tol):
 
 
 # ---- EGNN backward -----------------------------------------------------------------------------
+@pytest.mark.parametrize("tc", [False, True])
 @pytest.mark.parametrize("f,coord", [(64, True), (64, False), (20, True)])
-def test_egnn_backward_kernels(case, f, coord):
+def test_egnn_backward_kernels(case, f, coord, tc):
+    """tc=True: the tcgen05 edge backward (bf16x3) against the same contract at the same tolerance."""
     arrays, gb, cg = case
+    edge_bwd = _C.egnn_edge_bwd_tc if tc else _C.egnn_edge_bwd
     gen = torch.Generator().manual_seed(13)
     n, e = gb.n_nodes, gb.n_edges
     w = egnn_weights(gen, f)
@@ -253,8 +256,8 @@ def test_egnn_backward_kernels(case, f, coord):
     outs_d = [torch.empty(e, 64, device=DEV), torch.empty(n, 64, device=DEV), torch.empty(e, 3, device=DEV),
               torch.empty(n, 3, device=DEV), torch.empty(grid_e, 8512, device=DEV)]
     outs = [torch.empty(e, 64), torch.empty(n, 64), torch.empty(e, 3), torch.empty(n, 3), torch.empty(KC.FAKE_GRID, 8512)]
-    _C.egnn_edge_bwd(gb, PQ_d, x_d, ea.to(DEV), f, wd["W1"], wd["W2"], wd["b2"], wd["W3"], wd["b3"], wd["w4"],
-                     ghn_d, gx_out.to(DEV) if coord else None, *outs_d)
+    edge_bwd(gb, PQ_d, x_d, ea.to(DEV), f, wd["W1"], wd["W2"], wd["b2"], wd["W3"], wd["b3"], wd["w4"],
+             ghn_d, gx_out.to(DEV) if coord else None, *outs_d)
     KC.egnn_edge_bwd(cg, PQ, x, ea, f, w["W1"], w["W2"], w["b2"], w["W3"], w["b3"], w["w4"], ghn, gx_out, *outs)
     for name, a, b in zip(("gz1", "gQ", "gD", "gxd"), outs_d[:4], outs[:4]):
         close(a, b, what=name)
