@@ -98,6 +98,21 @@ __device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
     return s;
 }
 
+// SiLU and its derivative with the accurate expf and an approximate (1 ulp) reciprocal: the same arithmetic as
+// the training forward (tc_common.cuh act<PREC, false>), ~10 instructions instead of ~20 with a rounded reciprocal.
+__device__ __forceinline__ float sig_acc(float z) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + expf(-z)));
+    return r;
+}
+__device__ __forceinline__ float silu_acc(float z) { return z * sig_acc(z); }
+__device__ __forceinline__ float dsilu_acc(float z) { const float s = sig_acc(z); return s * (1.0f + z * (1.0f - s)); }
+__device__ __forceinline__ void silu_both_acc(float z, float& y, float& dy) {
+    const float s = sig_acc(z);
+    y = z * s;
+    dy = s * (1.0f + z * (1.0f - s));
+}
+
 // ---- bf16x3 GEMM issue with explicit operand geometry (ONE thread) ------------------------------------------
 struct OpGeom {
     uint32_t base;      // shared-memory address of split term 0
@@ -138,13 +153,14 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
     float* red = e_gd + 3 * IS_TM;                            // [16 warps][16] final vector reductions
     BwdMeta* meta = reinterpret_cast<BwdMeta*>(red + BT_NW * 16);   // [2]
     __shared__ int s_tile[2][4];
-    __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) uint64_t mbar;       // data path: z2, z3, gm, gt1
+    __shared__ __align__(8) uint64_t mbar_wg;    // weight-gradient MMAs (only their operand tiles are waited for)
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ldw1 = 2 * p.F + 2;
     if (warp == 0) tmem_alloc(&s_tmem, 512);
-    if (tid == 32) mbar_init(&mbar, 1);
+    if (tid == 32) { mbar_init(&mbar, 1); mbar_init(&mbar_wg, 1); }
     for (int idx = tid; idx < 64 * 64; idx += BT_NT) {
         const int n = idx >> 6, k = idx & 63;
         store_weight1<PREC_BF16X3>(sW2, WSPL, n, k, __ldg(p.W2 + idx));
@@ -191,7 +207,7 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
     const uint32_t id_wgrad = make_instr_desc(1u, 64, 64, 1, 1);
 
     float acc_gb2 = 0.f, acc_gb3 = 0.f, acc_gw4 = 0.f, acc_gwr = 0.f, acc_gwa = 0.f;   // column (lane>>1)&15 of this warp
-    uint32_t phase = 0, wg_started = 0;
+    uint32_t phase = 0, phase_wg = 0, wg_started = 0, wg_pending = 0;
     int cur = 0;
 
     // t1 = silu(P[src] + Q[dst] + wr r + wa a) for the tile's 128 rows -> operand tile `dst_tile`
@@ -213,14 +229,14 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
             const int j = u * 4 * BT_NW + warp * 4 + esub;
             const float r = rr[u], a = aa[u];
             float v[8];
-            v[0] = silu(pv[u][0].x + qv[u][0].x + wr0.x * r + wa0.x * a);
-            v[1] = silu(pv[u][0].y + qv[u][0].y + wr0.y * r + wa0.y * a);
-            v[2] = silu(pv[u][0].z + qv[u][0].z + wr0.z * r + wa0.z * a);
-            v[3] = silu(pv[u][0].w + qv[u][0].w + wr0.w * r + wa0.w * a);
-            v[4] = silu(pv[u][1].x + qv[u][1].x + wr1.x * r + wa1.x * a);
-            v[5] = silu(pv[u][1].y + qv[u][1].y + wr1.y * r + wa1.y * a);
-            v[6] = silu(pv[u][1].z + qv[u][1].z + wr1.z * r + wa1.z * a);
-            v[7] = silu(pv[u][1].w + qv[u][1].w + wr1.w * r + wa1.w * a);
+            v[0] = silu_acc(pv[u][0].x + qv[u][0].x + wr0.x * r + wa0.x * a);
+            v[1] = silu_acc(pv[u][0].y + qv[u][0].y + wr0.y * r + wa0.y * a);
+            v[2] = silu_acc(pv[u][0].z + qv[u][0].z + wr0.z * r + wa0.z * a);
+            v[3] = silu_acc(pv[u][0].w + qv[u][0].w + wr0.w * r + wa0.w * a);
+            v[4] = silu_acc(pv[u][1].x + qv[u][1].x + wr1.x * r + wa1.x * a);
+            v[5] = silu_acc(pv[u][1].y + qv[u][1].y + wr1.y * r + wa1.y * a);
+            v[6] = silu_acc(pv[u][1].z + qv[u][1].z + wr1.z * r + wa1.z * a);
+            v[7] = silu_acc(pv[u][1].w + qv[u][1].w + wr1.w * r + wa1.w * a);
             store_operand8<PREC_BF16X3>(dst_tile, ASPL, j, kc8, v);    // rows >= ne: finite, multiplied by zero gradients
         }
     };
@@ -240,11 +256,23 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
         fence_after_sync();
     };
 
+    // wait until the weight-gradient MMAs issued last have finished reading their operand tiles
+    auto wait_wg = [&]() {
+        if (wg_pending) {
+            if (tid == 0) mbar_wait(&mbar_wg, phase_wg);
+            phase_wg ^= 1;
+            wg_pending = 0;
+            __syncthreads();
+            fence_after_sync();
+        }
+    };
+
     while (true) {
         const int n0 = s_tile[cur][0], n1 = s_tile[cur][1], p0 = s_tile[cur][2], ne = s_tile[cur][3];
         if (n0 >= nend) break;
         const BwdMeta& mt = meta[cur];
         const bool row_valid = erow < ne;
+        wait_wg();              // WG 2 of the previous tile still reads X and Y
 
         // ---- t1 -> X ; MMA 1: z2 = t1 W2^T ; meanwhile prefetch the next tile's scalars ------------
         gather_t1(sX, mt, ne);
@@ -278,7 +306,7 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
             for (int g = 0; g < 2; ++g) {
                 float m8[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) silu_both(z[8 * g + i] + vec[BT_CW * cq + 8 * g + i], m8[i], d2[8 * g + i]);
+                for (int i = 0; i < 8; ++i) silu_both_acc(z[8 * g + i] + vec[BT_CW * cq + 8 * g + i], m8[i], d2[8 * g + i]);
                 if (HAS_COORD) store_operand8<PREC_BF16X3>(sY, ASPL, erow, 2 * cq + g, m8);
             }
         }
@@ -296,7 +324,7 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
 #pragma unroll
                 for (int i = 0; i < BT_CW; ++i) {
                     float u, d3;
-                    silu_both(z[i] + vec[64 + BT_CW * cq + i], u, d3);
+                    silu_both_acc(z[i] + vec[64 + BT_CW * cq + i], u, d3);
                     const float w = vec[128 + BT_CW * cq + i];
                     cpart = fmaf(w, u, cpart);
                     g3[i] = gc * w * d3;            // gc == 0 on rows beyond the tile
@@ -314,10 +342,21 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
                 }
             }
             // ---- MMA 3: gm = gz3 W3 ; WG 3: gW3 += gz3^T m --------------------------------------------------
-            run_mma([&] {
+            fence_async_smem();
+            fence_before_sync();
+            __syncthreads();
+            if (tid == 0) {
+                fence_after_sync();
                 issue_x3(tmem + 128, gX, gW3t, 4, id_dgrad, 0);
+                mma_commit(&mbar);
                 issue_x3(tmem + 320, gXt, gYt, 8, id_wgrad, wg_started);
-            });
+                mma_commit(&mbar_wg);
+                mbar_wait(&mbar, phase);
+            }
+            phase ^= 1;
+            wg_pending = 1;
+            __syncthreads();
+            fence_after_sync();
             tmem_ld<BT_CW>(t_lane + 128, gm);
         }
         // ---- gz2 = (gm + ghn[dst]) silu'(z2) -> X ; t1 re-gathered -> Y ---------------------------------------
@@ -338,6 +377,7 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
                 for (int i = 0; i < BT_CW; ++i) g2[i] = 0.0f;
             }
             acc_gb2 += warp_colsum16(g2, lane);
+            wait_wg();          // WG 3 (if any) must be done with X (gz3) and Y (m) before they are overwritten
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
                 float v8[8];
@@ -348,11 +388,22 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
         }
         gather_t1(sY, mt, ne);
         // ---- MMA 4: gt1 = gz2 W2 ; WG 2: gW2 += gz2^T t1 -------------------------------------------------------
-        run_mma([&] {
+        fence_async_smem();
+        fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            fence_after_sync();
             issue_x3(tmem + 192, gX, gW2t, 4, id_dgrad, 0);
+            mma_commit(&mbar);
             issue_x3(tmem + 256, gXt, gYt, 8, id_wgrad, wg_started);
-        });
+            mma_commit(&mbar_wg);
+            mbar_wait(&mbar, phase);
+        }
+        phase ^= 1;
+        wg_pending = 1;
         wg_started = 1;
+        __syncthreads();
+        fence_after_sync();
         // ---- epilogue 4: gz1 = gt1 silu'(z1) -> global + fp32 tile ; gr, gwr, gwa ------------------------------
         {
             float gt1[BT_CW], g1[BT_CW], gr_[BT_CW], ga_[BT_CW];
@@ -370,7 +421,7 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
                     for (int i = 0; i < 4; ++i) {
                         const int c = BT_CW * cq + 4 * g + i;
                         const float wrc = vec[192 + c];
-                        const float gz = gt1[4 * g + i] * dsilu(z1[i] + wrc * r + vec[256 + c] * a);
+                        const float gz = gt1[4 * g + i] * dsilu_acc(z1[i] + wrc * r + vec[256 + c] * a);
                         g1[4 * g + i] = gz;
                         gr_[4 * g + i] = gz * r;
                         ga_[4 * g + i] = gz * a;
@@ -432,11 +483,12 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
             }
         }
         cur ^= 1;
-        // no barrier needed: the next tile's first shared-memory writes go to X (all MMAs reading it were
-        // waited for); F32 / e_* are next written after several barriers of the next iteration
+        // the next iteration starts with wait_wg(): WG 2 is still reading X and Y; F32 / e_* are next written
+        // after several barriers of the next iteration
     }
 
     // ---- per-CTA partials: weight gradients from TMEM, vector gradients from the running registers -----------
+    wait_wg();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
