@@ -14,7 +14,7 @@
 
 namespace is {
 
-template <int PREC, int NT>
+template <int PREC, int NT, bool FAST>
 __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
 node_post_pre_tc_kernel(const float* __restrict__ h, int64_t ldh, int F, const float* __restrict__ hn,
                         const float* __restrict__ W5, const float* __restrict__ b5,
@@ -113,7 +113,7 @@ node_post_pre_tc_kernel(const float* __restrict__ h, int64_t ldh, int F, const f
             for (int g = 0; g < CW / 8; ++g) {
                 float v[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = act<PREC>(z[8 * g + i] + vec[CW * cq + 8 * g + i]);
+                for (int i = 0; i < 8; ++i) v[i] = act<PREC, FAST>(z[8 * g + i] + vec[CW * cq + 8 * g + i]);
                 store_operand8<PREC>(sA, ASPL, erow, (CW / 8) * cq + g, v);
             }
         }
@@ -162,20 +162,20 @@ node_post_pre_tc_kernel(const float* __restrict__ h, int64_t ldh, int F, const f
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
-template <int PREC, int NT>
+template <int PREC, int NT, bool FAST>
 static int launch_node_tc(const float* h, int64_t ldh, int F, const float* hn, const float* W5, const float* b5,
                           const float* W6, const float* b6, float* h_out, const float* W1n, const float* b1n,
                           float* PQn, int64_t M, cudaStream_t st) {
     using C = TcCfg<PREC>;
     const size_t smem = (size_t)C::NSPLIT * (C::A_BYTES + 5 * C::W_BYTES) + 3 * 64 * sizeof(float) + 128;
-    cudaError_t e = cudaFuncSetAttribute(node_post_pre_tc_kernel<PREC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(node_post_pre_tc_kernel<PREC, NT, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     int64_t tiles = (M + IS_TM - 1) / IS_TM;
     int64_t cap = (int64_t)sms * (NT == 256 ? 2 : 1);
     int grid = (int)(tiles < cap ? tiles : cap);
-    node_post_pre_tc_kernel<PREC, NT><<<grid < 1 ? 1 : grid, NT, smem, st>>>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, M);
+    node_post_pre_tc_kernel<PREC, NT, FAST><<<grid < 1 ? 1 : grid, NT, smem, st>>>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, M);
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
@@ -187,18 +187,21 @@ using namespace is;
 extern "C" {
 
 // node_mlp of layer l fused with the per-node half of layer l+1's first edge-MLP layer (W1n / b1n / PQn
-// may be NULL for the last layer).  precision: 0 = bf16, 3 = bf16x3 (fp32-accurate).  W1n must be the
+// may be NULL for the last layer).  precision: 0 = bf16, 3 = bf16x3 (fp32-accurate); fast_act: 5-instruction
+// SiLU (inference) vs accurate expf (training forward).  W1n must be the
 // [64, 130] weight of a 64-wide layer.
 int is_egnn_node_post_pre_tc(const float* h, int64_t ldh, int F, const float* hn, const float* W5, const float* b5,
                              const float* W6, const float* b6, float* h_out, const float* W1n, const float* b1n,
-                             float* PQn, int64_t n_nodes, int precision, void* stream) {
+                             float* PQn, int64_t n_nodes, int precision, int fast_act, void* stream) {
     if (!(F == 20 || F == 64) || n_nodes <= 0) return IS_ERR_ARG;
     if ((W1n == nullptr) != (PQn == nullptr)) return IS_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == PREC_BF16)
-        return launch_node_tc<PREC_BF16, 256>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, n_nodes, st);
+        return launch_node_tc<PREC_BF16, 256, true>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, n_nodes, st);
+    if (precision == PREC_BF16X3 && fast_act)
+        return launch_node_tc<PREC_BF16X3, 512, true>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, n_nodes, st);
     if (precision == PREC_BF16X3)
-        return launch_node_tc<PREC_BF16X3, 512>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, n_nodes, st);
+        return launch_node_tc<PREC_BF16X3, 512, false>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, n_nodes, st);
     return IS_ERR_ARG;
 }
 

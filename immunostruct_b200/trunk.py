@@ -46,10 +46,9 @@ class StructureTrunk:
             # inference: the whole stack through the fused kernels, nothing saved for a backward pass
             node_feat = IF.egnn_stack_infer(graph_data, xin, edge_feat, [l.kernel_params() for l in self.GCN_layers])
             return self.self_attention.pooled(graph_data, node_feat, want_attn=want_attn, want_nodes=want_nodes)
-        last = len(self.GCN_layers) - 1
-        for i, layer in enumerate(self.GCN_layers):
-            # the last layer's coordinates are never consumed (hybrid_models.py:323-326)
-            node_feat, coord_feat = layer(graph_data, node_feat, coord_feat, edge_feat, update_coords=i != last)
+        # training: one autograd node for the whole stack (the last layer's coordinates are never consumed,
+        # hybrid_models.py:323-326, so its coordinate branch is skipped and coord_mlp gets no gradient)
+        node_feat = IF.egnn_stack(graph_data, xin, edge_feat, [l.kernel_params() for l in self.GCN_layers])
         return self.self_attention.pooled(graph_data, node_feat, want_attn=want_attn, want_nodes=want_nodes)
 
 

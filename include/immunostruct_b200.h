@@ -62,7 +62,7 @@ int is_egnn_edge_fwd_tc(const int* indptr, const int* csr_src, const int* csr_ds
  * tensor cores (inference path).  W1n/b1n/PQn NULL for the last layer.  precision 0 = bf16, 3 = bf16x3. */
 int is_egnn_node_post_pre_tc(const float* h, int64_t ldh, int F, const float* hn, const float* W5, const float* b5,
                              const float* W6, const float* b6, float* h_out, const float* W1n, const float* b1n,
-                             float* PQn, int64_t n_nodes, int precision, void* stream);
+                             float* PQn, int64_t n_nodes, int precision, int fast_act, void* stream);
 int is_egnn_node_post_fwd(const float* h, int64_t ldh, int F, const float* hn, const float* W5, const float* b5,
                           const float* W6, const float* b6, float* h_out, int64_t n_nodes, void* stream);
 int is_egnn_node_post_bwd(const float* gh_out, const float* h, int64_t ldh, int F, const float* hn,

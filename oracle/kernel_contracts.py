@@ -117,7 +117,7 @@ def egnn_node_post_fwd(h, hn, W5, b5, W6, b6, h_out):
     h_out.copy_(F.linear(_silu(F.linear(torch.cat([h, hn], 1), W5, b5)), W6, b6))
 
 
-def egnn_node_post_pre_tc(h, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, precision):
+def egnn_node_post_pre_tc(h, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, precision, fast_act=True):
     egnn_node_post_fwd(h, hn, W5, b5, W6, b6, h_out)
     if W1n is not None:
         egnn_node_pre_fwd(h_out, W1n, b1n, PQn)
