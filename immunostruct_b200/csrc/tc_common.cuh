@@ -59,16 +59,14 @@ __device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
     return q;
 }
 
-// store 8 consecutive K values (k = 8*kc8 .. 8*kc8+7 of a 64-wide K block) of operand row `row`;
-// `split_bytes` = distance between the split-term copies of the tile
+// store 8 consecutive K values (one 16-byte bf16 chunk per split term) at byte address p0 of split term 0;
+// `split_bytes` = distance between the split-term copies of the tile.  bf16 / bf16x3 only.
 template <int PREC>
-__device__ __forceinline__ void store_operand8(uint8_t* __restrict__ tile, uint32_t split_bytes, int row, int kc8,
-                                               const float (&v)[8]) {
-    using C = TcCfg<PREC>;
-    const uint32_t rbase = (uint32_t)((row >> 3) * C::SBO + (row & 7) * 16);
+__device__ __forceinline__ void store_chunk8(uint8_t* __restrict__ p0, uint32_t split_bytes, const float (&v)[8]) {
+    static_assert(PREC == PREC_BF16 || PREC == PREC_BF16X3, "bf16 operand tiles only");
     if (PREC == PREC_BF16) {
-        *reinterpret_cast<uint4*>(tile + rbase + kc8 * kLBO) = pack8_bf16(v);
-    } else if (PREC == PREC_BF16X3) {
+        *reinterpret_cast<uint4*>(p0) = pack8_bf16(v);
+    } else {
         // three bf16 terms by truncation (top 16 bits); every residual is exact in fp32, so the sum of
         // the terms differs from v only by the truncation of the last one (2^-24 relative)
         uint32_t q1[4], q2[4], q3[4];
@@ -82,10 +80,21 @@ __device__ __forceinline__ void store_operand8(uint8_t* __restrict__ tile, uint3
             q2[i] = __byte_perm(a2, b2, 0x7632);
             q3[i] = __byte_perm(__float_as_uint(sa), __float_as_uint(sb), 0x7632);
         }
-        uint8_t* p0 = tile + rbase + kc8 * kLBO;
         *reinterpret_cast<uint4*>(p0) = make_uint4(q1[0], q1[1], q1[2], q1[3]);
         *reinterpret_cast<uint4*>(p0 + split_bytes) = make_uint4(q2[0], q2[1], q2[2], q2[3]);
         *reinterpret_cast<uint4*>(p0 + 2 * split_bytes) = make_uint4(q3[0], q3[1], q3[2], q3[3]);
+    }
+}
+
+// store 8 consecutive K values (k = 8*kc8 .. 8*kc8+7 of a 64-wide K block) of operand row `row`;
+// `split_bytes` = distance between the split-term copies of the tile
+template <int PREC>
+__device__ __forceinline__ void store_operand8(uint8_t* __restrict__ tile, uint32_t split_bytes, int row, int kc8,
+                                               const float (&v)[8]) {
+    using C = TcCfg<PREC>;
+    const uint32_t rbase = (uint32_t)((row >> 3) * C::SBO + (row & 7) * 16);
+    if constexpr (PREC != PREC_TF32X3) {
+        store_chunk8<PREC>(tile + rbase + kc8 * kLBO, split_bytes, v);
     } else {
         float hi[8], lo[8];
 #pragma unroll

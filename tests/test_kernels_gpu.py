@@ -161,10 +161,12 @@ def test_egnn_forward_kernels(case, f):
     assert int(gb.status.item()) == 0
 
 
-@pytest.mark.parametrize("prec,tol", [(_C.PREC_BF16X3, 1e-5), (_C.PREC_TF32X3, 1e-5), (_C.PREC_BF16, 2e-2)])
+@pytest.mark.parametrize("prec,tol", [(_C.PREC_BF16X3, 1e-5), (_C.PREC_TF32X3, 1e-5), (_C.PREC_BF16, 2e-2),
+                                      (_C.PREC_BF16X3 | 16, 1e-5), (_C.PREC_BF16 | 16, 2e-2)])
 @pytest.mark.parametrize("f", [20, 64])
 def test_egnn_edge_forward_tensor_core(case, f, prec, tol):
-    """tcgen05 edge kernel vs the same CPU contract: 3xTF32 at the fp32 tolerance, bf16 at 2e-2."""
+    """tcgen05 edge kernels vs the same CPU contract: bf16x3 / 3xTF32 at the fp32 tolerance, bf16 at 2e-2.
+    ``prec | 16`` = the first-generation kernel (SIMT destination-side sums), kept for A/B timing."""
     arrays, gb, cg = case
     gen = torch.Generator().manual_seed(37)
     n = gb.n_nodes
