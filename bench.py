@@ -362,7 +362,6 @@ def main():
             "bf16": lambda: _C.egnn_edge_fwd_tc(gb, PQ, x, arr["edge_attr"], 64, W1, W2, b2, W3, b3, w4, True, _C.PREC_BF16, hn, xo),
             # first-generation tensor-core kernel (SIMT destination-side sums), for comparison
             "bf16x3_gen1": lambda: _C.egnn_edge_fwd_tc(gb, PQ, x, arr["edge_attr"], 64, W1, W2, b2, W3, b3, w4, True, _C.PREC_BF16X3 | 16, hn, xo, fast_act=True),
-            "bf16x3_gen2": lambda: _C.egnn_edge_fwd_tc(gb, PQ, x, arr["edge_attr"], 64, W1, W2, b2, W3, b3, w4, True, _C.PREC_BF16X3 | 32, hn, xo, fast_act=True),
             "bf16_gen1": lambda: _C.egnn_edge_fwd_tc(gb, PQ, x, arr["edge_attr"], 64, W1, W2, b2, W3, b3, w4, True, _C.PREC_BF16 | 16, hn, xo),
         }
         t_all = {k: time_kernel(fn) for k, fn in variants.items()}

@@ -126,6 +126,7 @@ __device__ __forceinline__ void issue_x3(uint32_t tmem_d, const OpGeom& a, const
     uint32_t acc = accumulate;
 #pragma unroll
     for (int t = 0; t < 6; ++t)
+#pragma unroll 8
         for (int ks = 0; ks < nks; ++ks) {
             mma_bf16(tmem_d, make_smem_desc(a.base + ta[t] * a.split + ks * a.step, a.lbo, a.sbo),
                      make_smem_desc(b.base + tb[t] * b.split + ks * b.step, b.lbo, b.sbo), idesc, acc);
@@ -245,10 +246,13 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
-        if (tid == 0) {
-            fence_after_sync();
-            fn();
-            mma_commit(&mbar);
+        if (warp == 0) {              // one elected lane of the converged warp issues (bare UTCHMMA, no election loop)
+            if (elect_one()) {
+                fence_after_sync();
+                fn();
+                mma_commit(&mbar);
+            }
+            __syncwarp();
             mbar_wait(&mbar, phase);
         }
         phase ^= 1;
@@ -279,10 +283,13 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
-        if (tid == 0) {
-            fence_after_sync();
-            issue_x3(tmem + 0, gX, gW2, 4, id_fwd, 0);
-            mma_commit(&mbar);
+        if (warp == 0) {
+            if (elect_one()) {
+                fence_after_sync();
+                issue_x3(tmem + 0, gX, gW2, 4, id_fwd, 0);
+                mma_commit(&mbar);
+            }
+            __syncwarp();
         }
         if (warp >= BT_NW - 4) {
             int tn0, tn1, tp0, tne;
@@ -345,12 +352,15 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
             fence_async_smem();
             fence_before_sync();
             __syncthreads();
-            if (tid == 0) {
-                fence_after_sync();
-                issue_x3(tmem + 128, gX, gW3t, 4, id_dgrad, 0);
-                mma_commit(&mbar);
-                issue_x3(tmem + 320, gXt, gYt, 8, id_wgrad, wg_started);
-                mma_commit(&mbar_wg);
+            if (warp == 0) {
+                if (elect_one()) {
+                    fence_after_sync();
+                    issue_x3(tmem + 128, gX, gW3t, 4, id_dgrad, 0);
+                    mma_commit(&mbar);
+                    issue_x3(tmem + 320, gXt, gYt, 8, id_wgrad, wg_started);
+                    mma_commit(&mbar_wg);
+                }
+                __syncwarp();
                 mbar_wait(&mbar, phase);
             }
             phase ^= 1;
@@ -391,12 +401,15 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
-        if (tid == 0) {
-            fence_after_sync();
-            issue_x3(tmem + 192, gX, gW2t, 4, id_dgrad, 0);
-            mma_commit(&mbar);
-            issue_x3(tmem + 256, gXt, gYt, 8, id_wgrad, wg_started);
-            mma_commit(&mbar_wg);
+        if (warp == 0) {
+            if (elect_one()) {
+                fence_after_sync();
+                issue_x3(tmem + 192, gX, gW2t, 4, id_dgrad, 0);
+                mma_commit(&mbar);
+                issue_x3(tmem + 256, gXt, gYt, 8, id_wgrad, wg_started);
+                mma_commit(&mbar_wg);
+            }
+            __syncwarp();
             mbar_wait(&mbar, phase);
         }
         phase ^= 1;

@@ -160,10 +160,13 @@ edge_fwd_tc_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
         fence_async_smem();
         fence_before_sync();
         __syncthreads();                                                           // S1
-        if (tid == 0) {
-            fence_after_sync();
-            issue_gemm<PREC>(tmem, a_addr, C::A_BYTES, w2_addr, C::W_BYTES, 64, 0);
-            mma_commit(&mbar[0]);
+        if (warp == 0) {              // one elected lane of the converged warp issues (bare UTCHMMA, no election loop)
+            if (elect_one()) {
+                fence_after_sync();
+                issue_gemm<PREC>(tmem, a_addr, C::A_BYTES, w2_addr, C::W_BYTES, 64, 0);
+                mma_commit(&mbar[0]);
+            }
+            __syncwarp();
         }
         // ---- while MMA 1 runs: walk to the next tile and prefetch its per-edge scalars ------------
         if (warp >= NW - 4) {
@@ -202,10 +205,13 @@ edge_fwd_tc_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
         fence_async_smem();
         fence_before_sync();
         __syncthreads();                                                           // S3
-        if (HAS_COORD && tid == 0) {
-            fence_after_sync();
-            issue_gemm<PREC>(tmem + 64, a_addr, C::A_BYTES, w3_addr, C::W_BYTES, 64, 0);
-            mma_commit(&mbar[1]);
+        if (HAS_COORD && warp == 0) {
+            if (elect_one()) {
+                fence_after_sync();
+                issue_gemm<PREC>(tmem + 64, a_addr, C::A_BYTES, w3_addr, C::W_BYTES, 64, 0);
+                mma_commit(&mbar[1]);
+            }
+            __syncwarp();
         }
 
         // ---- hn aggregation (overlaps MMA 2): one warp per destination node -----------------------
@@ -292,11 +298,7 @@ static int launch_tc(const EdgeCommon& c, float* hn, float* x_out, int grid, cud
     return launch_tc2<PREC, HAS_COORD, NT, false>(c, hn, x_out, grid, st);
 }
 
-// second-generation kernel (egnn_tc2.cu): bf16 / bf16x3 with the destination-side sums on the tensor cores
-int launch_edge_fwd_tc2(const EdgeCommon& c, float* hn, float* x_out, int precision, bool update_coords, bool fast,
-                        cudaStream_t st);
-
-// third-generation kernel (egnn_tc2.cu): the same pipeline, warp-specialised and asynchronous
+// warp-specialised asynchronous kernel (egnn_tc2.cu): bf16 / bf16x3, destination-side sums on the tensor cores
 int launch_edge_fwd_ws(const EdgeCommon& c, float* hn, float* x_out, int precision, bool update_coords, bool fast,
                        cudaStream_t st);
 
@@ -307,8 +309,8 @@ using namespace is;
 extern "C" {
 
 // Tensor-core variant of is_egnn_edge_fwd.  precision: 0 = bf16 operands, 2 = 3xTF32, 3 = bf16x3 (both fp32-accurate).
-// precision | 16 selects the first-generation kernel of this file for bf16 / bf16x3, precision | 32 the lock-step
-// second-generation kernel (both kept for A/B timing); default = the warp-specialised kernel of egnn_tc2.cu.
+// precision | 16 selects the lock-step first-generation kernel of this file for bf16 / bf16x3 (kept for A/B timing);
+// default = the warp-specialised kernel of egnn_tc2.cu.
 // fast_act: use the 5-instruction SiLU in the fp32-accurate modes (inference); 0 keeps expf (training forward).
 int is_egnn_edge_fwd_tc(const int* indptr, const int* csr_src, const int* csr_dst, const int* csr_eid,
                         const float* PQ, const float* x, int64_t ldx, const float* edge_attr,
@@ -316,8 +318,8 @@ int is_egnn_edge_fwd_tc(const int* indptr, const int* csr_src, const int* csr_ds
                         const float* W3, const float* b3, const float* w4, int update_coords, int precision,
                         int fast_act, float* hn, float* x_out, int64_t n_nodes, int* status, void* stream) {
     if (!(F == 20 || F == 64) || n_nodes <= 0 || n_nodes > 0x7fffffff) return IS_ERR_ARG;
-    const bool legacy = (precision & 16) != 0, gen2 = (precision & 32) != 0;
-    precision &= ~48;
+    const bool legacy = (precision & 16) != 0;
+    precision &= ~16;
     if (precision != PREC_BF16 && precision != PREC_TF32X3 && precision != PREC_BF16X3) return IS_ERR_ARG;
     EdgeCommon c;
     c.indptr = indptr; c.csr_src = csr_src; c.csr_dst = csr_dst; c.csr_eid = csr_eid;
@@ -330,7 +332,6 @@ int is_egnn_edge_fwd_tc(const int* indptr, const int* csr_src, const int* csr_ds
     if (g > (int64_t)sms * per_sm) g = (int64_t)sms * per_sm;
     const int grid = (int)(g < 1 ? 1 : g);
     cudaStream_t st = (cudaStream_t)stream;
-    if (gen2 && precision != PREC_TF32X3) return launch_edge_fwd_tc2(c, hn, x_out, precision, update_coords != 0, fast_act != 0, st);
     if (!legacy && precision != PREC_TF32X3) return launch_edge_fwd_ws(c, hn, x_out, precision, update_coords != 0, fast_act != 0, st);
     if (precision == PREC_BF16)
         return update_coords ? launch_tc<PREC_BF16, true, 256>(c, hn, x_out, grid, st, fast_act != 0) : launch_tc<PREC_BF16, false, 256>(c, hn, x_out, grid, st, fast_act != 0);

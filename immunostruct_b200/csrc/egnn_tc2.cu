@@ -1,28 +1,30 @@
-// EGNN edge forward, second-generation tcgen05 kernel (bf16 and bf16x3 operands), sm_100a.
+// EGNN edge forward on the tcgen05 tensor cores, warp-specialised and asynchronous (bf16 and bf16x3 operands), sm_100a.
 //
-// Same contract as is::edge_fwd_kernel (egnn.cu) / edge_fwd_tc_kernel (egnn_tc.cu).  Differences to the
-// first tensor-core kernel, all driven by its ncu source counters (profiles/r01_tc_bf16x3_edge_fwd_full.md:
-// 35 % of the executed instructions were the two SIMT aggregation loops):
+// Same contract as is::edge_fwd_kernel (egnn.cu) / edge_fwd_tc_kernel (egnn_tc.cu, the lock-step first generation).
+// What changed, each step driven by ncu source counters of the previous kernel (profiles/):
 //
 //   * the destination-side feature sum  hn[v] = sum_{e -> v} m[e]  is a THIRD MMA of the tile:
 //         hn_tile[32 nodes, 64] = S[32, 128 edges] * m[128 edges, 64]
 //     with S the tile's 0/1 segment-selector matrix (exact in bf16, built from the tile's CSR offsets with two
 //     16-byte stores per thread) and m read straight from the operand tile that epilogue 1 has just written
 //     for MMA 2, through a descriptor with LBO / SBO swapped and the MN-major bit set (= its transpose, no
-//     second copy).  M = 64 accumulator (row r in TMEM lane 32 (r / 16) + r % 16), written over the dead
-//     accumulator of MMA 1, so the CTA still owns only 128 TMEM columns.  In the bf16x3 mode the three split
-//     terms of m are accumulated (S m3 + S m2 + S m1): hn keeps fp32 accuracy.
+//     second copy).  M = 64 accumulator (row r in TMEM lane 32 (r / 16) + r % 16).  In the bf16x3 mode the three
+//     split terms of m are accumulated (S m3 + S m2 + S m1): hn keeps fp32 accuracy.  (35 % of the first kernel's
+//     executed instructions were its two SIMT aggregation loops.)
 //   * the coordinate aggregation is one thread per (node, component) instead of one warp per node;
 //   * operand tiles are unpadded (LBO = 128 bytes): the gather maps a quarter-warp to 4 rows x 2 K-chunks with
-//     the row half chosen by the chunk parity, so every 16-byte operand store of a warp is conflict free
-//     without the 144-byte padding -- that is what makes room for S at two CTAs per SM in the bf16x3 mode.
+//     the row half chosen by the chunk parity, so every 16-byte operand store of a warp is conflict free;
+//   * MMAs are issued by ONE ELECTED LANE OF A CONVERGED WARP with compile-time descriptor offsets: ptxas then
+//     emits bare UTCHMMA instructions.  Issued under `if (tid == 0)` every MMA was wrapped in an election loop
+//     (~13 instructions, one issuing thread): 72 small MMAs per tile cost ~4 000 cycles of pure issue;
+//   * the phases of different tiles overlap (see the third-generation comment below).
 //
 // Per tile (<= 128 in-edges of <= 32 consecutive destination nodes, CSR order):
-//   build S, gather t1 = silu(P[src] + Q[dst] + w_r r + w_a a) -> A tile            (all warps)
-//   MMA 1  z2 = t1 W2^T            -> TMEM [0,64)      | prefetch of the next tile's per-edge scalars
-//   epilogue 1: m = silu(z2 + b2)  -> A tile (bf16 / three bf16 terms)
-//   MMA 2  z3 = m W3^T             -> TMEM [64,128)    (coordinate branch only)
-//   MMA 3  hn = S m                -> TMEM [0,64)      (M = 64)
+//   build S, gather t1 = silu(P[src] + Q[dst] + w_r r + w_a a) -> operand tile
+//   MMA 1  z2 = t1 W2^T            -> TMEM acc1
+//   epilogue 1: m = silu(z2 + b2)  -> operand tile (bf16 / three bf16 terms)
+//   MMA 2  z3 = m W3^T             -> TMEM acc2      (coordinate branch only)
+//   MMA 3  hn = S m                -> TMEM hn        (M = 64)
 //   epilogue 2: c = w4 . silu(z3 + b3);  hn rows TMEM -> global;  x' = x + mean(c dhat)
 #include "common.cuh"
 #include "egnn_common.cuh"
@@ -32,7 +34,6 @@
 namespace is {
 
 namespace e2 {
-constexpr int NT = 256;
 constexpr uint32_t LBO = 128;                    // bytes between K-adjacent core matrices (unpadded)
 constexpr uint32_t SBO = 8 * LBO;                // bytes between 8-row groups of a 64-wide bf16 tile
 constexpr uint32_t A_BYTES = 16 * SBO;           // 128-row operand tile, one split term (16 KB)
@@ -115,235 +116,10 @@ __device__ __forceinline__ void issue_segsum(uint32_t tmem_d, uint32_t s_addr, u
 }
 }  // namespace e2
 
-template <int PREC, bool HAS_COORD, bool FAST>
-__global__ void __launch_bounds__(e2::NT, PREC == PREC_BF16 ? 3 : 2)
-edge_fwd_tc2_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_out) {
-    using namespace e2;
-    using C = TcCfg<PREC>;
-    constexpr int NS = C::NSPLIT;
-    constexpr int NW = NT / 32;                 // 8 warps
-    constexpr int CW = 32;                      // accumulator columns per thread (two column halves)
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    uint8_t* sS = smem_raw;                                            // selector tile (rows 32..63 alias sA)
-    uint8_t* sA = sS + S_BYTES;                                        // [NS][A_BYTES] t1, then m
-    uint8_t* sW2 = sA + NS * A_BYTES;                                  // [NS][W_BYTES]
-    uint8_t* sW3 = sW2 + NS * W_BYTES;
-    float* vec = reinterpret_cast<float*>(sW3 + NS * W_BYTES);         // b2, b3, w4, wr, wa
-    float* e_c = vec + 5 * 64;                                         // [2][128] partial c per column half
-    Meta* meta = reinterpret_cast<Meta*>(e_c + 2 * IS_TM);             // [2]
-    __shared__ int s_tile[2][4];
-    __shared__ __align__(8) uint64_t mbar[2];
-    __shared__ uint32_t s_tmem;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ldw1 = 2 * p.F + 2;
-    if (warp == 0) tmem_alloc(&s_tmem, 128);
-    if (tid == 32) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
-    for (int idx = tid; idx < 64 * 64; idx += NT) {                    // stage W2 / W3 as B operands
-        const int n = idx >> 6, k = idx & 63;
-        store_weight1<PREC>(sW2, W_BYTES, n, k, __ldg(p.W2 + idx));
-        store_weight1<PREC>(sW3, W_BYTES, n, k, HAS_COORD ? __ldg(p.W3 + idx) : 0.0f);
-    }
-    if (tid < 64) {
-        vec[tid] = p.b2[tid];
-        vec[64 + tid] = HAS_COORD ? p.b3[tid] : 0.0f;
-        vec[128 + tid] = HAS_COORD ? p.w4[tid] : 0.0f;
-        vec[192 + tid] = p.W1[tid * ldw1 + 2 * p.F];
-        vec[256 + tid] = p.W1[tid * ldw1 + 2 * p.F + 1];
-    }
-    // the operand tile is read as "selector rows 32..63" by the M = 64 MMA before it is first written: any
-    // finite or non-finite content is harmless there (those accumulator rows are never read), but keep it defined
-    for (int idx = tid; idx < (int)(NS * A_BYTES / 16); idx += NT) reinterpret_cast<uint4*>(sA)[idx] = make_uint4(0, 0, 0, 0);
-    const int chunk = (p.n_nodes + gridDim.x - 1) / gridDim.x;
-    const int nbeg = blockIdx.x * chunk;
-    const int nend = min(p.n_nodes, nbeg + chunk);
-    // prologue: first tile + its per-edge scalars (the last four warps are the prefetch warps)
-    if (warp >= NW - 4) {
-        int tn0, tn1, tp0, tne;
-        next_tile(p.indptr, nbeg, nend, p.status, lane, tn0, tn1, tp0, tne);
-        if (warp == NW - 4 && lane == 0) { s_tile[0][0] = tn0; s_tile[0][1] = tn1; s_tile[0][2] = tp0; s_tile[0][3] = tne; }
-        load_meta(p, meta[0], (warp - (NW - 4)) * 32 + lane, tn0, tn1, tp0, tne);
-    }
-    fence_async_smem();
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-    const uint32_t tmem = s_tmem;
-    const uint32_t s_addr = smem_u32(sS), a_addr = smem_u32(sA), w2_addr = smem_u32(sW2), w3_addr = smem_u32(sW3);
-    // epilogue mapping: TMEM lane quarter q = warp % 4 (rows 32q + lane), column half cq = warp / 4
-    const int q = warp & 3, cq = warp >> 2, erow = 32 * q + lane;
-    const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16) + CW * cq;
-    // gather mapping: K-chunk kc (8 features) = lane / 4; a quarter-warp covers rows r4 + 4 * (chunk parity ^ pass
-    // parity) of an 8-row group for two adjacent chunks: its eight 16-byte stores fill 128 distinct bytes of a bank line
-    const int r4 = lane & 3, kc = lane >> 2;
-    const float4 wr0 = *reinterpret_cast<const float4*>(vec + 192 + 8 * kc), wr1 = *reinterpret_cast<const float4*>(vec + 196 + 8 * kc);
-    const float4 wa0 = *reinterpret_cast<const float4*>(vec + 256 + 8 * kc), wa1 = *reinterpret_cast<const float4*>(vec + 260 + 8 * kc);
-    uint32_t phase = 0;
-    int cur = 0;
-
-    while (true) {
-        const int n0 = s_tile[cur][0], n1 = s_tile[cur][1], ne = s_tile[cur][3];
-        if (n0 >= nend) break;
-        const Meta& mt = meta[cur];
-
-        // ---- selector tile: S[node][edge] = 1 for the node's in-edges (two 16-byte chunks per thread) ----------
-        {
-            const int nl = lane, c0 = warp;                         // chunks c0 and c0 + 8 of node row nl
-            const int jb = mt.nptr[nl], je = mt.nptr[nl + 1];       // rows beyond the tile: jb = je = ne
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int c = c0 + 8 * u;
-                const int lo = min(max(jb - 8 * c, 0), 8), hi = min(max(je - 8 * c, 0), 8);
-                const uint32_t mask = (1u << hi) - (1u << lo);      // bits lo .. hi-1 (0 when hi <= lo: je >= jb)
-                uint4 w;
-                w.x = ((mask >> 0) & 1u) * 0x3F80u + ((mask >> 1) & 1u) * 0x3F800000u;
-                w.y = ((mask >> 2) & 1u) * 0x3F80u + ((mask >> 3) & 1u) * 0x3F800000u;
-                w.z = ((mask >> 4) & 1u) * 0x3F80u + ((mask >> 5) & 1u) * 0x3F800000u;
-                w.w = ((mask >> 6) & 1u) * 0x3F80u + ((mask >> 7) & 1u) * 0x3F800000u;
-                *reinterpret_cast<uint4*>(sS + (nl >> 3) * S_SBO + c * S_LBO + (nl & 7) * 16) = w;
-            }
-        }
-
-        // ---- gather -> A operand (t1): each warp owns two 8-row groups; both passes of a group are loaded first --
-#pragma unroll
-        for (int gi = 0; gi < 2; ++gi) {
-            const int g8 = 8 * (2 * warp + gi);
-            float4 pv[2][2], qv[2][2];
-            float rr[2], aa[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int j = g8 + r4 + 4 * ((kc & 1) ^ u);
-                const bool valid = j < ne;
-                const int s = valid ? mt.src[j] : 0, d = n0 + (valid ? (int)mt.dloc[j] : 0);
-                rr[u] = valid ? mt.r[j] : 0.0f;
-                aa[u] = valid ? mt.a[j] : 0.0f;
-                const float4* pp = reinterpret_cast<const float4*>(p.PQ + (size_t)s * 128 + 8 * kc);
-                const float4* qp = reinterpret_cast<const float4*>(p.PQ + (size_t)d * 128 + 64 + 8 * kc);
-                pv[u][0] = __ldg(pp); pv[u][1] = __ldg(pp + 1); qv[u][0] = __ldg(qp); qv[u][1] = __ldg(qp + 1);
-            }
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int j = g8 + r4 + 4 * ((kc & 1) ^ u);
-                const float r = rr[u], a = aa[u];
-                float v[8];
-                v[0] = act<PREC, FAST>(pv[u][0].x + qv[u][0].x + wr0.x * r + wa0.x * a);
-                v[1] = act<PREC, FAST>(pv[u][0].y + qv[u][0].y + wr0.y * r + wa0.y * a);
-                v[2] = act<PREC, FAST>(pv[u][0].z + qv[u][0].z + wr0.z * r + wa0.z * a);
-                v[3] = act<PREC, FAST>(pv[u][0].w + qv[u][0].w + wr0.w * r + wa0.w * a);
-                v[4] = act<PREC, FAST>(pv[u][1].x + qv[u][1].x + wr1.x * r + wa1.x * a);
-                v[5] = act<PREC, FAST>(pv[u][1].y + qv[u][1].y + wr1.y * r + wa1.y * a);
-                v[6] = act<PREC, FAST>(pv[u][1].z + qv[u][1].z + wr1.z * r + wa1.z * a);
-                v[7] = act<PREC, FAST>(pv[u][1].w + qv[u][1].w + wr1.w * r + wa1.w * a);
-                // rows beyond the tile's edges hold finite values: the selector has zeros there
-                store_chunk8<PREC>(sA + (j >> 3) * SBO + (j & 7) * 16 + kc * LBO, A_BYTES, v);
-            }
-        }
-        fence_async_smem();
-        fence_before_sync();
-        __syncthreads();                                                           // S1
-        if (tid == 0) {
-            fence_after_sync();
-            issue_fwd<PREC>(tmem, a_addr, w2_addr);
-            mma_commit(&mbar[0]);
-        }
-        // ---- while MMA 1 runs: walk to the next tile and prefetch its per-edge scalars ------------
-        if (warp >= NW - 4) {
-            int tn0, tn1, tp0, tne;
-            next_tile(p.indptr, n1, nend, p.status, lane, tn0, tn1, tp0, tne);
-            if (warp == NW - 4 && lane == 0) {
-                s_tile[cur ^ 1][0] = tn0; s_tile[cur ^ 1][1] = tn1; s_tile[cur ^ 1][2] = tp0; s_tile[cur ^ 1][3] = tne;
-            }
-            load_meta(p, meta[cur ^ 1], (warp - (NW - 4)) * 32 + lane, tn0, tn1, tp0, tne);
-        }
-        if (tid == 0) mbar_wait(&mbar[0], phase);      // one poller; everybody else parks on the barrier
-        __syncthreads();                                                           // S2
-        fence_after_sync();
-
-        // ---- epilogue 1: m = silu(acc0 + b2) -> operand tile (A of MMA 2, transposed B of MMA 3) -------------
-        {
-            float z[CW];
-            tmem_ld<CW>(t_lane, z);
-#pragma unroll
-            for (int g = 0; g < CW / 8; ++g) {
-                const float4 b0 = *reinterpret_cast<const float4*>(vec + CW * cq + 8 * g);
-                const float4 b1 = *reinterpret_cast<const float4*>(vec + CW * cq + 8 * g + 4);
-                float m8[8];
-                m8[0] = act<PREC, FAST>(z[8 * g + 0] + b0.x); m8[1] = act<PREC, FAST>(z[8 * g + 1] + b0.y);
-                m8[2] = act<PREC, FAST>(z[8 * g + 2] + b0.z); m8[3] = act<PREC, FAST>(z[8 * g + 3] + b0.w);
-                m8[4] = act<PREC, FAST>(z[8 * g + 4] + b1.x); m8[5] = act<PREC, FAST>(z[8 * g + 5] + b1.y);
-                m8[6] = act<PREC, FAST>(z[8 * g + 6] + b1.z); m8[7] = act<PREC, FAST>(z[8 * g + 7] + b1.w);
-                store_chunk8<PREC>(sA + (erow >> 3) * SBO + (erow & 7) * 16 + ((CW / 8) * cq + g) * LBO, A_BYTES, m8);
-            }
-        }
-        fence_async_smem();
-        fence_before_sync();
-        __syncthreads();                                                           // S3
-        if (tid == 0) {
-            fence_after_sync();
-            if (HAS_COORD) issue_fwd<PREC>(tmem + 64, a_addr, w3_addr);
-            issue_segsum<PREC>(tmem, s_addr, a_addr, max(1, (ne + 15) >> 4));   // >= 1: zeroes the accumulator of an edge-less tile            // over the dead accumulator of MMA 1
-            mma_commit(&mbar[1]);
-            mbar_wait(&mbar[1], phase);
-        }
-        __syncthreads();                                                           // S4
-        fence_after_sync();
-
-        if (HAS_COORD) {
-            // ---- epilogue 2: c = w4 . silu(acc1 + b3) (each thread: one row, CW columns) ----------
-            float z[CW];
-            tmem_ld<CW>(t_lane + 64, z);
-            float c = 0.0f;
-#pragma unroll
-            for (int g = 0; g < CW / 4; ++g) {
-                const float4 b = *reinterpret_cast<const float4*>(vec + 64 + CW * cq + 4 * g);
-                const float4 w = *reinterpret_cast<const float4*>(vec + 128 + CW * cq + 4 * g);
-                c = fmaf(w.x, act<PREC, FAST>(z[4 * g + 0] + b.x), c);
-                c = fmaf(w.y, act<PREC, FAST>(z[4 * g + 1] + b.y), c);
-                c = fmaf(w.z, act<PREC, FAST>(z[4 * g + 2] + b.z), c);
-                c = fmaf(w.w, act<PREC, FAST>(z[4 * g + 3] + b.w), c);
-            }
-            e_c[cq * IS_TM + erow] = c;
-        }
-        // ---- hn rows: M = 64 accumulator, node row i sits in TMEM lane 32 (i / 16) + i % 16 ---------------------
-        if (q < 2) {
-            float z[CW];
-            tmem_ld<CW>(t_lane, z);
-            const int node = n0 + 16 * q + lane;
-            if (lane < 16 && node < n1) {
-                float4* dst = reinterpret_cast<float4*>(hn + (size_t)node * 64 + CW * cq);
-#pragma unroll
-                for (int g = 0; g < CW / 4; ++g) dst[g] = make_float4(z[4 * g], z[4 * g + 1], z[4 * g + 2], z[4 * g + 3]);
-            }
-        }
-        if (HAS_COORD) {
-            fence_before_sync();
-            __syncthreads();                                                       // S5
-            // ---- coordinate aggregation: one thread per (node, component) ----------------------------
-            if (tid < 3 * MAX_TILE_NODES) {
-                const int nl = tid / 3, comp = tid - 3 * nl, node = n0 + nl;
-                if (node < n1) {
-                    const int jb = mt.nptr[nl], je = mt.nptr[nl + 1];
-                    float sx = 0.0f;
-                    for (int j = jb; j < je; ++j) sx += (e_c[j] + e_c[IS_TM + j]) * mt.dh[j * 3 + comp];
-                    x_out[(size_t)node * 3 + comp] = __ldg(p.x + node * p.ldx + comp) + sx / (float)max(je - jb, 1);
-                }
-            }
-        }
-        // No barrier here: the next iteration first writes sS / sA (every MMA of this tile has been waited for) and
-        // reads meta[cur ^ 1]; e_c, meta[cur] and TMEM are next written after the barriers S1..S3 of that iteration,
-        // which every thread reaches only after it has finished reading them here.
-        phase ^= 1;
-        cur ^= 1;
-    }
-    fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 128);
-}
-
 // =====================================================================================================
-// Third generation: the same tile pipeline, warp-specialised and asynchronous (one 576-thread CTA per SM).
+// The tile pipeline, warp-specialised and asynchronous (one 704-thread CTA per SM).
 //
-// The lock-step kernel above leaves the SM idle 65 % of the issue slots: every phase of a tile ends in a CTA
+// The lock-step kernels (egnn_tc.cu) leave the SM idle 65 % of the issue slots: every phase of a tile ends in a CTA
 // barrier, the L2 gather latency, the dependent scalar prefetch chain and the MMA latencies are all exposed, and
 // two CTAs per SM are not enough to cover them (ncu: barrier 3.9 + long-scoreboard 2.5 stall cycles per issue).
 // Here the phases of DIFFERENT tiles overlap; mbarriers replace every CTA barrier:
@@ -701,41 +477,6 @@ int launch_edge_fwd_ws(const EdgeCommon& c, float* hn, float* x_out, int precisi
                              : launch_wsk<PREC_BF16X3, false, true>(c, hn, x_out, grid, st);
     return update_coords ? launch_wsk<PREC_BF16X3, true, false>(c, hn, x_out, grid, st)
                          : launch_wsk<PREC_BF16X3, false, false>(c, hn, x_out, grid, st);
-}
-
-template <int PREC>
-static size_t tc2_smem_bytes() {
-    using namespace e2;
-    return (size_t)S_BYTES + (size_t)TcCfg<PREC>::NSPLIT * (A_BYTES + 2 * W_BYTES) + sizeof(float) * (5 * 64 + 2 * IS_TM) + 2 * sizeof(Meta);
-}
-
-template <int PREC, bool HAS_COORD, bool FAST>
-static int launch_tc2k(const EdgeCommon& c, float* hn, float* x_out, int grid, cudaStream_t st) {
-    const size_t smem = tc2_smem_bytes<PREC>();
-    cudaError_t e = cudaFuncSetAttribute(edge_fwd_tc2_kernel<PREC, HAS_COORD, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    edge_fwd_tc2_kernel<PREC, HAS_COORD, FAST><<<grid, e2::NT, smem, st>>>(c, hn, x_out);
-    e = cudaGetLastError();
-    return e == cudaSuccess ? 0 : (int)e;
-}
-
-// entry used by is_egnn_edge_fwd_tc (egnn_tc.cu) for the bf16 / bf16x3 precisions
-int launch_edge_fwd_tc2(const EdgeCommon& c, float* hn, float* x_out, int precision, bool update_coords, bool fast,
-                        cudaStream_t st) {
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    const int per_sm = precision == PREC_BF16 ? 3 : 2;
-    int64_t g = ((int64_t)c.n_nodes + 31) / 32;
-    if (g > (int64_t)sms * per_sm) g = (int64_t)sms * per_sm;
-    const int grid = (int)(g < 1 ? 1 : g);
-    if (precision == PREC_BF16)
-        return update_coords ? launch_tc2k<PREC_BF16, true, true>(c, hn, x_out, grid, st)
-                             : launch_tc2k<PREC_BF16, false, true>(c, hn, x_out, grid, st);
-    if (fast)
-        return update_coords ? launch_tc2k<PREC_BF16X3, true, true>(c, hn, x_out, grid, st)
-                             : launch_tc2k<PREC_BF16X3, false, true>(c, hn, x_out, grid, st);
-    return update_coords ? launch_tc2k<PREC_BF16X3, true, false>(c, hn, x_out, grid, st)
-                         : launch_tc2k<PREC_BF16X3, false, false>(c, hn, x_out, grid, st);
 }
 
 }  // namespace is
