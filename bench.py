@@ -44,15 +44,16 @@ BYTES_PER_NODE_EDGE_KERNEL = 512 + 12 + 4 + 256 + 12       # read PQ row, x, ind
 BYTES_PER_EDGE_EDGE_KERNEL = 3 * 4 + 4                     # read csr_src/dst/eid + edge_attr
 GATHER_BYTES_PER_EDGE = 2 * 256                            # P[src] + Q[dst] rows (served by L2)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
-# (profiles/r01_tc_*_edge_fwd_full.md, profiles/r01_simt_edge_fwd_full.md), batch 512
-NCU_TRAFFIC_BYTES = {"bf16": 79.72e6 + 8.99e6, "tf32x3": 82.36e6 + 10.82e6, "fp32": 80.64e6 + 8.85e6}   # bf16x3: see profiles/
+# (profiles/r01_ws_*_edge_fwd_full.md, profiles/r01_simt_edge_fwd_full.md), batch 512
+NCU_TRAFFIC_BYTES = {"bf16x3": 82.38e6 + 11.43e6, "bf16": 83.17e6 + 8.50e6,        # profiles/r01_ws_*_edge_fwd_full.md
+                     "tf32x3": 82.36e6 + 10.82e6, "fp32": 80.64e6 + 8.85e6}
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12          # 74.4
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
@@ -369,12 +370,14 @@ def main():
         flops = e * FLOP_PER_EDGE_EDGE_KERNEL
         nbytes = e * BYTES_PER_EDGE_EDGE_KERNEL + n * BYTES_PER_NODE_EDGE_KERNEL
         gbs = nbytes / t_k / 1e9
-        kname = ("is::edge_fwd_kernel<true> (fp32 SIMT)" if args.precision == "fp32" else
-                 f"is::edge_fwd_tc_kernel<{args.precision}, true> (tcgen05 + TMEM)")
+        kname = {"fp32": "is::edge_fwd_kernel<true> (fp32 SIMT)",
+                 "tf32x3": "is::edge_fwd_tc_kernel<tf32x3, true> (tcgen05 + TMEM, lock-step)"}.get(
+            args.precision, f"is::edge_fwd_ws_kernel<{args.precision}, true> (tcgen05 + TMEM, warp-specialised)")
         # The fused kernel's two roofline terms: compulsory bytes / HBM peak and GEMM flops / tensor peak.
         # The byte term is the larger one, so "hbm" is the bound the schema asks for; in practice the
-        # kernel is limited by instruction issue / latency of its SIMT gather, SiLU and aggregation phases
-        # (issue slots 38 % busy, tensor pipe 4-11 %, DRAM 2 %: profiles/r01_tc_*_edge_fwd_full.md).
+        # kernel is limited by the SIMT work per edge -- 192 SiLUs (2 MUFU each in the fp32-accurate mode:
+        # 91 us of MUFU pipe per launch) and ~100 issued warp-instructions -- see `simt` below and
+        # profiles/r01_ws_*_edge_fwd_full.md (issue slots 47 %, MUFU 45 %, tensor pipe 33 %, DRAM 3 %).
         roofline = {"kernel": kname, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                     "frac": gbs / hbm_peak, "traffic": NCU_TRAFFIC_BYTES.get(args.precision) if B == BATCH else None,
                     "peak_source": src, "launch_ms": t_k * 1e3, "edges_per_launch": e,
@@ -382,6 +385,8 @@ def main():
                     "tensor": {"achieved": flops / t_k / 1e12, "peak": tensor_peak, "unit": "TFLOP/s",
                                "frac": flops / t_k / 1e12 / tensor_peak},
                     "l2_gather_gbs": e * GATHER_BYTES_PER_EDGE / t_k / 1e9,
+                    "simt": {"mufu_floor_ms": e * 192 * (1 if args.precision == "bf16" else 2) / (148 * 16 * 1.965e9) * 1e3,
+                             "note": "192 SiLU per edge, 1 (bf16: tanh.approx) or 2 (ex2 + rcp) MUFU ops each, 16 MUFU lanes / clk / SM"},
                     "roofline_time_ms": {"hbm": nbytes / hbm_peak / 1e6, "tensor": flops / tensor_peak / 1e9},
                     "launch_ms_by_precision": {k: v * 1e3 for k, v in t_all.items()},
                     "note": "edge-forward kernel of one EGNN layer (batch 512) timed alone with CUDA events after an "

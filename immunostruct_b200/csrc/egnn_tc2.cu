@@ -171,6 +171,11 @@ __device__ __forceinline__ void meta_edge(const EdgeCommon& p, Meta3& m, int j, 
 }
 }  // namespace e3
 
+#ifndef IS_WS_WAIT_HINT_NS
+#define IS_WS_WAIT_HINT_NS 2000
+#endif
+#define WS_WAIT(bar, parity) mbar_wait_hint(bar, parity, IS_WS_WAIT_HINT_NS)
+
 template <int PREC, bool HAS_COORD, bool FAST>
 __global__ void __launch_bounds__(e3::NT3, 1)
 edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_out) {
@@ -226,7 +231,7 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
         int cursor = nbeg;
         for (int i = 0;; ++i) {
             const int s = i % NM;
-            if (i >= NM) mbar_wait(&meta_free[s], ((i / NM) - 1) & 1);
+            if (i >= NM) WS_WAIT(&meta_free[s], ((i / NM) - 1) & 1);
             int tn0, tn1, tp0, tne;
             next_tile(p.indptr, cursor, nend, p.status, lane, tn0, tn1, tp0, tne);
             Meta3& m = meta[s];
@@ -260,18 +265,18 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
                 const int i = i2 + b;
-                mbar_wait(&meta_full[i % NM], (i / NM) & 1);
+                WS_WAIT(&meta_full[i % NM], (i / NM) & 1);
                 done = meta[i % NM].tile[0] >= nend;
                 if (done) break;
                 if (first) {
-                    mbar_wait(&a_full[b], (i >> 1) & 1);
+                    WS_WAIT(&a_full[b], (i >> 1) & 1);
                     fence_after_sync();
                     if (elect_one()) {
                         issue_fwd<PREC>(tmem + TM_ACC1 + 64 * b, a_addr + b * ABUF, w2_addr);
                         mma_commit(&acc1_full[b]);
                     }
                 } else {
-                    mbar_wait(&m_full[b], (i >> 1) & 1);
+                    WS_WAIT(&m_full[b], (i >> 1) & 1);
                     fence_after_sync();
                     if (elect_one()) {
                         if (HAS_COORD) {
@@ -295,11 +300,11 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
         const float4 wa0 = *reinterpret_cast<const float4*>(vec + 256 + 8 * kc), wa1 = *reinterpret_cast<const float4*>(vec + 260 + 8 * kc);
         for (int i = 0;; ++i) {
             const int b = i & 1;
-            mbar_wait(&meta_full[i % NM], (i / NM) & 1);
+            WS_WAIT(&meta_full[i % NM], (i / NM) & 1);
             const Meta3& mt = meta[i % NM];
             const int n0 = mt.tile[0], ne = mt.tile[2];
             if (n0 >= nend) break;
-            if (i >= 2) mbar_wait(&hn_full[b], ((i >> 1) - 1) & 1);        // MMA2 / MMA3 of tile i-2 are done with the buffer
+            if (i >= 2) WS_WAIT(&hn_full[b], ((i >> 1) - 1) & 1);        // MMA2 / MMA3 of tile i-2 are done with the buffer
             uint8_t* A = sA + b * ABUF;
             {   // selector tile: S[node][edge] = 1 for the node's in-edges (two 16-byte chunks per thread)
                 const int jb = mt.nptr[lane], je = mt.nptr[lane + 1];         // rows beyond the tile: jb = je = ne
@@ -359,11 +364,11 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
         const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16) + CW * cq;
         for (int i = 0;; ++i) {
             const int b = i & 1;
-            mbar_wait(&meta_full[i % NM], (i / NM) & 1);
+            WS_WAIT(&meta_full[i % NM], (i / NM) & 1);
             const bool done = meta[i % NM].tile[0] >= nend;
             if (!done) {
                 // ---- epilogue 1: m = silu(acc1 + b2) -> operand buffer (A of MMA 2, transposed B of MMA 3) ----
-                mbar_wait(&acc1_full[b], (i >> 1) & 1);
+                WS_WAIT(&acc1_full[b], (i >> 1) & 1);
                 fence_after_sync();
                 uint8_t* A = sA + b * ABUF;
                 float z[CW];
@@ -391,7 +396,7 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
                 float* ec = e_c + bp * 2 * IS_TM;
                 if (HAS_COORD) {
                     // ---- epilogue 2: c = w4 . silu(acc2 + b3) (each thread: one row, CW columns) ----
-                    mbar_wait(&acc2_full[bp], (j >> 1) & 1);
+                    WS_WAIT(&acc2_full[bp], (j >> 1) & 1);
                     fence_after_sync();
                     float z[CW];
                     tmem_ld<CW>(t_lane + TM_ACC2 + 64 * bp, z);
@@ -408,7 +413,7 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
                     ec[cq * IS_TM + erow] = c;
                 }
                 // ---- hn rows: M = 64 accumulator, node row r sits in TMEM lane 32 (r / 16) + r % 16 ----
-                mbar_wait(&hn_full[bp], (j >> 1) & 1);
+                WS_WAIT(&hn_full[bp], (j >> 1) & 1);
                 fence_after_sync();
                 if (q < 2) {
                     float z[CW];

@@ -76,6 +76,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// wait with a suspend-time hint (ns): the warp sleeps in hardware instead of re-issuing the poll; for the
+// producer / consumer waits of the warp-specialised kernels, where a polling warp steals issue slots from working ones
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t done = 0;
+    const uint32_t addr = smem_u32(bar);
+    while (!done) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n" : "=r"(done) : "r"(addr), "r"(parity), "r"(hint_ns) : "memory");
+    }
+}
 // one elected lane of a fully converged warp (the idiom ptxas recognises: no per-MMA election code)
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;

@@ -5,8 +5,9 @@ import csv
 import subprocess
 import sys
 
+# usage: summarize_profile.py TAG [LAUNCHES_CSV] [NCU_REP]
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-rows = list(csv.reader(open("gpurun_out/launches.csv")))
+rows = list(csv.reader(open(sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/launches.csv")))
 hdr, agg = None, collections.OrderedDict()
 for r in rows:
     if len(r) > 5 and r[0] == "ID":
@@ -27,7 +28,7 @@ for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1]))[:30]:
     out.append(f"| {sum(v) / tot * 100:.1f}% | {len(v)} | {sum(v) / len(v):.1f} | `{k}` |")
 open(f"profiles/{tag}_launches.md", "w").write("\n".join(out) + "\n")
 
-rep = sys.argv[2] if len(sys.argv) > 2 else None
+rep = sys.argv[3] if len(sys.argv) > 3 else None
 if rep:
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rr = list(csv.reader(raw.splitlines()))
@@ -37,13 +38,21 @@ if rep:
             "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
             "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
             "launch__registers_per_thread", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
-            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed.sum"]
+            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed.sum",
+            "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "launch__block_size", "launch__grid_size",
+            "launch__shared_mem_per_block_dynamic"]
     lines = [f"# ncu --set full capture ({tag}): {rep}", ""]
     for r in rr[2:]:
         d = dict(zip(h, r))
         for k in keys:
             if k in d:
                 lines.append(f"- `{k}` [{u[h.index(k)]}] = {d[k]}")
+        for k in h:
+            if "issue_stalled" in k and k.endswith("per_issue_active.ratio") and "not_issued" not in k and float(d[k]) > 0.05:
+                lines.append(f"- stall `{k.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', '')}` per issue = {float(d[k]):.2f}")
         lines.append("")
+    seg = subprocess.run([sys.executable, "scripts/ncu_segments.py", rep], capture_output=True, text=True).stdout
+    lines += ["## executed warp instructions / stall samples per code segment (split at barriers, TMEM loads, MMA commits)", "", "```"]
+    lines += [l for l in seg.splitlines() if l[:4].strip().isdigit() or l.startswith("total")] + ["```", ""]
     open(f"profiles/{tag}_edge_fwd_full.md", "w").write("\n".join(lines) + "\n")
 print("wrote profiles/")
