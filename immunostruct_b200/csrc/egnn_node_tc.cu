@@ -3,6 +3,8 @@
 //   node_post(l) :  h' = W6 silu(W5 [h | hn] + b5) + b6              (reference: EGNNConv node_mlp)
 //   node_pre(l+1):  P' = h' Ws'^T ,  Q' = h' Wd'^T + b1'              (first edge-MLP layer of layer l+1,
 //                                                                      split per node, see egnn.cu)
+//   or, after the LAST layer (next_kind = 2):  QKV = h' [Wq; Wk; Wv]^T + [bq; bk; bv]   (the three projections of
+//                                              the per-graph attention, models/layers.py:13-16 / :67-69)
 // Per tile of 128 nodes four chained tcgen05 GEMM groups run against weight blocks that stay resident
 // in shared memory for the CTA's lifetime; the activations never leave the SM between them:
 //   D1 = h W5h^T + hn W5n^T  -> +b5, SiLU -> D2 = t5 W6^T -> +b6 = h' (stored) -> D3 = h' [Ws'; Wd']^T (+b1')
@@ -19,15 +21,15 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
 node_post_pre_tc_kernel(const float* __restrict__ h, int64_t ldh, int F, const float* __restrict__ hn,
                         const float* __restrict__ W5, const float* __restrict__ b5,
                         const float* __restrict__ W6, const float* __restrict__ b6, float* __restrict__ h_out,
-                        const float* __restrict__ W1n /* next layer edge_mlp.0.weight [64,130] or null */,
-                        const float* __restrict__ b1n, float* __restrict__ PQn, int64_t M) {
+                        const float* __restrict__ W1n /* next layer edge_mlp.0.weight [64,130] | [Wq;Wk;Wv] [192,64] | null */,
+                        const float* __restrict__ b1n, float* __restrict__ PQn, int64_t M, int next_kind) {
     using C = TcCfg<PREC>;
     constexpr int NW = NT / 32, CQ = NW / 4, CW = 64 / CQ;
-    constexpr uint32_t ASPL = C::A_BYTES, WSPL = 5 * C::W_BYTES;          // split-term strides
+    constexpr uint32_t ASPL = C::A_BYTES, WSPL = 6 * C::W_BYTES;          // split-term strides
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t* sA = smem_raw;                                   // [NSPLIT][A_BYTES]
-    uint8_t* sW = sA + C::NSPLIT * ASPL;                      // [NSPLIT][5 blocks][W_BYTES]: W5h W5n W6 Ws' Wd'
-    float* vec = reinterpret_cast<float*>(sW + C::NSPLIT * WSPL);   // b5, b6, b1'
+    uint8_t* sW = sA + C::NSPLIT * ASPL;                      // [NSPLIT][6 blocks][W_BYTES]: W5h W5n W6 | Ws' Wd' - or Wq Wk Wv
+    float* vec = reinterpret_cast<float*>(sW + C::NSPLIT * WSPL);   // b5, b6, next bias (64: b1' for Q' | 192: bq bk bv)
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -41,14 +43,20 @@ node_post_pre_tc_kernel(const float* __restrict__ h, int64_t ldh, int F, const f
         store_weight1<PREC>(sW + 0 * C::W_BYTES, WSPL, n, k, k < F ? __ldg(W5 + n * K5 + k) : 0.0f);
         store_weight1<PREC>(sW + 1 * C::W_BYTES, WSPL, n, k, __ldg(W5 + n * K5 + F + k));
         store_weight1<PREC>(sW + 2 * C::W_BYTES, WSPL, n, k, __ldg(W6 + idx));
-        store_weight1<PREC>(sW + 3 * C::W_BYTES, WSPL, n, k, has_next ? __ldg(W1n + n * 130 + k) : 0.0f);
-        store_weight1<PREC>(sW + 4 * C::W_BYTES, WSPL, n, k, has_next ? __ldg(W1n + n * 130 + 64 + k) : 0.0f);
+        if (next_kind == 2) {
+            store_weight1<PREC>(sW + 3 * C::W_BYTES, WSPL, n, k, __ldg(W1n + idx));
+            store_weight1<PREC>(sW + 4 * C::W_BYTES, WSPL, n, k, __ldg(W1n + 4096 + idx));
+            store_weight1<PREC>(sW + 5 * C::W_BYTES, WSPL, n, k, __ldg(W1n + 8192 + idx));
+        } else {
+            store_weight1<PREC>(sW + 3 * C::W_BYTES, WSPL, n, k, has_next ? __ldg(W1n + n * 130 + k) : 0.0f);
+            store_weight1<PREC>(sW + 4 * C::W_BYTES, WSPL, n, k, has_next ? __ldg(W1n + n * 130 + 64 + k) : 0.0f);
+        }
     }
     if (tid < 64) {
         vec[tid] = b5[tid];
         vec[64 + tid] = b6[tid];
-        vec[128 + tid] = has_next ? b1n[tid] : 0.0f;
     }
+    if (tid < 192) vec[128 + tid] = !has_next ? 0.0f : next_kind == 2 ? b1n[tid] : (tid < 64 ? b1n[tid] : 0.0f);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -139,7 +147,25 @@ node_post_pre_tc_kernel(const float* __restrict__ h, int64_t ldh, int F, const f
                 if (has_next) store_operand8<PREC>(sA, ASPL, erow, (CW / 8) * cq + g, v);
             }
         }
-        if (has_next) {
+        if (has_next && next_kind == 2) {
+            // ---- D3 = h' [Wq; Wk; Wv]^T (N = 192: blocks 3..5), written over the dead accumulators D1 / D2 ----
+            run_gemm(tmem, 3, 192, 0);
+            const int64_t m = m0 + erow;
+#pragma unroll
+            for (int part = 0; part < 3; ++part) {
+                float z[CW];
+                tmem_ld<CW>(t_lane + 64 * part + CW * cq, z);
+                if (m < M) {
+#pragma unroll
+                    for (int g = 0; g < CW / 4; ++g) {
+                        const int c = 64 * part + CW * cq + 4 * g;
+                        *reinterpret_cast<float4*>(PQn + m * 192 + c) =
+                            make_float4(z[4 * g] + vec[128 + c], z[4 * g + 1] + vec[128 + c + 1],
+                                        z[4 * g + 2] + vec[128 + c + 2], z[4 * g + 3] + vec[128 + c + 3]);
+                    }
+                }
+            }
+        } else if (has_next) {
             // ---- D3 = h' [Ws'; Wd']^T (N = 128: weight blocks 3 and 4 are contiguous row groups) -------
             run_gemm(tmem + 128, 3, 128, 0);
             const int64_t m = m0 + erow;
@@ -168,9 +194,9 @@ node_post_pre_tc_kernel(const float* __restrict__ h, int64_t ldh, int F, const f
 template <int PREC, int NT, bool FAST>
 static int launch_node_tc(const float* h, int64_t ldh, int F, const float* hn, const float* W5, const float* b5,
                           const float* W6, const float* b6, float* h_out, const float* W1n, const float* b1n,
-                          float* PQn, int64_t M, cudaStream_t st) {
+                          float* PQn, int64_t M, int next_kind, cudaStream_t st) {
     using C = TcCfg<PREC>;
-    const size_t smem = (size_t)C::NSPLIT * (C::A_BYTES + 5 * C::W_BYTES) + 3 * 64 * sizeof(float) + 128;
+    const size_t smem = (size_t)C::NSPLIT * (C::A_BYTES + 6 * C::W_BYTES) + 5 * 64 * sizeof(float) + 128;
     cudaError_t e = cudaFuncSetAttribute(node_post_pre_tc_kernel<PREC, NT, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int sms = 148;
@@ -178,7 +204,7 @@ static int launch_node_tc(const float* h, int64_t ldh, int F, const float* hn, c
     int64_t tiles = (M + IS_TM - 1) / IS_TM;
     int64_t cap = (int64_t)sms * (NT == 256 ? 2 : 1);
     int grid = (int)(tiles < cap ? tiles : cap);
-    node_post_pre_tc_kernel<PREC, NT, FAST><<<grid < 1 ? 1 : grid, NT, smem, st>>>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, M);
+    node_post_pre_tc_kernel<PREC, NT, FAST><<<grid < 1 ? 1 : grid, NT, smem, st>>>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, M, next_kind);
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
@@ -190,21 +216,23 @@ using namespace is;
 extern "C" {
 
 // node_mlp of layer l fused with the per-node half of layer l+1's first edge-MLP layer (W1n / b1n / PQn
-// may be NULL for the last layer).  precision: 0 = bf16, 3 = bf16x3 (fp32-accurate); fast_act: 5-instruction
+// may be NULL for the last layer), or -- next_kind = 2 -- with the attention projections that follow the last
+// layer: W1n = [Wq; Wk; Wv] [192, 64], b1n [192], PQn = QKV [n_nodes, 192].  precision: 0 = bf16, 3 = bf16x3 (fp32-accurate); fast_act: 5-instruction
 // SiLU (inference) vs accurate expf (training forward).  W1n must be the
 // [64, 130] weight of a 64-wide layer.
 int is_egnn_node_post_pre_tc(const float* h, int64_t ldh, int F, const float* hn, const float* W5, const float* b5,
                              const float* W6, const float* b6, float* h_out, const float* W1n, const float* b1n,
-                             float* PQn, int64_t n_nodes, int precision, int fast_act, void* stream) {
+                             float* PQn, int64_t n_nodes, int precision, int fast_act, int next_kind, void* stream) {
     if (!(F == 20 || F == 64) || n_nodes <= 0) return IS_ERR_ARG;
     if ((W1n == nullptr) != (PQn == nullptr)) return IS_ERR_ARG;
+    if (W1n != nullptr && next_kind != 1 && next_kind != 2) return IS_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == PREC_BF16)
-        return launch_node_tc<PREC_BF16, 256, true>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, n_nodes, st);
+        return launch_node_tc<PREC_BF16, 256, true>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, n_nodes, next_kind, st);
     if (precision == PREC_BF16X3 && fast_act)
-        return launch_node_tc<PREC_BF16X3, 512, true>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, n_nodes, st);
+        return launch_node_tc<PREC_BF16X3, 512, true>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, n_nodes, next_kind, st);
     if (precision == PREC_BF16X3)
-        return launch_node_tc<PREC_BF16X3, 512, false>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, n_nodes, st);
+        return launch_node_tc<PREC_BF16X3, 512, false>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, n_nodes, next_kind, st);
     return IS_ERR_ARG;
 }
 

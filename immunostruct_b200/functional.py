@@ -143,9 +143,11 @@ def _egnn_layer_backward(g, h, x, edge_attr, PQ, hn, params, gh_out, gx_out, nee
     return gh, gx, (gW1, gb1, gW2, gb2, gW3, gb3, gw4, gW5, gb5, gW6, gb6)
 
 
-def _egnn_stack_forward(graph, x23, edge_attr, params, fast_act, keep):
+def _egnn_stack_forward(graph, x23, edge_attr, params, fast_act, keep, qkv=None):
     """Shared forward of the EGNN stack.  ``keep``: list that receives (h, x, PQ, hn) per layer for the
-    backward pass (None = inference, nothing kept)."""
+    backward pass (None = inference, nothing kept).  ``qkv`` = (W [192,64], b [192]): the attention projections
+    that follow the stack, fused into the last node kernel when it runs on the tensor cores; the function then
+    returns (h, QKV [N,192] or None)."""
     h, x = x23[:, :20], x23[:, 20:]
     n = h.shape[0]
     prec = _PRECISIONS[_precision]
@@ -156,6 +158,7 @@ def _egnn_stack_forward(graph, x23, edge_attr, params, fast_act, keep):
         # B200, tests/test_models_gpu.py), i.e. just outside the 1e-5 gradient tolerance.
         node_prec = None
     PQ = _new(h, n, 2 * H)
+    QKV = None
     _C.egnn_node_pre_fwd(h, params[0][0], params[0][1], PQ)
     last = len(params) - 1
     for l, (W1, b1, W2, b2, W3, b3, w4, W5, b5, W6, b6) in enumerate(params):
@@ -174,6 +177,10 @@ def _egnn_stack_forward(graph, x23, edge_attr, params, fast_act, keep):
             _C.egnn_node_post_fwd(h, hn, W5, b5, W6, b6, h_out)
             if upd:
                 _C.egnn_node_pre_fwd(h_out, nxt[0], nxt[1], PQ_next)
+        elif not upd and qkv is not None:
+            QKV = _new(h, n, 3 * H)
+            _C.egnn_node_post_pre_tc(h, hn, W5, b5, W6, b6, h_out, qkv[0], qkv[1], QKV, node_prec,
+                                     fast_act=fast_act, next_kind=2)
         else:
             _C.egnn_node_post_pre_tc(h, hn, W5, b5, W6, b6, h_out, nxt[0] if upd else None,
                                      nxt[1] if upd else None, PQ_next, node_prec, fast_act=fast_act)
@@ -182,7 +189,7 @@ def _egnn_stack_forward(graph, x23, edge_attr, params, fast_act, keep):
         h, PQ = h_out, PQ_next
         if upd:
             x = x_out
-    return h
+    return h if qkv is None else (h, QKV)
 
 
 class _EGNNStack(torch.autograd.Function):
@@ -229,13 +236,17 @@ def egnn_stack(graph, x23, edge_attr, layer_params):
     return _EGNNStack.apply(graph, len(layer_params), x23, edge_attr, *flat)
 
 
-def egnn_stack_infer(graph, x23, edge_attr, layer_params):
+def egnn_stack_infer(graph, x23, edge_attr, layer_params, qkv=None):
     """No-grad EGNN stack (models/hybrid_models.py:82,89-90): node_pre(0) -> [edge(l) -> node_post(l) +
     node_pre(l+1)]; the last layer's coordinate branch is skipped (its output is never consumed).  In the
     tensor-core precisions the node side runs fused across the layer boundary (csrc/egnn_node_tc.cu).
-    ``layer_params``: list of the 11-tuples of EGNNConv.kernel_params().  Returns the final h [N,64]."""
+    ``layer_params``: list of the 11-tuples of EGNNConv.kernel_params().  Returns the final h [N,64]; with
+    ``qkv`` = (W [192,64], b [192]) returns (h, QKV [N,192]) -- QKV is None when the node side runs on the SIMT
+    kernels (fp32 mode) and the caller applies the projection itself."""
     params = [[t.detach().contiguous() for t in lp] for lp in layer_params]
-    return _egnn_stack_forward(graph, x23, edge_attr.contiguous(), params, True, None)
+    if qkv is not None:
+        qkv = tuple(t.detach().contiguous() for t in qkv)
+    return _egnn_stack_forward(graph, x23, edge_attr.contiguous(), params, True, None, qkv)
 
 
 def egnn_layer(graph, h, x, edge_attr, params, update_coords=True):

@@ -70,14 +70,18 @@ class SelfAttention(nn.Module):
     def forward(self, x):
         return _dense_attention(self.query(x), self.key(x), self.value(x))
 
-    def _qkv(self, h):
-        w = torch.cat([self.query.weight, self.key.weight, self.value.weight], 0)
-        b = torch.cat([self.query.bias, self.key.bias, self.value.bias], 0)
-        return F.linear(h, w, b)
+    def qkv_params(self):
+        """([Wq;Wk;Wv] [192,64], [bq;bk;bv] [192]) for the fused projection."""
+        return (torch.cat([self.query.weight, self.key.weight, self.value.weight], 0),
+                torch.cat([self.query.bias, self.key.bias, self.value.bias], 0))
 
-    def pooled(self, graph, h, want_attn=False, want_nodes=False):
-        """h [N_total,64] -> (per-graph mean of the attention output [B,64], weights|None, per-node out|None)."""
-        O, pooled, attn = IF.attention_pool(graph, self._qkv(h), 1, want_attn, want_nodes)
+    def _qkv(self, h):
+        return F.linear(h, *self.qkv_params())
+
+    def pooled(self, graph, h, want_attn=False, want_nodes=False, qkv=None):
+        """h [N_total,64] -> (per-graph mean of the attention output [B,64], weights|None, per-node out|None).
+        ``qkv``: the projections [N,192] when a fused kernel has already computed them."""
+        O, pooled, attn = IF.attention_pool(graph, self._qkv(h) if qkv is None else qkv, 1, want_attn, want_nodes)
         if want_attn:
             attn = attn.squeeze(1)         # SelfAttention returns [B, n, n]
         return pooled, attn, (O if want_nodes else None)
@@ -114,17 +118,21 @@ class MultiHeadAttention(nn.Module):
         return self.w_concat(self.concat(score @ v)), score
 
     # ---- fused entry points used by the models ---------------------------------------------------
-    def _qkv(self, h):
-        w = torch.cat([self.w_q.weight, self.w_k.weight, self.w_v.weight], 0)
-        b = torch.cat([self.w_q.bias, self.w_k.bias, self.w_v.bias], 0)
-        return F.linear(h, w, b)
+    def qkv_params(self):
+        """([Wq;Wk;Wv] [192,64], [bq;bk;bv] [192]) for the fused projection."""
+        return (torch.cat([self.w_q.weight, self.w_k.weight, self.w_v.weight], 0),
+                torch.cat([self.w_q.bias, self.w_k.bias, self.w_v.bias], 0))
 
-    def pooled(self, graph, h, want_attn=False, want_nodes=False):
+    def _qkv(self, h):
+        return F.linear(h, *self.qkv_params())
+
+    def pooled(self, graph, h, want_attn=False, want_nodes=False, qkv=None):
         """Per-graph attention over node embeddings + global mean pool.  The mean commutes with the
-        affine ``w_concat``, so the projection is applied to the pooled [B,64] rows."""
+        affine ``w_concat``, so the projection is applied to the pooled [B,64] rows.  ``qkv``: the
+        projections [N,192] when a fused kernel has already computed them."""
         if self.feature_dim != 64 or self.input_dim != 64:
             raise NotImplementedError("fused per-graph attention is specialised for 64 channels")
-        O, pooled, attn = IF.attention_pool(graph, self._qkv(h), self.n_head, want_attn, want_nodes)
+        O, pooled, attn = IF.attention_pool(graph, self._qkv(h) if qkv is None else qkv, self.n_head, want_attn, want_nodes)
         nodes = self.w_concat(O) if want_nodes else None
         return self.w_concat(pooled), attn, nodes
 

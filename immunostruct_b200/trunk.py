@@ -44,8 +44,12 @@ class StructureTrunk:
         node_feat, coord_feat, edge_feat = xin[:, :20], xin[:, 20:], graph_data.edata["edge_attr"]
         if not torch.is_grad_enabled():
             # inference: the whole stack through the fused kernels, nothing saved for a backward pass
-            node_feat = IF.egnn_stack_infer(graph_data, xin, edge_feat, [l.kernel_params() for l in self.GCN_layers])
-            return self.self_attention.pooled(graph_data, node_feat, want_attn=want_attn, want_nodes=want_nodes)
+            # (the attention projections ride in the last node kernel when it runs on the tensor cores)
+            fuse_qkv = getattr(self.self_attention, "feature_dim", self.gat_hidden_channels) == 64 and self.gat_hidden_channels == 64
+            out = IF.egnn_stack_infer(graph_data, xin, edge_feat, [l.kernel_params() for l in self.GCN_layers],
+                                      qkv=self.self_attention.qkv_params() if fuse_qkv else None)
+            node_feat, qkv = out if fuse_qkv else (out, None)
+            return self.self_attention.pooled(graph_data, node_feat, want_attn=want_attn, want_nodes=want_nodes, qkv=qkv)
         # training: one autograd node for the whole stack (the last layer's coordinates are never consumed,
         # hybrid_models.py:323-326, so its coordinate branch is skipped and coord_mlp gets no gradient)
         node_feat = IF.egnn_stack(graph_data, xin, edge_feat, [l.kernel_params() for l in self.GCN_layers])

@@ -59,10 +59,13 @@ int is_egnn_edge_fwd_tc(const int* indptr, const int* csr_src, const int* csr_ds
                         const float* W3, const float* b3, const float* w4, int update_coords, int precision,
                         int fast_act, float* hn, float* x_out, int64_t n_nodes, int* status, void* stream);
 /* node_mlp of layer l fused with the per-node half (P', Q') of layer l+1's first edge-MLP layer, on the
- * tensor cores (inference path).  W1n/b1n/PQn NULL for the last layer.  precision 0 = bf16, 3 = bf16x3. */
+ * tensor cores (inference path).  W1n/b1n/PQn NULL = nothing follows.  next_kind 1: W1n = edge_mlp.0.weight
+ * [64,130] of layer l+1, PQn [n,128].  next_kind 2 (after the last layer): W1n = [Wq;Wk;Wv] [192,64], b1n [192],
+ * PQn = QKV [n,192], the projections of the per-graph attention (reference models/layers.py:13-16 / 67-69).
+ * precision 0 = bf16, 3 = bf16x3. */
 int is_egnn_node_post_pre_tc(const float* h, int64_t ldh, int F, const float* hn, const float* W5, const float* b5,
                              const float* W6, const float* b6, float* h_out, const float* W1n, const float* b1n,
-                             float* PQn, int64_t n_nodes, int precision, int fast_act, void* stream);
+                             float* PQn, int64_t n_nodes, int precision, int fast_act, int next_kind, void* stream);
 int is_egnn_node_post_fwd(const float* h, int64_t ldh, int F, const float* hn, const float* W5, const float* b5,
                           const float* W6, const float* b6, float* h_out, int64_t n_nodes, void* stream);
 int is_egnn_node_post_bwd(const float* gh_out, const float* h, int64_t ldh, int F, const float* hn,

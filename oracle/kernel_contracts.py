@@ -117,9 +117,11 @@ def egnn_node_post_fwd(h, hn, W5, b5, W6, b6, h_out):
     h_out.copy_(F.linear(_silu(F.linear(torch.cat([h, hn], 1), W5, b5)), W6, b6))
 
 
-def egnn_node_post_pre_tc(h, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, precision, fast_act=True):
+def egnn_node_post_pre_tc(h, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, precision, fast_act=True, next_kind=1):
     egnn_node_post_fwd(h, hn, W5, b5, W6, b6, h_out)
-    if W1n is not None:
+    if W1n is not None and next_kind == 2:          # QKV = h' [Wq;Wk;Wv]^T + b  (models/layers.py:13-16 / 67-69)
+        PQn.copy_(F.linear(h_out, W1n, b1n))
+    elif W1n is not None:
         egnn_node_pre_fwd(h_out, W1n, b1n, PQn)
 
 

@@ -213,6 +213,24 @@ def test_egnn_node_post_pre_tensor_core(case, f, with_next, prec, tol):
         close(PQn_d, PQn, tol, what=f"node tc PQ' prec={prec} f={f}")
 
 
+@pytest.mark.parametrize("prec,tol", [(_C.PREC_BF16X3, 1e-5), (_C.PREC_BF16, 2e-2)])
+def test_egnn_node_post_qkv_tensor_core(case, prec, tol):
+    """Last-layer node kernel with the attention projections fused (next_kind = 2): h' and QKV = h' [Wq;Wk;Wv]^T + b."""
+    arrays, gb, _ = case
+    gen = torch.Generator().manual_seed(43)
+    n = gb.n_nodes
+    w = egnn_weights(gen, 64)
+    h, hn = rnd(gen, n, 64), rnd(gen, n, 64, scale=3.0)
+    Wqkv, bqkv = rnd(gen, 192, 64, scale=0.3), rnd(gen, 192, scale=0.3)
+    ho, QKV = torch.empty(n, 64), torch.empty(n, 192)
+    ho_d, QKV_d = torch.full((n, 64), float("nan"), device=DEV), torch.full((n, 192), float("nan"), device=DEV)
+    KC.egnn_node_post_pre_tc(h, hn, w["W5"], w["b5"], w["W6"], w["b6"], ho, Wqkv, bqkv, QKV, prec, next_kind=2)
+    _C.egnn_node_post_pre_tc(h.to(DEV), hn.to(DEV), *dev(w["W5"], w["b5"], w["W6"], w["b6"]), ho_d,
+                             *dev(Wqkv, bqkv), QKV_d, prec, next_kind=2)
+    close(ho_d, ho, tol, what=f"node tc (qkv tail) h' prec={prec}")
+    close(QKV_d, QKV, tol, what=f"node tc QKV prec={prec}")
+
+
 # ---- EGNN backward -----------------------------------------------------------------------------
 @pytest.mark.parametrize("tc", [False, True])
 @pytest.mark.parametrize("f,coord", [(64, True), (64, False), (20, True)])
