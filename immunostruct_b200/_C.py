@@ -39,7 +39,7 @@ def exported_symbols():
             "is_loss_num_partials", "is_collate_csr", "is_egnn_node_pre_fwd", "is_egnn_edge_fwd",
             "is_egnn_node_post_fwd", "is_egnn_node_post_bwd", "is_egnn_edge_bwd", "is_egnn_node_pre_bwd",
             "is_reduce_partials", "is_attn_pool_fwd", "is_attn_pool_bwd", "is_fusion_attn_fwd",
-            "is_fusion_attn_bwd", "is_loss_fwd", "is_loss_bwd", "is_umma_selftest", "is_egnn_edge_fwd_tc", "is_attn_pool_infer", "is_egnn_node_post_pre_tc", "is_egnn_edge_bwd_tc"]
+            "is_fusion_attn_bwd", "is_loss_fwd", "is_loss_bwd", "is_umma_selftest", "is_egnn_edge_fwd_tc", "is_attn_pool_infer", "is_egnn_node_post_pre_tc", "is_egnn_edge_bwd_tc", "is_linear_tc", "is_linear_tc_split_k"]
 
 
 def _check(rc: int, name: str):
@@ -280,6 +280,29 @@ def loss_bwd(recon, seq, mu, logvar, logits, y, mode, pos_weight, w_pred, w_mse,
 
 
 # ---- tcgen05 self-test ---------------------------------------------------------------------------
+def linear_tc(x, weight, bias=None, relu=False, precision=PREC_BF16X3, out=None):
+    """``act(x @ weight.T + bias)`` on the tensor cores (csrc/linear_tc.cu): x [M,K] (any row stride), weight [N,K],
+    bias [N] or None -> [M,N] fp32.  precision PREC_BF16X3 (fp32-accurate) or PREC_BF16."""
+    global LAUNCHES
+    f32 = torch.float32
+    xp, lda = _rows(x, "x")
+    wp, ldw = _rows(weight, "weight")
+    m, k = x.shape
+    n = weight.shape[0]
+    if weight.shape[1] != k:
+        raise ValueError(f"linear_tc: x {tuple(x.shape)} vs weight {tuple(weight.shape)}")
+    if out is None:
+        out = torch.empty(m, n, dtype=f32, device=x.device)
+    split = int(lib().is_linear_tc_split_k(_i64(m), _i64(n), _i64(k)))
+    ws = torch.empty(split * m * n, dtype=f32, device=x.device) if split > 1 else None
+    cp, ldc = _rows(out, "out")
+    _call("is_linear_tc", xp, lda, wp, ldw, _t(bias, f32, "bias"), cp, ldc, _i64(m), _i64(n), _i64(k),
+          _i32(1 if relu else 0), _i32(precision), _i32(split), _t(ws, f32, "workspace"), _stream())
+    if split > 1:
+        LAUNCHES += 1
+    return out
+
+
 def umma_selftest(A, B, D, mode):
     """D[128,64] = A[128,64] @ B[64,64]^T on the tensor cores; mode 0 bf16, 1 tf32, 2 3xTF32."""
     f32 = torch.float32

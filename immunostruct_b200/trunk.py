@@ -56,8 +56,21 @@ class StructureTrunk:
         return self.self_attention.pooled(graph_data, node_feat, want_attn=want_attn, want_nodes=want_nodes)
 
 
+def _tc_linear(layer, x, relu=False):
+    """``layer(x)`` (+ ReLU) -- in no-grad CUDA calls through the tcgen05 Linear kernel (csrc/linear_tc.cu) in the
+    arithmetic of the current precision mode; with autograd (training) through torch / cuBLAS."""
+    prec = IF._PRECISIONS[IF.get_precision()]
+    if torch.is_grad_enabled() or not x.is_cuda or prec is None or x.dim() != 2:
+        y = layer(x)
+        return F.relu(y) if relu else y
+    node_prec = IF._C.PREC_BF16 if prec == IF._C.PREC_BF16 else IF._C.PREC_BF16X3
+    return IF._C.linear_tc(x, layer.weight.detach(), None if layer.bias is None else layer.bias.detach(), relu=relu,
+                           precision=node_prec)
+
+
 class SequenceVAE:
-    """Mixin: the sequence VAE branch (five Linear layers; cuBLAS GEMMs through torch)."""
+    """Mixin: the sequence VAE branch.  The two large Linear layers (vae_fc1, vae_fc4: the model's only big dense
+    contractions) run on the tensor cores in the no-grad path; the tiny ones stay torch / cuBLAS."""
 
     def _build_vae(self, vae_input_dim, vae_hidden_dim, vae_latent_dim, cond_dim):
         self.vae_input_dim, self.vae_hidden_dim, self.vae_latent_dim = vae_input_dim, vae_hidden_dim, vae_latent_dim
@@ -68,7 +81,7 @@ class SequenceVAE:
         self.vae_fc4 = nn.Linear(vae_hidden_dim, vae_input_dim)
 
     def encode_vae(self, x):
-        h1 = F.relu(self.vae_fc1(x))
+        h1 = _tc_linear(self.vae_fc1, x, relu=True)
         return self.vae_fc21(h1), self.vae_fc22(h1)
 
     def reparameterize(self, mu, logvar):
@@ -78,7 +91,7 @@ class SequenceVAE:
         return mu + eps * std
 
     def decode_vae(self, z):
-        return self.vae_fc4(F.relu(self.vae_fc3(z)))
+        return _tc_linear(self.vae_fc4, F.relu(self.vae_fc3(z)))
 
     def vae_branch(self, sequence_data, cond=None):
         mu, logvar = self.encode_vae(sequence_data.reshape(-1, self.vae_input_dim))

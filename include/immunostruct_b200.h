@@ -120,6 +120,14 @@ int is_loss_bwd(const float* recon, const float* seq, int64_t n_recon, const flo
 
 /* ---- tcgen05 self-test: D[128,64] = A[128,64] * B[64,64]^T through the hand-written UMMA helpers
  * (csrc/umma.cuh).  mode 0 = bf16 operands, 1 = tf32, 2 = 3xTF32 split (fp32-accurate). */
+/* Dense Linear layer on the tensor cores: C[M,N] = act(A[M,K] W[N,K]^T + bias), fp32 in / out, operands split
+ * on the fly into three bf16 terms (precision 3, fp32-accurate) or rounded to bf16 (precision 0).  Replaces the
+ * nn.Linear layers of the sequence VAE (reference models/hybrid_models.py:63-74: vae_fc1 with ReLU, vae_fc4) in the
+ * no-grad path.  lda / ldw / ldc = row strides in floats (any alignment); bias may be NULL; split_k > 1 (see
+ * is_linear_tc_split_k) needs workspace >= split_k * M * N floats and sums the K slices in order (deterministic). */
+int is_linear_tc_split_k(int64_t M, int64_t N, int64_t K);
+int is_linear_tc(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc,
+                 int64_t M, int64_t N, int64_t K, int relu, int precision, int split_k, float* workspace, void* stream);
 int is_umma_selftest(const float* A, const float* B, float* D, int mode, void* stream);
 
 #ifdef __cplusplus

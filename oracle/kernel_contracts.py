@@ -125,6 +125,16 @@ def egnn_node_post_pre_tc(h, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, precision
         egnn_node_pre_fwd(h_out, W1n, b1n, PQn)
 
 
+def linear_tc(x, weight, bias=None, relu=False, precision=None, out=None):
+    """nn.Linear (+ ReLU): reference models/hybrid_models.py:63-74."""
+    y = F.linear(x, weight, bias)
+    y = torch.relu(y) if relu else y
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
 # ---- EGNN backward (autograd = independent derivation) -------------------------------------------
 def _partials(rows, *tensors):
     flat = torch.cat([t.reshape(-1) for t in tensors])
@@ -302,6 +312,6 @@ def loss_bwd(recon, seq, mu, logvar, logits, y, mode, pos_weight, w_pred, w_mse,
 
 
 ALL = ["num_sms", "egnn_node_grid", "egnn_edge_bwd_grid", "attn_max_nodes", "loss_num_partials", "collate_csr",
-       "egnn_node_pre_fwd", "egnn_edge_fwd", "egnn_edge_fwd_tc", "egnn_node_post_pre_tc", "egnn_node_post_fwd", "egnn_node_post_bwd", "egnn_edge_bwd", "egnn_edge_bwd_tc",
+       "egnn_node_pre_fwd", "egnn_edge_fwd", "egnn_edge_fwd_tc", "egnn_node_post_pre_tc", "linear_tc", "egnn_node_post_fwd", "egnn_node_post_bwd", "egnn_edge_bwd", "egnn_edge_bwd_tc",
        "egnn_node_pre_bwd", "reduce_partials", "attn_pool_fwd", "attn_pool_infer", "attn_pool_bwd", "fusion_attn_fwd",
        "fusion_attn_bwd", "loss_fwd", "loss_bwd"]

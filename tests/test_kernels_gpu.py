@@ -231,6 +231,33 @@ def test_egnn_node_post_qkv_tensor_core(case, prec, tol):
     close(QKV_d, QKV, tol, what=f"node tc QKV prec={prec}")
 
 
+@pytest.mark.parametrize("prec,tol", [(_C.PREC_BF16X3, 1e-5), (_C.PREC_BF16, 2e-2)])
+@pytest.mark.parametrize("m,n,k,relu,bias", [(512, 512, 5943, True, True),      # vae_fc1: split-K, unaligned rows
+                                              (512, 5943, 512, False, True),     # vae_fc4: ragged N
+                                              (376, 32, 512, False, True),       # vae_fc21 on the last partial batch
+                                              (7, 130, 40, True, False),         # tiny, ragged everything
+                                              (129, 129, 65, False, True)])
+def test_linear_tensor_core(m, n, k, relu, bias, prec, tol):
+    """tcgen05 Linear vs the fp64 product: bf16x3 at the fp32 tolerance, bf16 at 2e-2 (of the result's scale)."""
+    gen = torch.Generator().manual_seed(47)
+    x, w = rnd(gen, m, k), rnd(gen, n, k, scale=0.3)
+    b = rnd(gen, n) if bias else None
+    ref = x.double() @ w.double().T + (b.double() if bias else 0.0)
+    ref = torch.relu(ref) if relu else ref
+    out = _C.linear_tc(x.to(DEV), w.to(DEV), b.to(DEV) if bias else None, relu=relu, precision=prec)
+    close(out, ref.float(), tol, what=f"linear_tc {m}x{n}x{k} prec={prec}")
+    # one-hot rows (the real vae_fc1 input) and a strided input view
+    if k == 5943:
+        oh = torch.zeros(m, 283, 21)
+        oh.scatter_(2, torch.randint(0, 21, (m, 283, 1), generator=gen), 1.0)
+        oh = oh.reshape(m, k)
+        ref = torch.relu(oh.double() @ w.double().T + b.double())
+        close(_C.linear_tc(oh.to(DEV), w.to(DEV), b.to(DEV), relu=True, precision=prec), ref.float(), tol, what="linear_tc one-hot")
+    big = rnd(gen, m, k + 5).to(DEV)
+    ref = big[:, 2:2 + k].double().cpu() @ w.double().T
+    close(_C.linear_tc(big[:, 2:2 + k], w.to(DEV), None, precision=prec), ref.float(), tol, what="linear_tc strided view")
+
+
 # ---- EGNN backward -----------------------------------------------------------------------------
 @pytest.mark.parametrize("tc", [False, True])
 @pytest.mark.parametrize("f,coord", [(64, True), (64, False), (20, True)])
