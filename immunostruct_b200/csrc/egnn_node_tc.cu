@@ -16,13 +16,14 @@
 
 namespace is {
 
-template <int PREC, int NT, bool FAST>
+template <int PREC, int NT, bool FAST, int NEXT_KIND>
 __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1)
 node_post_pre_tc_kernel(const float* __restrict__ h, int64_t ldh, int F, const float* __restrict__ hn,
                         const float* __restrict__ W5, const float* __restrict__ b5,
                         const float* __restrict__ W6, const float* __restrict__ b6, float* __restrict__ h_out,
                         const float* __restrict__ W1n /* next layer edge_mlp.0.weight [64,130] | [Wq;Wk;Wv] [192,64] | null */,
-                        const float* __restrict__ b1n, float* __restrict__ PQn, int64_t M, int next_kind) {
+                        const float* __restrict__ b1n, float* __restrict__ PQn, int64_t M) {
+    constexpr int next_kind = NEXT_KIND;
     using C = TcCfg<PREC>;
     constexpr int NW = NT / 32, CQ = NW / 4, CW = 64 / CQ;
     constexpr uint32_t ASPL = C::A_BYTES, WSPL = 6 * C::W_BYTES;          // split-term strides
@@ -191,22 +192,30 @@ node_post_pre_tc_kernel(const float* __restrict__ h, int64_t ldh, int F, const f
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
-template <int PREC, int NT, bool FAST>
-static int launch_node_tc(const float* h, int64_t ldh, int F, const float* hn, const float* W5, const float* b5,
+template <int PREC, int NT, bool FAST, int NEXT_KIND>
+static int launch_node_tc2(const float* h, int64_t ldh, int F, const float* hn, const float* W5, const float* b5,
                           const float* W6, const float* b6, float* h_out, const float* W1n, const float* b1n,
-                          float* PQn, int64_t M, int next_kind, cudaStream_t st) {
+                          float* PQn, int64_t M, cudaStream_t st) {
     using C = TcCfg<PREC>;
     const size_t smem = (size_t)C::NSPLIT * (C::A_BYTES + 6 * C::W_BYTES) + 5 * 64 * sizeof(float) + 128;
-    cudaError_t e = cudaFuncSetAttribute(node_post_pre_tc_kernel<PREC, NT, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(node_post_pre_tc_kernel<PREC, NT, FAST, NEXT_KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     int64_t tiles = (M + IS_TM - 1) / IS_TM;
     int64_t cap = (int64_t)sms * (NT == 256 ? 2 : 1);
     int grid = (int)(tiles < cap ? tiles : cap);
-    node_post_pre_tc_kernel<PREC, NT, FAST><<<grid < 1 ? 1 : grid, NT, smem, st>>>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, M, next_kind);
+    node_post_pre_tc_kernel<PREC, NT, FAST, NEXT_KIND><<<grid < 1 ? 1 : grid, NT, smem, st>>>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, M);
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
+}
+
+template <int PREC, int NT, bool FAST>
+static int launch_node_tc(const float* h, int64_t ldh, int F, const float* hn, const float* W5, const float* b5,
+                          const float* W6, const float* b6, float* h_out, const float* W1n, const float* b1n,
+                          float* PQn, int64_t M, int next_kind, cudaStream_t st) {
+    if (next_kind == 2) return launch_node_tc2<PREC, NT, FAST, 2>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, M, st);
+    return launch_node_tc2<PREC, NT, FAST, 1>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, M, st);
 }
 
 }  // namespace is

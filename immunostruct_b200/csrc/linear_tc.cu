@@ -15,7 +15,7 @@
 
 namespace is {
 namespace lin {
-constexpr int NT = 512, NW = NT / 32;
+constexpr int NT = 512;
 constexpr int BM = 128, BN = 128, BK = 64;
 constexpr uint32_t LBO = 128, SBO = 8 * LBO, T_BYTES = 16 * SBO;      // one 128-row operand tile, one split term
 }  // namespace lin
@@ -137,8 +137,11 @@ linear_tc_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
     }
     fence_after_sync();
     {
-        const int q = warp & 3, cq = warp >> 2;
-        const int64_t m = m0 + 32 * q + lane;
+        // TMEM -> registers (thread = one row x 32 columns) -> fp32 tile in the (now idle) operand buffers -> global
+        // memory with a warp per row and a lane per column: full 128-byte segments whatever the row stride
+        constexpr int LDT = BN + 1;                                   // odd stride: the row-per-lane writes are conflict free
+        float* T = reinterpret_cast<float*>(smem_raw);                // 128 x 129 floats = 66 KB
+        const int q = warp & 3, cq = warp >> 2, row = 32 * q + lane;
         float z[32];
         if (nkb > 0) {
             tmem_ld<32>(tmem + ((uint32_t)(32 * q) << 16) + 32 * cq, z);
@@ -146,18 +149,26 @@ linear_tc_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
 #pragma unroll
             for (int i = 0; i < 32; ++i) z[i] = 0.0f;
         }
-        if (m < M) {
-            const bool direct = split_k == 1;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) T[row * LDT + 32 * cq + i] = z[i];
+        __syncthreads();
+        const bool direct = split_k == 1;
+        float bv[BN / 32];
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j) {
+            const int64_t n = n0 + lane + 32 * j;
+            bv[j] = (direct && bias && n < N) ? __ldg(bias + n) : 0.0f;
+        }
+        for (int r = warp; r < BM; r += NT / 32) {
+            const int64_t m = m0 + r;
+            if (m >= M) break;
             float* dst = direct ? C + m * ldc : part + ((int64_t)blockIdx.z * M + m) * N;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int64_t n = n0 + 32 * cq + i;
+            for (int j = 0; j < BN / 32; ++j) {
+                const int64_t n = n0 + lane + 32 * j;
                 if (n < N) {
-                    float v = z[i];
-                    if (direct) {
-                        if (bias) v += __ldg(bias + n);
-                        if (relu) v = fmaxf(v, 0.0f);
-                    }
+                    float v = T[r * LDT + lane + 32 * j] + bv[j];
+                    if (direct && relu) v = fmaxf(v, 0.0f);
                     dst[n] = v;
                 }
             }
@@ -186,7 +197,9 @@ template <int PREC>
 static int launch_linear(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc,
                          float* part, int64_t M, int64_t N, int64_t K, int relu, int split_k, cudaStream_t st) {
     using namespace lin;
-    const size_t smem = (size_t)2 * 2 * TcCfg<PREC>::NSPLIT * T_BYTES;
+    size_t smem = (size_t)2 * 2 * TcCfg<PREC>::NSPLIT * T_BYTES;
+    const size_t epi = (size_t)BM * (BN + 1) * sizeof(float);          // the epilogue's fp32 tile reuses the operand buffers
+    if (smem < epi) smem = epi;
     cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel<PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), (unsigned)split_k);
