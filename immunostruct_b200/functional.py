@@ -304,7 +304,13 @@ def attention_pool(graph, QKV, n_head=1, want_attn=False, want_nodes=False):
     if not want_attn and not want_nodes and not (torch.is_grad_enabled() and QKV.requires_grad):
         QKV = QKV.contiguous()
         pooled = _new(QKV, graph.n_graphs, H)
-        _C.attn_pool_infer(QKV, graph.node_off, n_head, graph.max_nodes, pooled)
+        prec = _PRECISIONS[_precision]
+        if n_head == 1 and prec is not None and graph.max_nodes <= 256:
+            # single head: Q K^T on the tensor cores, softmax statistics straight from TMEM (csrc/attn_pool_tc.cu)
+            _C.attn_pool_infer_tc(QKV, graph.node_off, graph.max_nodes, pooled,
+                                  _C.PREC_BF16 if prec == _C.PREC_BF16 else _C.PREC_BF16X3)
+        else:
+            _C.attn_pool_infer(QKV, graph.node_off, n_head, graph.max_nodes, pooled)
         return None, pooled, None
     return _AttnPool.apply(graph, n_head, want_attn, QKV)
 

@@ -120,6 +120,12 @@ int is_loss_bwd(const float* recon, const float* seq, int64_t n_recon, const flo
 
 /* ---- tcgen05 self-test: D[128,64] = A[128,64] * B[64,64]^T through the hand-written UMMA helpers
  * (csrc/umma.cuh).  mode 0 = bf16 operands, 1 = tf32, 2 = 3xTF32 split (fp32-accurate). */
+/* Single-head per-graph attention + global mean pool on the tensor cores (inference: pooled rows only).  Same
+ * result as is_attn_pool_infer with n_head = 1 (reference models/layers.py:13-22 / 67-78 + global_mean_pool,
+ * hybrid_models.py:92-97 / 326-331).  QKV [N_total,192], node_off [n_graphs+1], pooled [n_graphs,64]; max_nodes <= 256;
+ * precision 0 = bf16, 3 = bf16x3 (fp32-accurate). */
+int is_attn_pool_infer_tc(const float* QKV, const int64_t* node_off, int n_graphs, int max_nodes, int precision,
+                          float* pooled, void* stream);
 /* Dense Linear layer on the tensor cores: C[M,N] = act(A[M,K] W[N,K]^T + bias), fp32 in / out, operands split
  * on the fly into three bf16 terms (precision 3, fp32-accurate) or rounded to bf16 (precision 0).  Replaces the
  * nn.Linear layers of the sequence VAE (reference models/hybrid_models.py:63-74: vae_fc1 with ReLU, vae_fc4) in the

@@ -240,6 +240,10 @@ def attn_pool_infer(QKV, node_off, n_head, max_nodes, pooled):
         pooled[gi] = _attn_graph(QKV[off[gi]:off[gi + 1]], n_head)[0].mean(0)
 
 
+def attn_pool_infer_tc(QKV, node_off, max_nodes, pooled, precision=None):
+    attn_pool_infer(QKV, node_off, 1, max_nodes, pooled)
+
+
 @torch.enable_grad()
 def attn_pool_bwd(QKV, O, LSE, node_off, n_head, max_nodes, g_pooled, gO_full, gQKV):
     off = node_off.tolist()
@@ -313,5 +317,5 @@ def loss_bwd(recon, seq, mu, logvar, logits, y, mode, pos_weight, w_pred, w_mse,
 
 ALL = ["num_sms", "egnn_node_grid", "egnn_edge_bwd_grid", "attn_max_nodes", "loss_num_partials", "collate_csr",
        "egnn_node_pre_fwd", "egnn_edge_fwd", "egnn_edge_fwd_tc", "egnn_node_post_pre_tc", "linear_tc", "egnn_node_post_fwd", "egnn_node_post_bwd", "egnn_edge_bwd", "egnn_edge_bwd_tc",
-       "egnn_node_pre_bwd", "reduce_partials", "attn_pool_fwd", "attn_pool_infer", "attn_pool_bwd", "fusion_attn_fwd",
+       "egnn_node_pre_bwd", "reduce_partials", "attn_pool_fwd", "attn_pool_infer", "attn_pool_infer_tc", "attn_pool_bwd", "fusion_attn_fwd",
        "fusion_attn_bwd", "loss_fwd", "loss_bwd"]

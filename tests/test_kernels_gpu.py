@@ -374,6 +374,16 @@ def test_attention_pool_kernels(case, n_head):
     pooled_i = torch.full((b, 64), float("nan"), device=DEV)
     _C.attn_pool_infer(QKV.to(DEV), gb.node_off, n_head, gb.max_nodes, pooled_i)
     close(pooled_i, pooled, what="pooled (inference kernel)")
+    if n_head == 1:
+        for prec, tol in ((_C.PREC_BF16X3, 1e-5), (_C.PREC_BF16, 2e-2)):
+            pooled_t = torch.full((b, 64), float("nan"), device=DEV)
+            _C.attn_pool_infer_tc(QKV.to(DEV), gb.node_off, gb.max_nodes, pooled_t, prec)
+            close(pooled_t, pooled, tol, what=f"pooled (tensor-core inference kernel, prec={prec})")
+            big = QKV.to(DEV) * 6.0                 # peaked softmax rows
+            ref_big = torch.empty(b, 64)
+            KC.attn_pool_infer(QKV * 6.0, cg.node_off, 1, gb.max_nodes, ref_big)
+            _C.attn_pool_infer_tc(big, gb.node_off, gb.max_nodes, pooled_t, prec)
+            close(pooled_t, ref_big, tol * (1 if prec == _C.PREC_BF16X3 else 4), what=f"pooled tc peaked prec={prec}")
     g_pooled, gO = rnd(gen, b, 64), rnd(gen, n, 64)
     for gp, go in ((g_pooled, None), (g_pooled, gO), (None, gO)):
         gQKV, gQKV_d = torch.empty(n, 192), torch.empty(n, 192, device=DEV)
