@@ -39,7 +39,7 @@ def exported_symbols():
             "is_loss_num_partials", "is_collate_csr", "is_egnn_node_pre_fwd", "is_egnn_edge_fwd",
             "is_egnn_node_post_fwd", "is_egnn_node_post_bwd", "is_egnn_edge_bwd", "is_egnn_node_pre_bwd",
             "is_reduce_partials", "is_attn_pool_fwd", "is_attn_pool_bwd", "is_fusion_attn_fwd",
-            "is_fusion_attn_bwd", "is_loss_fwd", "is_loss_bwd", "is_umma_selftest", "is_egnn_edge_fwd_tc", "is_attn_pool_infer", "is_egnn_node_post_pre_tc", "is_egnn_edge_bwd_tc", "is_linear_tc", "is_linear_tc_split_k", "is_attn_pool_infer_tc"]
+            "is_fusion_attn_bwd", "is_loss_fwd", "is_loss_bwd", "is_umma_selftest", "is_egnn_edge_fwd_tc", "is_attn_pool_infer", "is_egnn_node_post_pre_tc", "is_egnn_edge_bwd_tc", "is_linear_tc", "is_linear_tc_split_k", "is_attn_pool_infer_tc", "is_vae_mid_infer", "is_head_infer"]
 
 
 def _check(rc: int, name: str):
@@ -308,6 +308,37 @@ def linear_tc(x, weight, bias=None, relu=False, precision=PREC_BF16X3, out=None)
     if split > 1:
         LAUNCHES += 1
     return out
+
+
+def vae_mid_infer(h1, prop, eps, Wp0, bp0, Wp3, bp3, W21, b21, W22, b22, W3, b3):
+    """Eval-mode middle of the sequence branch in one kernel (csrc/head.cu) -> (mu, logvar, z_vae, h3)."""
+    f32 = torch.float32
+    b, hd = h1.shape
+    ld, pd = W21.shape[0], Wp3.shape[0]
+    if Wp0.shape != (32, 2) or Wp3.shape[1] != 32 or W3.shape != (hd, ld + pd) or eps.shape != (b, ld):
+        raise ValueError("vae_mid_infer: unexpected layer shapes")
+    mu, logvar = torch.empty(b, ld, dtype=f32, device=h1.device), torch.empty(b, ld, dtype=f32, device=h1.device)
+    zv, h3 = torch.empty(b, ld + pd, dtype=f32, device=h1.device), torch.empty(b, hd, dtype=f32, device=h1.device)
+    args = [_t(t, f32, n) for t, n in ((h1, "h1"), (prop, "prop"), (eps, "eps"), (Wp0, "Wp0"), (bp0, "bp0"), (Wp3, "Wp3"),
+                                       (bp3, "bp3"), (W21, "W21"), (b21, "b21"), (W22, "W22"), (b22, "b22"), (W3, "W3"),
+                                       (b3, "b3"), (mu, "mu"), (logvar, "logvar"), (zv, "z_vae"), (h3, "h3"))]
+    _call("is_vae_mid_infer", *args, _i32(b), _i32(hd), _i32(ld), _i32(pd), _stream())
+    return mu, logvar, zv, h3
+
+
+def head_infer(pooled, Wc, bc, z_vae, coef, n_head, W1, b1, W2, b2):
+    """Eval-mode fusion head in one kernel (csrc/head.cu) -> (x_gat [B,64], out [B,n_out] or [B,32] when W2 is None)."""
+    f32 = torch.float32
+    b, lz = z_vae.shape
+    if pooled.shape != (b, 64) or W1.shape != (32, 64 + lz):
+        raise ValueError("head_infer: unexpected shapes")
+    n_out = 0 if W2 is None else W2.shape[0]
+    x_gat = torch.empty(b, 64, dtype=f32, device=pooled.device)
+    out = torch.empty(b, n_out if W2 is not None else 32, dtype=f32, device=pooled.device)
+    _call("is_head_infer", _t(pooled, f32, "pooled"), _t(Wc, f32, "Wc"), _t(bc, f32, "bc"), _t(z_vae, f32, "z_vae"), _i32(lz),
+          _t(coef, f32, "coef"), _i32(n_head), _t(W1, f32, "W1"), _t(b1, f32, "b1"), _t(W2, f32, "W2"), _t(b2, f32, "b2"),
+          _i32(n_out), _t(x_gat, f32, "x_gat"), _t(out, f32, "out"), _i32(b), _stream())
+    return x_gat, out
 
 
 def umma_selftest(A, B, D, mode):

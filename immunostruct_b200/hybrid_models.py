@@ -39,7 +39,37 @@ class _Hybrid(nn.Module, StructureTrunk, SequenceVAE, LoadTrained):
         return classifier_mlp(self.vae_latent_dim + self.property_embedding_dim + self.gat_hidden_channels,
                               with_out=not self._ssl)
 
+    def _fused_eval_ok(self, graph_data, peptide_property, return_attention):
+        """The eval-mode small-layer fusions (csrc/head.cu) apply: no autograd, dropout inactive, CUDA inputs, the
+        reference's layer shapes, tensor-core arithmetic mode, attention weights not requested."""
+        from . import functional as IF
+        return (not torch.is_grad_enabled() and not self.training and not return_attention
+                and "reparameterize" not in self.__dict__          # a patched reparameterize must be honoured
+                and IF._PRECISIONS[IF.get_precision()] is not None and peptide_property.is_cuda
+                and peptide_property.dtype == torch.float32 and self.property_embedding[0].weight.shape == (32, 2)
+                and self.gat_hidden_channels == 64 and self.mlp_features == 32
+                and self.vae_latent_dim + self.property_embedding_dim <= 192)
+
+    def _forward_eval_fused(self, graph_data, sequence_data, peptide_property, return_embedding):
+        from . import functional as IF
+        pooled, _, _ = self.structure_embedding(graph_data, project=False)
+        recon_x, mu, logvar, z_vae = self.vae_branch_eval(sequence_data, self.property_embedding, peptide_property)
+        wc = self.self_attention.out_projection
+        fus = self.combined_attention if self._fusion_dim else None
+        cls1, cls2 = self.classifier[1], (None if self._ssl else self.classifier[4])
+        x_gat_node, out = IF._C.head_infer(
+            pooled, None if wc is None else wc.weight.detach(), None if wc is None else wc.bias.detach(), z_vae,
+            None if fus is None else fus.fusion_coefficients(), 0 if fus is None else fus.n_head,
+            cls1.weight.detach(), cls1.bias.detach(), None if cls2 is None else cls2.weight.detach(),
+            None if cls2 is None else cls2.bias.detach())
+        tail = (self.classifier_head(out), self.node_predictor_head(out)) if self._ssl else (out,)
+        if return_embedding:
+            return (x_gat_node, mu, logvar) + tail
+        return (recon_x, mu, logvar) + tail
+
     def forward(self, graph_data, sequence_data, peptide_property, return_embedding=False, return_attention=False):
+        if self._fused_eval_ok(graph_data, peptide_property, return_attention):
+            return self._forward_eval_fused(graph_data, sequence_data, peptide_property, return_embedding)
         x_gat_node, attention_weights, _ = self.structure_embedding(graph_data, want_attn=return_attention)
         peptide_property = self.property_embedding(peptide_property)          # consumes dropout RNG first
         recon_x, mu, logvar, z_vae = self.vae_branch(sequence_data, peptide_property)

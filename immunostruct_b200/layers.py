@@ -19,6 +19,22 @@ import torch.nn.functional as F
 from . import functional as IF
 
 
+def _cached_no_grad(module, name, params, build):
+    """Parameter-only preprocessing (concatenated projection weights, closed-form fusion coefficients) is a dozen
+    tiny kernels per forward; in no-grad mode cache the result on the module, keyed on the parameters' storage and
+    in-place version counters (optimizer steps and load_state_dict bump them)."""
+    if torch.is_grad_enabled():
+        return build()
+    key = tuple((p.data_ptr(), p._version) for p in params)
+    slot = module.__dict__.setdefault("_derived_cache", {})
+    hit = slot.get(name)
+    if hit is None or hit[0] != key:
+        with torch.no_grad():
+            hit = (key, build())
+        slot[name] = hit
+    return hit[1]
+
+
 class EGNNConv(nn.Module):
     def __init__(self, in_size, hidden_size, out_size, edge_feat_size=0):
         super().__init__()
@@ -72,13 +88,15 @@ class SelfAttention(nn.Module):
 
     def qkv_params(self):
         """([Wq;Wk;Wv] [192,64], [bq;bk;bv] [192]) for the fused projection."""
-        return (torch.cat([self.query.weight, self.key.weight, self.value.weight], 0),
-                torch.cat([self.query.bias, self.key.bias, self.value.bias], 0))
+        ps = (self.query.weight, self.key.weight, self.value.weight, self.query.bias, self.key.bias, self.value.bias)
+        return _cached_no_grad(self, "qkv", ps, lambda: (torch.cat(ps[:3], 0), torch.cat(ps[3:], 0)))
 
     def _qkv(self, h):
         return F.linear(h, *self.qkv_params())
 
-    def pooled(self, graph, h, want_attn=False, want_nodes=False, qkv=None):
+    out_projection = None                       # SelfAttention has no w_concat
+
+    def pooled(self, graph, h, want_attn=False, want_nodes=False, qkv=None, project=True):
         """h [N_total,64] -> (per-graph mean of the attention output [B,64], weights|None, per-node out|None).
         ``qkv``: the projections [N,192] when a fused kernel has already computed them."""
         O, pooled, attn = IF.attention_pool(graph, self._qkv(h) if qkv is None else qkv, 1, want_attn, want_nodes)
@@ -120,24 +138,32 @@ class MultiHeadAttention(nn.Module):
     # ---- fused entry points used by the models ---------------------------------------------------
     def qkv_params(self):
         """([Wq;Wk;Wv] [192,64], [bq;bk;bv] [192]) for the fused projection."""
-        return (torch.cat([self.w_q.weight, self.w_k.weight, self.w_v.weight], 0),
-                torch.cat([self.w_q.bias, self.w_k.bias, self.w_v.bias], 0))
+        ps = (self.w_q.weight, self.w_k.weight, self.w_v.weight, self.w_q.bias, self.w_k.bias, self.w_v.bias)
+        return _cached_no_grad(self, "qkv", ps, lambda: (torch.cat(ps[:3], 0), torch.cat(ps[3:], 0)))
 
     def _qkv(self, h):
         return F.linear(h, *self.qkv_params())
 
-    def pooled(self, graph, h, want_attn=False, want_nodes=False, qkv=None):
+    @property
+    def out_projection(self):
+        return self.w_concat
+
+    def pooled(self, graph, h, want_attn=False, want_nodes=False, qkv=None, project=True):
         """Per-graph attention over node embeddings + global mean pool.  The mean commutes with the
-        affine ``w_concat``, so the projection is applied to the pooled [B,64] rows.  ``qkv``: the
-        projections [N,192] when a fused kernel has already computed them."""
+        affine ``w_concat``, so the projection is applied to the pooled [B,64] rows (``project=False``: the
+        caller applies it, e.g. inside the fused head kernel).  ``qkv``: the projections [N,192] when a fused
+        kernel has already computed them."""
         if self.feature_dim != 64 or self.input_dim != 64:
             raise NotImplementedError("fused per-graph attention is specialised for 64 channels")
         O, pooled, attn = IF.attention_pool(graph, self._qkv(h) if qkv is None else qkv, self.n_head, want_attn, want_nodes)
         nodes = self.w_concat(O) if want_nodes else None
-        return self.w_concat(pooled), attn, nodes
+        return (self.w_concat(pooled) if project else pooled), attn, nodes
 
     def fusion_coefficients(self):
         """[A(H) | C(H) | alpha(H) | beta(H) | btilde] of the closed form in csrc/fusion.cu."""
+        return _cached_no_grad(self, "fusion", tuple(self.parameters()), self._fusion_coefficients)
+
+    def _fusion_coefficients(self):
         if self.input_dim != 1:
             raise NotImplementedError("closed-form fusion attention needs scalar tokens (input_dim = 1)")
         hh, dh = self.n_head, self.feature_dim // self.n_head

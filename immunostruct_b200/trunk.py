@@ -34,8 +34,9 @@ class StructureTrunk:
             self.GCN_layers.append(EGNNConv(hidden, hidden, hidden, 1))
         self.self_attention = SelfAttention(hidden) if attention == "sa" else MultiHeadAttention(hidden, heads)
 
-    def structure_embedding(self, graph_data, want_attn=False, want_nodes=False):
+    def structure_embedding(self, graph_data, want_attn=False, want_nodes=False, project=True):
         """-> (pooled [B,64], attention weights or None, per-node attention output or None).
+        ``project=False`` leaves the attention's output projection (w_concat) to the caller.
 
         The per-graph ``batch_tensor`` of the reference (B host syncs per forward,
         hybrid_models.py:86-87) is replaced by the segment offsets cached on the GraphBatch."""
@@ -49,11 +50,12 @@ class StructureTrunk:
             out = IF.egnn_stack_infer(graph_data, xin, edge_feat, [l.kernel_params() for l in self.GCN_layers],
                                       qkv=self.self_attention.qkv_params() if fuse_qkv else None)
             node_feat, qkv = out if fuse_qkv else (out, None)
-            return self.self_attention.pooled(graph_data, node_feat, want_attn=want_attn, want_nodes=want_nodes, qkv=qkv)
+            return self.self_attention.pooled(graph_data, node_feat, want_attn=want_attn, want_nodes=want_nodes, qkv=qkv,
+                                              project=project)
         # training: one autograd node for the whole stack (the last layer's coordinates are never consumed,
         # hybrid_models.py:323-326, so its coordinate branch is skipped and coord_mlp gets no gradient)
         node_feat = IF.egnn_stack(graph_data, xin, edge_feat, [l.kernel_params() for l in self.GCN_layers])
-        return self.self_attention.pooled(graph_data, node_feat, want_attn=want_attn, want_nodes=want_nodes)
+        return self.self_attention.pooled(graph_data, node_feat, want_attn=want_attn, want_nodes=want_nodes, project=project)
 
 
 def _tc_linear(layer, x, relu=False):
@@ -84,14 +86,32 @@ class SequenceVAE:
         h1 = _tc_linear(self.vae_fc1, x, relu=True)
         return self.vae_fc21(h1), self.vae_fc22(h1)
 
+    def sample_eps(self, like):
+        """The standard-normal draw of ``reparameterize`` (``torch.randn_like(std)``, hybrid_models.py:303) -- one
+        place for both the torch path and the fused eval kernel, so tests can inject a fixed noise tensor."""
+        return torch.randn_like(like)
+
     def reparameterize(self, mu, logvar):
         # sampled in eval mode too, exactly like the reference (hybrid_models.py:301-304)
         std = torch.exp(0.5 * logvar)
-        eps = torch.randn_like(std)
+        eps = self.sample_eps(std)
         return mu + eps * std
 
     def decode_vae(self, z):
         return _tc_linear(self.vae_fc4, F.relu(self.vae_fc3(z)))
+
+    def vae_branch_eval(self, sequence_data, prop_mlp, peptide_property):
+        """Eval-mode, no-grad sequence branch with the small layers fused (csrc/head.cu): vae_fc1 and vae_fc4 on the
+        tensor cores, property MLP + vae_fc21 / fc22 + reparameterisation + vae_fc3 in one kernel.  Same RNG draw as
+        ``reparameterize`` (one standard-normal [B, latent] tensor).  -> (recon, mu, logvar, z_vae)."""
+        h1 = _tc_linear(self.vae_fc1, sequence_data.reshape(-1, self.vae_input_dim), relu=True)
+        eps = self.sample_eps(torch.empty(h1.shape[0], self.vae_latent_dim, dtype=h1.dtype, device=h1.device)).contiguous()
+        d = lambda t: t.detach()
+        mu, logvar, z_vae, h3 = IF._C.vae_mid_infer(
+            h1, peptide_property.contiguous(), eps, d(prop_mlp[0].weight), d(prop_mlp[0].bias), d(prop_mlp[3].weight),
+            d(prop_mlp[3].bias), d(self.vae_fc21.weight), d(self.vae_fc21.bias), d(self.vae_fc22.weight),
+            d(self.vae_fc22.bias), d(self.vae_fc3.weight), d(self.vae_fc3.bias))
+        return _tc_linear(self.vae_fc4, h3), mu, logvar, z_vae
 
     def vae_branch(self, sequence_data, cond=None):
         mu, logvar = self.encode_vae(sequence_data.reshape(-1, self.vae_input_dim))

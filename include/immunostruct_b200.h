@@ -126,6 +126,19 @@ int is_loss_bwd(const float* recon, const float* seq, int64_t n_recon, const flo
  * precision 0 = bf16, 3 = bf16x3 (fp32-accurate). */
 int is_attn_pool_infer_tc(const float* QKV, const int64_t* node_off, int n_graphs, int max_nodes, int precision,
                           float* pooled, void* stream);
+/* Eval-mode small-layer fusions (csrc/head.cu; no autograd, dropout inactive).
+ * is_vae_mid_infer: property_embedding (reference models/hybrid_models.py:46-52 / 280-286), mu / logvar = vae_fc21 /
+ * vae_fc22 (h1), z = mu + eps exp(0.5 logvar) (:301-304, eps drawn by the caller), z_vae = [z | prop] (:339),
+ * h3 = ReLU(vae_fc3 z_vae) (:306-307).  is_head_infer: x_gat = w_concat(pooled) (Wc NULL: identity), combined =
+ * [x_gat | z_vae] (:341), closed-form fusion attention (coef NULL: none), classifier (:54-61, 351; W2 NULL: the 32
+ * hidden features are returned). */
+int is_vae_mid_infer(const float* h1, const float* prop, const float* eps, const float* Wp0, const float* bp0,
+                     const float* Wp3, const float* bp3, const float* W21, const float* b21, const float* W22,
+                     const float* b22, const float* W3, const float* b3, float* mu, float* logvar, float* z_vae,
+                     float* h3, int n_samples, int hidden, int latent, int prop_dim, void* stream);
+int is_head_infer(const float* pooled, const float* Wc, const float* bc, const float* z_vae, int LZ, const float* coef,
+                  int n_head, const float* W1, const float* b1, const float* W2, const float* b2, int n_out,
+                  float* x_gat, float* out, int n_samples, void* stream);
 /* Dense Linear layer on the tensor cores: C[M,N] = act(A[M,K] W[N,K]^T + bias), fp32 in / out, operands split
  * on the fly into three bf16 terms (precision 3, fp32-accurate) or rounded to bf16 (precision 0).  Replaces the
  * nn.Linear layers of the sequence VAE (reference models/hybrid_models.py:63-74: vae_fc1 with ReLU, vae_fc4) in the

@@ -125,6 +125,26 @@ def egnn_node_post_pre_tc(h, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, precision
         egnn_node_pre_fwd(h_out, W1n, b1n, PQn)
 
 
+def vae_mid_infer(h1, prop, eps, Wp0, bp0, Wp3, bp3, W21, b21, W22, b22, W3, b3):
+    """hybrid_models.py:46-52 (property MLP, eval), :299-307 (mu / logvar, reparameterize with the given eps, fc3)."""
+    pe = torch.relu(F.linear(torch.relu(F.linear(prop, Wp0, bp0)), Wp3, bp3))
+    mu, logvar = F.linear(h1, W21, b21), F.linear(h1, W22, b22)
+    zv = torch.cat([mu + eps * torch.exp(0.5 * logvar), pe], 1)
+    return mu, logvar, zv, torch.relu(F.linear(zv, W3, b3))
+
+
+def head_infer(pooled, Wc, bc, z_vae, coef, n_head, W1, b1, W2, b2):
+    """w_concat on the pooled rows, concat, closed-form fusion attention, classifier (hybrid_models.py:341-351)."""
+    x_gat = F.linear(pooled, Wc, bc) if Wc is not None else pooled.clone()
+    comb = torch.cat([x_gat, z_vae], 1)
+    if coef is not None:
+        fused = torch.empty_like(comb)
+        fusion_attn_fwd(comb, n_head, coef, fused)
+        comb = fused
+    hid = torch.relu(F.linear(comb, W1, b1))
+    return x_gat, (F.linear(hid, W2, b2) if W2 is not None else hid)
+
+
 def linear_tc(x, weight, bias=None, relu=False, precision=None, out=None):
     """nn.Linear (+ ReLU): reference models/hybrid_models.py:63-74."""
     y = F.linear(x, weight, bias)
@@ -316,6 +336,6 @@ def loss_bwd(recon, seq, mu, logvar, logits, y, mode, pos_weight, w_pred, w_mse,
 
 
 ALL = ["num_sms", "egnn_node_grid", "egnn_edge_bwd_grid", "attn_max_nodes", "loss_num_partials", "collate_csr",
-       "egnn_node_pre_fwd", "egnn_edge_fwd", "egnn_edge_fwd_tc", "egnn_node_post_pre_tc", "linear_tc", "egnn_node_post_fwd", "egnn_node_post_bwd", "egnn_edge_bwd", "egnn_edge_bwd_tc",
+       "egnn_node_pre_fwd", "egnn_edge_fwd", "egnn_edge_fwd_tc", "egnn_node_post_pre_tc", "linear_tc", "vae_mid_infer", "head_infer", "egnn_node_post_fwd", "egnn_node_post_bwd", "egnn_edge_bwd", "egnn_edge_bwd_tc",
        "egnn_node_pre_bwd", "reduce_partials", "attn_pool_fwd", "attn_pool_infer", "attn_pool_infer_tc", "attn_pool_bwd", "fusion_attn_fwd",
        "fusion_attn_bwd", "loss_fwd", "loss_bwd"]

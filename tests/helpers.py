@@ -19,13 +19,14 @@ def graph_batch(arrays, device="cpu"):
 
 
 def inject_eps(model, *eps_list):
-    """Make ``model.reparameterize`` consume the given noise tensors in order (instead of randn_like)."""
+    """Make the model's reparameterisation consume the given noise tensors in order (instead of randn_like);
+    ``sample_eps`` feeds both ``reparameterize`` and the fused eval-mode kernel."""
     it = iter(eps_list)
 
-    def reparameterize(self, mu, logvar):
-        return mu + next(it).to(mu.device, mu.dtype) * torch.exp(0.5 * logvar)
+    def sample_eps(self, like):
+        return next(it).to(like.device, like.dtype)
 
-    model.reparameterize = types.MethodType(reparameterize, model)
+    model.sample_eps = types.MethodType(sample_eps, model)
     return model
 
 

@@ -258,6 +258,28 @@ def test_linear_tensor_core(m, n, k, relu, bias, prec, tol):
     close(_C.linear_tc(big[:, 2:2 + k], w.to(DEV), None, precision=prec), ref.float(), tol, what="linear_tc strided view")
 
 
+@pytest.mark.parametrize("b", [512, 5])
+def test_vae_mid_and_head_kernels(b):
+    """Eval-mode small-layer fusions (csrc/head.cu) vs their torch contracts."""
+    gen = torch.Generator().manual_seed(53)
+    h1, prop, eps = rnd(gen, b, 512).abs(), torch.rand(b, 2, generator=gen), rnd(gen, b, 32)
+    ws = dict(Wp0=rnd(gen, 32, 2), bp0=rnd(gen, 32), Wp3=rnd(gen, 8, 32), bp3=rnd(gen, 8), W21=rnd(gen, 32, 512, scale=0.1),
+              b21=rnd(gen, 32), W22=rnd(gen, 32, 512, scale=0.05), b22=rnd(gen, 32), W3=rnd(gen, 512, 40), b3=rnd(gen, 512))
+    ref = KC.vae_mid_infer(h1, prop, eps, *ws.values())
+    got = _C.vae_mid_infer(h1.to(DEV), prop.to(DEV), eps.to(DEV), *(v.to(DEV) for v in ws.values()))
+    for name, r, g_ in zip(("mu", "logvar", "z_vae", "h3"), ref, got):
+        close(g_, r, what=f"vae_mid {name}")
+    pooled, zv = rnd(gen, b, 64), ref[2]
+    Wc, bc, coef = rnd(gen, 64, 64, scale=0.3), rnd(gen, 64), rnd(gen, 33, scale=0.5)
+    W1, b1, W2, b2 = rnd(gen, 32, 104, scale=0.3), rnd(gen, 32), rnd(gen, 1, 32), rnd(gen, 1)
+    for use_wc, use_coef, use_w2 in ((True, True, True), (False, False, True), (True, True, False)):
+        args = (pooled, Wc if use_wc else None, bc if use_wc else None, zv, coef if use_coef else None, 8, W1, b1,
+                W2 if use_w2 else None, b2 if use_w2 else None)
+        rx, ro = KC.head_infer(*args)
+        gx, go = _C.head_infer(*(a.to(DEV) if torch.is_tensor(a) else a for a in args))
+        close(gx, rx, what="head x_gat"); close(go, ro, what=f"head out wc={use_wc} fusion={use_coef} out={use_w2}")
+
+
 # ---- EGNN backward -----------------------------------------------------------------------------
 @pytest.mark.parametrize("tc", [False, True])
 @pytest.mark.parametrize("f,coord", [(64, True), (64, False), (20, True)])
