@@ -39,19 +39,17 @@ node_post_pre_tc_kernel(const float* __restrict__ h, int64_t ldh, int F, const f
 
     if (warp == 0) tmem_alloc(&s_tmem, 256);
     if (tid == 32) mbar_init(&mbar, 1);
-    for (int idx = tid; idx < 64 * 64; idx += NT) {
-        const int n = idx >> 6, k = idx & 63;
-        store_weight1<PREC>(sW + 0 * C::W_BYTES, WSPL, n, k, k < F ? __ldg(W5 + n * K5 + k) : 0.0f);
-        store_weight1<PREC>(sW + 1 * C::W_BYTES, WSPL, n, k, __ldg(W5 + n * K5 + F + k));
-        store_weight1<PREC>(sW + 2 * C::W_BYTES, WSPL, n, k, __ldg(W6 + idx));
-        if (next_kind == 2) {
-            store_weight1<PREC>(sW + 3 * C::W_BYTES, WSPL, n, k, __ldg(W1n + idx));
-            store_weight1<PREC>(sW + 4 * C::W_BYTES, WSPL, n, k, __ldg(W1n + 4096 + idx));
-            store_weight1<PREC>(sW + 5 * C::W_BYTES, WSPL, n, k, __ldg(W1n + 8192 + idx));
-        } else {
-            store_weight1<PREC>(sW + 3 * C::W_BYTES, WSPL, n, k, has_next ? __ldg(W1n + n * 130 + k) : 0.0f);
-            store_weight1<PREC>(sW + 4 * C::W_BYTES, WSPL, n, k, has_next ? __ldg(W1n + n * 130 + 64 + k) : 0.0f);
-        }
+    // six resident weight blocks (16-byte chunk stores; W5's two K halves, W6, then the "next" weights)
+    stage_weight_block<PREC>(sW + 0 * C::W_BYTES, WSPL, W5, K5, 0, F, tid, NT);
+    stage_weight_block<PREC>(sW + 1 * C::W_BYTES, WSPL, W5, K5, F, 64, tid, NT);
+    stage_weight_block<PREC>(sW + 2 * C::W_BYTES, WSPL, W6, 64, 0, 64, tid, NT);
+    if (next_kind == 2) {
+        stage_weight_block<PREC>(sW + 3 * C::W_BYTES, WSPL, W1n, 64, 0, 64, tid, NT);
+        stage_weight_block<PREC>(sW + 4 * C::W_BYTES, WSPL, W1n + 4096, 64, 0, 64, tid, NT);
+        stage_weight_block<PREC>(sW + 5 * C::W_BYTES, WSPL, W1n + 8192, 64, 0, 64, tid, NT);
+    } else {
+        stage_weight_block<PREC>(sW + 3 * C::W_BYTES, WSPL, has_next ? W1n : nullptr, 130, 0, 64, tid, NT);
+        stage_weight_block<PREC>(sW + 4 * C::W_BYTES, WSPL, has_next ? W1n : nullptr, 130, 64, 64, tid, NT);
     }
     if (tid < 64) {
         vec[tid] = b5[tid];

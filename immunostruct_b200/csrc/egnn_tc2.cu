@@ -205,11 +205,8 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
             mbar_init(&acc1_full[i], 1); mbar_init(&acc2_full[i], 1); mbar_init(&hn_full[i], 1);
         }
     }
-    for (int idx = tid; idx < 64 * 64; idx += NT3) {                   // stage W2 / W3 as B operands
-        const int n = idx >> 6, k = idx & 63;
-        store_weight1<PREC>(sW2, W_BYTES, n, k, __ldg(p.W2 + idx));
-        store_weight1<PREC>(sW3, W_BYTES, n, k, HAS_COORD ? __ldg(p.W3 + idx) : 0.0f);
-    }
+    stage_weight_block<PREC>(sW2, W_BYTES, p.W2, 64, 0, 64, tid, NT3);                 // W2 / W3 as B operands
+    stage_weight_block<PREC>(sW3, W_BYTES, HAS_COORD ? p.W3 : nullptr, 64, 0, 64, tid, NT3);
     if (tid < 64) {
         vec[tid] = p.b2[tid];
         vec[64 + tid] = HAS_COORD ? p.b3[tid] : 0.0f;

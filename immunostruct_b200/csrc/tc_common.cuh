@@ -144,6 +144,51 @@ __device__ __forceinline__ void store_weight1(uint8_t* __restrict__ tile, uint32
     }
 }
 
+// stage a whole 64 x 64 weight block (rows n = output feature, W[n * ldw + col0 + k], k < kvalid <= 64; zero beyond)
+// with 16-byte chunk stores: 512 (row, 8-wide K chunk) items over `nthreads` threads; consecutive threads take
+// consecutive rows of one chunk, so a warp's stores fill four 128-byte core matrices (conflict free).  Same split
+// arithmetic as store_weight1 (round-to-nearest terms).  W == nullptr stages zeros.
+template <int PREC>
+__device__ __forceinline__ void stage_weight_block(uint8_t* __restrict__ tile, uint32_t split_bytes, const float* __restrict__ W,
+                                                   int ldw, int col0, int kvalid, int tid, int nthreads) {
+    static_assert(PREC == PREC_BF16 || PREC == PREC_BF16X3, "bf16 weight tiles only");
+    for (int idx = tid; idx < 64 * 8; idx += nthreads) {
+        const int n = idx & 63, c = idx >> 6;
+        float w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = 0.0f;
+        if (W != nullptr) {
+            const float* src = W + (size_t)n * ldw + col0 + 8 * c;
+            if (8 * c + 8 <= kvalid && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[i] = (8 * c + i < kvalid) ? __ldg(src + i) : 0.0f;
+            }
+        }
+        uint8_t* dst = tile + (uint32_t)((n >> 3) * (8 * kLBO_W) + c * kLBO_W + (n & 7) * 16);
+        uint32_t q1[4], q2[4], q3[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat16 a1 = __float2bfloat16_rn(w[2 * i]), b1 = __float2bfloat16_rn(w[2 * i + 1]);
+            q1[i] = (uint32_t)__bfloat16_as_ushort(a1) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
+            if (PREC == PREC_BF16X3) {
+                const float ra = w[2 * i] - __bfloat162float(a1), rb = w[2 * i + 1] - __bfloat162float(b1);
+                const __nv_bfloat16 a2 = __float2bfloat16_rn(ra), b2 = __float2bfloat16_rn(rb);
+                const __nv_bfloat16 a3 = __float2bfloat16_rn(ra - __bfloat162float(a2)), b3 = __float2bfloat16_rn(rb - __bfloat162float(b2));
+                q2[i] = (uint32_t)__bfloat16_as_ushort(a2) | ((uint32_t)__bfloat16_as_ushort(b2) << 16);
+                q3[i] = (uint32_t)__bfloat16_as_ushort(a3) | ((uint32_t)__bfloat16_as_ushort(b3) << 16);
+            }
+        }
+        *reinterpret_cast<uint4*>(dst) = make_uint4(q1[0], q1[1], q1[2], q1[3]);
+        if (PREC == PREC_BF16X3) {
+            *reinterpret_cast<uint4*>(dst + split_bytes) = make_uint4(q2[0], q2[1], q2[2], q2[3]);
+            *reinterpret_cast<uint4*>(dst + 2 * split_bytes) = make_uint4(q3[0], q3[1], q3[2], q3[3]);
+        }
+    }
+}
+
 // issue D[tmem_d] (+)= A * W^T over one 64-wide K block (called by ONE thread); N = 64 or 128 output
 // columns (W tile rows); a_split / w_split = byte distance between split-term copies.
 template <int PREC>
