@@ -616,25 +616,51 @@ node_pre_bwd_kernel(const float* __restrict__ gz1, const float* __restrict__ gQ,
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int64_t m0 = t * IS_TM;
         __syncthreads();
-        // source-side reduction through the CSC transpose: one warp per node
-        for (int r = warp; r < IS_TM; r += IS_THREADS / 32) {
-            const int64_t n = m0 + r;
-            float2 s = make_float2(0.f, 0.f);
-            if (n < M) {
-                const int qb = __ldg(outptr + n), qe = __ldg(outptr + n + 1);
-                for (int q = qb; q < qe; ++q) {
-                    const int pos = __ldg(csc_pos + q);
-                    const float2 v = __ldg(reinterpret_cast<const float2*>(gz1 + (size_t)pos * 64) + lane);
-                    s.x += v.x; s.y += v.y;
-                }
-                if (gx && lane < 3) {
-                    float sx = __ldg(gxd + n * 3 + lane);
-                    if (gx_out) sx += __ldg(gx_out + n * 3 + lane);
-                    for (int q = qb; q < qe; ++q) sx += __ldg(gD + (size_t)__ldg(csc_pos + q) * 3 + lane);
-                    gx[n * 3 + lane] = sx;
-                }
+        // source-side reduction through the CSC transpose: one warp per node, sixteen nodes per warp.  The loads are
+        // batched (the dependent chain outptr -> csc_pos -> gz1 row used to be walked edge by edge: ~20 serial L2
+        // round trips per node, 75 % of this kernel's time): lane i preloads the CSC range of the warp's i-th node,
+        // the positions of up to 32 out-edges are loaded with one coalesced access and broadcast by shuffle, eight
+        // gz1 rows are in flight per lane.  Summation order is unchanged (ascending CSC position): bit-identical.
+        {
+            constexpr int NPW = IS_TM / (IS_THREADS / 32);                 // nodes per warp (16)
+            int my_qb = 0, my_qe = 0;
+            if (lane < NPW) {
+                const int64_t n = m0 + warp + (IS_THREADS / 32) * lane;
+                if (n < M) { my_qb = __ldg(outptr + n); my_qe = __ldg(outptr + n + 1); }
             }
-            *reinterpret_cast<float2*>(GP + r * IS_LD + 2 * lane) = s;
+            for (int i = 0; i < NPW; ++i) {
+                const int r = warp + (IS_THREADS / 32) * i;
+                const int64_t n = m0 + r;
+                const int qb = __shfl_sync(0xffffffffu, my_qb, i), qe = __shfl_sync(0xffffffffu, my_qe, i);
+                float2 s = make_float2(0.f, 0.f);
+                float sx = 0.0f;
+                const bool want_x = gx != nullptr && lane < 3 && n < M;
+                if (want_x) {
+                    sx = __ldg(gxd + n * 3 + lane);
+                    if (gx_out) sx += __ldg(gx_out + n * 3 + lane);
+                }
+                for (int q0 = qb; q0 < qe; q0 += 32) {
+                    const int cnt = min(32, qe - q0);
+                    const int my_pos = lane < cnt ? __ldg(csc_pos + q0 + lane) : 0;
+                    for (int j0 = 0; j0 < cnt; j0 += 8) {
+                        float2 v[8];
+                        float d[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int pos = __shfl_sync(0xffffffffu, my_pos, (j0 + u) & 31);
+                            const bool ok = j0 + u < cnt;
+                            v[u] = ok ? __ldg(reinterpret_cast<const float2*>(gz1 + (size_t)pos * 64) + lane) : make_float2(0.f, 0.f);
+                            d[u] = (ok && want_x) ? __ldg(gD + (size_t)pos * 3 + lane) : 0.0f;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (j0 + u < cnt) { s.x += v[u].x; s.y += v[u].y; sx += d[u]; }
+                        }
+                    }
+                }
+                if (want_x) gx[n * 3 + lane] = sx;
+                *reinterpret_cast<float2*>(GP + r * IS_LD + 2 * lane) = s;
+            }
         }
         load_rows(GQ, IS_LD, gQ, 64, m0, M, 64, tid);
         load_rows(A, lda, h, ldh, m0, M, F, tid);
