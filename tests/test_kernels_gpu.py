@@ -51,7 +51,24 @@ def random_multigraph_arrays(seed, node_counts, mean_deg):
             "node_counts": torch.tensor(node_counts), "edge_counts": torch.tensor(ecs)}
 
 
+def hub_and_isolated_arrays(seed):
+    """Edge cases of the tile walk: a run of 80 isolated nodes (edge-less tiles), hubs with in-degree 128 (the tile
+    limit) and 100, many in-degree-1 nodes (32-node tiles far below 128 edges), a graph without any edge."""
+    gen = torch.Generator().manual_seed(seed)
+    n0, n1 = 150, 90
+    dst = torch.cat([torch.full((128,), 80), torch.full((100,), 81), torch.arange(82, 150),
+                     torch.randint(82, 150, (70,), generator=gen)])
+    src = (dst + 1 + torch.randint(0, n0 - 1, (dst.numel(),), generator=gen)) % n0
+    x = torch.zeros(n0 + n1, 23)
+    x[torch.arange(n0 + n1), torch.randint(0, 20, (n0 + n1,), generator=gen)] = 1.0
+    x[:, 20:] = torch.randn(n0 + n1, 3, generator=gen) * 4.0
+    perm = torch.randperm(dst.numel(), generator=gen)                      # unsorted edge list
+    return {"x": x, "src": src[perm], "dst": dst[perm], "edge_attr": torch.rand(dst.numel(), 1, generator=gen) + 0.5,
+            "node_counts": torch.tensor([n0, n1]), "edge_counts": torch.tensor([dst.numel(), 0])}
+
+
 CASES = {
+    "hubs_isolated": lambda: hub_and_isolated_arrays(7),
     "knn_small": lambda: synthetic_graph_arrays(5, 37, 6, seed=3, n_pad=4, coord_scale=4.0),
     "knn_200": lambda: synthetic_graph_arrays(3, 200, 10, seed=4, n_pad=10),
     "ragged_multi": lambda: random_multigraph_arrays(5, [17, 1, 64, 33, 150, 2], 7.5),
