@@ -39,7 +39,7 @@ def exported_symbols():
             "is_loss_num_partials", "is_collate_csr", "is_egnn_node_pre_fwd", "is_egnn_edge_fwd",
             "is_egnn_node_post_fwd", "is_egnn_node_post_bwd", "is_egnn_edge_bwd", "is_egnn_node_pre_bwd",
             "is_reduce_partials", "is_attn_pool_fwd", "is_attn_pool_bwd", "is_fusion_attn_fwd",
-            "is_fusion_attn_bwd", "is_loss_fwd", "is_loss_bwd", "is_umma_selftest", "is_egnn_edge_fwd_tc", "is_attn_pool_infer", "is_egnn_node_post_pre_tc", "is_egnn_edge_bwd_tc", "is_linear_tc", "is_linear_tc_split_k", "is_attn_pool_infer_tc", "is_vae_mid_infer", "is_head_infer"]
+            "is_fusion_attn_bwd", "is_loss_fwd", "is_loss_bwd", "is_umma_selftest", "is_egnn_edge_fwd_tc", "is_attn_pool_infer", "is_egnn_node_post_pre_tc", "is_egnn_edge_bwd_tc", "is_linear_tc", "is_linear_tc_split_k", "is_attn_pool_infer_tc", "is_vae_mid_infer", "is_head_infer", "is_unpack_nodes", "is_unpack_edges", "is_onehot_tokens"]
 
 
 def _check(rc: int, name: str):
@@ -339,6 +339,22 @@ def head_infer(pooled, Wc, bc, z_vae, coef, n_head, W1, b1, W2, b2):
           _t(coef, f32, "coef"), _i32(n_head), _t(W1, f32, "W1"), _t(b1, f32, "b1"), _t(W2, f32, "W2"), _t(b2, f32, "b2"),
           _i32(n_out), _t(x_gat, f32, "x_gat"), _t(out, f32, "out"), _i32(b), _stream())
     return x_gat, out
+
+
+def unpack_nodes(aa, xyz, x):
+    _call("is_unpack_nodes", _t(aa, torch.uint8, "aa"), _t(xyz, torch.float32, "xyz"), _t(x, torch.float32, "x"),
+          _i64(aa.numel()), _stream())
+
+
+def unpack_edges(src, dst, edge_attr, src64, dst64, attr_out):
+    _call("is_unpack_edges", _t(src, torch.int32, "src"), _t(dst, torch.int32, "dst"), _t(edge_attr, torch.float32, "edge_attr"),
+          _t(src64, torch.int64, "src64"), _t(dst64, torch.int64, "dst64"), _t(attr_out, torch.float32, "attr_out"),
+          _i64(src.numel()), _stream())
+
+
+def onehot_tokens(tokens, out, vocab):
+    _call("is_onehot_tokens", _t(tokens, torch.uint8, "tokens"), _t(out, torch.float32, "out"), _i64(tokens.numel()),
+          _i32(vocab), _stream())
 
 
 def umma_selftest(A, B, D, mode):

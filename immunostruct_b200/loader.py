@@ -17,6 +17,7 @@ from __future__ import annotations
 import torch
 
 from .graph import GraphBatch
+from .packed import PackedGraphBatch, PackedSequence
 
 
 class DevicePrefetcher:
@@ -44,6 +45,10 @@ class DevicePrefetcher:
                               self._h2d(obj.edata["edge_attr"]), self._h2d(obj._node_counts),
                               self._h2d(obj._edge_counts), obj.max_nodes or int(obj._node_counts.max()),
                               collate_now=False)
+        if isinstance(obj, PackedGraphBatch):          # compact arrays over PCIe; expanded in _finish on the consumer's stream
+            return obj if obj.device.type != "cpu" else obj._map(self._h2d)
+        if isinstance(obj, PackedSequence):
+            return PackedSequence(self._h2d(obj.tokens), obj.vocab)
         if torch.is_tensor(obj):
             return self._h2d(obj)
         if isinstance(obj, (tuple, list)):
@@ -51,12 +56,16 @@ class DevicePrefetcher:
         return obj
 
     def _finish(self, obj):
+        """Consumer-stream work on a landed batch; returns the object the caller sees."""
         if isinstance(obj, GraphBatch):
             if obj.indptr is None and obj.ndata["x"].is_cuda:
                 obj._collate()                                                # on the consumer's stream
-        elif isinstance(obj, (tuple, list)):
-            for o in obj:
-                self._finish(o)
+            return obj
+        if isinstance(obj, (PackedGraphBatch, PackedSequence)):
+            return obj.expand()                                               # csrc/unpack.cu (+ collation)
+        if isinstance(obj, (tuple, list)):
+            return type(obj)(self._finish(o) for o in obj)
+        return obj
 
     def __iter__(self):
         it = iter(self.loader)
@@ -73,7 +82,6 @@ class DevicePrefetcher:
         nxt = stage_next()
         while nxt is not None:
             cur_stream.wait_stream(self.copy_stream)      # batch i has landed
-            cur = nxt
-            self._finish(cur)
+            cur = self._finish(nxt)
             nxt = stage_next()                            # batch i+1: H2D overlaps batch i's compute
             yield cur

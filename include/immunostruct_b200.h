@@ -126,6 +126,13 @@ int is_loss_bwd(const float* recon, const float* seq, int64_t n_recon, const flo
  * precision 0 = bf16, 3 = bf16x3 (fp32-accurate). */
 int is_attn_pool_infer_tc(const float* QKV, const int64_t* node_off, int n_graphs, int max_nodes, int precision,
                           float* pooled, void* stream);
+/* Compact input format -> dense model inputs, on the device and bit-exact (csrc/unpack.cu).
+ * Replaces shipping the reference's fp32 one-hots over PCIe: x = [one_hot_20 | xyz] (data/utils.py:75-89,
+ * preprocess.py:40-41,181), int64 endpoints, all-ones edge_attr (data/utils.py:60), [283,21] sequence one-hots. */
+int is_unpack_nodes(const uint8_t* aa, const float* xyz, float* x, int64_t n_nodes, void* stream);
+int is_unpack_edges(const int* src, const int* dst, const float* edge_attr, int64_t* src64, int64_t* dst64, float* attr_out,
+                    int64_t n_edges, void* stream);
+int is_onehot_tokens(const uint8_t* tokens, float* out, int64_t n_tokens, int vocab, void* stream);
 /* Eval-mode small-layer fusions (csrc/head.cu; no autograd, dropout inactive).
  * is_vae_mid_infer: property_embedding (reference models/hybrid_models.py:46-52 / 280-286), mu / logvar = vae_fc21 /
  * vae_fc22 (h1), z = mu + eps exp(0.5 logvar) (:301-304, eps drawn by the caller), z_vae = [z | prop] (:339),

@@ -125,6 +125,23 @@ def egnn_node_post_pre_tc(h, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, precision
         egnn_node_pre_fwd(h_out, W1n, b1n, PQn)
 
 
+def unpack_nodes(aa, xyz, x):
+    """x = [one_hot_20(aa) | xyz]; aa >= 20 -> zero feature row (reference data/utils.py:75-89, padded nodes :13-33)."""
+    oh = torch.zeros(aa.numel(), 20)
+    ok = aa < 20
+    oh[ok, aa[ok].long()] = 1.0
+    x.copy_(torch.cat([oh, xyz], 1))
+
+
+def unpack_edges(src, dst, edge_attr, src64, dst64, attr_out):
+    src64.copy_(src.long()); dst64.copy_(dst.long())
+    attr_out.copy_(edge_attr if edge_attr is not None else torch.ones(src.numel()))
+
+
+def onehot_tokens(tokens, out, vocab):
+    out.copy_(F.one_hot(tokens.long().clamp(max=vocab), vocab + 1)[..., :vocab].float().reshape(out.shape))
+
+
 def vae_mid_infer(h1, prop, eps, Wp0, bp0, Wp3, bp3, W21, b21, W22, b22, W3, b3):
     """hybrid_models.py:46-52 (property MLP, eval), :299-307 (mu / logvar, reparameterize with the given eps, fc3)."""
     pe = torch.relu(F.linear(torch.relu(F.linear(prop, Wp0, bp0)), Wp3, bp3))
@@ -336,6 +353,6 @@ def loss_bwd(recon, seq, mu, logvar, logits, y, mode, pos_weight, w_pred, w_mse,
 
 
 ALL = ["num_sms", "egnn_node_grid", "egnn_edge_bwd_grid", "attn_max_nodes", "loss_num_partials", "collate_csr",
-       "egnn_node_pre_fwd", "egnn_edge_fwd", "egnn_edge_fwd_tc", "egnn_node_post_pre_tc", "linear_tc", "vae_mid_infer", "head_infer", "egnn_node_post_fwd", "egnn_node_post_bwd", "egnn_edge_bwd", "egnn_edge_bwd_tc",
+       "egnn_node_pre_fwd", "egnn_edge_fwd", "egnn_edge_fwd_tc", "egnn_node_post_pre_tc", "linear_tc", "vae_mid_infer", "head_infer", "unpack_nodes", "unpack_edges", "onehot_tokens", "egnn_node_post_fwd", "egnn_node_post_bwd", "egnn_edge_bwd", "egnn_edge_bwd_tc",
        "egnn_node_pre_bwd", "reduce_partials", "attn_pool_fwd", "attn_pool_infer", "attn_pool_infer_tc", "attn_pool_bwd", "fusion_attn_fwd",
        "fusion_attn_bwd", "loss_fwd", "loss_bwd"]

@@ -159,3 +159,34 @@ def test_graph_batch_host_vocabulary():
     pair = I.collate([((graphs[0], graphs[1]), (torch.zeros(2), torch.ones(2)), torch.tensor(1.0),
                        (torch.zeros(2), torch.ones(2)))] * 2)
     assert pair[0][0].n_graphs == 2 and pair[1][1].shape == (2, 2)
+
+
+def test_pack_graph_batch_and_sequence_round_trip():
+    """Compact format (immunostruct_b200/packed.py): packing is lossless for one-hot / zero-padded inputs (checked
+    through the CPU contracts of the unpack kernels), refuses anything else, and is ~4x smaller than the dense form."""
+    from immunostruct_b200.graph import GraphBatch
+    from immunostruct_b200.packed import PAD_RESIDUE, pack_graph_batch, pack_sequence
+    from immunostruct_b200.synthetic import synthetic_dense, synthetic_graph_arrays
+    arr = synthetic_graph_arrays(3, 40, 6, seed=9, n_pad=5)
+    keys = ("x", "src", "dst", "edge_attr", "node_counts", "edge_counts")
+    gb = GraphBatch.from_arrays(*(arr[k] for k in keys), max_nodes=40)
+    pk = pack_graph_batch(gb)
+    assert pk.edge_attr is None and int((pk.aa == PAD_RESIDUE).sum()) == 15 and pk.aa.dtype == torch.uint8
+    x = torch.empty(gb.n_nodes, 23)
+    KC.unpack_nodes(pk.aa, pk.xyz, x)
+    assert torch.equal(x, arr["x"])
+    s64, d64, ea = torch.empty(gb.n_edges, dtype=torch.int64), torch.empty(gb.n_edges, dtype=torch.int64), torch.empty(gb.n_edges)
+    KC.unpack_edges(pk.src, pk.dst, pk.edge_attr, s64, d64, ea)
+    assert torch.equal(s64, arr["src"].long()) and torch.equal(d64, arr["dst"].long()) and torch.equal(ea, arr["edge_attr"].reshape(-1))
+    dense_bytes = sum(arr[k].numel() * arr[k].element_size() for k in keys)
+    assert pk.nbytes * 3 < dense_bytes
+    seq = synthetic_dense(3, seed=9)["seq"]
+    ps = pack_sequence(seq)
+    out = torch.empty_like(seq)
+    KC.onehot_tokens(ps.tokens, out, ps.vocab)
+    assert torch.equal(out, seq) and ps.nbytes * 80 < seq.numel() * 4
+    bad = arr["x"].clone(); bad[0, :20] = 1.0                      # the SSL "mask to one" row is not packable
+    with pytest.raises(ValueError):
+        pack_graph_batch(GraphBatch.from_arrays(bad, *(arr[k] for k in keys[1:]), max_nodes=40))
+    with pytest.raises(RuntimeError):
+        pk.expand()                                                 # expansion is a device operation: no CPU path

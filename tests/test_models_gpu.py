@@ -262,3 +262,35 @@ def test_device_prefetcher_matches_direct_path():
     assert len(fetched) == 3
     for a, b in zip(direct, fetched):
         assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_packed_batches_expand_bit_exactly_and_prefetch():
+    """Compact input format: device expansion == the dense batch (bit-exact arrays, CSR and logits), through
+    `.to(device)` and through the DevicePrefetcher; non-unit edge_attr travels explicitly."""
+    from immunostruct_b200.graph import GraphBatch
+    arr, dense, model, eps = _bench_shape_case(8, seed=23, n_pad=10)
+    model = model.to(DEV).eval()
+    keys = ("x", "src", "dst", "edge_attr", "node_counts", "edge_counts")
+    host = GraphBatch.from_arrays(*(arr[k] for k in keys), max_nodes=200)
+    pk, ps = I.pack_graph_batch(host), I.pack_sequence(dense["seq"])
+    assert pk.nbytes * 3 < sum(arr[k].numel() * arr[k].element_size() for k in keys)
+    g_dense, g_packed = host.to(DEV), pk.to(DEV)
+    for f in ("indptr", "csr_src", "csr_dst", "csr_eid", "outptr", "csc_pos", "node_off", "edge_off"):
+        assert torch.equal(getattr(g_dense, f), getattr(g_packed, f)), f
+    assert torch.equal(g_dense.ndata["x"], g_packed.ndata["x"]) and torch.equal(g_dense.edata["edge_attr"], g_packed.edata["edge_attr"])
+    seq_d = ps.to(DEV)
+    assert torch.equal(seq_d, dense["seq"].to(DEV))
+    with torch.no_grad():
+        inject_eps(model, eps)
+        ref = model(g_dense, dense["seq"].to(DEV), dense["prop"].to(DEV))[3]
+        inject_eps(model, eps)
+        got = model(g_packed, seq_d, dense["prop"].to(DEV))[3]
+        assert torch.equal(ref, got)
+        for g, seq, prop in I.DevicePrefetcher([(pk.pin_memory(), ps.pin_memory(), dense["prop"])], DEV):
+            assert isinstance(g, GraphBatch) and g.device.type == "cuda" and seq.shape == (8, 283, 21)
+            inject_eps(model, eps)
+            assert torch.equal(model(g, seq, prop)[3], ref)
+    arr2 = dict(arr, edge_attr=torch.rand_like(arr["edge_attr"]) + 0.5)
+    pk2 = I.pack_graph_batch(GraphBatch.from_arrays(*(arr2[k] for k in keys), max_nodes=200))
+    assert pk2.edge_attr is not None and torch.equal(pk2.to(DEV).edata["edge_attr"], arr2["edge_attr"].to(DEV))
