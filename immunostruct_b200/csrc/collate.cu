@@ -43,33 +43,56 @@ __global__ void offsets_kernel(const int64_t* __restrict__ node_counts, const in
     }
 }
 
-// one warp per graph: globalise endpoints, histogram, scan, stable fill of CSR and CSC
-__global__ void __launch_bounds__(128)
+// one warp per graph: globalise endpoints, histogram, scan, stable fill of CSR and CSC.  The per-node degree counters /
+// fill cursors of a graph live in shared memory when the graph has at most COLLATE_CAP nodes (every dependent
+// read-modify-write of the 63-step stable fill used to be a global-memory round trip); larger graphs use the global
+// scratch arrays.  Integer arithmetic only: the result does not depend on which path runs.
+#define COLLATE_WPB 4
+#define COLLATE_CAP 512
+__global__ void __launch_bounds__(32 * COLLATE_WPB)
 collate_kernel(const int64_t* __restrict__ src_local, const int64_t* __restrict__ dst_local,
                const int64_t* __restrict__ node_off, const int64_t* __restrict__ edge_off, int B,
                int64_t* __restrict__ edge_index /* [2,E] */, int64_t E, int64_t* __restrict__ batch,
                int* __restrict__ indptr, int* __restrict__ csr_src, int* __restrict__ csr_dst, int* __restrict__ csr_eid,
                int* __restrict__ outptr, int* __restrict__ csc_pos,
-               int* __restrict__ cur_in, int* __restrict__ cur_out /* scratch int32 [N] each */,
+               int* __restrict__ g_cur_in, int* __restrict__ g_cur_out /* scratch int32 [N] each */,
                int* __restrict__ stats) {
-    const int lane = threadIdx.x & 31;
-    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    __shared__ int s_cur[COLLATE_WPB][2][COLLATE_CAP];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int g = blockIdx.x * COLLATE_WPB + wib;
     if (g >= B) return;
     const int64_t n0 = node_off[g], n1 = node_off[g + 1], e0 = edge_off[g], e1 = edge_off[g + 1];
     const int ng = (int)(n1 - n0);
+    const bool in_smem = ng <= COLLATE_CAP;
+    // counters / cursors indexed by GLOBAL node id n: shared (offset by n0) or global scratch
+    int* cur_in = in_smem ? s_cur[wib][0] - n0 : g_cur_in;
+    int* cur_out = in_smem ? s_cur[wib][1] - n0 : g_cur_out;
     // phase 0: batch vector, zero the degree counters
     for (int64_t n = n0 + lane; n < n1; n += 32) { batch[n] = g; cur_in[n] = 0; cur_out[n] = 0; }
     __syncwarp();
-    // phase 1: globalise + degree histograms (integer atomics: order-independent result)
+    // phase 1: globalise + degree histograms (integer atomics: order-independent result); four 32-edge steps of
+    // loads are issued before the first is consumed (the walk is latency bound)
     int bad = 0;
-    for (int64_t e = e0 + lane; e < e1; e += 32) {
-        int64_t s = src_local[e], d = dst_local[e];
-        if (s < 0 || s >= ng || d < 0 || d >= ng) { bad++; s = 0; d = 0; }
-        s += n0; d += n0;
-        edge_index[e] = s;
-        edge_index[E + e] = d;
-        atomicAdd(cur_in + d, 1);
-        atomicAdd(cur_out + s, 1);
+    for (int64_t eb = e0; eb < e1; eb += 128) {
+        int64_t sl[4], dl[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t e = eb + 32 * u + lane;
+            sl[u] = e < e1 ? src_local[e] : 0; dl[u] = e < e1 ? dst_local[e] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t e = eb + 32 * u + lane;
+            if (e < e1) {
+                int64_t s = sl[u], d = dl[u];
+                if (s < 0 || s >= ng || d < 0 || d >= ng) { bad++; s = 0; d = 0; }
+                s += n0; d += n0;
+                edge_index[e] = s;
+                edge_index[E + e] = d;
+                atomicAdd(cur_in + d, 1);
+                atomicAdd(cur_out + s, 1);
+            }
+        }
     }
     if (bad) atomicAdd(stats + 1, bad);
     __syncwarp();
@@ -99,24 +122,41 @@ collate_kernel(const int64_t* __restrict__ src_local, const int64_t* __restrict_
         if (g == B - 1) { indptr[n1] = (int)e1; outptr[n1] = (int)e1; }
     }
     __syncwarp();
-    // phase 3: stable fill, 32 edges per step in ascending edge id
-    for (int64_t eb = e0; eb < e1; eb += 32) {
-        const int64_t e = eb + lane;
-        const bool act = e < e1;
-        const int s = act ? (int)edge_index[e] : -1 - lane, d = act ? (int)edge_index[E + e] : -1 - lane;
-        const unsigned md = __match_any_sync(0xffffffffu, d), ms = __match_any_sync(0xffffffffu, s);
-        const unsigned lt = (1u << lane) - 1u;
-        int pos_csr = 0;
-        if (act) {
-            pos_csr = cur_in[d] + __popc(md & lt);
-            csr_src[pos_csr] = s; csr_dst[pos_csr] = d; csr_eid[pos_csr] = (int)e;
+    // phase 3: stable fill, 32 edges per step in ascending edge id (endpoints recomputed from the inputs: the
+    // edge_index stores above need not be read back)
+    for (int64_t eb4 = e0; eb4 < e1; eb4 += 128) {
+        int64_t sl4[4], dl4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t e = eb4 + 32 * u + lane;
+            sl4[u] = e < e1 ? src_local[e] : 0; dl4[u] = e < e1 ? dst_local[e] : 0;
         }
-        __syncwarp();
-        if (act && (md & lt) == 0) cur_in[d] += __popc(md);       // group leader advances the cursor
-        if (act) csc_pos[cur_out[s] + __popc(ms & lt)] = pos_csr;
-        __syncwarp();
-        if (act && (ms & lt) == 0) cur_out[s] += __popc(ms);
-        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t eb = eb4 + 32 * u;
+            if (eb >= e1) break;                                  // warp-uniform
+            const int64_t e = eb + lane;
+            const bool act = e < e1;
+            int s = -1 - lane, d = -1 - lane;
+            if (act) {
+                int64_t sl = sl4[u], dl = dl4[u];
+                if (sl < 0 || sl >= ng || dl < 0 || dl >= ng) { sl = 0; dl = 0; }
+                s = (int)(sl + n0); d = (int)(dl + n0);
+            }
+            const unsigned md = __match_any_sync(0xffffffffu, d), ms = __match_any_sync(0xffffffffu, s);
+            const unsigned lt = (1u << lane) - 1u;
+            int pos_csr = 0;
+            if (act) {
+                pos_csr = cur_in[d] + __popc(md & lt);
+                csr_src[pos_csr] = s; csr_dst[pos_csr] = d; csr_eid[pos_csr] = (int)e;
+            }
+            __syncwarp();
+            if (act && (md & lt) == 0) cur_in[d] += __popc(md);       // group leader advances the cursor
+            if (act) csc_pos[cur_out[s] + __popc(ms & lt)] = pos_csr;
+            __syncwarp();
+            if (act && (ms & lt) == 0) cur_out[s] += __popc(ms);
+            __syncwarp();
+        }
     }
 }
 
@@ -138,7 +178,7 @@ int is_collate_csr(const int64_t* src_local, const int64_t* dst_local, const int
     if (e != cudaSuccess) return (int)e;
     offsets_kernel<<<1, 1024, 0, st>>>(node_counts, edge_counts, n_graphs, node_off, edge_off);
     IS_LAUNCH_CHECK();
-    const int wpb = 4;
+    const int wpb = COLLATE_WPB;
     collate_kernel<<<(n_graphs + wpb - 1) / wpb, wpb * 32, 0, st>>>(
         src_local, dst_local, node_off, edge_off, n_graphs, edge_index, n_edges, batch, indptr, csr_src, csr_dst,
         csr_eid, outptr, csc_pos, scratch, scratch + n_nodes, stats);

@@ -129,6 +129,18 @@ def test_collate_bit_exact(case):
     gb.validate()
 
 
+def test_collate_bit_exact_large_and_mixed_graphs():
+    """Graphs above and below the shared-memory cursor capacity of the collation kernel (512 nodes) in one batch."""
+    from immunostruct_b200.synthetic import split_graphs
+    arrays = random_multigraph_arrays(13, [700, 3, 512, 513, 40], 6.0)
+    gb = to_dev(arrays)
+    ref = R.dgl_batch(split_graphs(arrays))
+    csr = R.csr_from_coo(ref["src"], ref["dst"], ref["num_nodes"])
+    assert torch.equal(gb.edge_index.cpu(), torch.stack([ref["src"], ref["dst"]]))
+    for k in ("indptr", "csr_src", "csr_dst", "csr_eid", "outptr", "csc_pos"):
+        assert torch.equal(getattr(gb, k).cpu(), csr[k]), k
+
+
 def test_collate_flags_bad_endpoints():
     arrays = CASES["knn_small"]()
     arrays["src"][5] = 1000
