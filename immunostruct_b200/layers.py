@@ -25,7 +25,10 @@ def _cached_no_grad(module, name, params, build):
     in-place version counters (optimizer steps and load_state_dict bump them)."""
     if torch.is_grad_enabled():
         return build()
-    key = tuple((p.data_ptr(), p._version) for p in params)
+    try:
+        key = tuple((p.data_ptr(), p._version) for p in params)
+    except RuntimeError:                       # inference tensors carry no version counter: do not cache
+        return build()
     slot = module.__dict__.setdefault("_derived_cache", {})
     hit = slot.get(name)
     if hit is None or hit[0] != key:
