@@ -13,6 +13,8 @@ and property branches -> fusion attention -> classifier -> sigmoid.
                  model(...), probabilities copied back) -- H2D and D2H inside the timed region;
   * ``train``  : fwd + bwd + Adam step (BCE_loss with sequence loss) at the same batch per GPU, with
                  the NCCL gradient all-reduce when N > 1 (weak scaling);
+  * ``train_comparative``: BASELINE configs[2] -- one cancer fine-tune step (HybridModelv2_Comparative, 256 cancer /
+                 wild-type pairs, paired contrastive loss, AdamW) at N = 1;
   * ``roofline``: the dominant kernel (EGNN edge forward) timed alone with CUDA events;
   * ``cpu_baseline``: the CPU oracle port of the same forward on this box's host cores (bounded sample).
 ``--impl reference`` times the reference's CPU path (oracle port; the reference is pure Python +
@@ -350,6 +352,49 @@ def main():
                  "final_loss": float(loss.detach()), "allreduce_bytes": reducer.nbytes}
         model.eval()
 
+    # ---- BASELINE configs[2]: cancer fine-tune step (train_Cancer_wFT.py / procedures/train.py:84-123) ---------
+    # HybridModelv2_Comparative, 256 cancer / wild-type pairs (two independent graph draws sharing the target),
+    # BCE + sequence loss on both members, paired contrastive loss (coefficient 0.01), AdamW(1e-4, wd 1e-6).
+    train_cmp = None
+    if not args.no_train and world == 1:
+        P = B // 2
+        torch.manual_seed(1)
+        cmodel = I.model_map["HybridModelv2_Comparative"](vae_input_dim=VAE_IN, device=dev, use_wt_for_downstream=True).to(dev).train()
+        copt = torch.optim.AdamW(cmodel.parameters(), lr=1e-4, weight_decay=1e-6)
+        closs = I.Losses(VAE_IN, [0.81, 0.19], sequence=True)
+        pcl = I.PairedContrastiveLoss(embedding_dim=104, device=dev)
+        cpool = make_pool(P, 4, seed=4001, device=dev)
+
+        def cmp_step(i):
+            (ac, dc), (aw, dw) = cpool[i % 4], cpool[(i + 1) % 4]
+            gc = GraphBatch.from_arrays(*(ac[k] for k in keys), max_nodes=N_NODES)
+            gw = GraphBatch.from_arrays(*(aw[k] for k in keys), max_nodes=N_NODES)
+            embs, recons, mus, lvs, out = cmodel.forward_comparative((gc, gw), (dc["seq"], dw["seq"]), (dc["prop"], dw["prop"]))
+            y = dc["target"]
+            lc = closs.BCE_loss(recons[0], dc["seq"], mus[0], lvs[0], out, y)
+            lw = closs.BCE_loss(recons[1], dw["seq"], mus[1], lvs[1], out, y)
+            loss = (lc + lw) / 2 + 0.01 * pcl(embs[0], embs[1], y)
+            copt.zero_grad(set_to_none=True)
+            loss.backward()
+            copt.step()
+            return loss
+
+        kc = max(3, min(K, 10))
+        for i in range(W):
+            cmp_step(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(kc):
+            loss = cmp_step(i)
+        e1.record()
+        barrier()
+        ms_c = e0.elapsed_time(e1)
+        train_cmp = {"value": P * kc / (ms_c / 1e3), "unit": "pairs/s", "graphs_per_s": 2 * P * kc / (ms_c / 1e3), "steps": kc,
+                     "ms_per_step": ms_c / kc, "pairs_per_step": P, "model": "HybridModelv2_Comparative", "optimizer": "AdamW",
+                     "loss": "BCE_loss(sequence=True) on both members + 0.01 * PairedContrastiveLoss", "final_loss": float(loss.detach())}
+        del cmodel, copt, cpool
+
     # ---- roofline of the dominant kernel (EGNN edge forward), timed alone ------------------------
     roofline = None
     if rank == 0:
@@ -452,7 +497,7 @@ def main():
                                       "ms_per_step": ms_e2e_packed / K, "h2d_bytes_per_step": h2d_packed,
                                       "note": "same call path fed from immunostruct_b200.PackedGraphBatch / PackedSequence"}},
             "gpu_launches": launches,
-            "train": train, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "train": train, "train_comparative": train_cmp, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }))
     if world > 1:
         dist.destroy_process_group()
