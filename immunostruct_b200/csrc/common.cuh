@@ -46,6 +46,18 @@ __device__ __forceinline__ void silu_both(float z, float& y, float& dy) {
     dy = s * (1.0f + z * (1.0f - s));
 }
 
+// 256-bit global accesses (sm_100: LDG.256 / STG.256).  One lane moves a whole 32-byte sector per instruction, so a
+// warp-wide access whose lanes touch different rows is still sector complete (two 128-bit accesses per lane hit every
+// sector twice, half a sector each).  p must be 32-byte aligned.
+__device__ __forceinline__ void ldg256(const float* __restrict__ p, float (&v)[8]) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* __restrict__ p, const float (&v)[8]) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

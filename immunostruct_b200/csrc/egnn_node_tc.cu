@@ -78,7 +78,9 @@ node_post_pre_tc_kernel(const float* __restrict__ h, int64_t ldh, int F, const f
             for (int i = 0; i < 8; ++i) v[i] = 0.0f;
             if (m < M) {
                 const float* rp = src + m * ld + 8 * kc8;
-                if (ncols == 64 && (ld & 3) == 0) {
+                if (ncols == 64 && (ld & 7) == 0 && (reinterpret_cast<uintptr_t>(src) & 31) == 0) {
+                    ldg256(rp, v);                                  // one sector-complete 32-byte access per lane
+                } else if (ncols == 64 && (ld & 3) == 0) {
                     const float4 a = __ldg(reinterpret_cast<const float4*>(rp)), b = __ldg(reinterpret_cast<const float4*>(rp) + 1);
                     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
                 } else {
@@ -138,11 +140,7 @@ node_post_pre_tc_kernel(const float* __restrict__ h, int64_t ldh, int F, const f
                 float v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = z[8 * g + i] + vec[64 + CW * cq + 8 * g + i];
-                if (m < M) {
-                    float* dst = h_out + m * 64 + CW * cq + 8 * g;
-                    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                    *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                }
+                if (m < M) stg256(h_out + m * 64 + CW * cq + 8 * g, v);
                 if (has_next) store_operand8<PREC>(sA, ASPL, erow, (CW / 8) * cq + g, v);
             }
         }
@@ -156,11 +154,12 @@ node_post_pre_tc_kernel(const float* __restrict__ h, int64_t ldh, int F, const f
                 tmem_ld<CW>(t_lane + 64 * part + CW * cq, z);
                 if (m < M) {
 #pragma unroll
-                    for (int g = 0; g < CW / 4; ++g) {
-                        const int c = 64 * part + CW * cq + 4 * g;
-                        *reinterpret_cast<float4*>(PQn + m * 192 + c) =
-                            make_float4(z[4 * g] + vec[128 + c], z[4 * g + 1] + vec[128 + c + 1],
-                                        z[4 * g + 2] + vec[128 + c + 2], z[4 * g + 3] + vec[128 + c + 3]);
+                    for (int g = 0; g < CW / 8; ++g) {
+                        const int c = 64 * part + CW * cq + 8 * g;
+                        float o[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) o[i] = z[8 * g + i] + vec[128 + c + i];
+                        stg256(PQn + m * 192 + c, o);
                     }
                 }
             }
@@ -174,11 +173,12 @@ node_post_pre_tc_kernel(const float* __restrict__ h, int64_t ldh, int F, const f
                 tmem_ld<CW>(t_lane + 128 + 64 * half + CW * cq, z);
                 if (m < M) {
 #pragma unroll
-                    for (int g = 0; g < CW / 4; ++g) {
-                        const int c = CW * cq + 4 * g;
-                        float4 o = make_float4(z[4 * g], z[4 * g + 1], z[4 * g + 2], z[4 * g + 3]);
-                        if (half) { o.x += vec[128 + c]; o.y += vec[128 + c + 1]; o.z += vec[128 + c + 2]; o.w += vec[128 + c + 3]; }
-                        *reinterpret_cast<float4*>(PQn + m * 128 + 64 * half + c) = o;
+                    for (int g = 0; g < CW / 8; ++g) {
+                        const int c = CW * cq + 8 * g;
+                        float o[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) o[i] = z[8 * g + i] + (half ? vec[128 + c + i] : 0.0f);
+                        stg256(PQn + m * 128 + 64 * half + c, o);
                     }
                 }
             }
@@ -233,6 +233,7 @@ int is_egnn_node_post_pre_tc(const float* h, int64_t ldh, int F, const float* hn
     if (!(F == 20 || F == 64) || n_nodes <= 0) return IS_ERR_ARG;
     if ((W1n == nullptr) != (PQn == nullptr)) return IS_ERR_ARG;
     if (W1n != nullptr && next_kind != 1 && next_kind != 2) return IS_ERR_ARG;
+    if (((reinterpret_cast<uintptr_t>(h_out) | reinterpret_cast<uintptr_t>(PQn)) & 31) != 0) return IS_ERR_ARG;   // 256-bit stores
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == PREC_BF16)
         return launch_node_tc<PREC_BF16, 256, true>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, n_nodes, next_kind, st);

@@ -332,6 +332,7 @@ int is_egnn_edge_fwd_tc(const int* indptr, const int* csr_src, const int* csr_ds
     if (g > (int64_t)sms * per_sm) g = (int64_t)sms * per_sm;
     const int grid = (int)(g < 1 ? 1 : g);
     cudaStream_t st = (cudaStream_t)stream;
+    if (((reinterpret_cast<uintptr_t>(PQ) | reinterpret_cast<uintptr_t>(hn)) & 31) != 0) return IS_ERR_ARG;   // 256-bit accesses
     if (!legacy && precision != PREC_TF32X3) return launch_edge_fwd_ws(c, hn, x_out, precision, update_coords != 0, fast_act != 0, st);
     if (precision == PREC_BF16)
         return update_coords ? launch_tc<PREC_BF16, true, 256>(c, hn, x_out, grid, st, fast_act != 0) : launch_tc<PREC_BF16, false, 256>(c, hn, x_out, grid, st, fast_act != 0);

@@ -321,7 +321,7 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
 #pragma unroll
             for (int gi = 0; gi < 2; ++gi) {
                 const int g8 = 8 * (2 * pw + gi);
-                float4 pv[2][2], qv[2][2];
+                float pv[2][8], qv[2][8];
                 float rr[2], aa[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
@@ -330,23 +330,18 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
                     const int s = valid ? mt.src[j] : 0, d = n0 + (valid ? (int)mt.dloc[j] : 0);
                     rr[u] = valid ? mt.r[j] : 0.0f;
                     aa[u] = valid ? mt.a[j] : 0.0f;
-                    const float4* pp = reinterpret_cast<const float4*>(p.PQ + (size_t)s * 128 + 8 * kc);
-                    const float4* qp = reinterpret_cast<const float4*>(p.PQ + (size_t)d * 128 + 64 + 8 * kc);
-                    pv[u][0] = __ldg(pp); pv[u][1] = __ldg(pp + 1); qv[u][0] = __ldg(qp); qv[u][1] = __ldg(qp + 1);
+                    ldg256(p.PQ + (size_t)s * 128 + 8 * kc, pv[u]);            // one whole 32-byte sector per lane
+                    ldg256(p.PQ + (size_t)d * 128 + 64 + 8 * kc, qv[u]);
                 }
+                const float wr[8] = {wr0.x, wr0.y, wr0.z, wr0.w, wr1.x, wr1.y, wr1.z, wr1.w};
+                const float wa[8] = {wa0.x, wa0.y, wa0.z, wa0.w, wa1.x, wa1.y, wa1.z, wa1.w};
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int j = g8 + r4 + 4 * ((kc & 1) ^ u);
                     const float r = rr[u], a = aa[u];
                     float v[8];
-                    v[0] = act<PREC, FAST>(pv[u][0].x + qv[u][0].x + wr0.x * r + wa0.x * a);
-                    v[1] = act<PREC, FAST>(pv[u][0].y + qv[u][0].y + wr0.y * r + wa0.y * a);
-                    v[2] = act<PREC, FAST>(pv[u][0].z + qv[u][0].z + wr0.z * r + wa0.z * a);
-                    v[3] = act<PREC, FAST>(pv[u][0].w + qv[u][0].w + wr0.w * r + wa0.w * a);
-                    v[4] = act<PREC, FAST>(pv[u][1].x + qv[u][1].x + wr1.x * r + wa1.x * a);
-                    v[5] = act<PREC, FAST>(pv[u][1].y + qv[u][1].y + wr1.y * r + wa1.y * a);
-                    v[6] = act<PREC, FAST>(pv[u][1].z + qv[u][1].z + wr1.z * r + wa1.z * a);
-                    v[7] = act<PREC, FAST>(pv[u][1].w + qv[u][1].w + wr1.w * r + wa1.w * a);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = act<PREC, FAST>(pv[u][i] + qv[u][i] + wr[i] * r + wa[i] * a);
                     // rows beyond the tile's edges hold finite values: the selector has zeros there
                     store_chunk8<PREC>(A + (j >> 3) * SBO + (j & 7) * 16 + kc * LBO, A_BYTES, v);
                 }
@@ -417,9 +412,11 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
                     tmem_ld<CW>(t_lane + TM_HN + 64 * bp, z);
                     const int node = n0 + 16 * q + lane;
                     if (lane < 16 && node < n1) {
-                        float4* dst = reinterpret_cast<float4*>(hn + (size_t)node * 64 + CW * cq);
 #pragma unroll
-                        for (int g = 0; g < CW / 4; ++g) dst[g] = make_float4(z[4 * g], z[4 * g + 1], z[4 * g + 2], z[4 * g + 3]);
+                        for (int g = 0; g < CW / 8; ++g) {
+                            const float o[8] = {z[8 * g], z[8 * g + 1], z[8 * g + 2], z[8 * g + 3], z[8 * g + 4], z[8 * g + 5], z[8 * g + 6], z[8 * g + 7]};
+                            stg256(hn + (size_t)node * 64 + CW * cq + 8 * g, o);
+                        }
                     }
                 }
                 if (HAS_COORD) {
