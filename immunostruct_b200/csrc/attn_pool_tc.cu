@@ -88,23 +88,25 @@ attn_pool_tc_kernel(const float* __restrict__ QKV, const int64_t* __restrict__ n
         const int n = (int)(__ldg(node_off + g + 1) - n0);
         // ---- stage Q (scaled) and K rows; rows >= n are zero (zero scores, masked below) ----------------------
         for (int grp = warp; grp < NPAD / 8; grp += NT / 32) {
-            float4 qv[2][2], kv[2][2];
+            float qv[2][8], kv[2][8];
 #pragma unroll
             for (int p = 0; p < 2; ++p) {
                 const int row = 8 * grp + r4 + 4 * ((kc & 1) ^ p);
-                qv[p][0] = qv[p][1] = kv[p][0] = kv[p][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) qv[p][i] = kv[p][i] = 0.0f;
                 if (row < n) {
-                    const float4* src = reinterpret_cast<const float4*>(QKV + (n0 + row) * 192 + 8 * kc);
-                    qv[p][0] = __ldg(src); qv[p][1] = __ldg(src + 1);
-                    kv[p][0] = __ldg(src + 16); kv[p][1] = __ldg(src + 17);
+                    const float* src = QKV + (n0 + row) * 192 + 8 * kc;      // 768-byte rows: every chunk is one 32-byte sector
+                    ldg256(src, qv[p]);
+                    ldg256(src + 64, kv[p]);
                 }
             }
 #pragma unroll
             for (int p = 0; p < 2; ++p) {
                 const int row = 8 * grp + r4 + 4 * ((kc & 1) ^ p);
-                const float vq[8] = {qv[p][0].x * qscale, qv[p][0].y * qscale, qv[p][0].z * qscale, qv[p][0].w * qscale,
-                                     qv[p][1].x * qscale, qv[p][1].y * qscale, qv[p][1].z * qscale, qv[p][1].w * qscale};
-                const float vk[8] = {kv[p][0].x, kv[p][0].y, kv[p][0].z, kv[p][0].w, kv[p][1].x, kv[p][1].y, kv[p][1].z, kv[p][1].w};
+                float vq[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vq[i] = qv[p][i] * qscale;
+                const float (&vk)[8] = kv[p];
                 const int rq = row & 127;
                 store_chunk8<PREC>(sQ + (row >> 7) * NS * QT_BYTES + (rq >> 3) * SBO + (rq & 7) * 16 + kc * LBO, QT_BYTES, vq);
                 store_chunk8<PREC>(sK + (row >> 3) * SBO + (row & 7) * 16 + kc * LBO, KT_BYTES, vk);
@@ -226,6 +228,7 @@ int is_attn_pool_infer_tc(const float* QKV, const int64_t* node_off, int n_graph
                           float* pooled, void* stream) {
     if (n_graphs <= 0 || max_nodes <= 0) return IS_ERR_ARG;
     if (max_nodes > 256) return IS_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(QKV) & 31) != 0) return IS_ERR_ARG;          // 256-bit row loads
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == PREC_BF16)
         return max_nodes <= 128 ? launch_attn_tc<PREC_BF16, 128>(QKV, node_off, n_graphs, pooled, st)

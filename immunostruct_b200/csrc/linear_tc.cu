@@ -45,6 +45,7 @@ linear_tc_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
     fence_after_sync();
     const uint32_t tmem = s_tmem;
     const uint32_t base = smem_u32(smem_raw);
+    const bool vec8 = ((lda | ldw) & 7) == 0 && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W)) & 31) == 0;
     const bool vec4 = ((lda | ldw) & 3) == 0 && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W)) & 15) == 0;
     // staging: warp w owns 8-row group w of both operands; a quarter-warp covers rows r4 + 4 * (chunk parity ^ pass
     // parity) for two adjacent 8-wide K chunks (kc = lane / 4): its eight 16-byte stores fill one 128-byte bank line
@@ -58,7 +59,12 @@ linear_tc_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
             const int64_t m = m0 + row, n = n0 + row;
             const float* ap = A + m * lda + k;
             const float* wp = W + n * ldw + k;
-            if (vec4 && k + 8 <= K) {
+            if (vec8 && k + 8 <= K) {                              // one sector-complete 256-bit access per operand
+#pragma unroll
+                for (int i = 0; i < 8; ++i) va[u][i] = vw[u][i] = 0.0f;
+                if (m < M) ldg256(ap, va[u]);
+                if (n < N) ldg256(wp, vw[u]);
+            } else if (vec4 && k + 8 <= K) {
                 float4 a0 = make_float4(0, 0, 0, 0), a1 = a0, w0 = a0, w1 = a0;
                 if (m < M) { a0 = __ldg(reinterpret_cast<const float4*>(ap)); a1 = __ldg(reinterpret_cast<const float4*>(ap) + 1); }
                 if (n < N) { w0 = __ldg(reinterpret_cast<const float4*>(wp)); w1 = __ldg(reinterpret_cast<const float4*>(wp) + 1); }
