@@ -221,9 +221,11 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
             const bool valid = j < ne;
             const int s = valid ? mt.src[j] : 0, d = valid ? mt.dst[j] : 0;
             rr[u] = mt.r[j]; aa[u] = mt.a[j];
-            const float4* pp = reinterpret_cast<const float4*>(p.PQ + (size_t)s * 128 + 8 * kc8);
-            const float4* qp = reinterpret_cast<const float4*>(p.PQ + (size_t)d * 128 + 64 + 8 * kc8);
-            pv[u][0] = __ldg(pp); pv[u][1] = __ldg(pp + 1); qv[u][0] = __ldg(qp); qv[u][1] = __ldg(qp + 1);
+            float p8[8], q8[8];
+            ldg256(p.PQ + (size_t)s * 128 + 8 * kc8, p8);               // 256-bit loads: whole sectors per lane
+            ldg256(p.PQ + (size_t)d * 128 + 64 + 8 * kc8, q8);
+            pv[u][0] = make_float4(p8[0], p8[1], p8[2], p8[3]); pv[u][1] = make_float4(p8[4], p8[5], p8[6], p8[7]);
+            qv[u][0] = make_float4(q8[0], q8[1], q8[2], q8[3]); qv[u][1] = make_float4(q8[4], q8[5], q8[6], q8[7]);
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -443,7 +445,10 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
                 }
                 float* go = gz1 + (size_t)(p0 + erow) * 64 + BT_CW * cq;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) *reinterpret_cast<float4*>(go + 4 * g) = make_float4(g1[4 * g], g1[4 * g + 1], g1[4 * g + 2], g1[4 * g + 3]);
+                for (int g = 0; g < 2; ++g) {                 // 256-bit stores: whole 32-byte sectors per lane
+                    const float o[8] = {g1[8 * g], g1[8 * g + 1], g1[8 * g + 2], g1[8 * g + 3], g1[8 * g + 4], g1[8 * g + 5], g1[8 * g + 6], g1[8 * g + 7]};
+                    stg256(go + 8 * g, o);
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < BT_CW; ++i) { g1[i] = 0.0f; gr_[i] = 0.0f; ga_[i] = 0.0f; }
@@ -554,6 +559,7 @@ int is_egnn_edge_bwd_tc(const int* indptr, const int* csr_src, const int* csr_ds
                         float* gz1, float* gQ, float* gD, float* gxd, float* partials,
                         int64_t n_nodes, int* status, void* stream) {
     if (!(F == 20 || F == 64) || n_nodes <= 0 || n_nodes > 0x7fffffff) return IS_ERR_ARG;
+    if (((reinterpret_cast<uintptr_t>(PQ) | reinterpret_cast<uintptr_t>(gz1)) & 31) != 0) return IS_ERR_ARG;   // 256-bit accesses
     EdgeCommon c;
     c.indptr = indptr; c.csr_src = csr_src; c.csr_dst = csr_dst; c.csr_eid = csr_eid;
     c.PQ = PQ; c.x = x; c.ldx = ldx; c.edge_attr = edge_attr; c.W1 = W1; c.F = F;
