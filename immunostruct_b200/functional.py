@@ -105,7 +105,8 @@ def _egnn_layer_backward(g, h, x, edge_attr, PQ, hn, params, gh_out, gx_out, nee
     ghn = _new(h, n, H)
     gh_direct = _new(h, n, H) if need_gh else None
     p_post = _new(h, grid_n, H * k + H + H * H + H)
-    _C.egnn_node_post_bwd(gh_out, h, hn, W5, b5, W6, gh_direct, ghn, p_post)
+    tc = _PRECISIONS[_precision] is not None          # tensor-core (bf16x3) backward kernels in every mode but "fp32"
+    (_C.egnn_node_post_bwd_tc if tc else _C.egnn_node_post_bwd)(gh_out, h, hn, W5, b5, W6, gh_direct, ghn, p_post)
     # edge backward
     gz1, gQ, gD, gxd = _new(h, e, H), _new(h, n, H), _new(h, e, 3), _new(h, n, 3)
     p_edge = _new(h, grid_e, 2 * H * H + 5 * H)

@@ -71,6 +71,10 @@ int is_egnn_node_post_fwd(const float* h, int64_t ldh, int F, const float* hn, c
 int is_egnn_node_post_bwd(const float* gh_out, const float* h, int64_t ldh, int F, const float* hn,
                           const float* W5, const float* b5, const float* W6,
                           float* gh_direct, float* ghn, float* partials, int64_t n_nodes, void* stream);
+/* tcgen05 (bf16x3, fp32-accurate) variant: same outputs, same partial layout, same grid. */
+int is_egnn_node_post_bwd_tc(const float* gh_out, const float* h, int64_t ldh, int F, const float* hn,
+                          const float* W5, const float* b5, const float* W6,
+                          float* gh_direct, float* ghn, float* partials, int64_t n_nodes, void* stream);
 int is_egnn_edge_bwd(const int* indptr, const int* csr_src, const int* csr_dst, const int* csr_eid,
                      const float* PQ, const float* x, int64_t ldx, const float* edge_attr,
                      const float* W1, int F, const float* W2, const float* b2,

@@ -339,7 +339,8 @@ def test_egnn_backward_kernels(case, f, coord, tc):
     ghn_d, pp_d = torch.empty(n, 64, device=DEV), torch.empty(grid_n, 64 * k + 64 + 4096 + 64, device=DEV)
     ghd = torch.empty(n, 64) if need_gh else None
     ghn, pp = torch.empty(n, 64), torch.empty(KC.FAKE_GRID, 64 * k + 64 + 4096 + 64)
-    _C.egnn_node_post_bwd(gh_out.to(DEV), h_d, hn_d, wd["W5"], wd["b5"], wd["W6"], ghd_d, ghn_d, pp_d)
+    node_post_bwd = _C.egnn_node_post_bwd_tc if tc else _C.egnn_node_post_bwd
+    node_post_bwd(gh_out.to(DEV), h_d, hn_d, wd["W5"], wd["b5"], wd["W6"], ghd_d, ghn_d, pp_d)
     KC.egnn_node_post_bwd(gh_out, h, hn, w["W5"], w["b5"], w["W6"], ghd, ghn, pp)
     close(ghn_d, ghn, what="ghn")
     if need_gh:
@@ -355,8 +356,9 @@ def test_egnn_backward_kernels(case, f, coord, tc):
     outs_d = [torch.empty(e, 64, device=DEV), torch.empty(n, 64, device=DEV), torch.empty(e, 3, device=DEV),
               torch.empty(n, 3, device=DEV), torch.empty(grid_e, 8512, device=DEV)]
     outs = [torch.empty(e, 64), torch.empty(n, 64), torch.empty(e, 3), torch.empty(n, 3), torch.empty(KC.FAKE_GRID, 8512)]
+    # (each kernel is checked in isolation: it consumes the CONTRACT's upstream values, not the device's)
     edge_bwd(gb, PQ_d, x_d, ea.to(DEV), f, wd["W1"], wd["W2"], wd["b2"], wd["W3"], wd["b3"], wd["w4"],
-             ghn_d, gx_out.to(DEV) if coord else None, *outs_d)
+             ghn.to(DEV), gx_out.to(DEV) if coord else None, *outs_d)
     KC.egnn_edge_bwd(cg, PQ, x, ea, f, w["W1"], w["W2"], w["b2"], w["W3"], w["b3"], w["w4"], ghn, gx_out, *outs)
     for name, a, b in zip(("gz1", "gQ", "gD", "gxd"), outs_d[:4], outs[:4]):
         close(a, b, what=name)
@@ -376,8 +378,8 @@ def test_egnn_backward_kernels(case, f, coord, tc):
     p3_d = torch.empty(grid_n, 2 * 64 * f + 64, device=DEV)
     gh = torch.empty(n, 64) if need_gh else None
     gx, p3 = torch.empty(n, 3), torch.empty(KC.FAKE_GRID, 2 * 64 * f + 64)
-    _C.egnn_node_pre_bwd(gz1_d, gQ_d, gD_d, gxd_d, gx_out.to(DEV) if coord else None, ghd_d, gb, h_d, wd["W1"],
-                         gh_d, gx_d, p3_d)
+    _C.egnn_node_pre_bwd(gz1.to(DEV), gQ.to(DEV), gD.to(DEV), gxd.to(DEV), gx_out.to(DEV) if coord else None,
+                         ghd.to(DEV) if need_gh else None, gb, h_d, wd["W1"], gh_d, gx_d, p3_d)
     KC.egnn_node_pre_bwd(gz1, gQ, gD, gxd, gx_out, ghd, cg, h, w["W1"], gh, gx, p3)
     close(gx_d, gx, what="gx")
     if need_gh:
