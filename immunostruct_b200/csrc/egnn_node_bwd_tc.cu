@@ -343,6 +343,203 @@ node_post_bwd_tc_kernel(const float* __restrict__ gh_out, const float* __restric
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+
+// =====================================================================================================================
+__global__ void __launch_bounds__(nb::NT, 1)
+node_pre_bwd_tc_kernel(const float* __restrict__ gz1, const float* __restrict__ gQ, const float* __restrict__ gD,
+                       const float* __restrict__ gxd, const float* __restrict__ gx_out /* or null */,
+                       const float* __restrict__ gh_direct /* [M,64] or null */,
+                       const int* __restrict__ outptr, const int* __restrict__ csc_pos,
+                       const float* __restrict__ h, int64_t ldh, int F, const float* __restrict__ W1,
+                       float* __restrict__ gh /* [M,64] or null */, float* __restrict__ gx /* [M,3] or null */,
+                       float* __restrict__ partials, int64_t M) {
+    using namespace nb;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t* sP = smem_raw;                               // [3][T_BYTES]  gP (source-side sums of gz1)
+    uint8_t* sQ = sP + 3 * T_BYTES;                       // [3][T_BYTES]  gQ
+    uint8_t* sH = sQ + 3 * T_BYTES;                       // [3][T_BYTES]  h
+    uint8_t* sW = sH + 3 * T_BYTES;                       // [2 blocks][3][W_BYTES]: Ws | Wd
+    __shared__ __align__(8) uint64_t mbar, mbar_wg;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ldw = 2 * F + 2;
+    if (warp == 0) tmem_alloc(&s_tmem, 256);
+    if (tid == 32) { mbar_init(&mbar, 1); mbar_init(&mbar_wg, 1); }
+    stage_weight_block<PREC_BF16X3>(sW, W_BYTES, gh ? W1 : nullptr, ldw, 0, F, tid, NT);
+    stage_weight_block<PREC_BF16X3>(sW + 3 * W_BYTES, W_BYTES, gh ? W1 : nullptr, ldw, F, F, tid, NT);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = s_tmem;
+    // TMEM columns: D gh [0,64) | DWs [64,128) | DWd [128,192)
+    const int q = warp & 3, cq = warp >> 2, erow = 32 * q + lane;
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16) + CW * cq;
+    const int r4 = lane & 3, kc = lane >> 2;
+    const Geom gP = act_k(smem_u32(sP)), gQk = act_k(smem_u32(sQ));
+    const Geom gPt = act_t(smem_u32(sP)), gQt = act_t(smem_u32(sQ)), gHt = act_t(smem_u32(sH));
+    const Geom wst = wgt_t(smem_u32(sW)), wdt = wgt_t(smem_u32(sW + 3 * W_BYTES));
+    const uint32_t id_dgrad = umma::make_instr_desc(1u, 128, 64, 0, 1);
+    const uint32_t id_wgrad = umma::make_instr_desc(1u, 64, 64, 1, 1);
+    uint32_t phase = 0, phase_wg = 0, started = 0;
+    bool wg_pending = false;
+    float gb1[8];                         // columns 8 kc .. 8 kc + 7 of gQ over this thread's staged rows
+#pragma unroll
+    for (int i = 0; i < 8; ++i) gb1[i] = 0.0f;
+
+    const int64_t ntiles = (M + IS_TM - 1) / IS_TM;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t m0 = t * IS_TM;
+        if (wg_pending) { mbar_wait(&mbar_wg, phase_wg); phase_wg ^= 1; wg_pending = false; fence_after_sync(); }
+        // ---- gQ and h rows travel while the CSC gather runs -------------------------------------------------------------
+        float vq[2][8], vh[2][8];
+        load2(vq, gQ, 64, 64, m0, M, warp, r4, kc);
+        load2(vh, h, ldh, F, m0, M, warp, r4, kc);
+        // ---- source-side reduction through the CSC transpose: one warp per node, eight nodes per warp, batched loads,
+        // ascending CSC position (= the SIMT kernel's order: bit-identical sums) ----------------------------------------------
+        {
+            constexpr int NPW = IS_TM / NW;                    // 8
+            int my_qb = 0, my_qe = 0;
+            if (lane < NPW) {
+                const int64_t n = m0 + warp + NW * lane;
+                if (n < M) { my_qb = __ldg(outptr + n); my_qe = __ldg(outptr + n + 1); }
+            }
+            for (int i = 0; i < NPW; ++i) {
+                const int r = warp + NW * i;
+                const int64_t n = m0 + r;
+                const int qb = __shfl_sync(0xffffffffu, my_qb, i), qe = __shfl_sync(0xffffffffu, my_qe, i);
+                float2 s = make_float2(0.f, 0.f);
+                float sx = 0.0f;
+                const bool want_x = gx != nullptr && lane < 3 && n < M;
+                if (want_x) {
+                    sx = __ldg(gxd + n * 3 + lane);
+                    if (gx_out) sx += __ldg(gx_out + n * 3 + lane);
+                }
+                for (int q0 = qb; q0 < qe; q0 += 32) {
+                    const int cnt = min(32, qe - q0);
+                    const int my_pos = lane < cnt ? __ldg(csc_pos + q0 + lane) : 0;
+                    for (int j0 = 0; j0 < cnt; j0 += 8) {
+                        float2 v[8];
+                        float d[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const int pos = __shfl_sync(0xffffffffu, my_pos, (j0 + u) & 31);
+                            const bool ok = j0 + u < cnt;
+                            v[u] = ok ? __ldg(reinterpret_cast<const float2*>(gz1 + (size_t)pos * 64) + lane) : make_float2(0.f, 0.f);
+                            d[u] = (ok && want_x) ? __ldg(gD + (size_t)pos * 3 + lane) : 0.0f;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (j0 + u < cnt) { s.x += v[u].x; s.y += v[u].y; sx += d[u]; }
+                        }
+                    }
+                }
+                if (want_x) gx[n * 3 + lane] = sx;
+                // lane L holds features 2L, 2L+1: the four lanes of a chunk hand their pairs to its first lane
+                float c8[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    c8[2 * j] = __shfl_sync(0xffffffffu, s.x, (lane & ~3) + j);
+                    c8[2 * j + 1] = __shfl_sync(0xffffffffu, s.y, (lane & ~3) + j);
+                }
+                if ((lane & 3) == 0) store_chunk8<PREC_BF16X3>(chunk_at(sP, r, lane >> 2), T_BYTES, c8);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) gb1[i] += vq[u][i];
+        store2(sQ, vq, warp, r4, kc);
+        store2(sH, vh, warp, r4, kc);
+        fence_async_smem();
+        fence_before_sync();
+        __syncthreads();
+        if (warp == 0) {
+            if (elect_one()) {
+                fence_after_sync();
+                if (gh) {
+                    issue6(tmem + 0, gP, wst, 4, id_dgrad, 0);
+                    issue6(tmem + 0, gQk, wdt, 4, id_dgrad, 1);
+                    mma_commit(&mbar);
+                }
+                issue6(tmem + 64, gPt, gHt, 8, id_wgrad, started);
+                issue6(tmem + 128, gQt, gHt, 8, id_wgrad, started);
+                mma_commit(&mbar_wg);
+            }
+            __syncwarp();
+        }
+        wg_pending = true;
+        started = 1;
+        if (gh) {
+            const int64_t m = m0 + erow;
+            float g[CW];
+#pragma unroll
+            for (int i = 0; i < CW; ++i) g[i] = 0.0f;
+            if (gh_direct && m < M) {                        // in flight under the MMAs
+                ldg256(gh_direct + m * 64 + CW * cq, *reinterpret_cast<float(*)[8]>(g));
+                ldg256(gh_direct + m * 64 + CW * cq + 8, *reinterpret_cast<float(*)[8]>(g + 8));
+            }
+            mbar_wait(&mbar, phase);
+            phase ^= 1;
+            fence_after_sync();
+            float z[CW];
+            tmem_ld<CW>(t_lane, z);
+            if (m < M) {
+#pragma unroll
+                for (int gg = 0; gg < CW / 8; ++gg) {
+                    float o[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] = z[8 * gg + i] + g[8 * gg + i];
+                    stg256(gh + m * 64 + CW * cq + 8 * gg, o);
+                }
+            }
+            fence_before_sync();
+        }
+    }
+
+    // ---- per-CTA partials: [gWs 64 x F][gWd 64 x F][gb1 64] ----------------------------------------------------------------
+    if (wg_pending) { mbar_wait(&mbar_wg, phase_wg); fence_after_sync(); }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    float* P = partials + (size_t)blockIdx.x * (2 * 64 * F + 64);
+    {
+        float w[CW];
+        const int o = 16 * q + lane;                          // M = 64 accumulator: row r in TMEM lane 32 (r / 16) + r % 16
+        if (started) tmem_ld<CW>(t_lane + 64, w);
+        if (lane < 16) {
+#pragma unroll
+            for (int i = 0; i < CW; ++i) {
+                const int k = CW * cq + i;
+                if (k < F) P[o * F + k] = started ? w[i] : 0.0f;
+            }
+        }
+        if (started) tmem_ld<CW>(t_lane + 128, w);
+        if (lane < 16) {
+#pragma unroll
+            for (int i = 0; i < CW; ++i) {
+                const int k = CW * cq + i;
+                if (k < F) P[64 * F + o * F + k] = started ? w[i] : 0.0f;
+            }
+        }
+    }
+    float* scr = reinterpret_cast<float*>(sP);               // [NT][8]
+#pragma unroll
+    for (int i = 0; i < 8; ++i) scr[tid * 8 + i] = gb1[i];
+    __syncthreads();
+    if (tid < 64) {
+        const int kcc = tid >> 3, i = tid & 7;
+        float s = 0.0f;
+        for (int w = 0; w < NW; ++w)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) s += scr[(w * 32 + kcc * 4 + r) * 8 + i];
+        P[2 * 64 * F + tid] = s;
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
 }  // namespace is
 
 using namespace is;
@@ -364,6 +561,26 @@ int is_egnn_node_post_bwd_tc(const float* gh_out, const float* h, int64_t ldh, i
     const int64_t tiles = (n_nodes + IS_TM - 1) / IS_TM;
     const int grid = (int)(tiles < sms ? tiles : sms);
     node_post_bwd_tc_kernel<<<grid, nb::NT, smem, (cudaStream_t)stream>>>(gh_out, h, ldh, F, hn, W5, b5, W6, gh_direct, ghn, partials, n_nodes);
+    IS_LAUNCH_CHECK();
+    return IS_OK;
+}
+
+// Tensor-core variant of is_egnn_node_pre_bwd (same outputs, same partial layout, grid = is_egnn_node_grid).
+int is_egnn_node_pre_bwd_tc(const float* gz1, const float* gQ, const float* gD, const float* gxd, const float* gx_out,
+                            const float* gh_direct, const int* outptr, const int* csc_pos, const float* h, int64_t ldh, int F,
+                            const float* W1, float* gh, float* gx, float* partials, int64_t n_nodes, void* stream) {
+    if (!(F == 20 || F == 64) || n_nodes <= 0) return IS_ERR_ARG;
+    if (gh && F != 64) return IS_ERR_ARG;
+    if (((reinterpret_cast<uintptr_t>(gh) | reinterpret_cast<uintptr_t>(gh_direct)) & 31) != 0) return IS_ERR_ARG;   // 256-bit accesses
+    const size_t smem = 9 * (size_t)nb::T_BYTES + 6 * (size_t)nb::W_BYTES;
+    cudaError_t e = cudaFuncSetAttribute(node_pre_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int64_t tiles = (n_nodes + IS_TM - 1) / IS_TM;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    node_pre_bwd_tc_kernel<<<grid, nb::NT, smem, (cudaStream_t)stream>>>(gz1, gQ, gD, gxd, gx_out, gh_direct, outptr, csc_pos, h, ldh, F,
+                                                                        W1, gh, gx, partials, n_nodes);
     IS_LAUNCH_CHECK();
     return IS_OK;
 }

@@ -116,7 +116,7 @@ def _egnn_layer_backward(g, h, x, edge_attr, PQ, hn, params, gh_out, gx_out, nee
     gh = _new(h, n, H) if need_gh else None
     gx = _new(h, n, 3) if need_gx else None
     p_pre = _new(h, grid_n, 2 * H * f + H)
-    _C.egnn_node_pre_bwd(gz1, gQ, gD, gxd, gx_out, gh_direct, g, h, W1, gh, gx, p_pre)
+    (_C.egnn_node_pre_bwd_tc if tc else _C.egnn_node_pre_bwd)(gz1, gQ, gD, gxd, gx_out, gh_direct, g, h, W1, gh, gx, p_pre)
     # deterministic reduction of the per-CTA weight-gradient partials
     r_post, r_edge, r_pre = _new(h, p_post.shape[1]), _new(h, p_edge.shape[1]), _new(h, p_pre.shape[1])
     _C.reduce_partials(p_post, r_post)

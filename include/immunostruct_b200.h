@@ -94,6 +94,11 @@ int is_egnn_node_pre_bwd(const float* gz1, const float* gQ, const float* gD, con
                          const float* gx_out, const float* gh_direct,
                          const int* outptr, const int* csc_pos, const float* h, int64_t ldh, int F,
                          const float* W1, float* gh, float* gx, float* partials, int64_t n_nodes, void* stream);
+/* tcgen05 (bf16x3, fp32-accurate) variant: same outputs, same partial layout, same grid. */
+int is_egnn_node_pre_bwd_tc(const float* gz1, const float* gQ, const float* gD, const float* gxd,
+                         const float* gx_out, const float* gh_direct,
+                         const int* outptr, const int* csc_pos, const float* h, int64_t ldh, int F,
+                         const float* W1, float* gh, float* gx, float* partials, int64_t n_nodes, void* stream);
 int is_reduce_partials(const float* partials, int nparts, int64_t stride, float* out, void* stream);
 
 /* ---- per-graph attention + global_mean_pool (models/layers.py:13-22,29-48,67-78;

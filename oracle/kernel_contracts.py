@@ -184,6 +184,10 @@ def egnn_node_post_bwd_tc(*args):
     return egnn_node_post_bwd(*args)
 
 
+def egnn_node_pre_bwd_tc(*args):
+    return egnn_node_pre_bwd(*args)
+
+
 @torch.enable_grad()
 def egnn_node_post_bwd(gh_out, h, hn, W5, b5, W6, gh_direct, ghn, partials):
     leaves = [t.detach().clone().requires_grad_(True) for t in (h, hn, W5, b5, W6)]
@@ -357,6 +361,6 @@ def loss_bwd(recon, seq, mu, logvar, logits, y, mode, pos_weight, w_pred, w_mse,
 
 
 ALL = ["num_sms", "egnn_node_grid", "egnn_edge_bwd_grid", "attn_max_nodes", "loss_num_partials", "collate_csr",
-       "egnn_node_pre_fwd", "egnn_edge_fwd", "egnn_edge_fwd_tc", "egnn_node_post_pre_tc", "linear_tc", "vae_mid_infer", "head_infer", "unpack_nodes", "unpack_edges", "onehot_tokens", "egnn_node_post_fwd", "egnn_node_post_bwd", "egnn_node_post_bwd_tc", "egnn_edge_bwd", "egnn_edge_bwd_tc",
+       "egnn_node_pre_fwd", "egnn_edge_fwd", "egnn_edge_fwd_tc", "egnn_node_post_pre_tc", "linear_tc", "vae_mid_infer", "head_infer", "unpack_nodes", "unpack_edges", "onehot_tokens", "egnn_node_post_fwd", "egnn_node_post_bwd", "egnn_node_post_bwd_tc", "egnn_node_pre_bwd_tc", "egnn_edge_bwd", "egnn_edge_bwd_tc",
        "egnn_node_pre_bwd", "reduce_partials", "attn_pool_fwd", "attn_pool_infer", "attn_pool_infer_tc", "attn_pool_bwd", "fusion_attn_fwd",
        "fusion_attn_bwd", "loss_fwd", "loss_bwd"]

@@ -378,8 +378,9 @@ def test_egnn_backward_kernels(case, f, coord, tc):
     p3_d = torch.empty(grid_n, 2 * 64 * f + 64, device=DEV)
     gh = torch.empty(n, 64) if need_gh else None
     gx, p3 = torch.empty(n, 3), torch.empty(KC.FAKE_GRID, 2 * 64 * f + 64)
-    _C.egnn_node_pre_bwd(gz1.to(DEV), gQ.to(DEV), gD.to(DEV), gxd.to(DEV), gx_out.to(DEV) if coord else None,
-                         ghd.to(DEV) if need_gh else None, gb, h_d, wd["W1"], gh_d, gx_d, p3_d)
+    node_pre_bwd = _C.egnn_node_pre_bwd_tc if tc else _C.egnn_node_pre_bwd
+    node_pre_bwd(gz1.to(DEV), gQ.to(DEV), gD.to(DEV), gxd.to(DEV), gx_out.to(DEV) if coord else None,
+                 ghd.to(DEV) if need_gh else None, gb, h_d, wd["W1"], gh_d, gx_d, p3_d)
     KC.egnn_node_pre_bwd(gz1, gQ, gD, gxd, gx_out, ghd, cg, h, w["W1"], gh, gx, p3)
     close(gx_d, gx, what="gx")
     if need_gh:
