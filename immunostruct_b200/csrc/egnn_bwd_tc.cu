@@ -212,8 +212,12 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
     int cur = 0;
 
     // t1 = silu(P[src] + Q[dst] + wr r + wa a) for the tile's 128 rows -> operand tile `dst_tile`
+    // t1 = silu(P[src] + Q[dst] + wr r + wa a) for this thread's two (row, chunk) items -> operand tile `dst_tile`; the
+    // sixteen values stay in registers (t1v) so that the second use of t1 (weight gradient of W2) is a re-store, not a
+    // second gather + SiLU pass
+    float t1v[2][8];
     auto gather_t1 = [&](uint8_t* dst_tile, const BwdMeta& mt, int ne) {
-        float4 pv[2][2], qv[2][2];
+        float pv[2][8], qv[2][8];
         float rr[2], aa[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -221,27 +225,22 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
             const bool valid = j < ne;
             const int s = valid ? mt.src[j] : 0, d = valid ? mt.dst[j] : 0;
             rr[u] = mt.r[j]; aa[u] = mt.a[j];
-            float p8[8], q8[8];
-            ldg256(p.PQ + (size_t)s * 128 + 8 * kc8, p8);               // 256-bit loads: whole sectors per lane
-            ldg256(p.PQ + (size_t)d * 128 + 64 + 8 * kc8, q8);
-            pv[u][0] = make_float4(p8[0], p8[1], p8[2], p8[3]); pv[u][1] = make_float4(p8[4], p8[5], p8[6], p8[7]);
-            qv[u][0] = make_float4(q8[0], q8[1], q8[2], q8[3]); qv[u][1] = make_float4(q8[4], q8[5], q8[6], q8[7]);
+            ldg256(p.PQ + (size_t)s * 128 + 8 * kc8, pv[u]);               // 256-bit loads: whole sectors per lane
+            ldg256(p.PQ + (size_t)d * 128 + 64 + 8 * kc8, qv[u]);
         }
+        const float wr[8] = {wr0.x, wr0.y, wr0.z, wr0.w, wr1.x, wr1.y, wr1.z, wr1.w};
+        const float wa[8] = {wa0.x, wa0.y, wa0.z, wa0.w, wa1.x, wa1.y, wa1.z, wa1.w};
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int j = u * 4 * BT_NW + warp * 4 + esub;
-            const float r = rr[u], a = aa[u];
-            float v[8];
-            v[0] = silu_acc(pv[u][0].x + qv[u][0].x + wr0.x * r + wa0.x * a);
-            v[1] = silu_acc(pv[u][0].y + qv[u][0].y + wr0.y * r + wa0.y * a);
-            v[2] = silu_acc(pv[u][0].z + qv[u][0].z + wr0.z * r + wa0.z * a);
-            v[3] = silu_acc(pv[u][0].w + qv[u][0].w + wr0.w * r + wa0.w * a);
-            v[4] = silu_acc(pv[u][1].x + qv[u][1].x + wr1.x * r + wa1.x * a);
-            v[5] = silu_acc(pv[u][1].y + qv[u][1].y + wr1.y * r + wa1.y * a);
-            v[6] = silu_acc(pv[u][1].z + qv[u][1].z + wr1.z * r + wa1.z * a);
-            v[7] = silu_acc(pv[u][1].w + qv[u][1].w + wr1.w * r + wa1.w * a);
-            store_operand8<PREC_BF16X3>(dst_tile, ASPL, j, kc8, v);    // rows >= ne: finite, multiplied by zero gradients
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t1v[u][i] = silu_acc(pv[u][i] + qv[u][i] + wr[i] * rr[u] + wa[i] * aa[u]);
+            store_operand8<PREC_BF16X3>(dst_tile, ASPL, j, kc8, t1v[u]);    // rows >= ne: finite, multiplied by zero gradients
         }
+    };
+    auto restore_t1 = [&](uint8_t* dst_tile) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) store_operand8<PREC_BF16X3>(dst_tile, ASPL, u * 4 * BT_NW + warp * 4 + esub, kc8, t1v[u]);
     };
     // publish smem operand writes, let thread 0 issue `fn` + commit, wait for completion
     auto run_mma = [&](auto&& fn) {
@@ -398,7 +397,7 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
                 store_operand8<PREC_BF16X3>(sX, ASPL, erow, 2 * cq + g, v8);
             }
         }
-        gather_t1(sY, mt, ne);
+        restore_t1(sY);
         // ---- MMA 4: gt1 = gz2 W2 ; WG 2: gW2 += gz2^T t1 -------------------------------------------------------
         fence_async_smem();
         fence_before_sync();
@@ -426,12 +425,15 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
             float grpart = 0.0f;
             if (row_valid) {
                 const float r = mt.r[erow], a = mt.a[erow];
-                const float4* pp = reinterpret_cast<const float4*>(p.PQ + (size_t)mt.src[erow] * 128 + BT_CW * cq);
-                const float4* qp = reinterpret_cast<const float4*>(p.PQ + (size_t)mt.dst[erow] * 128 + 64 + BT_CW * cq);
+                float p16[2][8], q16[2][8];
+                ldg256(p.PQ + (size_t)mt.src[erow] * 128 + BT_CW * cq, p16[0]);
+                ldg256(p.PQ + (size_t)mt.src[erow] * 128 + BT_CW * cq + 8, p16[1]);
+                ldg256(p.PQ + (size_t)mt.dst[erow] * 128 + 64 + BT_CW * cq, q16[0]);
+                ldg256(p.PQ + (size_t)mt.dst[erow] * 128 + 64 + BT_CW * cq + 8, q16[1]);
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                    const float4 pv = __ldg(pp + g), qv = __ldg(qp + g);
-                    const float z1[4] = {pv.x + qv.x, pv.y + qv.y, pv.z + qv.z, pv.w + qv.w};
+                    const float z1[4] = {p16[g >> 1][4 * (g & 1)] + q16[g >> 1][4 * (g & 1)], p16[g >> 1][4 * (g & 1) + 1] + q16[g >> 1][4 * (g & 1) + 1],
+                                         p16[g >> 1][4 * (g & 1) + 2] + q16[g >> 1][4 * (g & 1) + 2], p16[g >> 1][4 * (g & 1) + 3] + q16[g >> 1][4 * (g & 1) + 3]};
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int c = BT_CW * cq + 4 * g + i;
