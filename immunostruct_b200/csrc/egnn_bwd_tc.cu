@@ -233,9 +233,13 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int j = u * 4 * BT_NW + warp * 4 + esub;
+            float d1[8];                                               // silu'(z1): parked in the fp32 tile for epilogue 4
 #pragma unroll
-            for (int i = 0; i < 8; ++i) t1v[u][i] = silu_acc(pv[u][i] + qv[u][i] + wr[i] * rr[u] + wa[i] * aa[u]);
+            for (int i = 0; i < 8; ++i) silu_both_acc(pv[u][i] + qv[u][i] + wr[i] * rr[u] + wa[i] * aa[u], t1v[u][i], d1[i]);
             store_operand8<PREC_BF16X3>(dst_tile, ASPL, j, kc8, t1v[u]);    // rows >= ne: finite, multiplied by zero gradients
+            float* dd = F32 + j * IS_LD + 8 * kc8;
+            *reinterpret_cast<float4*>(dd) = make_float4(d1[0], d1[1], d1[2], d1[3]);
+            *reinterpret_cast<float4*>(dd + 4) = make_float4(d1[4], d1[5], d1[6], d1[7]);
         }
     };
     auto restore_t1 = [&](uint8_t* dst_tile) {
@@ -425,20 +429,16 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
             float grpart = 0.0f;
             if (row_valid) {
                 const float r = mt.r[erow], a = mt.a[erow];
-                float p16[2][8], q16[2][8];
-                ldg256(p.PQ + (size_t)mt.src[erow] * 128 + BT_CW * cq, p16[0]);
-                ldg256(p.PQ + (size_t)mt.src[erow] * 128 + BT_CW * cq + 8, p16[1]);
-                ldg256(p.PQ + (size_t)mt.dst[erow] * 128 + 64 + BT_CW * cq, q16[0]);
-                ldg256(p.PQ + (size_t)mt.dst[erow] * 128 + 64 + BT_CW * cq + 8, q16[1]);
+                const float* dd = F32 + erow * IS_LD + BT_CW * cq;          // silu'(z1) of this row, written by the gather
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                    const float z1[4] = {p16[g >> 1][4 * (g & 1)] + q16[g >> 1][4 * (g & 1)], p16[g >> 1][4 * (g & 1) + 1] + q16[g >> 1][4 * (g & 1) + 1],
-                                         p16[g >> 1][4 * (g & 1) + 2] + q16[g >> 1][4 * (g & 1) + 2], p16[g >> 1][4 * (g & 1) + 3] + q16[g >> 1][4 * (g & 1) + 3]};
+                    const float4 d4 = *reinterpret_cast<const float4*>(dd + 4 * g);
+                    const float d1[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int c = BT_CW * cq + 4 * g + i;
                         const float wrc = vec[192 + c];
-                        const float gz = gt1[4 * g + i] * dsilu_acc(z1[i] + wrc * r + vec[256 + c] * a);
+                        const float gz = gt1[4 * g + i] * d1[i];
                         g1[4 * g + i] = gz;
                         gr_[4 * g + i] = gz * r;
                         ga_[4 * g + i] = gz * a;
