@@ -47,7 +47,7 @@ BYTES_PER_EDGE_EDGE_KERNEL = 3 * 4 + 4                     # read csr_src/dst/ei
 GATHER_BYTES_PER_EDGE = 2 * 256                            # P[src] + Q[dst] rows (served by L2)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
 # (profiles/r01_ws_*_edge_fwd_full.md, profiles/r01_simt_edge_fwd_full.md), batch 512
-NCU_TRAFFIC_BYTES = {"bf16x3": 82.22e6 + 10.10e6, "bf16": 83.00e6 + 8.58e6,        # profiles/r01_ws_*_edge_fwd_full.md
+NCU_TRAFFIC_BYTES = {"bf16x3": 82.50e6 + 9.23e6, "bf16": 83.34e6 + 9.10e6,        # profiles/r01_ws_*_edge_fwd_full.md
                      "tf32x3": 82.36e6 + 10.82e6, "fp32": 80.64e6 + 8.85e6}
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12          # 74.4
 
