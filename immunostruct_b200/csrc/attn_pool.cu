@@ -183,6 +183,9 @@ attn_fwd_kernel(const float* __restrict__ QKV, const int64_t* __restrict__ node_
 
 // Backward.  gO[i] = gO_full[i] (optional) + g_pooled[g] / n.  Two register-blocked passes with
 // recomputed scores: row blocks (gQ) then column blocks (gK, gV), fixed summation order.
+// Pooled-only case (gO_full == NULL: every model's training path): all rows of gO equal g0 = g_pooled / n, so
+// dP_ij = g0 . V_j =: c_j does not depend on i and gV_j = (sum_i P_ij) g0 -- c is computed once per graph and three of
+// the seven n x n x 64 products (both dP passes and the P^T gO product) disappear.
 __global__ void __launch_bounds__(IS_THREADS)
 attn_bwd_kernel(const float* __restrict__ QKV, const float* __restrict__ O, const float* __restrict__ LSE,
                 const int64_t* __restrict__ node_off, int H, float scale,
@@ -215,10 +218,21 @@ attn_bwd_kernel(const float* __restrict__ QKV, const float* __restrict__ O, cons
         *reinterpret_cast<float4*>(S1 + r * IS_ATT_LD4 + 4 * c4) = __ldg(reinterpret_cast<const float4*>(QKV + (n0 + r) * 192 + 128) + c4);
     }
     __syncthreads();
+    const bool pooled_only = gO_full == nullptr && gp_row != nullptr;
+    float* cvec = rb;                               // [8 heads][NMAX] c_j per head (pooled-only: rb is not used for gO rows)
+    if (pooled_only) {
+        for (int idx = tid; idx < n * H; idx += IS_THREADS) {
+            const int j = idx / H, h = idx - j * H;
+            float c = 0.0f;
+            for (int k = 0; k < dh; ++k) c = fmaf(__ldg(gp_row + h * dh + k) * inv_n, S1[j * IS_ATT_LD4 + h * dh + k], c);
+            cvec[h * IS_ATT_NMAX + j] = c;
+        }
+        __syncthreads();
+    }
     for (int i0 = 4 * warp; i0 < n; i0 += 4 * (IS_THREADS / 32)) {
         __syncwarp();
         stage4(A, QKV, 192, n0, i0, n, lane);
-        stage4(Bv, gO_full, 64, n0, i0, n, lane, gp_row, inv_n);
+        if (!pooled_only) stage4(Bv, gO_full, 64, n0, i0, n, lane, gp_row, inv_n);
         __syncwarp();
         for (int h = 0; h < H; ++h) {
             // D[r] = sum over this head's channels of gO[r][c] * O[r][c]
@@ -227,13 +241,23 @@ attn_bwd_kernel(const float* __restrict__ QKV, const float* __restrict__ O, cons
             for (int r = 0; r < 4; ++r) {
                 float dpart = 0.0f;
                 if (i0 + r < n)
-                    for (int k = lane; k < dh; k += 32) dpart += Bv[r * 64 + h * dh + k] * __ldg(O + (n0 + i0 + r) * 64 + h * dh + k);
+                    for (int k = lane; k < dh; k += 32)
+                        dpart += (pooled_only ? __ldg(gp_row + h * dh + k) * inv_n : Bv[r * 64 + h * dh + k]) * __ldg(O + (n0 + i0 + r) * 64 + h * dh + k);
                 D[r] = warp_sum(dpart);
                 if (lane == 0 && i0 + r < n) Dn[(i0 + r) * 8 + h] = D[r];
             }
             float s[4][IS_ATT_JB], gp[4][IS_ATT_JB];
             blocked_dots(s, A, S0, h * dh, dh, n, lane);
-            blocked_dots(gp, Bv, S1, h * dh, dh, n, lane);
+            if (pooled_only) {
+#pragma unroll
+                for (int jj = 0; jj < IS_ATT_JB; ++jj) {
+                    const float c = (jj * 32 < n && jj * 32 + lane < n) ? cvec[h * IS_ATT_NMAX + jj * 32 + lane] : 0.0f;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) gp[r][jj] = c;
+                }
+            } else {
+                blocked_dots(gp, Bv, S1, h * dh, dh, n, lane);
+            }
             __syncwarp();
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
@@ -260,21 +284,33 @@ attn_bwd_kernel(const float* __restrict__ QKV, const float* __restrict__ O, cons
     for (int idx = tid; idx < n * 64; idx += IS_THREADS) {
         const int r = idx >> 6, c = idx & 63;
         S0[r * IS_ATT_LD4 + c] = __ldg(QKV + (n0 + r) * 192 + c);
-        float v = gp_row ? __ldg(gp_row + c) * inv_n : 0.0f;
-        if (gO_full) v += __ldg(gO_full + (n0 + r) * 64 + c);
-        S1[r * IS_ATT_LD4 + c] = v;
+        if (!pooled_only) {
+            float v = gp_row ? __ldg(gp_row + c) * inv_n : 0.0f;
+            if (gO_full) v += __ldg(gO_full + (n0 + r) * 64 + c);
+            S1[r * IS_ATT_LD4 + c] = v;
+        }
     }
     __syncthreads();
     for (int j0 = 4 * warp; j0 < n; j0 += 4 * (IS_THREADS / 32)) {
         __syncwarp();
         stage4(A, QKV + 64, 192, n0, j0, n, lane);       // K rows of the 4 columns
-        stage4(Bv, QKV + 128, 192, n0, j0, n, lane);     // V rows
+        if (!pooled_only) stage4(Bv, QKV + 128, 192, n0, j0, n, lane);     // V rows
         __syncwarp();
         for (int h = 0; h < H; ++h) {
             float s[4][IS_ATT_JB], gp[4][IS_ATT_JB];
             blocked_dots(s, A, S0, h * dh, dh, n, lane);       // s[c][i] = k_c . q_i
-            blocked_dots(gp, Bv, S1, h * dh, dh, n, lane);     // gp[c][i] = v_c . gO_i
+            if (pooled_only) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float cj = j0 + c < n ? cvec[h * IS_ATT_NMAX + j0 + c] : 0.0f;
+#pragma unroll
+                    for (int jj = 0; jj < IS_ATT_JB; ++jj) gp[c][jj] = cj;
+                }
+            } else {
+                blocked_dots(gp, Bv, S1, h * dh, dh, n, lane);     // gp[c][i] = v_c . gO_i
+            }
             __syncwarp();
+            float psum[4] = {0.0f, 0.0f, 0.0f, 0.0f};            // pooled-only: sum_i p_ic (this lane's rows)
 #pragma unroll
             for (int jj = 0; jj < IS_ATT_JB; ++jj) {
                 const int i = jj * 32 + lane;
@@ -285,7 +321,7 @@ attn_bwd_kernel(const float* __restrict__ QKV, const float* __restrict__ O, cons
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const float pij = (vi && j0 + c < n) ? expf(s[c][jj] * scale - lse) : 0.0f;
-                        WB[c * IS_ATT_NMAX + i] = pij;
+                        if (pooled_only) psum[c] += pij; else WB[c * IS_ATT_NMAX + i] = pij;
                         WA[c * IS_ATT_NMAX + i] = pij * (gp[c][jj] - Di);
                     }
                 }
@@ -293,7 +329,16 @@ attn_bwd_kernel(const float* __restrict__ QKV, const float* __restrict__ O, cons
             __syncwarp();
             float2 gk[4], gv[4];
             blocked_wsum(gk, WA, S0, h * dh, dh, n, lane);
-            blocked_wsum(gv, WB, S1, h * dh, dh, n, lane);
+            if (pooled_only) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float w = warp_sum(psum[c]);
+                    gv[c] = 2 * lane < dh ? make_float2(w * __ldg(gp_row + h * dh + 2 * lane) * inv_n, w * __ldg(gp_row + h * dh + 2 * lane + 1) * inv_n)
+                                          : make_float2(0.0f, 0.0f);
+                }
+            } else {
+                blocked_wsum(gv, WB, S1, h * dh, dh, n, lane);
+            }
             if (2 * lane < dh) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
