@@ -98,7 +98,7 @@ node_post_pre_tc_kernel(const float* __restrict__ h, int64_t ldh, int F, const f
         if (tid < 32) {               // one elected lane of the converged warp issues (bare UTCHMMA, no election loop)
             if (elect_one()) {
                 fence_after_sync();
-                issue_gemm<PREC>(tmem_d, a_addr, ASPL, w_addr + wblock * C::W_BYTES, WSPL, ncols, accumulate);
+                issue_gemm<PREC, !FAST>(tmem_d, a_addr, ASPL, w_addr + wblock * C::W_BYTES, WSPL, ncols, accumulate);
                 mma_commit(&mbar);
             }
             __syncwarp();

@@ -191,17 +191,20 @@ __device__ __forceinline__ void stage_weight_block(uint8_t* __restrict__ tile, u
 
 // issue D[tmem_d] (+)= A * W^T over one 64-wide K block (called by ONE thread); N = 64 or 128 output
 // columns (W tile rows); a_split / w_split = byte distance between split-term copies.
-template <int PREC>
+// FULL = true adds the two 2^-24 products a2 w3 + a3 w2 (eight partial products instead of six): the result is then
+// limited by the fp32 accumulator only -- used by the training forward of the node kernel, whose outputs feed the
+// gradient parity test at 1e-5.
+template <int PREC, bool FULL = false>
 __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_addr, uint32_t a_split, uint32_t w_addr,
                                            uint32_t w_split, uint32_t n_cols, uint32_t accumulate) {
     using C = TcCfg<PREC>;
     const uint32_t idesc = make_instr_desc(C::FMT, 128, n_cols);
     uint32_t acc = accumulate;
     if (PREC == PREC_BF16X3) {
-        // (a-term, w-term), smallest products first: a3w1 a1w3 a2w2 a2w1 a1w2 a1w1
-        const uint32_t ta[6] = {2, 0, 1, 1, 0, 0}, tw[6] = {0, 2, 1, 0, 1, 0};
+        // (a-term, w-term), smallest products first: [a3w2 a2w3] a3w1 a1w3 a2w2 a2w1 a1w2 a1w1
+        const uint32_t ta[8] = {2, 1, 2, 0, 1, 1, 0, 0}, tw[8] = {1, 2, 0, 2, 1, 0, 1, 0};
 #pragma unroll
-        for (int t = 0; t < 6; ++t)
+        for (int t = FULL ? 0 : 2; t < 8; ++t)
 #pragma unroll
             for (int ks = 0; ks < C::KCH / 2; ++ks) {
                 mma_bf16(tmem_d, make_smem_desc(a_addr + ta[t] * a_split + ks * 2 * kLBO, kLBO, C::SBO),

@@ -153,11 +153,9 @@ def _egnn_stack_forward(graph, x23, edge_attr, params, fast_act, keep, qkv=None)
     n = h.shape[0]
     prec = _PRECISIONS[_precision]
     node_prec = {None: None, _C.PREC_BF16: _C.PREC_BF16, _C.PREC_TF32X3: _C.PREC_BF16X3, _C.PREC_BF16X3: _C.PREC_BF16X3}[prec]
-    if keep is not None and node_prec == _C.PREC_BF16X3:
-        # Training forward in the fp32-accurate modes keeps the fp32 SIMT node kernels: with the tensor-core
-        # node kernel a handful of parameter gradients landed at 1.0-1.3e-5 of their scale (measured on the
-        # B200, tests/test_models_gpu.py), i.e. just outside the 1e-5 gradient tolerance.
-        node_prec = None
+    # (training forward: the fused tensor-core node kernel with the accurate SiLU and all eight bf16x3 partial
+    #  products, fast_act = False -- with six products a handful of parameter gradients landed at 1.0-1.3e-5 of
+    #  their scale on the B200, just outside the 1e-5 gradient tolerance)
     PQ = _new(h, n, 2 * H)
     QKV = None
     _C.egnn_node_pre_fwd(h, params[0][0], params[0][1], PQ)
