@@ -127,3 +127,70 @@ def pack_sequence(sequence_data: torch.Tensor) -> PackedSequence:
         raise ValueError("sequence rows must be one-hot or all-zero to be packed")
     tok = torch.where(ones == 1, sequence_data.argmax(2), torch.full_like(ones, v))
     return PackedSequence(tok.to(torch.uint8), v)
+
+
+class PackedGraphDataset:
+    """A whole dataset in a handful of flat compact arrays.
+
+    The reference keeps a python list of DGL graphs, ``copy.deepcopy``s each sample, concatenates them one by one in
+    ``dgl.batch`` inside DataLoader workers and pickles the batch to the main process (train_IEDB_wFT.py:82-87,
+    data/util_dataloader.py:25-50, data/utils.py:148-163).  Here the samples are packed once
+    (``from_samples``); a batch is then a VECTORISED gather over the flat arrays -- no per-graph python work, no
+    pickling, optionally pinned so that the H2D copy of the compact batch is asynchronous -- and ``loader`` yields
+    ``(PackedGraphBatch, PackedSequence, target, property)`` tuples that ``DevicePrefetcher`` turns into the dense
+    device batch of the unchanged model API.
+    """
+
+    def __init__(self, aa, xyz, src, dst, edge_attr, node_counts, edge_counts, tokens, targets, properties, vocab=21):
+        self.aa, self.xyz, self.src, self.dst, self.edge_attr = aa, xyz, src, dst, edge_attr
+        self.node_counts, self.edge_counts = node_counts.to(torch.int64), edge_counts.to(torch.int64)
+        self.tokens, self.targets, self.properties, self.vocab = tokens, targets, properties, vocab
+        z = torch.zeros(1, dtype=torch.int64)
+        self.node_off = torch.cat([z, torch.cumsum(self.node_counts, 0)])
+        self.edge_off = torch.cat([z, torch.cumsum(self.edge_counts, 0)])
+
+    @classmethod
+    def from_samples(cls, graphs, sequences, targets, properties):
+        """graphs: sequence of ``Graph`` (one-hot / zero-padded features); sequences [S, L, V] one-hot floats;
+        targets [S]; properties [S, 2]."""
+        from .graph import batch as _batch
+        pk = pack_graph_batch(_batch(list(graphs)))
+        ps = pack_sequence(torch.as_tensor(sequences))
+        return cls(pk.aa, pk.xyz, pk.src, pk.dst, pk.edge_attr, pk.node_counts, pk.edge_counts, ps.tokens,
+                   torch.as_tensor(targets), torch.as_tensor(properties), ps.vocab)
+
+    def __len__(self):
+        return int(self.node_counts.numel())
+
+    @staticmethod
+    def _ranges(starts, counts):
+        """Concatenated index ranges [starts_i, starts_i + counts_i) without a python loop."""
+        total = int(counts.sum())
+        if total == 0:
+            return torch.zeros(0, dtype=torch.int64)
+        out_off = torch.cumsum(counts, 0) - counts
+        return torch.arange(total) + torch.repeat_interleave(starts - out_off, counts)
+
+    def batch(self, indices, pin_memory: bool = False):
+        """-> (PackedGraphBatch, PackedSequence, target [B], property [B,2]) for the given sample indices."""
+        idx = torch.as_tensor(indices, dtype=torch.int64).reshape(-1)
+        nc, ec = self.node_counts[idx], self.edge_counts[idx]
+        ni, ei = self._ranges(self.node_off[idx], nc), self._ranges(self.edge_off[idx], ec)
+        pk = PackedGraphBatch(self.aa[ni], self.xyz[ni], self.src[ei], self.dst[ei],
+                              None if self.edge_attr is None else self.edge_attr[ei], nc.to(torch.int32), ec.to(torch.int32),
+                              int(nc.max()) if idx.numel() else 0)
+        ps = PackedSequence(self.tokens[idx], self.vocab)
+        tgt, prop = self.targets[idx], self.properties[idx]
+        if pin_memory:
+            pk, ps, tgt, prop = pk.pin_memory(), ps.pin_memory(), tgt.pin_memory(), prop.pin_memory()
+        return pk, ps, tgt, prop
+
+    def loader(self, batch_size: int, shuffle: bool = False, drop_last: bool = False, generator=None, pin_memory: bool = False):
+        """Batches in the reference loader's order semantics (last partial batch kept unless ``drop_last``)."""
+        n = len(self)
+        order = torch.randperm(n, generator=generator) if shuffle else torch.arange(n)
+        for lo in range(0, n, batch_size):
+            sel = order[lo:lo + batch_size]
+            if drop_last and sel.numel() < batch_size:
+                return
+            yield self.batch(sel, pin_memory=pin_memory)

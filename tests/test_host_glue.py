@@ -190,3 +190,33 @@ def test_pack_graph_batch_and_sequence_round_trip():
         pack_graph_batch(GraphBatch.from_arrays(bad, *(arr[k] for k in keys[1:]), max_nodes=40))
     with pytest.raises(RuntimeError):
         pk.expand()                                                 # expansion is a device operation: no CPU path
+
+
+def test_packed_dataset_batches_equal_reference_collate():
+    """PackedGraphDataset.batch (vectorised gather over flat arrays) == packing the reference-style collate of the same
+    samples, for contiguous, shuffled and repeated index sets; the loader keeps the last partial batch."""
+    import immunostruct_b200 as I
+    from immunostruct_b200.packed import PackedGraphDataset, pack_graph_batch
+    from immunostruct_b200.synthetic import split_graphs, synthetic_dense, synthetic_graph_arrays
+    arr = synthetic_graph_arrays(7, 30, 5, seed=21, n_pad=3)
+    dense = synthetic_dense(7, seed=21)
+    samples = []
+    for g in split_graphs(arr):
+        gr = I.graph((g["src"], g["dst"]), num_nodes=g["x"].shape[0])
+        gr.ndata["x"], gr.edata["edge_attr"] = g["x"], g["edge_attr"]
+        samples.append(gr)
+    ds = PackedGraphDataset.from_samples(samples, dense["seq"], dense["target"], dense["prop"])
+    assert len(ds) == 7
+    for idx in ([0, 1, 2], [5, 2, 6, 0], [3, 3]):
+        pk, ps, tgt, prop = ds.batch(idx)
+        ref = pack_graph_batch(I.batch([samples[i] for i in idx]))
+        for a, b in ((pk.aa, ref.aa), (pk.xyz, ref.xyz), (pk.src, ref.src), (pk.dst, ref.dst),
+                     (pk.node_counts, ref.node_counts), (pk.edge_counts, ref.edge_counts)):
+            assert torch.equal(a, b)
+        assert pk.edge_attr is None and pk.max_nodes == 30
+        assert torch.equal(tgt, dense["target"][idx]) and torch.equal(prop, dense["prop"][idx])
+        assert torch.equal(ps.tokens, dense["seq"][idx].argmax(2).to(torch.uint8))
+    sizes = [b[0].node_counts.numel() for b in ds.loader(3)]
+    assert sizes == [3, 3, 1] and [b[0].node_counts.numel() for b in ds.loader(3, drop_last=True)] == [3, 3]
+    g = torch.Generator().manual_seed(0)
+    assert sorted(int(t) for b in ds.loader(2, shuffle=True, generator=g) for t in b[2].tolist()) == sorted(int(t) for t in dense["target"].tolist())
