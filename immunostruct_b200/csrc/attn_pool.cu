@@ -185,9 +185,11 @@ attn_fwd_kernel(const float* __restrict__ QKV, const int64_t* __restrict__ node_
 // recomputed scores: row blocks (gQ) then column blocks (gK, gV), fixed summation order.
 // Pooled-only case (gO_full == NULL: every model's training path): all rows of gO equal g0 = g_pooled / n, so
 // dP_ij = g0 . V_j =: c_j does not depend on i and gV_j = (sum_i P_ij) g0 -- c is computed once per graph and three of
-// the seven n x n x 64 products (both dP passes and the P^T gO product) disappear.
+// the seven n x n x 64 products (both dP passes and the P^T gO product) disappear.  With O == NULL (pooled-only, forward
+// run by the pooled-rows-only tensor-core kernel) the row statistics are recomputed here: pass A derives lse_i from the
+// score row it holds anyway and D_i = sum_j P_ij c_j, and parks lse_i in the LSE array (then an OUTPUT scratch) for pass B.
 __global__ void __launch_bounds__(IS_THREADS)
-attn_bwd_kernel(const float* __restrict__ QKV, const float* __restrict__ O, const float* __restrict__ LSE,
+attn_bwd_kernel(const float* __restrict__ QKV, const float* __restrict__ O /* or null: recompute */, float* __restrict__ LSE,
                 const int64_t* __restrict__ node_off, int H, float scale,
                 const float* __restrict__ g_pooled /* [B,64] or null */, const float* __restrict__ gO_full /* or null */,
                 float* __restrict__ gQKV) {
@@ -240,11 +242,11 @@ attn_bwd_kernel(const float* __restrict__ QKV, const float* __restrict__ O, cons
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 float dpart = 0.0f;
-                if (i0 + r < n)
+                if (i0 + r < n && O != nullptr)
                     for (int k = lane; k < dh; k += 32)
                         dpart += (pooled_only ? __ldg(gp_row + h * dh + k) * inv_n : Bv[r * 64 + h * dh + k]) * __ldg(O + (n0 + i0 + r) * 64 + h * dh + k);
                 D[r] = warp_sum(dpart);
-                if (lane == 0 && i0 + r < n) Dn[(i0 + r) * 8 + h] = D[r];
+                if (lane == 0 && i0 + r < n && O != nullptr) Dn[(i0 + r) * 8 + h] = D[r];
             }
             float s[4][IS_ATT_JB], gp[4][IS_ATT_JB];
             blocked_dots(s, A, S0, h * dh, dh, n, lane);
@@ -261,7 +263,30 @@ attn_bwd_kernel(const float* __restrict__ QKV, const float* __restrict__ O, cons
             __syncwarp();
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                const float lse = (i0 + r < n) ? __ldg(LSE + (n0 + i0 + r) * H + h) : 0.0f;
+                float lse = 0.0f;
+                if (O != nullptr) {
+                    lse = (i0 + r < n) ? LSE[(n0 + i0 + r) * H + h] : 0.0f;
+                } else {
+                    // recompute the row's log-sum-exp and D = sum_j p_j c_j from the scores held in registers
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int jj = 0; jj < IS_ATT_JB; ++jj)
+                        if (jj * 32 + lane < n) mx = fmaxf(mx, s[r][jj] * scale);
+                    mx = warp_max(mx);
+                    float z = 0.0f, dsum = 0.0f;
+#pragma unroll
+                    for (int jj = 0; jj < IS_ATT_JB; ++jj)
+                        if (jj * 32 + lane < n) {
+                            const float e = expf(s[r][jj] * scale - mx);
+                            z += e;
+                            dsum = fmaf(e, gp[r][jj], dsum);
+                        }
+                    z = warp_sum(z);
+                    dsum = warp_sum(dsum);
+                    lse = mx + logf(z);
+                    D[r] = dsum / z;
+                    if (lane == 0 && i0 + r < n) { LSE[(n0 + i0 + r) * H + h] = lse; Dn[(i0 + r) * 8 + h] = D[r]; }
+                }
 #pragma unroll
                 for (int jj = 0; jj < IS_ATT_JB; ++jj) {
                     const int j = jj * 32 + lane;
@@ -316,7 +341,7 @@ attn_bwd_kernel(const float* __restrict__ QKV, const float* __restrict__ O, cons
                 const int i = jj * 32 + lane;
                 if (jj * 32 < n) {
                     const bool vi = i < n;
-                    const float lse = vi ? __ldg(LSE + (n0 + i) * H + h) : 0.0f;
+                    const float lse = vi ? LSE[(n0 + i) * H + h] : 0.0f;
                     const float Di = vi ? Dn[i * 8 + h] : 0.0f;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
@@ -499,9 +524,10 @@ int is_attn_pool_infer(const float* QKV, const int64_t* node_off, int n_graphs, 
     return IS_OK;
 }
 
-int is_attn_pool_bwd(const float* QKV, const float* O, const float* LSE, const int64_t* node_off, int n_graphs,
+int is_attn_pool_bwd(const float* QKV, const float* O, float* LSE, const int64_t* node_off, int n_graphs,
                      int n_head, int max_nodes, const float* g_pooled, const float* gO_full, float* gQKV, void* stream) {
     if (n_graphs <= 0 || !(n_head == 1 || n_head == 2 || n_head == 4 || n_head == 8)) return IS_ERR_ARG;
+    if (O == nullptr && (gO_full != nullptr || g_pooled == nullptr)) return IS_ERR_ARG;   // statistics are recomputed only in the pooled-only case
     if (max_nodes > IS_ATT_NMAX) return IS_ERR_UNSUPPORTED;
     const float scale = 1.0f / sqrtf((float)(64 / n_head));
     size_t smem = sizeof(float) * (2 * IS_ATT_NMAX * IS_ATT_LD4 + 2 * 8 * 256 + 2 * 8 * 4 * IS_ATT_NMAX + IS_ATT_NMAX * 8);

@@ -259,15 +259,28 @@ def egnn_layer(graph, h, x, edge_attr, params, update_coords=True):
 class _AttnPool(torch.autograd.Function):
     """softmax(QK^T/sqrt(d)) V per graph and head, plus the per-graph mean of the rows.
 
-    forward(graph, n_head, want_attn, QKV [N,192]) -> (O [N,64], pooled [B,64], attn or None)
-    ``attn`` is the dense weights tensor [B, H, n, n] (equal node counts) when requested.
+    forward(graph, n_head, want_attn, want_nodes, QKV [N,192]) -> (O [N,64] or None, pooled [B,64], attn or None)
+    ``attn`` is the dense weights tensor [B, H, n, n] (equal node counts) when requested.  When only the pooled rows
+    are wanted (every model's training path) and the arithmetic mode is a tensor-core one, the forward is the
+    pooled-rows-only tcgen05 kernel (csrc/attn_pool_tc.cu) and nothing but QKV is saved: the backward recomputes the
+    row statistics (is_attn_pool_bwd with O = NULL).
     """
 
     @staticmethod
-    def forward(ctx, graph, n_head, want_attn, QKV):
+    def forward(ctx, graph, n_head, want_attn, want_nodes, QKV):
         QKV = QKV.contiguous()
         n = QKV.shape[0]
         b = graph.n_graphs
+        ctx.graph, ctx.n_head = graph, n_head
+        ctx.set_materialize_grads(False)
+        prec = _PRECISIONS[_precision]
+        if not want_attn and not want_nodes and n_head == 1 and prec is not None and graph.max_nodes <= 256:
+            pooled = _new(QKV, b, H)
+            _C.attn_pool_infer_tc(QKV, graph.node_off, graph.max_nodes, pooled,
+                                  _C.PREC_BF16 if prec == _C.PREC_BF16 else _C.PREC_BF16X3)
+            ctx.pooled_only = True
+            ctx.save_for_backward(QKV)
+            return None, pooled, None
         O, LSE, pooled = _new(QKV, n, H), _new(QKV, n, n_head), _new(QKV, b, H)
         attn = attn_off = None
         if want_attn:
@@ -277,24 +290,33 @@ class _AttnPool(torch.autograd.Function):
             attn = _new(QKV, b, n_head, m, m)
             attn_off = torch.arange(b, device=QKV.device, dtype=torch.int64) * (n_head * m * m)
         _C.attn_pool_fwd(QKV, graph.node_off, n_head, graph.max_nodes, O, LSE, pooled, attn, attn_off)
-        ctx.graph, ctx.n_head = graph, n_head
+        ctx.pooled_only = False
         ctx.save_for_backward(QKV, O, LSE)
-        ctx.set_materialize_grads(False)
         if want_attn:
             ctx.mark_non_differentiable(attn)
         return O, pooled, attn
 
     @staticmethod
     def backward(ctx, gO, g_pooled, _g_attn):
+        if ctx.pooled_only:
+            (QKV,) = ctx.saved_tensors
+            gQKV = _new(QKV, *QKV.shape)
+            if g_pooled is None:
+                gQKV.zero_()
+                return None, None, None, None, gQKV
+            lse = _new(QKV, QKV.shape[0], ctx.n_head)             # scratch: row statistics recomputed by the kernel
+            _C.attn_pool_bwd(QKV, None, lse, ctx.graph.node_off, ctx.n_head, ctx.graph.max_nodes,
+                             g_pooled.contiguous(), None, gQKV)
+            return None, None, None, None, gQKV
         QKV, O, LSE = ctx.saved_tensors
         gQKV = _new(QKV, *QKV.shape)
         if gO is None and g_pooled is None:
             gQKV.zero_()
-            return None, None, None, gQKV
+            return None, None, None, None, gQKV
         gO = gO.contiguous() if gO is not None else None
         g_pooled = g_pooled.contiguous() if g_pooled is not None else None
         _C.attn_pool_bwd(QKV, O, LSE, ctx.graph.node_off, ctx.n_head, ctx.graph.max_nodes, g_pooled, gO, gQKV)
-        return None, None, None, gQKV
+        return None, None, None, None, gQKV
 
 
 def attention_pool(graph, QKV, n_head=1, want_attn=False, want_nodes=False):
@@ -311,7 +333,7 @@ def attention_pool(graph, QKV, n_head=1, want_attn=False, want_nodes=False):
         else:
             _C.attn_pool_infer(QKV, graph.node_off, n_head, graph.max_nodes, pooled)
         return None, pooled, None
-    return _AttnPool.apply(graph, n_head, want_attn, QKV)
+    return _AttnPool.apply(graph, n_head, want_attn, want_nodes, QKV)
 
 
 # ==================================================================================================

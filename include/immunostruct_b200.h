@@ -105,7 +105,9 @@ int is_reduce_partials(const float* partials, int nparts, int64_t stride, float*
  * models/hybrid_models.py:92-97 / 326-331).  QKV [n,192], O [n,64], LSE [n,H], pooled [B,64]. */
 int is_attn_pool_fwd(const float* QKV, const int64_t* node_off, int n_graphs, int n_head, int max_nodes,
                      float* O, float* LSE, float* pooled, float* attn, const int64_t* attn_off, void* stream);
-int is_attn_pool_bwd(const float* QKV, const float* O, const float* LSE, const int64_t* node_off, int n_graphs,
+/* O == NULL (only with g_pooled != NULL and gO_full == NULL): the row statistics are recomputed and LSE [N, n_head] is
+ * an output scratch -- for a forward pass that ran the pooled-rows-only kernel (is_attn_pool_infer_tc). */
+int is_attn_pool_bwd(const float* QKV, const float* O, float* LSE, const int64_t* node_off, int n_graphs,
                      int n_head, int max_nodes, const float* g_pooled, const float* gO_full, float* gQKV, void* stream);
 /* inference-only: pooled [B,64] from column sums of the attention matrix (no O / LSE / weights) */
 int is_attn_pool_infer(const float* QKV, const int64_t* node_off, int n_graphs, int n_head, int max_nodes,

@@ -445,6 +445,11 @@ def test_attention_pool_kernels(case, n_head):
                          gp.to(DEV) if gp is not None else None, go.to(DEV) if go is not None else None, gQKV_d)
         KC.attn_pool_bwd(QKV, O, LSE, cg.node_off, n_head, gb.max_nodes, gp, go, gQKV)
         close(gQKV_d, gQKV, what=f"gQKV pooled={gp is not None} full={go is not None}")
+        if gp is not None and go is None:                    # O = None: row statistics recomputed inside the kernel
+            gQKV_r, lse_r = torch.full((n, 192), float("nan"), device=DEV), torch.empty(n, n_head, device=DEV)
+            _C.attn_pool_bwd(QKV.to(DEV), None, lse_r, gb.node_off, n_head, gb.max_nodes, gp.to(DEV), None, gQKV_r)
+            close(gQKV_r, gQKV, what="gQKV pooled-only, recomputed statistics")
+            close(lse_r, LSE, what="recomputed LSE")
 
 
 def test_attention_weights_output():
