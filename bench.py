@@ -47,6 +47,10 @@ BYTES_PER_EDGE_EDGE_KERNEL = 3 * 4 + 4                     # read csr_src/dst/ei
 GATHER_BYTES_PER_EDGE = 2 * 256                            # P[src] + Q[dst] rows (served by L2)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
 # (profiles/r01_ws_*_edge_fwd_full.md, profiles/r01_simt_edge_fwd_full.md), batch 512
+# pipe utilisation of the same launch from the committed ncu --set full captures (profiles/r01_ws_*_edge_fwd_full.md):
+# issue slots / MUFU (xu) pipe / tensor pipe busy, executed warp instructions
+NCU_PIPES = {"bf16x3": {"issue_active_pct": 47.1, "mufu_pipe_pct": 45.8, "tensor_pipe_pct": 33.7, "warp_instructions": 110.5e6},
+             "bf16": {"issue_active_pct": 42.0, "mufu_pipe_pct": 32.0, "tensor_pipe_pct": 10.4, "warp_instructions": 70.8e6}}
 NCU_TRAFFIC_BYTES = {"bf16x3": 82.50e6 + 9.23e6, "bf16": 83.34e6 + 9.10e6,        # profiles/r01_ws_*_edge_fwd_full.md
                      "tf32x3": 82.36e6 + 10.82e6, "fp32": 80.64e6 + 8.85e6}
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12          # 74.4
@@ -453,6 +457,7 @@ def main():
                     "tensor": {"achieved": flops / t_k / 1e12, "peak": tensor_peak, "unit": "TFLOP/s",
                                "frac": flops / t_k / 1e12 / tensor_peak},
                     "l2_gather_gbs": e * GATHER_BYTES_PER_EDGE / t_k / 1e9,
+                    "ncu": NCU_PIPES.get(args.precision),
                     "simt": {"mufu_floor_ms": e * 192 * (1 if args.precision == "bf16" else 2) / (148 * 16 * 1.965e9) * 1e3,
                              "note": "192 SiLU per edge, 1 (bf16: tanh.approx) or 2 (ex2 + rcp) MUFU ops each, 16 MUFU lanes / clk / SM"},
                     "roofline_time_ms": {"hbm": nbytes / hbm_peak / 1e6, "tensor": flops / tensor_peak / 1e9},
