@@ -359,6 +359,7 @@ node_pre_bwd_tc_kernel(const float* __restrict__ gz1, const float* __restrict__ 
     uint8_t* sQ = sP + 3 * T_BYTES;                       // [3][T_BYTES]  gQ
     uint8_t* sH = sQ + 3 * T_BYTES;                       // [3][T_BYTES]  h
     uint8_t* sW = sH + 3 * T_BYTES;                       // [2 blocks][3][W_BYTES]: Ws | Wd
+    float* sS = reinterpret_cast<float*>(sW + 6 * W_BYTES);   // [NW][8][64] fp32 staging of the gathered sums
     __shared__ __align__(8) uint64_t mbar, mbar_wg;
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -387,7 +388,17 @@ node_pre_bwd_tc_kernel(const float* __restrict__ gz1, const float* __restrict__ 
 #pragma unroll
     for (int i = 0; i < 8; ++i) gb1[i] = 0.0f;
 
+    // The head of the gather's dependent chain (CSC range of this warp's eight nodes -> first 32 CSC positions) is fetched
+    // one tile ahead, under the MMAs and the epilogue of the tile before.
+    int pf_ptr = 0, pf_pos = 0;
+    auto prefetch_run = [&](int64_t m0n) {
+        const int64_t n0 = m0n + (IS_TM / NW) * warp;
+        pf_ptr = lane <= IS_TM / NW ? __ldg(outptr + (n0 + lane < M ? n0 + lane : M)) : 0;
+        const int qb = __shfl_sync(0xffffffffu, pf_ptr, 0), qe = __shfl_sync(0xffffffffu, pf_ptr, IS_TM / NW);
+        pf_pos = qb + lane < qe ? __ldg(csc_pos + qb + lane) : 0;
+    };
     const int64_t ntiles = (M + IS_TM - 1) / IS_TM;
+    prefetch_run((int64_t)blockIdx.x * IS_TM);
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int64_t m0 = t * IS_TM;
         if (wg_pending) { mbar_wait(&mbar_wg, phase_wg); phase_wg ^= 1; wg_pending = false; fence_after_sync(); }
@@ -395,55 +406,77 @@ node_pre_bwd_tc_kernel(const float* __restrict__ gz1, const float* __restrict__ 
         float vq[2][8], vh[2][8];
         load2(vq, gQ, 64, 64, m0, M, warp, r4, kc);
         load2(vh, h, ldh, F, m0, M, warp, r4, kc);
-        // ---- source-side reduction through the CSC transpose: one warp per node, eight nodes per warp, batched loads,
-        // ascending CSC position (= the SIMT kernel's order: bit-identical sums) ----------------------------------------------
+        // ---- source-side reduction through the CSC transpose.  A warp owns EIGHT CONSECUTIVE nodes, so their CSC ranges
+        // form one contiguous run of positions; the run is walked GB rows at a time with all GB row loads in flight and the
+        // next 32 positions already fetched, and a node's sum is flushed when the walk crosses its end.  Each node's sum
+        // still starts at zero and adds its rows in ascending CSC position (= the SIMT kernel's order: bit-identical). ----
         {
             constexpr int NPW = IS_TM / NW;                    // 8
-            int my_qb = 0, my_qe = 0;
-            if (lane < NPW) {
-                const int64_t n = m0 + warp + NW * lane;
-                if (n < M) { my_qb = __ldg(outptr + n); my_qe = __ldg(outptr + n + 1); }
+            constexpr int GB = 16;                             // row loads in flight per warp
+            const int r0 = NPW * warp;
+            const int64_t n0 = m0 + r0;
+            const bool lane_x = gx != nullptr && lane < 3;
+            const float* gz_lane = gz1 + 2 * lane;
+            const float* gd_lane = gD + lane;
+            const int my_ptr = pf_ptr;                         // fetched under the previous tile's MMAs
+            float my_gx0 = 0.0f;                               // lanes 0..23: the eight nodes' direct coordinate gradients
+            if (gx != nullptr && lane < 3 * NPW && n0 * 3 + lane < M * 3) {
+                my_gx0 = __ldg(gxd + n0 * 3 + lane);
+                if (gx_out) my_gx0 += __ldg(gx_out + n0 * 3 + lane);
             }
-            for (int i = 0; i < NPW; ++i) {
-                const int r = warp + NW * i;
-                const int64_t n = m0 + r;
-                const int qb = __shfl_sync(0xffffffffu, my_qb, i), qe = __shfl_sync(0xffffffffu, my_qe, i);
-                float2 s = make_float2(0.f, 0.f);
-                float sx = 0.0f;
-                const bool want_x = gx != nullptr && lane < 3 && n < M;
-                if (want_x) {
-                    sx = __ldg(gxd + n * 3 + lane);
-                    if (gx_out) sx += __ldg(gx_out + n * 3 + lane);
-                }
-                for (int q0 = qb; q0 < qe; q0 += 32) {
-                    const int cnt = min(32, qe - q0);
-                    const int my_pos = lane < cnt ? __ldg(csc_pos + q0 + lane) : 0;
-                    for (int j0 = 0; j0 < cnt; j0 += 8) {
-                        float2 v[8];
-                        float d[8];
+            const int qbeg = __shfl_sync(0xffffffffu, my_ptr, 0), qend = __shfl_sync(0xffffffffu, my_ptr, NPW);
+            int node_i = 0, q_next = __shfl_sync(0xffffffffu, my_ptr, 1);
+            float2 s = make_float2(0.f, 0.f);
+            float sx = __shfl_sync(0xffffffffu, my_gx0, lane % 3);
+            // A finished sum goes to the warp's fp32 staging rows (lane L holds features 2L, 2L+1; the 8-float chunk index is
+            // XORed with the row so that both this store and the row-per-lane read below are bank-conflict free); the operand
+            // split into sP happens once per tile with all 32 lanes busy.
+            float* stage = sS + warp * (NPW * 64);
+            auto flush = [&]() {
+                const int r = r0 + node_i;
+                if (lane_x && m0 + r < M) gx[(m0 + r) * 3 + lane] = sx;
+                *reinterpret_cast<float2*>(stage + node_i * 64 + (((lane >> 2) ^ node_i) & 7) * 8 + (lane & 3) * 2) = s;
+                ++node_i;
+                s = make_float2(0.f, 0.f);
+                sx = __shfl_sync(0xffffffffu, my_gx0, (3 * node_i + lane % 3) & 31);
+                q_next = __shfl_sync(0xffffffffu, my_ptr, (node_i + 1) & 31);
+            };
+            int pos_next = pf_pos;
+            for (int c0 = qbeg; c0 < qend; c0 += 32) {
+                const int my_pos = pos_next;
+                if (c0 + 32 + lane < qend) pos_next = __ldg(csc_pos + c0 + 32 + lane);
+                const int cnt = min(32, qend - c0);
+                for (int j0 = 0; j0 < cnt; j0 += GB) {
+                    float2 v[GB];
+                    float d[GB];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int pos = __shfl_sync(0xffffffffu, my_pos, (j0 + u) & 31);
-                            const bool ok = j0 + u < cnt;
-                            v[u] = ok ? __ldg(reinterpret_cast<const float2*>(gz1 + (size_t)pos * 64) + lane) : make_float2(0.f, 0.f);
-                            d[u] = (ok && want_x) ? __ldg(gD + (size_t)pos * 3 + lane) : 0.0f;
-                        }
+                    for (int u = 0; u < GB; ++u) {
+                        // past the end of the run the position is 0: row 0 exists (the run is not empty) and is not summed,
+                        // so the GB loads issue back to back with no branch between them
+                        const int pos = __shfl_sync(0xffffffffu, my_pos, (j0 + u) & 31);
+                        v[u] = __ldg(reinterpret_cast<const float2*>(gz_lane + (size_t)(uint32_t)pos * 64));
+                        d[u] = lane_x ? __ldg(gd_lane + (size_t)(uint32_t)pos * 3) : 0.0f;
+                    }
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            if (j0 + u < cnt) { s.x += v[u].x; s.y += v[u].y; sx += d[u]; }
+                    for (int u = 0; u < GB; ++u) {
+                        if (j0 + u < cnt) {
+                            while (c0 + j0 + u >= q_next) flush();      // warp-uniform; also passes over edge-less nodes
+                            s.x += v[u].x; s.y += v[u].y; sx += d[u];
                         }
                     }
                 }
-                if (want_x) gx[n * 3 + lane] = sx;
-                // lane L holds features 2L, 2L+1: the four lanes of a chunk hand their pairs to its first lane
-                float c8[8];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    c8[2 * j] = __shfl_sync(0xffffffffu, s.x, (lane & ~3) + j);
-                    c8[2 * j + 1] = __shfl_sync(0xffffffffu, s.y, (lane & ~3) + j);
-                }
-                if ((lane & 3) == 0) store_chunk8<PREC_BF16X3>(chunk_at(sP, r, lane >> 2), T_BYTES, c8);
             }
+            while (node_i < NPW) flush();
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int row = lane & 7, cc = (lane >> 3) + 4 * u;
+                const float4* sp = reinterpret_cast<const float4*>(stage + row * 64 + ((cc ^ row) & 7) * 8);
+                const float4 a = sp[0], b = sp[1];
+                const float c8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                store_chunk8<PREC_BF16X3>(chunk_at(sP, r0 + row, cc), T_BYTES, c8);
+            }
+            __syncwarp();
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u)
@@ -470,6 +503,7 @@ node_pre_bwd_tc_kernel(const float* __restrict__ gz1, const float* __restrict__ 
         }
         wg_pending = true;
         started = 1;
+        prefetch_run((t + gridDim.x) * IS_TM);
         if (gh) {
             const int64_t m = m0 + erow;
             float g[CW];
@@ -572,7 +606,7 @@ int is_egnn_node_pre_bwd_tc(const float* gz1, const float* gQ, const float* gD, 
     if (!(F == 20 || F == 64) || n_nodes <= 0) return IS_ERR_ARG;
     if (gh && F != 64) return IS_ERR_ARG;
     if (((reinterpret_cast<uintptr_t>(gh) | reinterpret_cast<uintptr_t>(gh_direct)) & 31) != 0) return IS_ERR_ARG;   // 256-bit accesses
-    const size_t smem = 9 * (size_t)nb::T_BYTES + 6 * (size_t)nb::W_BYTES;
+    const size_t smem = 9 * (size_t)nb::T_BYTES + 6 * (size_t)nb::W_BYTES + (size_t)IS_TM * 64 * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(node_pre_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int sms = 148;
