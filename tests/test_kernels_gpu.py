@@ -67,8 +67,25 @@ def hub_and_isolated_arrays(seed):
             "node_counts": torch.tensor([n0, n1]), "edge_counts": torch.tensor([dst.numel(), 0])}
 
 
+def out_hub_arrays(seed):
+    """Edge cases of the source-side (CSC) walk: out-degrees 100 and 40 (one node's run spans several 32-position
+    chunks and 16-row batches), nodes without out-edges next to them, a trailing graph of a single node."""
+    gen = torch.Generator().manual_seed(seed)
+    n0 = 140
+    src = torch.cat([torch.full((100,), 3), torch.full((40,), 4), torch.randint(8, n0, (200,), generator=gen)])
+    dst = torch.cat([torch.arange(10, 110), torch.arange(60, 100), torch.randint(0, n0, (200,), generator=gen)])
+    dst = torch.where(dst == src, (dst + 1) % n0, dst)
+    x = torch.zeros(n0 + 1, 23)
+    x[torch.arange(n0 + 1), torch.randint(0, 20, (n0 + 1,), generator=gen)] = 1.0
+    x[:, 20:] = torch.randn(n0 + 1, 3, generator=gen) * 4.0
+    perm = torch.randperm(src.numel(), generator=gen)
+    return {"x": x, "src": src[perm], "dst": dst[perm], "edge_attr": torch.rand(src.numel(), 1, generator=gen) + 0.5,
+            "node_counts": torch.tensor([n0, 1]), "edge_counts": torch.tensor([src.numel(), 0])}
+
+
 CASES = {
     "hubs_isolated": lambda: hub_and_isolated_arrays(7),
+    "out_hubs": lambda: out_hub_arrays(11),
     "knn_small": lambda: synthetic_graph_arrays(5, 37, 6, seed=3, n_pad=4, coord_scale=4.0),
     "knn_200": lambda: synthetic_graph_arrays(3, 200, 10, seed=4, n_pad=10),
     "ragged_multi": lambda: random_multigraph_arrays(5, [17, 1, 64, 33, 150, 2], 7.5),
