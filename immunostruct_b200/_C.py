@@ -39,7 +39,7 @@ def exported_symbols():
             "is_loss_num_partials", "is_collate_csr", "is_egnn_node_pre_fwd", "is_egnn_edge_fwd",
             "is_egnn_node_post_fwd", "is_egnn_node_post_bwd", "is_egnn_edge_bwd", "is_egnn_node_pre_bwd",
             "is_reduce_partials", "is_attn_pool_fwd", "is_attn_pool_bwd", "is_fusion_attn_fwd",
-            "is_fusion_attn_bwd", "is_loss_fwd", "is_loss_bwd", "is_umma_selftest", "is_egnn_edge_fwd_tc", "is_attn_pool_infer", "is_egnn_node_post_pre_tc", "is_egnn_edge_bwd_tc", "is_linear_tc", "is_linear_tc_split_k", "is_attn_pool_infer_tc", "is_vae_mid_infer", "is_head_infer", "is_unpack_nodes", "is_unpack_edges", "is_onehot_tokens", "is_egnn_node_post_bwd_tc", "is_egnn_node_pre_bwd_tc"]
+            "is_fusion_attn_bwd", "is_loss_fwd", "is_loss_bwd", "is_umma_selftest", "is_egnn_edge_fwd_tc", "is_attn_pool_infer", "is_egnn_node_post_pre_tc", "is_egnn_edge_bwd_tc", "is_linear_tc", "is_linear_tc_split_k", "is_attn_pool_infer_tc", "is_vae_mid_infer", "is_head_infer", "is_unpack_nodes", "is_unpack_edges", "is_onehot_tokens", "is_egnn_node_post_bwd_tc", "is_egnn_node_pre_bwd_tc", "is_attn_pool_bwd_tc"]
 
 
 def _check(rc: int, name: str):
@@ -261,6 +261,13 @@ def attn_pool_infer_tc(QKV, node_off, max_nodes, pooled, precision=PREC_BF16X3):
     f32, i64 = torch.float32, torch.int64
     _call("is_attn_pool_infer_tc", _t(QKV, f32, "QKV"), _t(node_off, i64, "node_off"), _i32(node_off.numel() - 1),
           _i32(max_nodes), _i32(precision), _t(pooled, f32, "pooled"), _stream())
+
+
+def attn_pool_bwd_tc(QKV, node_off, max_nodes, g_pooled, gQKV):
+    """backward of attn_pool_infer_tc (single head, pooled rows only) on the tensor cores (csrc/attn_pool_bwd_tc.cu)"""
+    f32, i64 = torch.float32, torch.int64
+    _call("is_attn_pool_bwd_tc", _t(QKV, f32, "QKV"), _t(node_off, i64, "node_off"), _i32(node_off.numel() - 1),
+          _i32(max_nodes), _t(g_pooled, f32, "g_pooled"), _t(gQKV, f32, "gQKV"), _stream())
 
 
 def attn_pool_bwd(QKV, O, LSE, node_off, n_head, max_nodes, g_pooled, gO_full, gQKV):

@@ -262,8 +262,8 @@ class _AttnPool(torch.autograd.Function):
     forward(graph, n_head, want_attn, want_nodes, QKV [N,192]) -> (O [N,64] or None, pooled [B,64], attn or None)
     ``attn`` is the dense weights tensor [B, H, n, n] (equal node counts) when requested.  When only the pooled rows
     are wanted (every model's training path) and the arithmetic mode is a tensor-core one, the forward is the
-    pooled-rows-only tcgen05 kernel (csrc/attn_pool_tc.cu) and nothing but QKV is saved: the backward recomputes the
-    row statistics (is_attn_pool_bwd with O = NULL).
+    pooled-rows-only tcgen05 kernel (csrc/attn_pool_tc.cu) and nothing but QKV is saved: the backward
+    (csrc/attn_pool_bwd_tc.cu) recomputes the scores and their row statistics on the tensor cores.
     """
 
     @staticmethod
@@ -304,9 +304,8 @@ class _AttnPool(torch.autograd.Function):
             if g_pooled is None:
                 gQKV.zero_()
                 return None, None, None, None, gQKV
-            lse = _new(QKV, QKV.shape[0], ctx.n_head)             # scratch: row statistics recomputed by the kernel
-            _C.attn_pool_bwd(QKV, None, lse, ctx.graph.node_off, ctx.n_head, ctx.graph.max_nodes,
-                             g_pooled.contiguous(), None, gQKV)
+            # row statistics, both score products and the two gradient products on the tensor cores (bf16x3)
+            _C.attn_pool_bwd_tc(QKV, ctx.graph.node_off, ctx.graph.max_nodes, g_pooled.contiguous(), gQKV)
             return None, None, None, None, gQKV
         QKV, O, LSE = ctx.saved_tensors
         gQKV = _new(QKV, *QKV.shape)

@@ -137,6 +137,13 @@ int is_loss_bwd(const float* recon, const float* seq, int64_t n_recon, const flo
  * precision 0 = bf16, 3 = bf16x3 (fp32-accurate). */
 int is_attn_pool_infer_tc(const float* QKV, const int64_t* node_off, int n_graphs, int max_nodes, int precision,
                           float* pooled, void* stream);
+/* Backward of the pooled-rows-only single-head attention on the tensor cores (bf16x3, fp32-accurate;
+ * csrc/attn_pool_bwd_tc.cu): what torch autograd derives for MultiHeadAttention + global_mean_pool in the reference
+ * (models/layers.py:13-22 / 67-78, hybrid_models.py:92-97 / 326-331) when only the pooled rows feed the loss.  Same result
+ * as is_attn_pool_bwd with n_head = 1, O = NULL, gO_full = NULL.  g_pooled [n_graphs,64] -> gQKV [N_total,192];
+ * max_nodes <= 256. */
+int is_attn_pool_bwd_tc(const float* QKV, const int64_t* node_off, int n_graphs, int max_nodes, const float* g_pooled,
+                        float* gQKV, void* stream);
 /* Compact input format -> dense model inputs, on the device and bit-exact (csrc/unpack.cu).
  * Replaces shipping the reference's fp32 one-hots over PCIe: x = [one_hot_20 | xyz] (data/utils.py:75-89,
  * preprocess.py:40-41,181), int64 endpoints, all-ones edge_attr (data/utils.py:60), [283,21] sequence one-hots. */

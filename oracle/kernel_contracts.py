@@ -304,6 +304,10 @@ def attn_pool_bwd(QKV, O, LSE, node_off, n_head, max_nodes, g_pooled, gO_full, g
         gQKV[a:b] = torch.autograd.grad(o, leaf, go)[0]
 
 
+def attn_pool_bwd_tc(QKV, node_off, max_nodes, g_pooled, gQKV):
+    attn_pool_bwd(QKV, None, None, node_off, 1, max_nodes, g_pooled, None, gQKV)
+
+
 # ---- fusion attention (closed form; the dense equivalence is tested separately) -----------------
 def _fusion(c, coef, n_head):
     hh = n_head
@@ -362,5 +366,5 @@ def loss_bwd(recon, seq, mu, logvar, logits, y, mode, pos_weight, w_pred, w_mse,
 
 ALL = ["num_sms", "egnn_node_grid", "egnn_edge_bwd_grid", "attn_max_nodes", "loss_num_partials", "collate_csr",
        "egnn_node_pre_fwd", "egnn_edge_fwd", "egnn_edge_fwd_tc", "egnn_node_post_pre_tc", "linear_tc", "vae_mid_infer", "head_infer", "unpack_nodes", "unpack_edges", "onehot_tokens", "egnn_node_post_fwd", "egnn_node_post_bwd", "egnn_node_post_bwd_tc", "egnn_node_pre_bwd_tc", "egnn_edge_bwd", "egnn_edge_bwd_tc",
-       "egnn_node_pre_bwd", "reduce_partials", "attn_pool_fwd", "attn_pool_infer", "attn_pool_infer_tc", "attn_pool_bwd", "fusion_attn_fwd",
+       "egnn_node_pre_bwd", "reduce_partials", "attn_pool_fwd", "attn_pool_infer", "attn_pool_infer_tc", "attn_pool_bwd", "attn_pool_bwd_tc", "fusion_attn_fwd",
        "fusion_attn_bwd", "loss_fwd", "loss_bwd"]

@@ -467,6 +467,17 @@ def test_attention_pool_kernels(case, n_head):
             _C.attn_pool_bwd(QKV.to(DEV), None, lse_r, gb.node_off, n_head, gb.max_nodes, gp.to(DEV), None, gQKV_r)
             close(gQKV_r, gQKV, what="gQKV pooled-only, recomputed statistics")
             close(lse_r, LSE, what="recomputed LSE")
+            if n_head == 1:                                  # tensor-core backward (bf16x3): same contract
+                for mult in (1.0, 6.0):                      # 6.0: peaked softmax rows
+                    gQKV_t = torch.full((n, 192), float("nan"), device=DEV)
+                    _C.attn_pool_bwd_tc(QKV.to(DEV) * mult, gb.node_off, gb.max_nodes, gp.to(DEV), gQKV_t)
+                    ref_t = torch.empty(n, 192)
+                    O_m, LSE_m, pooled_m = torch.empty(n, 64), torch.empty(n, 1), torch.empty(b, 64)
+                    KC.attn_pool_fwd(QKV * mult, cg.node_off, 1, gb.max_nodes, O_m, LSE_m, pooled_m)
+                    KC.attn_pool_bwd(QKV * mult, O_m, LSE_m, cg.node_off, 1, gb.max_nodes, gp, None, ref_t)
+                    # x6: scores of magnitude ~100, where ONE fp32 ulp of a score (7.6e-6) is already a relative error
+                    # of 7.6e-6 in exp(score) -- the fp32 oracle itself is no closer to the exact gradient than that
+                    close(gQKV_t, ref_t, 1e-5 if mult == 1.0 else 3e-5, what=f"gQKV tensor-core backward x{mult}")
 
 
 def test_attention_weights_output():
