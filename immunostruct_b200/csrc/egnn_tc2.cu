@@ -43,34 +43,6 @@ constexpr uint32_t S_SBO = 16 * S_LBO;
 constexpr uint32_t S_BYTES = 4 * S_SBO;          // 32 node rows (8 KB); the M = 64 MMA also reads the 8 KB behind it
 constexpr int MAX_TILE_NODES = 32;
 
-struct Meta {                // per-edge scalars of one tile + its CSR offsets, produced by the prefetch warps
-    int src[IS_TM];
-    float r[IS_TM];
-    float a[IS_TM];
-    float dh[IS_TM * 3];
-    int nptr[MAX_TILE_NODES + 1];   // indptr[n0 + i] - p0
-    uint8_t dloc[IS_TM];            // destination node - n0
-};
-
-__device__ __forceinline__ void load_meta(const EdgeCommon& p, Meta& m, int j, int n0, int n1, int p0, int ne) {
-    if (j < ne) {
-        const int e = p0 + j;
-        const int s = __ldg(p.csr_src + e), d = __ldg(p.csr_dst + e);
-        const float a = __ldg(p.edge_attr + __ldg(p.csr_eid + e));
-        const float dx = __ldg(p.x + s * p.ldx + 0) - __ldg(p.x + d * p.ldx + 0);
-        const float dy = __ldg(p.x + s * p.ldx + 1) - __ldg(p.x + d * p.ldx + 1);
-        const float dz = __ldg(p.x + s * p.ldx + 2) - __ldg(p.x + d * p.ldx + 2);
-        const float r = dx * dx + dy * dy + dz * dz;
-        const float inv = 1.0f / (sqrtf(r) + 1e-30f);
-        m.src[j] = s; m.dloc[j] = (uint8_t)(d - n0); m.r[j] = r; m.a[j] = a;
-        m.dh[j * 3 + 0] = dx * inv; m.dh[j * 3 + 1] = dy * inv; m.dh[j * 3 + 2] = dz * inv;
-    }
-    if (j <= MAX_TILE_NODES) {
-        const int node = n0 + j;
-        m.nptr[j] = node <= n1 ? __ldg(p.indptr + node) - p0 : ne;
-    }
-}
-
 // D[tmem_d] = A * W^T over the 64-wide K block (ONE thread); bf16: 4 MMAs, bf16x3: 24
 template <int PREC>
 __device__ __forceinline__ void issue_fwd(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr) {
