@@ -168,3 +168,24 @@ def test_restatement_matches_reference_code_live():
     got = R.hybrid_forward(dict(model.state_dict()), g, dense["seq"], dense["prop"], eps)
     for a, b in zip(got, ref):
         assert rel_err(a, b.detach()) < TOL
+
+
+def test_pooled_only_attention_backward_closed_form():
+    """The algebra csrc/attn_pool_bwd_tc.cu implements (its header comment), checked in fp64 against autograd of the
+    oracle's attention + mean pool: with g0 = g_pooled / n every row of gO equals g0, so c_j = V_j . g0,
+    D_i = sum_j P_ij c_j, G_ij = P_ij (c_j - D_i), gQ = G K / 8, gK = G^T Q / 8, gV_j = (sum_i P_ij) g0."""
+    from oracle import kernel_contracts as KC
+    gen = torch.Generator().manual_seed(3)
+    for n in (1, 7, 130):
+        qkv = torch.randn(n, 192, generator=gen, dtype=torch.float64).requires_grad_(True)
+        gp = torch.randn(64, generator=gen, dtype=torch.float64)
+        o, _, _ = KC._attn_graph(qkv, 1)
+        (ref,) = torch.autograd.grad(o.mean(0), qkv, gp)
+        Q, K, V = (qkv.detach()[:, 64 * i:64 * i + 64] for i in range(3))
+        P = torch.softmax(Q @ K.T / 8.0, dim=1)
+        g0 = gp / n
+        c = V @ g0
+        G = P * (c[None, :] - (P @ c)[:, None])
+        closed = torch.cat([G @ K / 8.0, G.T @ Q / 8.0, P.sum(0)[:, None] * g0[None, :]], dim=1)
+        assert rel_err(closed, ref) < 1e-12
+        assert float(G.sum(1).abs().max()) < 1e-14          # shift invariance: every row of G sums to zero
