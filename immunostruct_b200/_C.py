@@ -39,7 +39,9 @@ def exported_symbols():
             "is_loss_num_partials", "is_collate_csr", "is_egnn_node_pre_fwd", "is_egnn_edge_fwd",
             "is_egnn_node_post_fwd", "is_egnn_node_post_bwd", "is_egnn_edge_bwd", "is_egnn_node_pre_bwd",
             "is_reduce_partials", "is_attn_pool_fwd", "is_attn_pool_bwd", "is_fusion_attn_fwd",
-            "is_fusion_attn_bwd", "is_loss_fwd", "is_loss_bwd", "is_umma_selftest", "is_egnn_edge_fwd_tc", "is_attn_pool_infer", "is_egnn_node_post_pre_tc", "is_egnn_edge_bwd_tc", "is_linear_tc", "is_linear_tc_split_k", "is_attn_pool_infer_tc", "is_vae_mid_infer", "is_head_infer", "is_unpack_nodes", "is_unpack_edges", "is_onehot_tokens", "is_egnn_node_post_bwd_tc", "is_egnn_node_pre_bwd_tc", "is_attn_pool_bwd_tc"]
+            "is_fusion_attn_bwd", "is_loss_fwd", "is_loss_bwd", "is_umma_selftest", "is_egnn_edge_fwd_tc", "is_attn_pool_infer", "is_egnn_node_post_pre_tc", "is_egnn_edge_bwd_tc", "is_linear_tc", "is_linear_tc_split_k", "is_attn_pool_infer_tc", "is_vae_mid_infer", "is_head_infer", "is_unpack_nodes", "is_unpack_edges", "is_onehot_tokens", "is_egnn_node_post_bwd_tc", "is_egnn_node_pre_bwd_tc", "is_attn_pool_bwd_tc",
+            "is_segment_pool_fwd", "is_segment_pool_bwd", "is_contrastive_scratch_floats", "is_contrastive_fwd",
+            "is_contrastive_bwd", "is_fused_adam", "is_rotate_coords", "is_mask_single_residue", "is_mask_rows"]
 
 
 def _check(rc: int, name: str):
@@ -72,7 +74,8 @@ def _stream():
 
 
 LAUNCHES = 0          # number of immunostruct_b200 kernels enqueued so far (bench.py reports the delta)
-_KERNELS_PER_CALL = {"is_collate_csr": 2, "is_loss_fwd": 2, "is_loss_bwd": 2}
+_KERNELS_PER_CALL = {"is_collate_csr": 2, "is_loss_fwd": 2, "is_loss_bwd": 2, "is_contrastive_fwd": 9,
+                     "is_contrastive_bwd": 9}
 
 
 def _call(name, *args):
@@ -387,3 +390,80 @@ def umma_selftest(A, B, D, mode):
     """D[128,64] = A[128,64] @ B[64,64]^T on the tensor cores; mode 0 bf16, 1 tf32, 2 3xTF32."""
     f32 = torch.float32
     _call("is_umma_selftest", _t(A, f32, "A"), _t(B, f32, "B"), _t(D, f32, "D"), _i32(mode), _stream())
+
+
+# ---- segment pooling -----------------------------------------------------------------------------
+POOL_MODES = {"mean": 0, "max": 1, "sum": 2}
+
+
+def segment_pool_fwd(X, node_off, mode, out):
+    xp, ldx = _rows(X, "X")
+    _call("is_segment_pool_fwd", xp, ldx, _i32(X.shape[1]), _t(node_off, torch.int64, "node_off"),
+          _i32(node_off.numel() - 1), _i32(POOL_MODES[mode]), _t(out, torch.float32, "out"), _stream())
+
+
+def segment_pool_bwd(X, node_off, mode, pooled, g_out, gX):
+    xp, ldx = _rows(X, "X")
+    gp, ldg = _rows(gX, "gX")
+    _call("is_segment_pool_bwd", xp, ldx, _i32(X.shape[1]), _t(node_off, torch.int64, "node_off"),
+          _i32(node_off.numel() - 1), _i32(POOL_MODES[mode]), _t(pooled, torch.float32, "pooled"),
+          _t(g_out, torch.float32, "g_out"), gp, ldg, _stream())
+
+
+# ---- paired contrastive loss ---------------------------------------------------------------------
+def contrastive_scratch_floats(b: int, z: int) -> int:
+    fn = lib().is_contrastive_scratch_floats
+    fn.restype = ctypes.c_int64
+    return int(fn(_i32(b), _i32(z)))
+
+
+def contrastive_fwd(Ec, Ew, target, W1, gamma, beta, W2, bn_eps, momentum, run_mean, run_var, n_tracked, lambda_off,
+                    scratch, out):
+    f32 = torch.float32
+    b, d = Ec.shape
+    z = W1.shape[0]
+    _call("is_contrastive_fwd", _t(Ec, f32, "Ec"), _t(Ew, f32, "Ew"), _t(target, f32, "target"), _i32(b), _i32(d), _i32(z),
+          _t(W1, f32, "W1"), _t(gamma, f32, "gamma"), _t(beta, f32, "beta"), _t(W2, f32, "W2"), _f32(bn_eps),
+          _f32(momentum), _t(run_mean, f32, "run_mean"), _t(run_var, f32, "run_var"),
+          _t(n_tracked, torch.int64, "num_batches_tracked"), _f32(lambda_off), _t(scratch, f32, "scratch"),
+          _t(out, f32, "out"), _stream())
+
+
+def contrastive_bwd(Ec, Ew, W1, gamma, beta, W2, scratch, gout, work, gEc, gEw, gW1, g_gamma, g_beta, gW2):
+    f32 = torch.float32
+    b, d = Ec.shape
+    z = W1.shape[0]
+    _call("is_contrastive_bwd", _t(Ec, f32, "Ec"), _t(Ew, f32, "Ew"), _i32(b), _i32(d), _i32(z), _t(W1, f32, "W1"),
+          _t(gamma, f32, "gamma"), _t(beta, f32, "beta"), _t(W2, f32, "W2"), _t(scratch, f32, "scratch"),
+          _t(gout, f32, "gout"), _t(work, f32, "work"), _t(gEc, f32, "gEc"), _t(gEw, f32, "gEw"), _t(gW1, f32, "gW1"),
+          _t(g_gamma, f32, "g_gamma"), _t(g_beta, f32, "g_beta"), _t(gW2, f32, "gW2"), _stream())
+
+
+# ---- fused Adam ----------------------------------------------------------------------------------
+def fused_adam(p, g, m, v, lr, beta1, beta2, eps, weight_decay, decoupled, step_size, inv_bc2_sqrt, grad_scale=1.0):
+    f32 = torch.float32
+    _call("is_fused_adam", _t(p, f32, "p"), _t(g, f32, "g"), _t(m, f32, "m"), _t(v, f32, "v"), _i64(p.numel()), _f32(lr),
+          _f32(beta1), _f32(beta2), _f32(eps), _f32(weight_decay), _i32(1 if decoupled else 0), _f32(step_size),
+          _f32(inv_bc2_sqrt), _f32(grad_scale), _stream())
+
+
+# ---- augmentations -------------------------------------------------------------------------------
+def rotate_coords(x, c0, node_off, M, Qout=None):
+    xp, ldx = _rows(x, "x")
+    _call("is_rotate_coords", xp, ldx, _i32(c0), _t(node_off, torch.int64, "node_off"), _i32(node_off.numel() - 1),
+          _t(M, torch.float32, "M"), _t(Qout, torch.float32, "Qout"), _stream())
+
+
+def mask_single_residue(x, n_feat, node_off, u, want_aa, aa_out, node_out=None):
+    xp, ldx = _rows(x, "x")
+    i64 = torch.int64
+    _call("is_mask_single_residue", xp, ldx, _i32(n_feat), _t(node_off, i64, "node_off"), _i32(node_off.numel() - 1),
+          _t(u, torch.float32, "u"), _t(want_aa, i64, "want_aa"), _t(aa_out, i64, "aa_out"), _t(node_out, i64, "node_out"),
+          _stream())
+
+
+def mask_rows(data, n_cols, seg_off, limit, keys, count, fill_col, max_rows):
+    dp, ld = _rows(data, "data")
+    i64 = torch.int64
+    _call("is_mask_rows", dp, ld, _i32(n_cols), _t(seg_off, i64, "seg_off"), _t(limit, i64, "limit"),
+          _i32(seg_off.numel() - 1), _t(keys, torch.float32, "keys"), _i32(count), _i32(fill_col), _i32(max_rows), _stream())

@@ -9,6 +9,8 @@ from .mapping import model_map  # noqa: F401
 from .functional import get_precision, set_precision  # noqa: F401
 from .loader import DevicePrefetcher  # noqa: F401
 from .packed import PackedGraphBatch, PackedGraphDataset, PackedSequence, pack_graph_batch, pack_sequence  # noqa: F401
-from . import dataloading, nn  # noqa: F401
+from .optim import FusedAdam, FusedAdamW  # noqa: F401
+from .augment import TrainAugment  # noqa: F401
+from . import augment, dataloading, nn, optim  # noqa: F401
 
 DGLGraph = Graph     # `import immunostruct_b200 as dgl` keeps data/utils.py's isinstance checks working

@@ -5,6 +5,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from . import functional as IF
 from .trunk import LoadTrained, SequenceVAE, StructureTrunk, classifier_mlp
 
 __all__ = ["SequenceModel", "SequenceFpModel", "StructureModel", "StructureModel_SSL", "StructureModelv2", "DualModel"]
@@ -52,10 +53,9 @@ class _Structure(nn.Module, StructureTrunk, LoadTrained):
     def forward(self, graph_data, sequence_data, peptide_property, return_embedding=False, return_attention=False):
         pooled, _, nodes = self.structure_embedding(graph_data, want_nodes=self._maxpool)
         if self._maxpool:
-            # global_max_pool over each graph's rows (ablation_models.py:296-299); equal node counts
-            # per graph as everywhere in the reference, so the segment max is a dense reduction
-            b = graph_data.n_graphs
-            pooled = torch.cat([pooled, nodes.view(b, -1, nodes.shape[-1]).amax(dim=1)], dim=-1)
+            # global_max_pool over each graph's rows (ablation_models.py:296-299): segment max kernel
+            # (csrc/segment_pool.cu), ragged node counts allowed
+            pooled = torch.cat([pooled, IF.segment_pool(graph_data, nodes, "max")], dim=-1)
         out = self.classifier(pooled)
         if self._ssl:
             return 0, 0, 0, self.classifier_head(out), self.node_predictor_head(out)

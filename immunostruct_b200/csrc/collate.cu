@@ -10,7 +10,7 @@
 //          edge order preserved), batch int64 [N]; CSR by destination (stable in edge id):
 //          indptr int32 [N+1], csr_src/csr_dst/csr_eid int32 [E]; CSC transpose by source:
 //          outptr int32 [N+1], csc_pos int32 [E] (CSR position of every out-edge, stable in edge id);
-//          stats int32 [4] = {max in-degree, #endpoints out of range, 0, 0}.
+//          stats int32 [4] = {max in-degree, #endpoints out of range, max nodes per graph, #empty graphs}.
 #include "common.cuh"
 
 namespace is {
@@ -43,60 +43,29 @@ __global__ void offsets_kernel(const int64_t* __restrict__ node_counts, const in
     }
 }
 
-// one warp per graph: globalise endpoints, histogram, scan, stable fill of CSR and CSC.  The per-node degree counters /
-// fill cursors of a graph live in shared memory when the graph has at most COLLATE_CAP nodes (every dependent
-// read-modify-write of the 63-step stable fill used to be a global-memory round trip); larger graphs use the global
-// scratch arrays.  Integer arithmetic only: the result does not depend on which path runs.
-#define COLLATE_WPB 4
-#define COLLATE_CAP 512
-__global__ void __launch_bounds__(32 * COLLATE_WPB)
-collate_kernel(const int64_t* __restrict__ src_local, const int64_t* __restrict__ dst_local,
-               const int64_t* __restrict__ node_off, const int64_t* __restrict__ edge_off, int B,
-               int64_t* __restrict__ edge_index /* [2,E] */, int64_t E, int64_t* __restrict__ batch,
-               int* __restrict__ indptr, int* __restrict__ csr_src, int* __restrict__ csr_dst, int* __restrict__ csr_eid,
-               int* __restrict__ outptr, int* __restrict__ csc_pos,
-               int* __restrict__ g_cur_in, int* __restrict__ g_cur_out /* scratch int32 [N] each */,
-               int* __restrict__ stats) {
-    __shared__ int s_cur[COLLATE_WPB][2][COLLATE_CAP];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int g = blockIdx.x * COLLATE_WPB + wib;
-    if (g >= B) return;
-    const int64_t n0 = node_off[g], n1 = node_off[g + 1], e0 = edge_off[g], e1 = edge_off[g + 1];
+// ---- one warp walks one graph (graphs with more than CB_CAP nodes): counters / cursors in global scratch --------
+// globalise endpoints, histogram, scan, stable fill of CSR and CSC.  Integer arithmetic only.
+__device__ void collate_graph_warp(const int64_t* __restrict__ src_local, const int64_t* __restrict__ dst_local,
+                                   int64_t n0, int64_t n1, int64_t e0, int64_t e1, int g, bool last,
+                                   int64_t* __restrict__ edge_index, int64_t E, int64_t* __restrict__ batch,
+                                   int* __restrict__ indptr, int* __restrict__ csr_src, int* __restrict__ csr_dst,
+                                   int* __restrict__ csr_eid, int* __restrict__ outptr, int* __restrict__ csc_pos,
+                                   int* __restrict__ cur_in, int* __restrict__ cur_out, int* __restrict__ stats, int lane) {
     const int ng = (int)(n1 - n0);
-    const bool in_smem = ng <= COLLATE_CAP;
-    // counters / cursors indexed by GLOBAL node id n: shared (offset by n0) or global scratch
-    int* cur_in = in_smem ? s_cur[wib][0] - n0 : g_cur_in;
-    int* cur_out = in_smem ? s_cur[wib][1] - n0 : g_cur_out;
-    // phase 0: batch vector, zero the degree counters
     for (int64_t n = n0 + lane; n < n1; n += 32) { batch[n] = g; cur_in[n] = 0; cur_out[n] = 0; }
     __syncwarp();
-    // phase 1: globalise + degree histograms (integer atomics: order-independent result); four 32-edge steps of
-    // loads are issued before the first is consumed (the walk is latency bound)
     int bad = 0;
-    for (int64_t eb = e0; eb < e1; eb += 128) {
-        int64_t sl[4], dl[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int64_t e = eb + 32 * u + lane;
-            sl[u] = e < e1 ? src_local[e] : 0; dl[u] = e < e1 ? dst_local[e] : 0;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int64_t e = eb + 32 * u + lane;
-            if (e < e1) {
-                int64_t s = sl[u], d = dl[u];
-                if (s < 0 || s >= ng || d < 0 || d >= ng) { bad++; s = 0; d = 0; }
-                s += n0; d += n0;
-                edge_index[e] = s;
-                edge_index[E + e] = d;
-                atomicAdd(cur_in + d, 1);
-                atomicAdd(cur_out + s, 1);
-            }
-        }
+    for (int64_t e = e0 + lane; e < e1; e += 32) {
+        int64_t s = src_local[e], d = dst_local[e];
+        if (s < 0 || s >= ng || d < 0 || d >= ng) { bad++; s = 0; d = 0; }
+        s += n0; d += n0;
+        edge_index[e] = s;
+        edge_index[E + e] = d;
+        atomicAdd(cur_in + d, 1);
+        atomicAdd(cur_out + s, 1);
     }
     if (bad) atomicAdd(stats + 1, bad);
     __syncwarp();
-    // phase 2: exclusive scans -> indptr / outptr (global positions), cursors, max in-degree
     int run_in = (int)e0, run_out = (int)e0, maxdeg = 0;
     for (int64_t nb = n0; nb < n1; nb += 32) {
         const int64_t n = nb + lane;
@@ -119,36 +88,180 @@ collate_kernel(const int64_t* __restrict__ src_local, const int64_t* __restrict_
     for (int o = 16; o > 0; o >>= 1) maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, o));
     if (lane == 0) {
         atomicMax(stats, maxdeg);
-        if (g == B - 1) { indptr[n1] = (int)e1; outptr[n1] = (int)e1; }
+        if (last) { indptr[n1] = (int)e1; outptr[n1] = (int)e1; }
     }
     __syncwarp();
-    // phase 3: stable fill, 32 edges per step in ascending edge id (endpoints recomputed from the inputs: the
-    // edge_index stores above need not be read back)
-    for (int64_t eb4 = e0; eb4 < e1; eb4 += 128) {
+    for (int64_t eb = e0; eb < e1; eb += 32) {
+        const int64_t e = eb + lane;
+        const bool act = e < e1;
+        int s = -1 - lane, d = -1 - lane;
+        if (act) {
+            int64_t sl = src_local[e], dl = dst_local[e];
+            if (sl < 0 || sl >= ng || dl < 0 || dl >= ng) { sl = 0; dl = 0; }
+            s = (int)(sl + n0); d = (int)(dl + n0);
+        }
+        const unsigned md = __match_any_sync(0xffffffffu, d), ms = __match_any_sync(0xffffffffu, s);
+        const unsigned lt = (1u << lane) - 1u;
+        int pos_csr = 0;
+        if (act) {
+            pos_csr = cur_in[d] + __popc(md & lt);
+            csr_src[pos_csr] = s; csr_dst[pos_csr] = d; csr_eid[pos_csr] = (int)e;
+        }
+        __syncwarp();
+        if (act && (md & lt) == 0) cur_in[d] += __popc(md);
+        if (act) csc_pos[cur_out[s] + __popc(ms & lt)] = pos_csr;
+        __syncwarp();
+        if (act && (ms & lt) == 0) cur_out[s] += __popc(ms);
+        __syncwarp();
+    }
+}
+
+// ---- one CTA (CB_WARPS warps) per graph: block-level STABLE counting sort -----------------------------------------
+// The graph's edge list is cut into CB_WARPS contiguous chunks (ascending edge id).  Every warp histograms its chunk
+// into its OWN per-node counters in shared memory; a block scan turns the per-node totals into indptr / outptr and
+// the per-warp counters into per-(warp, node) start cursors (node start + edges of that node in earlier chunks);
+// then every warp fills its chunk 32 edges per step with __match_any_sync ranks.  Chunks are ordered by edge id and
+// each warp's fill is stable, so the result is the stable sort (bit-exact against the single-warp walk) -- with an
+// 8x shorter dependent chain per graph (8 steps instead of 63 at 2 000 edges) and 8x more warps in flight.
+#define CB_WARPS 8
+#define CB_CAP 512
+__global__ void __launch_bounds__(32 * CB_WARPS)
+collate_kernel(const int64_t* __restrict__ src_local, const int64_t* __restrict__ dst_local,
+               const int64_t* __restrict__ node_off, const int64_t* __restrict__ edge_off, int B,
+               int64_t* __restrict__ edge_index /* [2,E] */, int64_t E, int64_t* __restrict__ batch,
+               int* __restrict__ indptr, int* __restrict__ csr_src, int* __restrict__ csr_dst, int* __restrict__ csr_eid,
+               int* __restrict__ outptr, int* __restrict__ csc_pos,
+               int* __restrict__ g_cur_in, int* __restrict__ g_cur_out /* scratch int32 [N] each */,
+               int* __restrict__ stats) {
+    __shared__ int s_cnt[2][CB_WARPS][CB_CAP];          // [in | out][warp][local node]: counts, then cursors (32 KB)
+    __shared__ int s_wsum[2][CB_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int g = blockIdx.x;
+    const int64_t n0 = node_off[g], n1 = node_off[g + 1], e0 = edge_off[g], e1 = edge_off[g + 1];
+    const int ng = (int)(n1 - n0);
+    if (tid == 0) {
+        atomicMax(stats + 2, ng);
+        if (ng == 0) atomicAdd(stats + 3, 1);
+    }
+    if (ng > CB_CAP) {                                  // large graph: single-warp walk over the global scratch
+        if (w == 0)
+            collate_graph_warp(src_local, dst_local, n0, n1, e0, e1, g, g == B - 1, edge_index, E, batch, indptr, csr_src,
+                               csr_dst, csr_eid, outptr, csc_pos, g_cur_in, g_cur_out, stats, lane);
+        return;
+    }
+    for (int n = tid; n < ng; n += 32 * CB_WARPS) batch[n0 + n] = g;
+    for (int n = tid; n < ng; n += 32 * CB_WARPS)
+#pragma unroll
+        for (int kw = 0; kw < 2 * CB_WARPS; ++kw) (&s_cnt[0][0][0])[kw * CB_CAP + n] = 0;
+    __syncthreads();
+    // this warp's chunk (multiple of 32 edges so that every step is a full warp except the graph's last)
+    const int64_t ne = e1 - e0;
+    const int64_t per = ((ne + CB_WARPS - 1) / CB_WARPS + 31) / 32 * 32;
+    const int64_t ws = min(e1, e0 + w * per), we = min(e1, ws + per);
+    // phase 1: globalise + per-warp degree histograms
+    int bad = 0;
+    for (int64_t eb = ws; eb < we; eb += 128) {
+        int64_t sl[4], dl[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t e = eb + 32 * u + lane;
+            sl[u] = e < we ? src_local[e] : 0; dl[u] = e < we ? dst_local[e] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t e = eb + 32 * u + lane;
+            if (e < we) {
+                int64_t s = sl[u], d = dl[u];
+                if (s < 0 || s >= ng || d < 0 || d >= ng) { bad++; s = 0; d = 0; }
+                edge_index[e] = s + n0;
+                edge_index[E + e] = d + n0;
+                atomicAdd(&s_cnt[0][w][d], 1);
+                atomicAdd(&s_cnt[1][w][s], 1);
+            }
+        }
+    }
+    if (bad) atomicAdd(stats + 1, bad);
+    __syncthreads();
+    // phase 2: per-node totals (two consecutive nodes per thread), block exclusive scan, cursors
+    int tot[2][2], maxdeg = 0;                          // [in | out][node 2 tid, 2 tid + 1]
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int n = 2 * tid + j;
+            int t = 0;
+            if (n < ng) {
+#pragma unroll
+                for (int ww = 0; ww < CB_WARPS; ++ww) {           // counts -> exclusive prefix over the warps
+                    const int c = s_cnt[k][ww][n];
+                    s_cnt[k][ww][n] = t;
+                    t += c;
+                }
+            }
+            tot[k][j] = t;
+        }
+    maxdeg = max(tot[0][0], tot[0][1]);
+    int incl[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        int v = tot[k][0] + tot[k][1];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        incl[k] = v;
+        if (lane == 31) s_wsum[k][w] = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, o));
+    if (lane == 0) atomicMax(stats, maxdeg);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        int base = (int)e0;
+        for (int ww = 0; ww < w; ++ww) base += s_wsum[k][ww];
+        const int ex0 = base + incl[k] - tot[k][0] - tot[k][1];       // start of node 2 tid
+        const int ex1 = ex0 + tot[k][0];
+        int* ptr = k == 0 ? indptr : outptr;
+        if (2 * tid < ng) ptr[n0 + 2 * tid] = ex0;
+        if (2 * tid + 1 < ng) ptr[n0 + 2 * tid + 1] = ex1;
+#pragma unroll
+        for (int ww = 0; ww < CB_WARPS; ++ww) {
+            if (2 * tid < ng) s_cnt[k][ww][2 * tid] += ex0;
+            if (2 * tid + 1 < ng) s_cnt[k][ww][2 * tid + 1] += ex1;
+        }
+    }
+    if (tid == 0 && g == B - 1) { indptr[n1] = (int)e1; outptr[n1] = (int)e1; }
+    __syncthreads();
+    // phase 3: stable fill of this warp's chunk, 32 edges per step in ascending edge id
+    int* cur_in = s_cnt[0][w];
+    int* cur_out = s_cnt[1][w];
+    for (int64_t eb4 = ws; eb4 < we; eb4 += 128) {
         int64_t sl4[4], dl4[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int64_t e = eb4 + 32 * u + lane;
-            sl4[u] = e < e1 ? src_local[e] : 0; dl4[u] = e < e1 ? dst_local[e] : 0;
+            sl4[u] = e < we ? src_local[e] : 0; dl4[u] = e < we ? dst_local[e] : 0;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int64_t eb = eb4 + 32 * u;
-            if (eb >= e1) break;                                  // warp-uniform
+            if (eb >= we) break;                                  // warp-uniform
             const int64_t e = eb + lane;
-            const bool act = e < e1;
-            int s = -1 - lane, d = -1 - lane;
+            const bool act = e < we;
+            int s = -1 - lane, d = -1 - lane;                     // local node ids; inactive lanes match nobody
             if (act) {
                 int64_t sl = sl4[u], dl = dl4[u];
                 if (sl < 0 || sl >= ng || dl < 0 || dl >= ng) { sl = 0; dl = 0; }
-                s = (int)(sl + n0); d = (int)(dl + n0);
+                s = (int)sl; d = (int)dl;
             }
             const unsigned md = __match_any_sync(0xffffffffu, d), ms = __match_any_sync(0xffffffffu, s);
             const unsigned lt = (1u << lane) - 1u;
             int pos_csr = 0;
             if (act) {
                 pos_csr = cur_in[d] + __popc(md & lt);
-                csr_src[pos_csr] = s; csr_dst[pos_csr] = d; csr_eid[pos_csr] = (int)e;
+                csr_src[pos_csr] = s + (int)n0; csr_dst[pos_csr] = d + (int)n0; csr_eid[pos_csr] = (int)e;
             }
             __syncwarp();
             if (act && (md & lt) == 0) cur_in[d] += __popc(md);       // group leader advances the cursor
@@ -178,8 +291,7 @@ int is_collate_csr(const int64_t* src_local, const int64_t* dst_local, const int
     if (e != cudaSuccess) return (int)e;
     offsets_kernel<<<1, 1024, 0, st>>>(node_counts, edge_counts, n_graphs, node_off, edge_off);
     IS_LAUNCH_CHECK();
-    const int wpb = COLLATE_WPB;
-    collate_kernel<<<(n_graphs + wpb - 1) / wpb, wpb * 32, 0, st>>>(
+    collate_kernel<<<n_graphs, 32 * CB_WARPS, 0, st>>>(
         src_local, dst_local, node_off, edge_off, n_graphs, edge_index, n_edges, batch, indptr, csr_src, csr_dst,
         csr_eid, outptr, csc_pos, scratch, scratch + n_nodes, stats);
     IS_LAUNCH_CHECK();

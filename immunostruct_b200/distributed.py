@@ -2,17 +2,26 @@
 
 The reference is single-device (no torch.distributed call anywhere).  Every graph (or cancer / wild-
 type pair) is independent in the forward pass, so the path shards by contiguous ranges of the graph
-list: inference scans need NO collective; training needs one gradient all-reduce per step
-(6.33 M fp32 = 25.3 MB for HybridModelv2), done here over NCCL (NVLink 5 / NVSwitch) on a flat
-buffer.  Parameters whose gradient is ``None`` (the last EGNN layer's coord_mlp) are left untouched
-on every rank, so optimizers skip them exactly as in the single-GPU run.
+list: inference scans need NO collective; training needs the gradient averaged across ranks once per step
+(6.33 M fp32 = 25.3 MB for HybridModelv2) between the two lines ``loss.backward()`` / ``optimizer.step()`` of
+reference procedures/train.py:27-28.
+
+``BucketedGradientReducer`` keeps the gradients in one flat buffer that the parameters' ``.grad`` alias
+(``optim.FlatGradients``: reverse parameter order, so it fills front to back during the backward pass), cuts it
+into buckets and launches each bucket's NCCL all-reduce IN PLACE from a post-accumulate-grad hook as soon as its
+last gradient is written: ``vae_fc4`` (12.2 MB, the first gradient autograd produces) is reduced under the whole
+GNN backward; only the last bucket (``vae_fc1`` + the first EGNN layer) is exposed.  No staging copies.
+Parameters whose gradient is ``None`` (the last EGNN layer's coord_mlp) are left untouched on every rank, so
+optimizers skip them exactly as in the single-GPU run.
 """
 from __future__ import annotations
 
-from typing import Iterable, Tuple
+from typing import Iterable, List, Tuple
 
 import torch
 import torch.distributed as dist
+
+from .optim import FlatGradients, flatten_gradients
 
 
 def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
@@ -31,47 +40,90 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> N
             dist.broadcast(t, src=src, group=group)
 
 
-class GradientAllReducer:
-    """Average gradients across ranks with one all-reduce over a persistent flat buffer.
+class BucketedGradientReducer:
+    """Average gradients across ranks: bucketed, in place on the flat gradient buffer, overlapped with backward.
 
-    ``step()`` is called between ``loss.backward()`` and ``optimizer.step()`` (the two lines at
-    reference procedures/train.py:27-28).  The set of parameters that receive gradients is discovered
-    on the first call and must be the same on every rank (it is: same model, same code path).
+    Call ``step()`` between ``loss.backward()`` and ``optimizer.step()``.  The first call discovers which
+    parameters receive gradients (identical on every rank: same model, same code path), builds the flat buffer
+    and reduces it in one piece; from the second step on the buckets are reduced from autograd hooks during the
+    backward pass and ``step()`` only waits for them.  One ``backward()`` per ``step()`` (as in the reference's
+    loops); use ``optimizer.zero_grad(set_to_none=False)`` / ``FusedAdam.zero_grad()`` / ``reducer.zero_grad()`` so
+    that the views survive (a fresh ``.grad`` tensor is copied back in, at the price of that copy).
     """
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], group=None):
+    def __init__(self, params: Iterable[torch.nn.Parameter], group=None, bucket_bytes: int = 13 << 20):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
-        self.flat = None
-        self.live = None
+        self.bucket_bytes = int(bucket_bytes)
+        self.fg: FlatGradients = None
+        self.buckets: List[Tuple[int, int]] = []     # [lo, hi) element ranges of the flat buffer
+        self.overlapped_last_step = 0                 # buckets launched from hooks during the last backward
 
+    # ---- setup --------------------------------------------------------------------------------
     def _setup(self):
-        self.live = [p for p in self.params if p.grad is not None]
-        n = sum(p.grad.numel() for p in self.live)
-        g0 = self.live[0].grad
-        self.flat = torch.empty(n, dtype=g0.dtype, device=g0.device)
-        self.views, o = [], 0
-        for p in self.live:
-            k = p.grad.numel()
-            self.views.append(self.flat[o:o + k].view_as(p.grad))
-            o += k
+        self.fg = flatten_gradients(self.params)
+        fg = self.fg
+        esz = fg.flat.element_size()
+        self.bucket_of, self.buckets, lo, cur = [], [], 0, 0
+        for i, p in enumerate(fg.params):
+            end = fg.offsets[i + 1] if i + 1 < len(fg.params) else fg.flat.numel()
+            self.bucket_of.append(len(self.buckets))
+            if (end - lo) * esz >= self.bucket_bytes or i + 1 == len(fg.params):
+                self.buckets.append((lo, end))
+                lo = end
+        self.count = [self.bucket_of.count(b) for b in range(len(self.buckets))]
+        self.pending = list(self.count)
+        self.works = [None] * len(self.buckets)
+        self._world = dist.get_world_size(self.group)
+        self._avg = dist.get_backend(self.group) == "nccl"
+        for i, p in enumerate(fg.params):
+            p.register_post_accumulate_grad_hook(self._make_hook(i))
 
+    def _make_hook(self, i):
+        def hook(p):
+            v = self.fg.views[i]
+            if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                v.copy_(p.grad)
+                p.grad = v
+            b = self.bucket_of[i]
+            self.pending[b] -= 1
+            if self.pending[b] == 0:
+                self._launch(b)
+        return hook
+
+    def _launch(self, b):
+        lo, hi = self.buckets[b]
+        op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+        self.works[b] = dist.all_reduce(self.fg.flat[lo:hi], op=op, group=self.group, async_op=True)
+
+    # ---- per step -----------------------------------------------------------------------------
     def step(self) -> None:
-        if not dist.is_initialized():
+        if not dist.is_initialized() or dist.get_world_size(self.group) == 1:
             return
-        world = dist.get_world_size(self.group)
-        if world == 1:
-            return
-        if self.flat is None:
+        if self.fg is None:
             self._setup()
-        grads = [p.grad for p in self.live]
-        if any(g is None for g in grads):
-            raise RuntimeError("the set of parameters with gradients changed between steps")
-        torch._foreach_copy_(self.views, grads)
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-        self.flat.div_(world)
-        torch._foreach_copy_(grads, self.views)
+            self.pending = [0] * len(self.buckets)       # first step: nothing was launched from hooks
+            self.overlapped_last_step = 0
+        else:
+            self.overlapped_last_step = sum(w is not None for w in self.works)
+        for b in range(len(self.buckets)):
+            if self.works[b] is None:                      # not launched from a hook (first step / unused parameter)
+                self._launch(b)
+        for b, w in enumerate(self.works):
+            w.wait()
+            if not self._avg:
+                lo, hi = self.buckets[b]
+                self.fg.flat[lo:hi].div_(self._world)
+        self.works = [None] * len(self.buckets)
+        self.pending = list(self.count)
+
+    def zero_grad(self) -> None:
+        if self.fg is not None:
+            self.fg.zero_()
 
     @property
     def nbytes(self) -> int:
-        return 0 if self.flat is None else self.flat.numel() * self.flat.element_size()
+        return 0 if self.fg is None else sum(p.numel() for p in self.fg.params) * self.fg.flat.element_size()
+
+
+GradientAllReducer = BucketedGradientReducer      # previous name

@@ -415,3 +415,76 @@ def fused_loss(recon, seq, mu, logvar, logits, y, mode, pos_weight, w_pred, w_ms
     total, comps = _FusedLoss.apply(recon, seq, mu, logvar, logits, y, int(mode), float(pos_weight),
                                     float(w_pred), float(w_mse), float(w_kld))
     return (total, comps) if return_components else total
+
+
+# ==================================================================================================
+# segment pooling (global_mean_pool / global_max_pool)
+# ==================================================================================================
+class _SegmentPool(torch.autograd.Function):
+    """torch_geometric.nn.global_{mean,max}_pool over the batch's node segments (models/hybrid_models.py:97,331;
+    models/ablation_models.py:296-297) -- csrc/segment_pool.cu."""
+
+    @staticmethod
+    def forward(ctx, X, node_off, mode):
+        X = X if X.stride(-1) == 1 else X.contiguous()
+        out = _new(X, node_off.numel() - 1, X.shape[1])
+        _C.segment_pool_fwd(X, node_off, mode, out)
+        ctx.mode = mode
+        ctx.save_for_backward(X, node_off, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        X, node_off, out = ctx.saved_tensors
+        gX = _new(X, *X.shape)
+        _C.segment_pool_bwd(X, node_off, ctx.mode, out, g_out.contiguous(), gX)
+        return gX, None, None
+
+
+def segment_pool(graph_or_offsets, X, mode="mean"):
+    """Per-graph mean / max / sum of the rows of X [N, C] -> [B, C]; segments = the batch's node offsets."""
+    node_off = getattr(graph_or_offsets, "node_off", graph_or_offsets)
+    if mode not in _C.POOL_MODES:
+        raise ValueError(f"mode must be one of {sorted(_C.POOL_MODES)}")
+    return _SegmentPool.apply(X, node_off, mode)
+
+
+# ==================================================================================================
+# paired contrastive loss
+# ==================================================================================================
+class _Contrastive(torch.autograd.Function):
+    """PairedContrastiveLoss.forward (utils/contrastive.py:37-83) -- csrc/contrastive.cu.
+
+    forward(Ec, Ew, target, W1, gamma, beta, W2, run_mean, run_var, n_tracked, bn_eps, momentum, lambda_off) -> loss"""
+
+    @staticmethod
+    def forward(ctx, Ec, Ew, target, W1, gamma, beta, W2, run_mean, run_var, n_tracked, bn_eps, momentum, lambda_off):
+        Ec, Ew, W1, gamma, beta, W2 = (t.contiguous() for t in (Ec, Ew, W1, gamma, beta, W2))
+        target = target.reshape(-1).float().contiguous()
+        b, z = Ec.shape[0], W1.shape[0]
+        scratch = _new(Ec, _C.contrastive_scratch_floats(b, z))
+        out = _new(Ec, 4)
+        _C.contrastive_fwd(Ec, Ew, target, W1, gamma, beta, W2, bn_eps, momentum, run_mean, run_var, n_tracked,
+                           lambda_off, scratch, out)
+        ctx.save_for_backward(Ec, Ew, W1, gamma, beta, W2, scratch)
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        Ec, Ew, W1, gamma, beta, W2, scratch = ctx.saved_tensors
+        b, z = Ec.shape[0], W1.shape[0]
+        need = ctx.needs_input_grad
+        gEc, gEw = _new(Ec, *Ec.shape), _new(Ew, *Ew.shape)
+        gW1 = _new(W1, *W1.shape) if need[3] else None
+        gg = _new(gamma, z) if need[4] else None
+        gb = _new(beta, z) if need[5] else None
+        gW2 = _new(W2, *W2.shape) if need[6] else None
+        work = _new(Ec, 4 * b * z)
+        _C.contrastive_bwd(Ec, Ew, W1, gamma, beta, W2, scratch, gout.reshape(1).contiguous().float(), work,
+                           gEc, gEw, gW1, gg, gb, gW2)
+        return gEc, gEw, None, gW1, gg, gb, gW2, None, None, None, None, None, None
+
+
+def paired_contrastive(Ec, Ew, target, W1, gamma, beta, W2, run_mean, run_var, n_tracked, bn_eps, momentum, lambda_off):
+    return _Contrastive.apply(Ec, Ew, target, W1, gamma, beta, W2, run_mean, run_var, n_tracked, float(bn_eps),
+                              float(momentum), float(lambda_off))

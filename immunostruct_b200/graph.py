@@ -23,6 +23,45 @@ import torch
 from . import _C
 
 MAX_IN_DEGREE = 128     # edge tiles hold <= 128 in-edges of whole destination nodes (csrc/egnn.cu)
+MAX_GRAPH_NODES = 256   # largest graph the per-graph attention kernels stage on chip (csrc/attn_pool*.cu)
+
+# Collation statistics are checked by default, without a per-batch host synchronisation: the first batch of a
+# process is validated synchronously; every later batch copies its four statistics words to pinned host memory
+# asynchronously and they are inspected when the NEXT batch is collated (or at validate()).  A bad batch therefore
+# raises one batch late at the latest instead of silently producing garbage.  set_validation("off") disables it.
+_validation = {"mode": "deferred", "first_done": False, "pending": []}
+
+
+def set_validation(mode: str) -> None:
+    """"deferred" (default), "sync" (check every batch immediately: one host sync per batch) or "off"."""
+    if mode not in ("deferred", "sync", "off"):
+        raise ValueError("validation mode must be 'deferred', 'sync' or 'off'")
+    _validation["mode"] = mode
+
+
+def _raise_on_stats(max_deg, bad, max_nodes, n_empty, status, claimed_max_nodes=None):
+    if bad:
+        raise ValueError(f"{bad} edge endpoints fall outside their graph's node range")
+    if max_deg > MAX_IN_DEGREE:
+        raise ValueError(f"max in-degree {max_deg} exceeds the supported {MAX_IN_DEGREE}")
+    if claimed_max_nodes is not None and max_nodes > claimed_max_nodes:
+        raise ValueError(f"a graph has {max_nodes} nodes but the batch was built with max_nodes={claimed_max_nodes}")
+    if status:
+        raise RuntimeError("an EGNN kernel met a node with more than 128 in-edges")
+
+
+def _drain_pending(block: bool = False) -> None:
+    keep = []
+    for ev, host, claimed in _validation["pending"]:
+        if block:
+            ev.synchronize()
+        elif not ev.query():
+            keep.append((ev, host, claimed))
+            continue
+        vals = host.tolist()
+        _validation["pending"] = keep          # drop before raising so that the error is reported once
+        _raise_on_stats(vals[0], vals[1], vals[2], vals[3], vals[4], claimed)
+    _validation["pending"] = keep
 
 
 class Graph:
@@ -117,18 +156,27 @@ class GraphBatch:
         self.status = torch.zeros(1, **i32)
         if self.max_nodes is None:
             self.max_nodes = int(self._node_counts.max()) if b else 0
+        mode = _validation["mode"]
+        if mode == "off" or not self.stats.is_cuda:
+            return
+        if mode == "sync" or not _validation["first_done"]:
+            _validation["first_done"] = True
+            self.validate()
+            return
+        _drain_pending()
+        host = torch.empty(5, dtype=torch.int32).pin_memory()
+        host[:4].copy_(self.stats, non_blocking=True)
+        host[4:].copy_(self.status, non_blocking=True)      # status of the previous use of a recycled batch: 0 here
+        ev = torch.cuda.Event()
+        ev.record()
+        _validation["pending"].append((ev, host, self.max_nodes))
 
     def validate(self):
-        """Host check of the collation statistics (one device->host read)."""
+        """Host check of the collation statistics and the EGNN status flag (one device->host read)."""
         if self.stats is None:
             raise RuntimeError("validate() needs a device-resident batch")
-        max_deg, bad = self.stats[:2].tolist()
-        if bad:
-            raise ValueError(f"{bad} edge endpoints fall outside their graph's node range")
-        if max_deg > MAX_IN_DEGREE:
-            raise ValueError(f"max in-degree {max_deg} exceeds the supported {MAX_IN_DEGREE}")
-        if int(self.status.item()):
-            raise RuntimeError("an EGNN kernel met a node with more than 128 in-edges")
+        max_deg, bad, max_nodes, n_empty = self.stats.tolist()
+        _raise_on_stats(max_deg, bad, max_nodes, n_empty, int(self.status.item()), self.max_nodes)
         return self
 
     # ---- DGL vocabulary -------------------------------------------------------------------------

@@ -1,0 +1,169 @@
+"""Flat gradient storage and the fused Adam / AdamW step.
+
+The reference steps ``torch.optim.Adam`` / ``AdamW`` over ~60 separate parameter tensors
+(train_IEDB_wFT.py:74,97; train_Cancer_wFT.py:98,122; procedures/train.py:28,122).  Here the parameters that
+receive gradients live in ONE flat fp32 buffer (each ``nn.Parameter`` is a view of it, so ``state_dict``,
+``torch.save`` and ``load_state_dict`` are unchanged), their gradients in a second flat buffer, and one launch of
+``is_fused_adam`` (csrc/optim.cu) updates everything.  The flat gradient buffer is shared with
+``distributed.BucketedGradientReducer``, which all-reduces slices of it in place while the backward pass is still
+running.
+
+Parameters whose gradient is ``None`` after the first backward pass (the last EGNN layer's ``coord_mlp``,
+hybrid_models.py:323-326) stay outside the flat buffers and are never touched -- exactly what torch's optimisers do
+with ``grad is None`` (no moment update, no weight decay).
+"""
+from __future__ import annotations
+
+import math
+from typing import Iterable, List
+
+import torch
+
+from . import _C
+
+__all__ = ["FlatGradients", "flatten_gradients", "FusedAdam", "FusedAdamW"]
+
+
+class FlatGradients:
+    """Gradients of ``params`` (those that have one) as views of a single buffer, in REVERSE parameter order:
+    autograd finishes the last layers first, so the buffer fills front to back during the backward pass."""
+
+    def __init__(self, params: List[torch.nn.Parameter]):
+        self.params = [p for p in reversed(params) if p.grad is not None]
+        if not self.params:
+            raise RuntimeError("no parameter has a gradient yet: call after the first backward()")
+        g0 = self.params[0].grad
+        # every view starts on a 16-byte boundary (vector accesses of the fused optimiser, NCCL alignment)
+        self.offsets, o = [], 0
+        for p in self.params:
+            self.offsets.append(o)
+            o += (p.numel() + 3) // 4 * 4
+        self.flat = torch.zeros(o, dtype=g0.dtype, device=g0.device)
+        self.views = [self.flat[a:a + p.numel()].view_as(p) for a, p in zip(self.offsets, self.params)]
+        self.realias()
+        for p in self.params:
+            p._is_flat_grad = self
+
+    def realias(self) -> None:
+        """Make every ``p.grad`` the view of the flat buffer again (copying a foreign gradient tensor in)."""
+        for p, v in zip(self.params, self.views):
+            g = p.grad
+            if g is None:
+                v.zero_()
+            elif g.data_ptr() != v.data_ptr():
+                v.copy_(g)
+            p.grad = v
+
+    def zero_(self) -> None:
+        self.flat.zero_()
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+    def index(self, p) -> int:
+        for i, q in enumerate(self.params):
+            if q is p:
+                return i
+        raise KeyError("parameter not in this FlatGradients")
+
+
+def flatten_gradients(params: Iterable[torch.nn.Parameter]) -> FlatGradients:
+    """The ``FlatGradients`` of ``params`` -- created on first use, shared by every later caller with the same
+    live parameter set (the gradient reducer and the optimiser of one model)."""
+    params = [p for p in params if p.requires_grad]
+    live = [p for p in params if p.grad is not None]
+    fg = getattr(live[0], "_is_flat_grad", None) if live else None
+    if fg is not None and len(fg.params) == len(live) and all(a is b for a, b in zip(fg.params, reversed(live))):
+        return fg
+    return FlatGradients(params)
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """``torch.optim.Adam`` (``decoupled=False``) / ``AdamW`` (``decoupled=True``) with the whole step in one kernel.
+
+    Same defaults, hyper-parameter names (``param_groups[i]['lr']`` is read every step, so LR schedulers work) and
+    per-parameter state keys (``step``, ``exp_avg``, ``exp_avg_sq``) as torch's optimisers; ``amsgrad`` /
+    ``maximize`` are not supported.  ``zero_grad()`` zeroes the flat gradient buffer and keeps the views
+    (``set_to_none`` would break the aliasing the gradient reducer relies on)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False, grad_scale=1.0):
+        if lr < 0 or eps < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1 or weight_decay < 0:
+            raise ValueError("invalid Adam hyper-parameter")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, decoupled=decoupled))
+        self.grad_scale = float(grad_scale)
+        self._flat = {}       # group index -> dict(fg, p, m, v, runs, step)
+
+    def _setup_group(self, gi, group):
+        fg = flatten_gradients(group["params"])
+        mine = {id(p) for p in group["params"]}
+        idx = [i for i, p in enumerate(fg.params) if id(p) in mine]
+        n = sum((fg.params[i].numel() + 3) // 4 * 4 for i in idx)
+        dev = fg.flat.device
+        fp = torch.zeros(n, dtype=torch.float32, device=dev)
+        fm, fv = torch.zeros_like(fp), torch.zeros_like(fp)
+        runs, o = [], 0           # (param offset, grad offset, length) merged while contiguous in both buffers
+        for i in idx:
+            p = fg.params[i]
+            k, kp = p.numel(), (p.numel() + 3) // 4 * 4
+            with torch.no_grad():
+                fp[o:o + k].copy_(p.detach().reshape(-1))
+            p.data = fp[o:o + k].view_as(p)
+            st = self.state[p]
+            st["step"] = torch.tensor(0.0)
+            st["exp_avg"] = fm[o:o + k].view_as(p)
+            st["exp_avg_sq"] = fv[o:o + k].view_as(p)
+            go = fg.offsets[i]
+            if runs and runs[-1][0] + runs[-1][2] == o and runs[-1][1] + runs[-1][2] == go:
+                runs[-1] = (runs[-1][0], runs[-1][1], runs[-1][2] + kp)
+            else:
+                runs.append((o, go, kp))
+            o += kp
+        self._flat[gi] = dict(fg=fg, p=fp, m=fm, v=fv, runs=runs, step=0, idx=idx)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for gi, group in enumerate(self.param_groups):
+            if gi not in self._flat:
+                if all(p.grad is None for p in group["params"]):
+                    continue
+                self._setup_group(gi, group)
+            fl = self._flat[gi]
+            fg = fl["fg"]
+            for i in fl["idx"]:                                   # a foreign .grad tensor (set_to_none happened): copy in
+                p, v = fg.params[i], fg.views[i]
+                if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                    if p.grad is None:
+                        v.zero_()
+                    else:
+                        v.copy_(p.grad)
+                    p.grad = v
+            fl["step"] += 1
+            t = fl["step"]
+            b1, b2 = group["betas"]
+            lr = float(group["lr"])
+            step_size = lr / (1.0 - b1 ** t)
+            inv_bc2_sqrt = 1.0 / math.sqrt(1.0 - b2 ** t)
+            for po, go, n in fl["runs"]:
+                _C.fused_adam(fl["p"][po:po + n], fg.flat[go:go + n], fl["m"][po:po + n], fl["v"][po:po + n], lr, b1, b2,
+                              group["eps"], group["weight_decay"], group["decoupled"], step_size, inv_bc2_sqrt,
+                              self.grad_scale)
+            for i in fl["idx"]:
+                self.state[fg.params[i]]["step"] = torch.tensor(float(t))
+        return loss
+
+    def zero_grad(self, set_to_none: bool = False):
+        done = set()
+        for fl in self._flat.values():
+            if id(fl["fg"]) not in done:
+                fl["fg"].zero_()
+                done.add(id(fl["fg"]))
+        if not self._flat:
+            super().zero_grad(set_to_none=True)
+
+
+class FusedAdamW(FusedAdam):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, grad_scale=1.0):
+        super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, decoupled=True, grad_scale=grad_scale)

@@ -31,7 +31,8 @@ int is_attn_max_nodes(void);                  /* largest graph the attention ker
 int is_loss_num_partials(void);
 
 /* ---- collation: dgl.batch (data/utils.py:163,169-170) + DGL's lazy dst-sorted CSC + its transpose.
- * scratch: int32[2*n_nodes]; stats: int32[4] = {max in-degree, #endpoints out of range, 0, 0}. */
+ * scratch: int32[2*n_nodes]; stats: int32[4] = {max in-degree, #endpoints out of range,
+ * max nodes per graph, #empty graphs}. */
 int is_collate_csr(const int64_t* src_local, const int64_t* dst_local, const int64_t* node_counts,
                    const int64_t* edge_counts, int n_graphs, int64_t n_nodes, int64_t n_edges,
                    int64_t* node_off, int64_t* edge_off, int64_t* edge_index, int64_t* batch,
@@ -173,6 +174,52 @@ int is_linear_tc_split_k(int64_t M, int64_t N, int64_t K);
 int is_linear_tc(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc,
                  int64_t M, int64_t N, int64_t K, int relu, int precision, int split_k, float* workspace, void* stream);
 int is_umma_selftest(const float* A, const float* B, float* D, int mode, void* stream);
+
+/* ---- segment pooling (csrc/segment_pool.cu): torch_geometric.nn.global_mean_pool / global_max_pool
+ * (models/hybrid_models.py:97,331; models/ablation_models.py:296-297).  X [n, C] with row stride ldx, segments =
+ * node_off [n_graphs + 1]; mode 0 mean, 1 max (0 for an empty segment), 2 sum; out [n_graphs, C].  Backward of max
+ * splits the gradient evenly among the rows attaining the maximum (scatter_reduce 'amax'); `pooled` = forward output. */
+int is_segment_pool_fwd(const float* X, int64_t ldx, int C, const int64_t* node_off, int n_graphs, int mode,
+                        float* out, void* stream);
+int is_segment_pool_bwd(const float* X, int64_t ldx, int C, const int64_t* node_off, int n_graphs, int mode,
+                        const float* pooled, const float* g_out, float* gX, int64_t ldg, void* stream);
+
+/* ---- PairedContrastiveLoss (utils/contrastive.py:37-83; csrc/contrastive.cu): projector Linear(D, Z, no bias) ->
+ * BatchNorm1d (batch statistics; running statistics updated for the cancer then the wild-type call when the gate is
+ * open) -> ReLU -> Linear(Z, Z, no bias); centring, std hinge, pair-similarity and cross-correlation terms; the
+ * "exactly two target values" gate is evaluated on the device.  out [4] = {loss, pair, corr, std}.  scratch:
+ * is_contrastive_scratch_floats(B, Z) floats written by the forward and read by the backward; work: 4 * B * Z floats.
+ * Parameter-gradient outputs of the backward may be NULL. */
+int64_t is_contrastive_scratch_floats(int B, int Z);
+int is_contrastive_fwd(const float* Ec, const float* Ew, const float* target, int B, int D, int Z, const float* W1,
+                       const float* gamma, const float* beta, const float* W2, float bn_eps, float momentum,
+                       float* run_mean, float* run_var, int64_t* n_tracked, float lambda_off, float* scratch, float* out,
+                       void* stream);
+int is_contrastive_bwd(const float* Ec, const float* Ew, int B, int D, int Z, const float* W1, const float* gamma,
+                       const float* beta, const float* W2, const float* scratch, const float* gout, float* work,
+                       float* gEc, float* gEw, float* gW1, float* g_gamma, float* g_beta, float* gW2, void* stream);
+
+/* ---- fused Adam / AdamW step over a flat fp32 buffer (csrc/optim.cu): torch.optim.Adam / AdamW as constructed at
+ * train_IEDB_wFT.py:74,97 and train_Cancer_wFT.py:98,122, stepped at procedures/train.py:28,122.  decoupled = 1 is
+ * AdamW.  step_size = lr / (1 - beta1^t), inv_bc2_sqrt = 1 / sqrt(1 - beta2^t); grad_scale multiplies g first. */
+int is_fused_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int decoupled, float step_size, float inv_bc2_sqrt, float grad_scale, void* stream);
+
+/* ---- on-device training augmentations (csrc/augment.cu) ------------------------------------
+ * is_rotate_coords: RandomRotation (data/utils.py:148-155): x[:, c0:c0+3] @= Q_g, Q_g = Householder-QR orthogonal factor
+ *   (LAPACK sign convention = numpy.linalg.qr) of the caller's 3x3 normal draw M_g; Qout [n_graphs, 9] or NULL.
+ * is_mask_single_residue: mask_single_structure (data/immmunopred_dataloader.py:104-115, :248-266): residue
+ *   floor(u_g * n_valid) of graph g's valid residues (optionally of type want_aa[g]) gets an all-ones one-hot;
+ *   aa_out = its type (0 if none), node_out = its row (-1 if none) or NULL.
+ * is_mask_rows: mask_structure (:92-102; fill_col < 0: zero the one-hot unless the row sums to more than 1) and
+ *   mask_sequence (:78-90; fill_col = padding token): the `count` smallest keys among the first limit[g] rows
+ *   (limit NULL: all) of every segment. */
+int is_rotate_coords(float* x, int64_t ldx, int c0, const int64_t* node_off, int n_graphs, const float* M, float* Qout,
+                     void* stream);
+int is_mask_single_residue(float* x, int64_t ldx, int n_feat, const int64_t* node_off, int n_graphs, const float* u,
+                           const int64_t* want_aa, int64_t* aa_out, int64_t* node_out, void* stream);
+int is_mask_rows(float* data, int64_t ld, int n_cols, const int64_t* seg_off, const int64_t* limit, int n_segments,
+                 const float* keys, int count, int fill_col, int max_rows, void* stream);
 
 #ifdef __cplusplus
 }

@@ -65,7 +65,8 @@ def collate_csr(src_local, dst_local, node_counts, edge_counts, n_nodes, n_edges
     deg = torch.bincount(dst, minlength=n_nodes)
     ng = torch.repeat_interleave(node_counts, edge_counts)
     bad = int(((src_local < 0) | (src_local >= ng) | (dst_local < 0) | (dst_local >= ng)).sum())
-    out["stats"].copy_(torch.tensor([int(deg.max()) if n_edges else 0, bad, 0, 0], dtype=torch.int32))
+    out["stats"].copy_(torch.tensor([int(deg.max()) if n_edges else 0, bad, int(node_counts.max()) if b else 0,
+                                     int((node_counts == 0).sum())], dtype=torch.int32))
 
 
 # ---- EGNN forward -------------------------------------------------------------------------------
@@ -364,7 +365,159 @@ def loss_bwd(recon, seq, mu, logvar, logits, y, mode, pos_weight, w_pred, w_mse,
         g_logits.copy_(torch.autograd.grad(total, lg, gout.reshape(()))[0])
 
 
+# ---- segment pooling (PyG global_mean_pool / global_max_pool = scatter(reduce=...), published algorithm) ------
+POOL_MODES = {"mean": 0, "max": 1, "sum": 2}
+
+
+def _segment_pool(X, node_off, mode):
+    rows = []
+    for g in range(node_off.numel() - 1):
+        seg = X[int(node_off[g]):int(node_off[g + 1])]
+        if seg.shape[0] == 0:
+            rows.append(torch.zeros(X.shape[1], dtype=X.dtype))
+        elif mode == "mean":
+            rows.append(seg.mean(0))
+        elif mode == "sum":
+            rows.append(seg.sum(0))
+        else:
+            rows.append(seg.amax(0))      # amax: gradient split evenly among ties, like scatter_reduce('amax')
+    return torch.stack(rows) if rows else torch.zeros(0, X.shape[1])
+
+
+def segment_pool_fwd(X, node_off, mode, out):
+    out.copy_(_segment_pool(X.detach(), node_off, mode))
+
+
+@torch.enable_grad()
+def segment_pool_bwd(X, node_off, mode, pooled, g_out, gX):
+    x = X.detach().clone().requires_grad_(True)
+    gX.copy_(torch.autograd.grad(_segment_pool(x, node_off, mode), x, g_out)[0])
+
+
+# ---- paired contrastive loss (utils/contrastive.py:37-83) ---------------------------------------------------------
+def contrastive_scratch_floats(b, z):
+    return 3 + b
+
+
+def _contrastive(Ec, Ew, imm, W1, gamma, beta, W2, bn_eps, lam):
+    p = {"projector.0.weight": W1, "projector.1.weight": gamma, "projector.1.bias": beta, "projector.3.weight": W2}
+    # R.paired_contrastive evaluates the gate itself; feed it a two-valued target that reproduces `imm`
+    return R.paired_contrastive(p, Ec, Ew, imm, z_dim=W1.shape[0], lambda_off=lam, bn_eps=bn_eps)
+
+
+def contrastive_fwd(Ec, Ew, target, W1, gamma, beta, W2, bn_eps, momentum, run_mean, run_var, n_tracked, lambda_off,
+                    scratch, out):
+    with torch.no_grad():
+        t = target.reshape(-1).float()
+        gate = float(torch.unique(t).numel() == 2)
+        imm = (t > t.mean()).float()
+        scratch[0] = gate
+        scratch[1] = bn_eps
+        scratch[2] = lambda_off
+        scratch[3:3 + t.numel()] = imm
+        if gate:
+            loss = _contrastive(Ec, Ew, imm, W1, gamma, beta, W2, bn_eps, lambda_off)
+            if run_mean is not None:
+                b = Ec.shape[0]
+                for e in (Ec, Ew):
+                    y = e @ W1.T
+                    run_mean.mul_(1 - momentum).add_(momentum * y.mean(0))
+                    run_var.mul_(1 - momentum).add_(momentum * y.var(0, unbiased=True))
+                n_tracked += 2
+        else:
+            loss = torch.zeros(())
+        out.zero_()
+        out[0] = loss
+
+
+@torch.enable_grad()
+def contrastive_bwd(Ec, Ew, W1, gamma, beta, W2, scratch, gout, work, gEc, gEw, gW1, g_gamma, g_beta, gW2):
+    b = Ec.shape[0]
+    gate, bn_eps, lam, imm = float(scratch[0]), float(scratch[1]), float(scratch[2]), scratch[3:3 + b]
+    outs = [gEc, gEw, gW1, g_gamma, g_beta, gW2]
+    if not gate:
+        for o in outs:
+            if o is not None:
+                o.zero_()
+        return
+    leaves = [t.detach().clone().requires_grad_(True) for t in (Ec, Ew, W1, gamma, beta, W2)]
+    loss = _contrastive(leaves[0], leaves[1], imm, leaves[2], leaves[3], leaves[4], leaves[5], bn_eps, lam)
+    grads = torch.autograd.grad(loss, leaves, gout.reshape(()))
+    for o, g in zip(outs, grads):
+        if o is not None:
+            o.copy_(g)
+
+
+# ---- fused Adam (torch.optim.Adam / AdamW single-tensor arithmetic) ------------------------------------------------
+def fused_adam(p, g, m, v, lr, beta1, beta2, eps, weight_decay, decoupled, step_size, inv_bc2_sqrt, grad_scale=1.0):
+    with torch.no_grad():
+        g = g * grad_scale
+        if decoupled:
+            p.mul_(1 - lr * weight_decay)
+        elif weight_decay != 0:
+            g = g.add(p, alpha=weight_decay)
+        m.lerp_(g, 1 - beta1)
+        v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+        denom = (v.sqrt() * inv_bc2_sqrt).add_(eps)
+        p.addcdiv_(m, denom, value=-step_size)
+
+
+# ---- augmentations (data/utils.py:148-155; data/immmunopred_dataloader.py:78-115) ---------------------------------
+def rotate_coords(x, c0, node_off, M, Qout=None):
+    import numpy as np
+    for g in range(node_off.numel() - 1):
+        q, _ = np.linalg.qr(M[g].reshape(3, 3).double().numpy())
+        q = torch.from_numpy(q).float()
+        a, b = int(node_off[g]), int(node_off[g + 1])
+        x[a:b, c0:c0 + 3] = x[a:b, c0:c0 + 3] @ q
+        if Qout is not None:
+            Qout[g] = q.reshape(-1)
+
+
+def mask_single_residue(x, n_feat, node_off, u, want_aa, aa_out, node_out=None):
+    import numpy as np
+    for g in range(node_off.numel() - 1):
+        a, b = int(node_off[g]), int(node_off[g + 1])
+        cand = []
+        for r in range(a, b):
+            nz = torch.nonzero(x[r, :n_feat]).flatten()
+            if nz.numel() and (want_aa is None or int(want_aa[g]) < 0 or int(nz[0]) == int(want_aa[g])):
+                cand.append((r, int(nz[0])))
+        if not cand:
+            aa_out[g] = 0
+            if node_out is not None:
+                node_out[g] = -1
+            continue
+        pick = min(int(np.float32(u[g].item()) * np.float32(len(cand))), len(cand) - 1)
+        r, aa = cand[pick]
+        x[r, :n_feat] = 1.0
+        aa_out[g] = aa
+        if node_out is not None:
+            node_out[g] = r
+
+
+def mask_rows(data, n_cols, seg_off, limit, keys, count, fill_col, max_rows):
+    for g in range(seg_off.numel() - 1):
+        a, b = int(seg_off[g]), int(seg_off[g + 1])
+        n = b - a
+        if limit is not None:
+            n = min(n, int(limit[g]))
+        k = min(count, n)
+        if k <= 0:
+            continue
+        order = torch.argsort(keys[a:a + n], stable=True)[:k]
+        for i in order.tolist():
+            row = data[a + i]
+            if fill_col < 0:
+                if not float(row[:n_cols].sum()) > 1.0:
+                    row[:n_cols] = 0.0
+            else:
+                row[:n_cols] = 0.0
+                row[fill_col] = 1.0
+
+
 ALL = ["num_sms", "egnn_node_grid", "egnn_edge_bwd_grid", "attn_max_nodes", "loss_num_partials", "collate_csr",
        "egnn_node_pre_fwd", "egnn_edge_fwd", "egnn_edge_fwd_tc", "egnn_node_post_pre_tc", "linear_tc", "vae_mid_infer", "head_infer", "unpack_nodes", "unpack_edges", "onehot_tokens", "egnn_node_post_fwd", "egnn_node_post_bwd", "egnn_node_post_bwd_tc", "egnn_node_pre_bwd_tc", "egnn_edge_bwd", "egnn_edge_bwd_tc",
        "egnn_node_pre_bwd", "reduce_partials", "attn_pool_fwd", "attn_pool_infer", "attn_pool_infer_tc", "attn_pool_bwd", "attn_pool_bwd_tc", "fusion_attn_fwd",
-       "fusion_attn_bwd", "loss_fwd", "loss_bwd"]
+       "fusion_attn_bwd", "loss_fwd", "loss_bwd", "segment_pool_fwd", "segment_pool_bwd", "contrastive_scratch_floats",
+       "contrastive_fwd", "contrastive_bwd", "fused_adam", "rotate_coords", "mask_single_residue", "mask_rows"]

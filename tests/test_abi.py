@@ -10,7 +10,7 @@ from immunostruct_b200 import _C, build
 
 def header_symbols():
     text = open(os.path.join(ROOT, "include", "immunostruct_b200.h")).read()
-    return sorted(set(re.findall(r"^int\s+(is_\w+)\s*\(", text, flags=re.M)))
+    return sorted(set(re.findall(r"^(?:int|int64_t)\s+(is_\w+)\s*\(", text, flags=re.M)))
 
 
 def test_library_exports_every_declared_symbol():

@@ -93,7 +93,7 @@ def test_structure_model_v2_matches_reference_golden(cpu_backend):
     assert_grads_close(named_grads(model), gd["grads"], 1e-4)
 
 
-def test_contrastive_gate_is_zero_without_two_classes():
+def test_contrastive_gate_is_zero_without_two_classes(cpu_backend):
     pcl = I.PairedContrastiveLoss(embedding_dim=104)
     e1, e2 = torch.randn(6, 104, requires_grad=True), torch.randn(6, 104)
     for target in (torch.ones(6), torch.linspace(0, 1, 6)):
