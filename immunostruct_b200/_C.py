@@ -33,6 +33,11 @@ def lib():
     return _lib
 
 
+def lib_is_patched() -> bool:
+    """True when a test has replaced the kernel entry points by the CPU contracts (tests/test_host_glue.py)."""
+    return getattr(split_planes, "__module__", __name__) != __name__
+
+
 def exported_symbols():
     """Names declared in include/immunostruct_b200.h (used by the CPU symbol-presence test)."""
     return ["is_num_sms", "is_egnn_node_grid", "is_egnn_edge_bwd_grid", "is_attn_max_nodes",
@@ -41,7 +46,8 @@ def exported_symbols():
             "is_reduce_partials", "is_attn_pool_fwd", "is_attn_pool_bwd", "is_fusion_attn_fwd",
             "is_fusion_attn_bwd", "is_loss_fwd", "is_loss_bwd", "is_umma_selftest", "is_egnn_edge_fwd_tc", "is_attn_pool_infer", "is_egnn_node_post_pre_tc", "is_egnn_edge_bwd_tc", "is_linear_tc", "is_linear_tc_split_k", "is_attn_pool_infer_tc", "is_vae_mid_infer", "is_head_infer", "is_unpack_nodes", "is_unpack_edges", "is_onehot_tokens", "is_egnn_node_post_bwd_tc", "is_egnn_node_pre_bwd_tc", "is_attn_pool_bwd_tc",
             "is_segment_pool_fwd", "is_segment_pool_bwd", "is_contrastive_scratch_floats", "is_contrastive_fwd",
-            "is_contrastive_bwd", "is_fused_adam", "is_rotate_coords", "is_mask_single_residue", "is_mask_rows"]
+            "is_contrastive_bwd", "is_fused_adam", "is_rotate_coords", "is_mask_single_residue", "is_mask_rows", "is_gemm_tma_split_k",
+            "is_split_planes", "is_gemm_planes_tma"]
 
 
 def _check(rc: int, name: str):
@@ -467,3 +473,43 @@ def mask_rows(data, n_cols, seg_off, limit, keys, count, fill_col, max_rows):
     i64 = torch.int64
     _call("is_mask_rows", dp, ld, _i32(n_cols), _t(seg_off, i64, "seg_off"), _t(limit, i64, "limit"),
           _i32(seg_off.numel() - 1), _t(keys, torch.float32, "keys"), _i32(count), _i32(fill_col), _i32(max_rows), _stream())
+
+
+# ---- TMA-fed tcgen05 GEMM on pre-split bf16 planes (csrc/gemm_tma.cu) ----------------------------------
+def split_planes(x, n_planes=3, rows=True, transposed=False, relu_src=None, colsum=False, flag=False):
+    """fp32 x [R, C] -> (planes [n, R, Cp] | None, planes_t [n, C, Rp] | None, colsum partials [gr, C] | None,
+    residual flag int32 [1] | None); Cp / Rp = C / R rounded up to 8 (zero padded)."""
+    xp, ld = _rows(x, "x")
+    r, c = x.shape
+    cp, rp = (c + 7) // 8 * 8, (r + 7) // 8 * 8
+    bf, dev = torch.bfloat16, x.device
+    planes = torch.empty(n_planes, r, cp, dtype=bf, device=dev) if rows else None
+    planes_t = torch.empty(n_planes, c, rp, dtype=bf, device=dev) if transposed else None
+    gr = ((rp if transposed else r) + 31) // 32
+    part = torch.empty(gr, c, dtype=torch.float32, device=dev) if colsum else None
+    fl = torch.zeros(1, dtype=torch.int32, device=dev) if flag else None
+    rsp, ldr = (None, _i64(0)) if relu_src is None else _rows(relu_src, "relu_src")
+    _call("is_split_planes", xp, ld, _i64(r), _i64(c), rsp, ldr, _i32(n_planes), _t(planes, bf, "planes"),
+          _t(planes_t, bf, "planes_t"), _t(part, torch.float32, "colsum"), _t(fl, torch.int32, "flag"), _stream())
+    return planes, planes_t, part, fl
+
+
+def gemm_planes(a_planes, b_planes, bias=None, relu=False, out=None, a_flag=None, b_flag=None):
+    """out [M, N] = act(A B^T + bias): A planes [n, M, Kp], B planes [n, N, Kp] (bf16, from split_planes)."""
+    global LAUNCHES
+    bf, f32 = torch.bfloat16, torch.float32
+    npl, m, kp = a_planes.shape
+    n = b_planes.shape[1]
+    if b_planes.shape[0] != npl or b_planes.shape[2] != kp:
+        raise ValueError(f"gemm_planes: A planes {tuple(a_planes.shape)} vs B planes {tuple(b_planes.shape)}")
+    if out is None:
+        out = torch.empty(m, n, dtype=f32, device=a_planes.device)
+    split = int(lib().is_gemm_tma_split_k(_i64(m), _i64(n), _i64(kp)))
+    ws = torch.empty(split * m * n, dtype=f32, device=a_planes.device) if split > 1 else None
+    cp, ldc = _rows(out, "out")
+    _call("is_gemm_planes_tma", _t(a_planes, bf, "A planes"), _i64(m), _t(b_planes, bf, "B planes"), _i64(n), _i64(kp),
+          _i32(npl), _t(a_flag, torch.int32, "a_flag"), _t(b_flag, torch.int32, "b_flag"), _t(bias, f32, "bias"),
+          _i32(1 if relu else 0), cp, ldc, _i32(split), _t(ws, f32, "workspace"), _stream())
+    if split > 1:
+        LAUNCHES += 1
+    return out

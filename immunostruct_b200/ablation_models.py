@@ -11,7 +11,7 @@ from .trunk import LoadTrained, SequenceVAE, StructureTrunk, classifier_mlp
 __all__ = ["SequenceModel", "SequenceFpModel", "StructureModel", "StructureModel_SSL", "StructureModelv2", "DualModel"]
 
 
-class SequenceModel(nn.Module, SequenceVAE, LoadTrained):          # reference ablation_models.py:10-66
+class SequenceModel(LoadTrained, nn.Module, SequenceVAE):          # reference ablation_models.py:10-66
     _cond = 0
 
     def __init__(self, vae_input_dim, device, gcn_layers=5, vae_hidden_dim=512, vae_latent_dim=32,
@@ -33,7 +33,7 @@ class SequenceFpModel(SequenceModel):                              # reference a
     _cond = 2
 
 
-class _Structure(nn.Module, StructureTrunk, LoadTrained):
+class _Structure(LoadTrained, nn.Module, StructureTrunk):
     _ssl, _maxpool = False, False
 
     def __init__(self, vae_input_dim, device, gcn_layers=5, vae_hidden_dim=512, vae_latent_dim=32,
@@ -74,7 +74,7 @@ class StructureModelv2(_Structure):                                # reference a
     _ssl, _maxpool, _head_attr = True, True, "classifier_head"
 
 
-class DualModel(nn.Module, StructureTrunk, SequenceVAE, LoadTrained):   # reference ablation_models.py:309-398
+class DualModel(LoadTrained, nn.Module, StructureTrunk, SequenceVAE):   # reference ablation_models.py:309-398
     def __init__(self, vae_input_dim, device, gcn_layers=5, vae_hidden_dim=512, vae_latent_dim=32,
                  gat_hidden_channels=64):
         super().__init__()

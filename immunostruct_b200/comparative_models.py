@@ -12,7 +12,7 @@ __all__ = ["HybridModel_Comparative", "HybridModel_Comparative_SSL",
            "HybridModelv2_Comparative", "HybridModelv2_Comparative_SSL"]
 
 
-class _Comparative(nn.Module, StructureTrunk, SequenceVAE, LoadTrained):
+class _Comparative(LoadTrained, nn.Module, StructureTrunk, SequenceVAE):
     _attention, _fusion_dim, _ssl = "sa", None, False
 
     def __init__(self, vae_input_dim, device, gcn_layers=5, vae_hidden_dim=512, vae_latent_dim=32,

@@ -35,6 +35,24 @@ def get_precision() -> str:
     return _precision
 
 
+# Generation counter of every parameter-derived cache (fused projection weights, fusion coefficients, pre-split weight
+# planes).  The caches are keyed on (storage pointer, in-place version counter) of their source parameters, which
+# misses writes through ``p.data`` (EMA, clipping, legacy init code: they do not bump the version counter); model
+# ``train()`` / ``load_state_dict()`` / ``to()`` bump this generation, and ``invalidate_caches()`` does so explicitly.
+_cache_generation = 0
+
+
+def invalidate_caches() -> None:
+    """Drop every cached parameter-derived tensor (call after writing parameters through ``.data``)."""
+    global _cache_generation
+    _cache_generation += 1
+    _weight_planes.clear()
+
+
+def cache_generation() -> int:
+    return _cache_generation
+
+
 def _new(like, *shape):
     return torch.empty(*shape, dtype=torch.float32, device=like.device)
 
@@ -488,3 +506,70 @@ class _Contrastive(torch.autograd.Function):
 def paired_contrastive(Ec, Ew, target, W1, gamma, beta, W2, run_mean, run_var, n_tracked, bn_eps, momentum, lambda_off):
     return _Contrastive.apply(Ec, Ew, target, W1, gamma, beta, W2, run_mean, run_var, n_tracked, float(bn_eps),
                               float(momentum), float(lambda_off))
+
+
+# ==================================================================================================
+# dense Linear on the TMA-fed tensor-core GEMM (forward, dgrad, wgrad)
+# ==================================================================================================
+_linear_impl = "tma"       # "tma": csrc/gemm_tma.cu (default); "fused": csrc/linear_tc.cu in the no-grad path (A/B timing)
+_weight_planes = {}       # id(weight) -> (key, planes [n, out, in_p], planes_t [n, in, out_p])
+
+
+def _n_planes():
+    prec = _PRECISIONS[_precision]
+    return 1 if prec == _C.PREC_BF16 else 3
+
+
+def _planes_of_weight(weight, need_t):
+    """Pre-split bf16 planes of a weight matrix, row-major ([out, in]: forward) and transposed ([in, out]: dgrad),
+    cached per parameter version -- in inference the weights are constants, in training they change once per step."""
+    n = _n_planes()
+    try:
+        key = (weight.data_ptr(), weight._version, n, _cache_generation)
+    except RuntimeError:
+        key = None
+    hit = _weight_planes.get(id(weight))
+    if key is not None and hit is not None and hit[0] == key and (hit[2] is not None or not need_t):
+        return hit[1], hit[2]
+    with torch.no_grad():
+        planes, planes_t, _, _ = _C.split_planes(weight.detach(), n, rows=True, transposed=need_t)
+    if key is not None:
+        _weight_planes[id(weight)] = (key, planes, planes_t)
+    return planes, planes_t
+
+
+class _LinearTC(torch.autograd.Function):
+    """``relu?(x @ W^T + b)`` with all three GEMMs of the layer (forward, input gradient, weight gradient) on the
+    TMA-fed tcgen05 kernel (csrc/gemm_tma.cu), fp32-accurate through the bf16x3 split.  Reference: the nn.Linear
+    layers of the sequence VAE and their autograd (models/hybrid_models.py:63-74 / 297-308)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        n = _n_planes()
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        xp, xpt, _, xflag = _C.split_planes(x, n, rows=True, transposed=need_dw, flag=(n == 3))
+        wp, wpt = _planes_of_weight(weight, need_dx)
+        y = _C.gemm_planes(xp, wp, None if bias is None else bias.detach().contiguous(), relu, a_flag=xflag)
+        ctx.relu, ctx.n, ctx.has_bias = relu, n, bias is not None
+        ctx.save_for_backward(xpt, xflag, wpt, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        xpt, xflag, wpt, y = ctx.saved_tensors
+        need_dx, need_dw, need_db = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        gy = gy if gy.stride(-1) == 1 else gy.contiguous()
+        gp, gpt, part, _ = _C.split_planes(gy, ctx.n, rows=need_dx, transposed=need_dw, relu_src=y if ctx.relu else None,
+                                           colsum=need_db)
+        gx = _C.gemm_planes(gp, wpt) if need_dx else None                     # gX = gY W
+        gw = _C.gemm_planes(gpt, xpt, b_flag=xflag) if need_dw else None       # gW = gY^T X
+        gb = None
+        if need_db:
+            gb = _new(gy, gy.shape[1])
+            _C.reduce_partials(part, gb)
+        return gx, gw, gb, None
+
+
+def linear_tc(x, weight, bias=None, relu=False):
+    """Differentiable ``relu?(F.linear(x, weight, bias))`` on the tensor cores; x [M, K] fp32 with unit inner stride."""
+    return _LinearTC.apply(x, weight, bias, relu)

@@ -52,16 +52,35 @@ def _raise_on_stats(max_deg, bad, max_nodes, n_empty, status, claimed_max_nodes=
 
 def _drain_pending(block: bool = False) -> None:
     keep = []
-    for ev, host, claimed in _validation["pending"]:
+    pend = _validation["pending"]
+    for i, (ev, host, claimed, owner) in enumerate(pend):
         if block:
             ev.synchronize()
         elif not ev.query():
-            keep.append((ev, host, claimed))
+            keep.append((ev, host, claimed, owner))
             continue
         vals = host.tolist()
-        _validation["pending"] = keep          # drop before raising so that the error is reported once
-        _raise_on_stats(vals[0], vals[1], vals[2], vals[3], vals[4], claimed)
+        if vals[1] or vals[0] > MAX_IN_DEGREE or vals[4] or (claimed is not None and vals[2] > claimed):
+            _validation["pending"] = keep + pend[i + 1:]          # drop before raising: the error is reported once
+            _raise_on_stats(vals[0], vals[1], vals[2], vals[3], vals[4], claimed)
     _validation["pending"] = keep
+
+
+_PINNED_SLOTS = 64
+
+
+def _pinned_slot():
+    """Round-robin slot of a small pinned ring for the asynchronous statistics read-back (allocating pinned memory per
+    batch would cost more than the copy)."""
+    ring = _validation.get("ring")
+    if ring is None:
+        ring = _validation["ring"] = torch.empty(_PINNED_SLOTS, 5, dtype=torch.int32).pin_memory()
+        _validation["next"] = 0
+    if len(_validation["pending"]) >= _PINNED_SLOTS - 1:
+        _drain_pending(block=True)
+    i = _validation["next"]
+    _validation["next"] = (i + 1) % _PINNED_SLOTS
+    return ring[i]
 
 
 class Graph:
@@ -157,25 +176,26 @@ class GraphBatch:
         if self.max_nodes is None:
             self.max_nodes = int(self._node_counts.max()) if b else 0
         mode = _validation["mode"]
-        if mode == "off" or not self.stats.is_cuda:
+        if mode == "off" or not self.stats.is_cuda or torch.cuda.is_current_stream_capturing():
             return
         if mode == "sync" or not _validation["first_done"]:
             _validation["first_done"] = True
             self.validate()
             return
         _drain_pending()
-        host = torch.empty(5, dtype=torch.int32).pin_memory()
+        host = _pinned_slot()
         host[:4].copy_(self.stats, non_blocking=True)
-        host[4:].copy_(self.status, non_blocking=True)      # status of the previous use of a recycled batch: 0 here
+        host[4:].copy_(self.status, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
-        _validation["pending"].append((ev, host, self.max_nodes))
+        _validation["pending"].append((ev, host, self.max_nodes, id(self)))
 
     def validate(self):
         """Host check of the collation statistics and the EGNN status flag (one device->host read)."""
         if self.stats is None:
             raise RuntimeError("validate() needs a device-resident batch")
         max_deg, bad, max_nodes, n_empty = self.stats.tolist()
+        _validation["pending"] = [e for e in _validation["pending"] if e[3] != id(self)]     # reported here, not again later
         _raise_on_stats(max_deg, bad, max_nodes, n_empty, int(self.status.item()), self.max_nodes)
         return self
 

@@ -12,7 +12,7 @@ from .trunk import LoadTrained, SequenceVAE, StructureTrunk, classifier_mlp, pro
 __all__ = ["HybridModel", "HybridModelv2", "HybridModel_SSL", "HybridModelv2_SSL"]
 
 
-class _Hybrid(nn.Module, StructureTrunk, SequenceVAE, LoadTrained):
+class _Hybrid(LoadTrained, nn.Module, StructureTrunk, SequenceVAE):
     """Common body of the four hybrid models.  ``fusion_dim``: None = plain concat (v1), else the
     feature_dim of ``combined_attention`` (16 for v2, 32 for v2-SSL); ``ssl``: two heads."""
 

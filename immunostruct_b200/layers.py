@@ -26,7 +26,7 @@ def _cached_no_grad(module, name, params, build):
     if torch.is_grad_enabled():
         return build()
     try:
-        key = tuple((p.data_ptr(), p._version) for p in params)
+        key = (IF.cache_generation(),) + tuple((p.data_ptr(), p._version) for p in params)
     except RuntimeError:                       # inference tensors carry no version counter: do not cache
         return build()
     slot = module.__dict__.setdefault("_derived_cache", {})

@@ -150,8 +150,10 @@ class FusedAdam(torch.optim.Optimizer):
                 _C.fused_adam(fl["p"][po:po + n], fg.flat[go:go + n], fl["m"][po:po + n], fl["v"][po:po + n], lr, b1, b2,
                               group["eps"], group["weight_decay"], group["decoupled"], step_size, inv_bc2_sqrt,
                               self.grad_scale)
-            for i in fl["idx"]:
-                self.state[fg.params[i]]["step"] = torch.tensor(float(t))
+            live = [fg.params[i] for i in fl["idx"]]
+            torch.autograd.graph.increment_version(live)          # the kernel wrote through raw pointers: caches keyed on
+            for p in live:                                        # the version counters must see the update
+                self.state[p]["step"] = torch.tensor(float(t))
         return loss
 
     def zero_grad(self, set_to_none: bool = False):

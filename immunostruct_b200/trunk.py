@@ -59,15 +59,21 @@ class StructureTrunk:
 
 
 def _tc_linear(layer, x, relu=False):
-    """``layer(x)`` (+ ReLU) -- in no-grad CUDA calls through the tcgen05 Linear kernel (csrc/linear_tc.cu) in the
-    arithmetic of the current precision mode; with autograd (training) through torch / cuBLAS."""
+    """``layer(x)`` (+ ReLU) for the two large Linear layers.  On CUDA, in every tensor-core precision mode, forward AND
+    backward run on the TMA-fed tcgen05 GEMM (csrc/gemm_tma.cu: pre-split bf16 planes, weights split once per
+    parameter version); the "fp32" mode keeps torch's fp32 GEMM (a plain library GEMM)."""
     prec = IF._PRECISIONS[IF.get_precision()]
-    if torch.is_grad_enabled() or not x.is_cuda or prec is None or x.dim() != 2:
+    if prec is None or x.dim() != 2 or not (x.is_cuda or IF._C.lib_is_patched()):
         y = layer(x)
         return F.relu(y) if relu else y
-    node_prec = IF._C.PREC_BF16 if prec == IF._C.PREC_BF16 else IF._C.PREC_BF16X3
-    return IF._C.linear_tc(x, layer.weight.detach(), None if layer.bias is None else layer.bias.detach(), relu=relu,
-                           precision=node_prec)
+    if x.stride(-1) != 1:
+        x = x.contiguous()
+    if IF._linear_impl == "fused" and not torch.is_grad_enabled():
+        # the round-1 kernel (csrc/linear_tc.cu: operands split on the fly by SIMT threads); kept for A/B timing
+        node_prec = IF._C.PREC_BF16 if prec == IF._C.PREC_BF16 else IF._C.PREC_BF16X3
+        return IF._C.linear_tc(x, layer.weight.detach(), None if layer.bias is None else layer.bias.detach(), relu=relu,
+                               precision=node_prec)
+    return IF.linear_tc(x, layer.weight, layer.bias, relu)
 
 
 class SequenceVAE:
@@ -133,9 +139,23 @@ def classifier_mlp(in_dim, with_out=True):
 
 
 class LoadTrained:
-    """``load_trained(path, new_head, map_location)`` (hybrid_models.py:310-313, :197-200 for SSL)."""
+    """``load_trained(path, new_head, map_location)`` (hybrid_models.py:310-313, :197-200 for SSL).  Also the cache
+    hygiene of every model class: ``train()`` / ``eval()``, ``load_state_dict()`` and ``to()`` / ``cuda()`` drop the
+    parameter-derived caches (fused projection weights, fusion coefficients, pre-split weight planes)."""
 
     _head_attr = "classifier"
+
+    def train(self, mode: bool = True):
+        IF.invalidate_caches()
+        return super().train(mode)
+
+    def load_state_dict(self, *args, **kwargs):
+        IF.invalidate_caches()
+        return super().load_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        IF.invalidate_caches()
+        return super()._apply(fn, *args, **kwargs)
 
     def load_trained(self, path, new_head=False, map_location=None):
         self.load_state_dict(torch.load(path, map_location=map_location))

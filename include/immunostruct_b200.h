@@ -175,6 +175,24 @@ int is_linear_tc(const float* A, int64_t lda, const float* W, int64_t ldw, const
                  int64_t M, int64_t N, int64_t K, int relu, int precision, int split_k, float* workspace, void* stream);
 int is_umma_selftest(const float* A, const float* B, float* D, int mode, void* stream);
 
+/* ---- TMA-fed tcgen05 GEMM for the dense Linear layers, forward and backward (csrc/gemm_tma.cu): the nn.Linear
+ * layers of the sequence VAE (models/hybrid_models.py:63-74 / 297-308) and what autograd derives for them.
+ * is_split_planes: fp32 X [R, C] (row stride ld) -> bf16 planes (a = a1 + a2 + a3; n_planes 3, or 1 = rounded) in
+ *   row-major [n_planes][R][Cp] and / or transposed [n_planes][C][Rp] form (Cp / Rp = C / R rounded up to 8, zero
+ *   padded); optional ReLU mask (X kept where relu_src > 0), per-row-block column sums colsum_part [gr][C] with
+ *   gr = ceil((planes_t ? Rp : R) / 32) (bias gradient: sum with is_reduce_partials), resid_flag set to 1 if X is
+ *   not exact in bf16 (caller zeroes it first).
+ * is_gemm_planes_tma: C[M, N] = act(A B^T + bias) from planes A [n_planes][M][Kp], B [n_planes][N][Kp]; operand tiles
+ *   arrive by cp.async.bulk.tensor (128-byte swizzle), six bf16 partial products accumulate in TMEM (fp32-accurate);
+ *   a/b_resid_flag (device, or NULL) = 0 skips the products of that operand's second / third plane.  split_k > 1
+ *   (is_gemm_tma_split_k) needs workspace >= split_k * M * N floats; slices are summed in order (deterministic). */
+int is_gemm_tma_split_k(int64_t M, int64_t N, int64_t Kp);
+int is_split_planes(const float* X, int64_t ld, int64_t R, int64_t C, const float* relu_src, int64_t ld_relu, int n_planes,
+                    void* planes, void* planes_t, float* colsum_part, int* resid_flag, void* stream);
+int is_gemm_planes_tma(const void* A_planes, int64_t M, const void* B_planes, int64_t N, int64_t Kp, int n_planes,
+                       const int* a_resid_flag, const int* b_resid_flag, const float* bias, int relu, float* C, int64_t ldc,
+                       int split_k, float* workspace, void* stream);
+
 /* ---- segment pooling (csrc/segment_pool.cu): torch_geometric.nn.global_mean_pool / global_max_pool
  * (models/hybrid_models.py:97,331; models/ablation_models.py:296-297).  X [n, C] with row stride ldx, segments =
  * node_off [n_graphs + 1]; mode 0 mean, 1 max (0 for an empty segment), 2 sum; out [n_graphs, C].  Backward of max

@@ -516,8 +516,52 @@ def mask_rows(data, n_cols, seg_off, limit, keys, count, fill_col, max_rows):
                 row[fill_col] = 1.0
 
 
+# ---- TMA GEMM on bf16 planes (csrc/gemm_tma.cu): nn.Linear forward / dgrad / wgrad -------------------------------------
+def split_planes(x, n_planes=3, rows=True, transposed=False, relu_src=None, colsum=False, flag=False):
+    x = x.detach().float()
+    if relu_src is not None:
+        x = torch.where(relu_src > 0, x, torch.zeros_like(x))
+    r, c = x.shape
+    cp, rp = (c + 7) // 8 * 8, (r + 7) // 8 * 8
+
+    def planes_of(m, pad_to):
+        out = torch.zeros(n_planes, m.shape[0], pad_to, dtype=torch.bfloat16)
+        rest = m.clone()
+        for i in range(n_planes):
+            p = rest.to(torch.bfloat16)
+            out[i, :, :m.shape[1]] = p
+            rest = rest - p.float()
+        return out
+
+    planes = planes_of(x, cp) if rows else None
+    planes_t = planes_of(x.t().contiguous(), rp) if transposed else None
+    part = None
+    if colsum:
+        gr = ((rp if transposed else r) + 31) // 32
+        part = torch.zeros(gr, c)
+        for i in range(gr):
+            part[i] = x[32 * i:32 * i + 32].sum(0)
+    fl = None
+    if flag:
+        fl = torch.tensor([int(bool((x - x.to(torch.bfloat16).float()).abs().max() > 0))], dtype=torch.int32)
+    return planes, planes_t, part, fl
+
+
+def gemm_planes(a_planes, b_planes, bias=None, relu=False, out=None, a_flag=None, b_flag=None):
+    a, b = a_planes.double().sum(0), b_planes.double().sum(0)
+    y = (a @ b.t()).float()
+    if bias is not None:
+        y = y + bias
+    if relu:
+        y = torch.relu(y)
+    if out is None:
+        return y
+    out.copy_(y)
+    return out
+
+
 ALL = ["num_sms", "egnn_node_grid", "egnn_edge_bwd_grid", "attn_max_nodes", "loss_num_partials", "collate_csr",
        "egnn_node_pre_fwd", "egnn_edge_fwd", "egnn_edge_fwd_tc", "egnn_node_post_pre_tc", "linear_tc", "vae_mid_infer", "head_infer", "unpack_nodes", "unpack_edges", "onehot_tokens", "egnn_node_post_fwd", "egnn_node_post_bwd", "egnn_node_post_bwd_tc", "egnn_node_pre_bwd_tc", "egnn_edge_bwd", "egnn_edge_bwd_tc",
        "egnn_node_pre_bwd", "reduce_partials", "attn_pool_fwd", "attn_pool_infer", "attn_pool_infer_tc", "attn_pool_bwd", "attn_pool_bwd_tc", "fusion_attn_fwd",
        "fusion_attn_bwd", "loss_fwd", "loss_bwd", "segment_pool_fwd", "segment_pool_bwd", "contrastive_scratch_floats",
-       "contrastive_fwd", "contrastive_bwd", "fused_adam", "rotate_coords", "mask_single_residue", "mask_rows"]
+       "contrastive_fwd", "contrastive_bwd", "fused_adam", "rotate_coords", "mask_single_residue", "mask_rows", "split_planes", "gemm_planes"]

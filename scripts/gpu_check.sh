@@ -3,7 +3,11 @@
 mkdir -p gpurun_out
 rm -f gpurun_out/kernel_errors.txt
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-python -m pytest tests -m gpu -q -p no:cacheprovider --timeout=600 > gpurun_out/pytest_gpu.log 2>&1
+# new kernels first, under a short wall-clock limit (a hung kernel must not eat the box)
+timeout 240 python -m pytest tests/test_round2_gpu.py -m gpu -q -x -p no:cacheprovider -k "split_planes or gemm_planes or linear_tc" > gpurun_out/pytest_new.log 2>&1
+echo "pytest-new exit: $?" >> gpurun_out/pytest_new.log
+tail -15 gpurun_out/pytest_new.log
+timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout=600 > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit: $?" >> gpurun_out/pytest_gpu.log
 tail -40 gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit: $?" >> gpurun_out/smoke.log

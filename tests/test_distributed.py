@@ -33,7 +33,7 @@ def _worker(rank, world, port, q):
     out = model[1](model[0](data[lo:hi]))               # model[2] unused -> grad None
     (out.pow(2).sum() / 8).backward()                   # sum over shards == full-batch mean * ... below
     red.step()
-    q.put((rank, w0, model[0].weight.grad.clone(), model[2].weight.grad is None, red.nbytes))
+    q.put((rank, w0.tolist(), model[0].weight.grad.tolist(), model[2].weight.grad is None, red.nbytes))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -50,6 +50,7 @@ def test_gradient_allreduce_world2_gloo():
         p.join(60)
         assert p.exitcode == 0
     (_, w_a, g_a, none_a, nb), (_, w_b, g_b, none_b, _) = res
+    w_a, g_a, w_b, g_b = (torch.tensor(t) for t in (w_a, g_a, w_b, g_b))
     assert torch.equal(w_a, w_b)                        # broadcast made the replicas identical
     assert torch.equal(g_a, g_b) and none_a and none_b  # averaged grads agree; unused layer untouched
     assert nb == (5 * 4 + 4 + 4 * 3 + 3) * 4

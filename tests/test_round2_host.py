@@ -147,7 +147,8 @@ def _reducer_worker(rank, world, port, q):
             red.zero_grad() if step else None
         (model[2](model[1](model[0](data[lo:hi] + step))).pow(2).sum() / 8).backward()
         red.step()
-        out.append((model[0].weight.grad.clone(), model[2].bias.grad.clone(), red.overlapped_last_step, len(red.buckets)))
+        # plain lists: tensors would travel as file descriptors that die with this process
+        out.append((model[0].weight.grad.tolist(), model[2].bias.grad.tolist(), red.overlapped_last_step, len(red.buckets)))
     q.put((rank, out, model[3].weight.grad is None))
     dist.barrier()
     dist.destroy_process_group()
@@ -172,8 +173,8 @@ def test_bucketed_reducer_overlaps_and_matches_full_batch_world2_gloo():
         (model[2](model[1](model[0](data + step))).pow(2).sum() / 8).backward()
         for r in range(2):
             gw, gb, overlapped, nb = res[r][1][step]
-            assert torch.allclose(gw * 2, model[0].weight.grad, rtol=1e-5, atol=1e-6)
-            assert torch.allclose(gb * 2, model[2].bias.grad, rtol=1e-5, atol=1e-6)
+            assert torch.allclose(torch.tensor(gw) * 2, model[0].weight.grad, rtol=1e-5, atol=1e-6)
+            assert torch.allclose(torch.tensor(gb) * 2, model[2].bias.grad, rtol=1e-5, atol=1e-6)
             assert nb >= 2
             assert overlapped == (0 if step == 0 else nb)       # from step 2 on every bucket is launched from a hook
     assert res[0][2] and res[1][2]                               # unused layer: grad stays None
