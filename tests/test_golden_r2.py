@@ -1,0 +1,144 @@
+"""Round-2 golden vectors (tests/golden/make_golden_r2.py: the UNMODIFIED reference classes run through oracle/shim.py):
+every remaining model class, HybridModelv2 at the production width (5943 -> 512 -> 5943), and a train-mode trace that
+pins the RNG draw order and two optimizer steps.  The same checks run on CPU (host logic over the kernel contracts)
+and, marked ``gpu``, on the B200 through the C ABI."""
+import pytest
+import torch
+
+import immunostruct_b200 as I
+from immunostruct_b200 import _C, trunk
+from oracle import kernel_contracts as KC
+
+from conftest import assert_grads_close, load_golden, rel_err
+from golden_util import flatten_outputs, objective, sample_big, seeded_state_dict
+from helpers import graph_batch, inject_eps, named_grads
+
+SINGLE = ["HybridModel_SSL", "HybridModelv2_SSL", "DualModel", "SequenceModel", "SequenceFpModel", "StructureModel",
+          "StructureModel_SSL"]
+PAIR = ["HybridModel_Comparative", "HybridModel_Comparative_SSL", "HybridModelv2_Comparative_SSL"]
+
+
+@pytest.fixture
+def cpu_backend(monkeypatch):
+    for name in KC.ALL:
+        monkeypatch.setattr(_C, name, getattr(KC, name))
+    monkeypatch.setattr(trunk, "_require_device_batch", lambda g: None)
+    yield
+
+
+def run_class_case(cls, device, tol, grad_tol):
+    gd = load_golden(f"r2_{cls}")
+    seed, pair = int(gd["meta"]["seed"]), bool(int(gd["meta"]["pair"]))
+    model = I.model_map[cls](vae_input_dim=231, device=device, gcn_layers=1, vae_hidden_dim=32)
+    missing = model.load_state_dict(seeded_state_dict(model, seed), strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    model = model.to(device).eval()
+    d = {k: v.to(device) for k, v in gd["dense"].items()}
+    if pair:
+        inject_eps(model, d["eps_c"], d["eps_w"])
+        outs = model.forward_comparative((graph_batch(gd["graph_c"], device), graph_batch(gd["graph_w"], device)),
+                                         (d["seq_c"], d["seq_w"]), (d["prop_c"], d["prop_w"]))
+    else:
+        inject_eps(model, d["eps"])
+        outs = model(graph_batch(gd["graph"], device), d["seq"], d["prop"])
+    flat = flatten_outputs(outs)
+    assert len(flat) == int(gd["meta"]["n_out"])
+    for i, t in enumerate(flat):
+        ref, ref64 = gd["out"][f"o{i}"], gd["out64"][f"o{i}"]
+        assert t.shape == ref.shape, (i, t.shape, ref.shape)
+        assert rel_err(t, ref) < tol, (cls, i, rel_err(t, ref))
+        assert rel_err(t, ref64) < tol, (cls, i, "fp64")
+    objective(flat).backward()
+    assert_grads_close(named_grads(model), gd["grads"], grad_tol, truth=gd["grads64"])
+
+
+@pytest.mark.parametrize("cls", SINGLE + PAIR)
+def test_class_golden_host_logic(cpu_backend, cls):
+    run_class_case(cls, "cpu", 2e-5, 1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cls", SINGLE + PAIR)
+def test_class_golden_gpu(cls):
+    run_class_case(cls, "cuda", 1e-5, 1e-5)
+
+
+def _split_sample(product_tensor, stored):
+    """(norm, strided sample) of a product tensor next to the stored [norm, sample...] (or the tensors unchanged)."""
+    if product_tensor.numel() <= 4096:
+        return None, product_tensor, None, stored
+    s = sample_big(product_tensor.detach().cpu())
+    return s[0], s[1:], stored[0], stored[1:]
+
+
+def run_big_case(device, tol):
+    gd = load_golden("r2_big_hybrid_v2")
+    seed = int(gd["meta"]["seed"])
+    model = I.model_map["HybridModelv2"](vae_input_dim=5943, device=device, gcn_layers=2)
+    model.load_state_dict(seeded_state_dict(model, seed))
+    model = model.to(device).eval()
+    d, o = gd["dense"], gd["out"]
+    seq = torch.nn.functional.one_hot(d["seq_tokens"].long(), 21).float().to(device)
+    inject_eps(model, d["eps"].to(device))
+    recon, mu, logvar, out = model(graph_batch(gd["graph"], device), seq, d["prop"].to(device))
+    assert rel_err(out, o["logits"]) < tol and rel_err(out, o["logits64"]) < tol
+    assert rel_err(mu, o["mu"]) < tol and rel_err(logvar, o["logvar"]) < tol
+    n_r, s_r, n_ref, s_ref = _split_sample(recon, o["recon_sample"])
+    assert rel_err(s_r, s_ref) < tol and abs(float(n_r) - float(n_ref)) < tol * float(n_ref)
+    loss = I.Losses(5943, [float(gd["meta"]["pos_weight"]), 1.0], sequence=True).BCE_loss(
+        recon, seq, mu, logvar, out, d["target"].to(device))
+    assert rel_err(loss, o["loss"]) < tol and rel_err(loss, o["loss64"]) < tol
+    loss.backward()
+    got, ref, truth = {}, {}, {}
+    for k, p in model.named_parameters():
+        r, t = gd["grads"][k], gd["grads64"][k]
+        if r is None or p.grad is None:
+            got[k], ref[k], truth[k] = p.grad, r, t
+            continue
+        n_g, s_g, n_ref, s_ref = _split_sample(p.grad, r)
+        got[k], ref[k] = s_g, s_ref
+        truth[k] = t[1:] if n_g is not None else t
+        if n_g is not None:                      # the two 3 M-element matrices: norm as well as the strided sample
+            assert abs(float(n_g) - float(t[0])) < max(tol * float(t[0]), 3 * abs(float(n_ref) - float(t[0]))), k
+    assert_grads_close(got, ref, tol, truth=truth)
+    assert model.vae_fc1.weight.grad.shape == (512, 5943) and model.vae_fc4.weight.grad.shape == (5943, 512)
+
+
+def test_production_width_golden_host_logic(cpu_backend):
+    run_big_case("cpu", 2e-5)
+
+
+@pytest.mark.gpu
+def test_production_width_golden_gpu():
+    run_big_case("cuda", 1e-5)
+
+
+def test_train_mode_trace_matches_reference(cpu_backend):
+    """Dropout live, reparameterisation sampled: identical losses over two Adam steps and an identical generator state
+    afterwards <=> the product consumes torch's RNG exactly like the reference."""
+    gd = load_golden("r2_train_mode")
+    seed = int(gd["meta"]["seed"])
+    model = I.model_map["HybridModelv2"](vae_input_dim=231, device="cpu", gcn_layers=1, vae_hidden_dim=32).train()
+    model.load_state_dict(seeded_state_dict(model, seed))
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-6)
+    losses = I.Losses(231, [2.0, 1.0], sequence=True)
+    d, o = gd["dense"], gd["out"]
+    g = graph_batch(gd["graph"])
+    torch.manual_seed(seed)
+    for step in range(2):
+        opt.zero_grad()
+        recon, mu, logvar, out = model(g, d["seq"], d["prop"])
+        loss = losses.BCE_loss(recon, d["seq"], mu, logvar, out, d["target"])
+        loss.backward()
+        opt.step()
+        assert rel_err(loss, o[f"loss{step}"]) < 2e-5, step
+        assert rel_err(out, o[f"logits{step}"]) < 2e-5 and rel_err(mu, o[f"mu{step}"]) < 2e-5, step
+    assert torch.equal(torch.rand(4), o["rng_after"])
+    for k, v in model.state_dict().items():
+        ref = gd["final"][k]
+        # Adam normalises: a parameter whose gradient is pure rounding noise (the key bias under softmax shift
+        # invariance) moves by lr per step in a noise-determined direction: at most 2 steps x 2 lr apart
+        assert float((v - ref).abs().max()) <= 4.5e-3 * max(float(ref.abs().max()), 1.0), k
+    big = [k for k in gd["final"] if k.endswith("vae_fc1.weight") or k.endswith("classifier.1.weight")]
+    for k in big:
+        assert rel_err(model.state_dict()[k], gd["final"][k]) < 1e-3, k

@@ -369,7 +369,12 @@ def test_linear_tc_autograd_matches_fp64(b, k, n, relu):
     y.backward(gy.to(DEV))
     x64, w64, b64 = (t.double().requires_grad_(True) for t in (x, w, bias))
     y64 = torch.nn.functional.linear(x64, w64, b64)
-    y64 = torch.relu(y64) if relu else y64
+    if relu:
+        # the product's own activation pattern: among 3 M outputs a few dozen lie within rounding of zero, and a flipped
+        # ReLU there changes whole gradient rows (a discontinuity of the function, not an error of the kernel)
+        mask = (y.detach().cpu() > 0).double()
+        assert float(((y64 > 0).double() - mask).abs().mean()) < 1e-4
+        y64 = y64 * mask
     y64.backward(gy.double())
     close(y, y64, 1e-5, "linear_tc y")
     close(xd.grad, x64.grad, 1e-5, "linear_tc gx")
