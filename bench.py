@@ -45,14 +45,21 @@ FLOP_PER_EDGE_EDGE_KERNEL = 2 * 64 * 64 * 2 + 2 * 64      # two 64x64 per-edge G
 BYTES_PER_NODE_EDGE_KERNEL = 512 + 12 + 4 + 256 + 12       # read PQ row, x, indptr ; write hn row, x'
 BYTES_PER_EDGE_EDGE_KERNEL = 3 * 4 + 4                     # read csr_src/dst/eid + edge_attr
 GATHER_BYTES_PER_EDGE = 2 * 256                            # P[src] + Q[dst] rows (served by L2)
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures
-# (profiles/r01_ws_*_edge_fwd_full.md, profiles/r01_simt_edge_fwd_full.md), batch 512
-# pipe utilisation of the same launch from the committed ncu --set full captures (profiles/r01_ws_*_edge_fwd_full.md):
-# issue slots / MUFU (xu) pipe / tensor pipe busy, executed warp instructions
-NCU_PIPES = {"bf16x3": {"issue_active_pct": 47.1, "mufu_pipe_pct": 45.8, "tensor_pipe_pct": 33.7, "warp_instructions": 110.5e6},
-             "bf16": {"issue_active_pct": 42.0, "mufu_pipe_pct": 32.0, "tensor_pipe_pct": 10.4, "warp_instructions": 70.8e6}}
-NCU_TRAFFIC_BYTES = {"bf16x3": 82.50e6 + 9.23e6, "bf16": 83.34e6 + 9.10e6,        # profiles/r01_ws_*_edge_fwd_full.md
-                     "tf32x3": 82.36e6 + 10.82e6, "fp32": 80.64e6 + 8.85e6}
+# ncu counters of the dominant kernel (DRAM bytes per launch, pipe utilisation) are read from a committed capture
+# summary, profiles/ncu_edge_fwd.json (written by scripts/ncu_to_json.py from an `ncu --set full` report; it records
+# the commit and date of the capture) -- never hard-coded here.
+def ncu_record(precision):
+    path = os.path.join(ROOT, "profiles", "ncu_edge_fwd.json")
+    if not os.path.exists(path):
+        return None
+    rec = json.load(open(path))
+    k = rec.get("kernels", {}).get(precision)
+    if k is None:
+        return None
+    return dict(k, source={"file": "profiles/ncu_edge_fwd.json", "commit": rec.get("commit"), "captured": rec.get("captured"),
+                           "batch": rec.get("batch")})
+
+
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12          # 74.4
 
 
@@ -146,32 +153,97 @@ def oracle_inference(params, arr, dense, eps):
         return torch.sigmoid(out[3]).squeeze()
 
 
+def oracle_train_step(params, arr, dense, eps, pos_weight=4.25):
+    """fwd + bwd of the CPU oracle: HybridModelv2, BCE_loss(sequence=True) (BASELINE configs[0])."""
+    from immunostruct_b200.synthetic import split_graphs
+    from oracle import reference_ops as R
+    for p in params.values():
+        p.grad = None
+    g = R.dgl_batch(split_graphs(arr))
+    recon, mu, logvar, out = R.hybrid_forward(params, g, dense["seq"], dense["prop"], eps)
+    loss = R.bce_loss(recon, dense["seq"], mu, logvar, out, dense["target"], pos_weight)
+    loss.backward()
+    return loss
+
+
+class ReferenceCPU:
+    """The reference's CPU implementation of the path: its own model code (through oracle/shim.py) when a reference
+    tree is present (/root/reference, or baseline/_ref written by oracle/install_ref.py), else the oracle port."""
+
+    def __init__(self):
+        from oracle import shim
+        import immunostruct_b200 as I
+        torch.manual_seed(1)
+        state = I.model_map["HybridModelv2"](vae_input_dim=VAE_IN, device="cpu").state_dict()
+        self.kind, self.shim = "port", shim
+        if shim.reference_available():
+            try:
+                model_map, self.Losses, _ = shim.load_reference()
+                self.model = model_map["HybridModelv2"](vae_input_dim=VAE_IN, device="cpu")
+                self.model.load_state_dict(state)
+                self.kind = "reference"
+            except Exception as exc:                     # fall back to the port, say why
+                print("reference tree present but not loadable:", repr(exc), file=sys.stderr)
+        self.params = {k: v.detach().clone() for k, v in state.items()}
+
+    def graph(self, arr):
+        from immunostruct_b200.synthetic import split_graphs
+        from oracle import reference_ops as R
+        return self.shim.graph_from_dict(R.dgl_batch(split_graphs(arr)))
+
+    def infer(self, arr, dense, eps):
+        if self.kind == "port":
+            return oracle_inference(self.params, arr, dense, eps)
+        self.model.eval()
+        with torch.no_grad():                            # procedures/infer.py:14-22
+            out = self.model(self.graph(arr), dense["seq"], dense["prop"])[3]
+            return torch.sigmoid(out).squeeze()
+
+    def train_step(self, arr, dense, eps):
+        if self.kind == "port":
+            params = {k: v.requires_grad_(True) for k, v in self.params.items()}
+            return oracle_train_step(params, arr, dense, eps)
+        self.model.train()                               # procedures/train.py:23-27 (no optimizer step: fwd + bwd)
+        self.model.zero_grad()
+        recon, mu, logvar, out = self.model(self.graph(arr), dense["seq"], dense["prop"])
+        loss = self.Losses(VAE_IN, [4.25, 1.0], sequence=True).BCE_loss(recon, dense["seq"], mu, logvar, out, dense["target"])
+        loss.backward()
+        return loss
+
+    def describe(self):
+        return ("the reference's own models/hybrid_models.py HybridModelv2 through oracle/shim.py (stand-ins for dgl / "
+                "torch_geometric only)" if self.kind == "reference" else "oracle/reference_ops.py hybrid_forward (port)")
+
+
+WORKLOAD = ("IEDB HybridModelv2 inference, batch 512 per GPU, 200-node 10-NN graphs, 283x21 sequence, fp32 "
+            "(BASELINE configs[1])")
+
+
 def cpu_reference_arm(args):
-    """The reference's CPU implementation of the path (oracle port), all host threads."""
-    import immunostruct_b200 as I
+    """The reference's CPU implementation of the path, all host threads, SAME workload: every step is one 512-graph
+    batch (about 1.5 s on 16 cores, so the default K = 20, W = 3 run ends in well under a minute)."""
     torch.set_num_threads(os.cpu_count() or 1)
-    sample = 64
-    pool = make_pool(sample, 2, seed=1, device="cpu")
-    torch.manual_seed(1)
-    params = {k: v.detach() for k, v in I.model_map["HybridModelv2"](vae_input_dim=VAE_IN, device="cpu").state_dict().items()}
-    eps = torch.randn(sample, 32)
+    ref = ReferenceCPU()
+    B = args.batch
+    pool = make_pool(B, 2, seed=1, device="cpu")
+    eps = torch.randn(B, 32)
     for i in range(args.warmup):
-        oracle_inference(params, *pool[i % 2], eps)
+        ref.infer(*pool[i % 2], eps)
     t0 = time.perf_counter()
     for i in range(args.steps):
-        oracle_inference(params, *pool[i % 2], eps)
+        ref.infer(*pool[i % 2], eps)
     dt = time.perf_counter() - t0
-    v = sample * args.steps / dt
+    v = B * args.steps / dt
     cores = torch.get_num_threads()
     print(json.dumps({
         "impl": "reference", "metric": "pMHC graphs/sec (HybridModelv2 inference, fp32)", "value": v,
         "unit": "graphs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "IEDB HybridModelv2 inference, batch 512 per GPU, 200-node 10-NN graphs, fp32",
-                   "step_sample": f"{sample} graphs per step (bounded sample of the 512-graph batch)"},
-        "cpu_baseline": {"value": v, "unit": "graphs/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} x {sample}-graph batches, oracle/reference_ops.py hybrid_forward, torch CPU"},
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "nodes_per_graph": N_NODES, "edges_per_graph": N_NODES * KNN,
+                   "parallelism": "cpu"},
+        "cpu_baseline": {"value": v, "unit": "graphs/s", "cores": cores, "kind": ref.kind,
+                         "sample": f"{args.steps} x {B}-graph batches, {ref.describe()}, torch CPU fp32"},
         "e2e": {"value": v, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -246,6 +318,28 @@ def main():
         ms = max_over_ranks(e0.elapsed_time(e1))
     launches = _C.LAUNCHES - launches0
     value = world * B * K / (ms / 1e3)
+
+    # ---- BASELINE configs[1], literally: a scan of 27 000 graphs = 52 full batches of 512 + one of 376 (the last,
+    # partial batch of the reference's no-drop_last loader, procedures/infer.py:14-31); per rank at N > 1 ------------
+    scan = None
+    if B == BATCH:
+        n_scan, tail = 27000, 27000 % BATCH
+        tail_arr = {k: (v[:tail * N_NODES] if k in ("x",) else v[:tail * N_NODES * KNN] if k in ("src", "dst", "edge_attr")
+                        else v[:tail]) for k, v in pool[1][0].items()}
+        tail_dense = {k: v[:tail] for k, v in pool[1][1].items()}
+        with torch.no_grad():
+            infer_step(tail_arr, tail_dense)                     # warm the 376-graph shapes
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(n_scan // BATCH):
+                infer_step(*pool[i % POOL])
+            p_tail = infer_step(tail_arr, tail_dense)
+            e1.record()
+            barrier()
+            ms_scan = max_over_ranks(e0.elapsed_time(e1))
+        scan = {"graphs": n_scan, "batches": n_scan // BATCH + 1, "tail_batch": tail, "ms": ms_scan,
+                "value": world * n_scan / (ms_scan / 1e3), "unit": "graphs/s", "tail_outputs": int(p_tail.numel())}
 
     # ---- end to end from pinned host buffers through the public API -----------------------------
     host = []
@@ -323,38 +417,69 @@ def main():
     I.set_precision(args.precision)
 
     # ---- training step: fwd + bwd + Adam (+ NCCL gradient all-reduce) ---------------------------
+    # Optimiser: immunostruct_b200.FusedAdam (one kernel over the flat parameter buffer, csrc/optim.cu); gradients
+    # live in one flat buffer that distributed.BucketedGradientReducer all-reduces bucket by bucket DURING backward.
     train = None
     if not args.no_train:
-        model.train()
-        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
         losses = I.Losses(VAE_IN, [0.81, 0.19], sequence=True)
-        reducer = GradientAllReducer(model.parameters())
         kt = max(5, min(K, 20))
         wt = max(W, 5)                 # the training path touches far more kernels / allocator blocks than inference
 
-        def train_step(arr, dense):
-            gb = GraphBatch.from_arrays(*(arr[k] for k in keys), max_nodes=N_NODES)
-            opt.zero_grad(set_to_none=True)
-            recon, mu, logvar, out = model(gb, dense["seq"], dense["prop"])
-            loss = losses.BCE_loss(recon, dense["seq"], mu, logvar, out, dense["target"])
-            loss.backward()
-            reducer.step()
-            opt.step()
-            return loss
+        def run_training(tmodel, opt, reducer, tpool, batch, steps, warm):
+            tmodel.train()
 
-        for i in range(wt):
-            train_step(*pool[i % POOL])
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(kt):
-            loss = train_step(*pool[i % POOL])
-        e1.record()
-        barrier()
-        ms_t = max_over_ranks(e0.elapsed_time(e1))
-        train = {"value": world * B * kt / (ms_t / 1e3), "unit": "graphs/s", "steps": kt, "warmup": wt, "ms_per_step": ms_t / kt,
-                 "global_batch": world * B, "optimizer": "Adam", "loss": "BCE_loss(sequence=True)",
-                 "final_loss": float(loss.detach()), "allreduce_bytes": reducer.nbytes}
+            def train_step(arr, dense):
+                gb = GraphBatch.from_arrays(*(arr[k] for k in keys), max_nodes=N_NODES)
+                opt.zero_grad()
+                recon, mu, logvar, out = tmodel(gb, dense["seq"], dense["prop"])
+                loss = losses.BCE_loss(recon, dense["seq"], mu, logvar, out, dense["target"])
+                loss.backward()
+                reducer.step()
+                opt.step()
+                return loss
+
+            for i in range(warm):
+                train_step(*tpool[i % len(tpool)])
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(steps):
+                loss = train_step(*tpool[i % len(tpool)])
+            e1.record()
+            barrier()
+            ms_t = max_over_ranks(e0.elapsed_time(e1))
+            tmodel.eval()
+            return {"value": world * batch * steps / (ms_t / 1e3), "unit": "graphs/s", "steps": steps, "warmup": warm,
+                    "ms_per_step": ms_t / steps, "global_batch": world * batch, "loss": "BCE_loss(sequence=True)",
+                    "final_loss": float(loss.detach()), "allreduce_bytes": reducer.nbytes,
+                    "allreduce_buckets": len(reducer.buckets), "buckets_overlapped_with_backward": reducer.overlapped_last_step}
+
+        import copy
+        state0 = copy.deepcopy(model.state_dict())
+        opt = I.FusedAdam(model.parameters(), lr=1e-3)
+        train = run_training(model, opt, GradientAllReducer(model.parameters()), pool, B, kt, wt)
+        train["optimizer"] = "immunostruct_b200.FusedAdam (one launch, flat buffers)"
+        # the same step with torch.optim.Adam (the optimiser the reference constructs, train_IEDB_wFT.py:74), N = 1 only
+        if world == 1:
+            tm = I.model_map["HybridModelv2"](vae_input_dim=VAE_IN, device=dev).to(dev)
+            tm.load_state_dict(state0)
+            t_adam = run_training(tm, torch.optim.Adam(tm.parameters(), lr=1e-3), GradientAllReducer(tm.parameters()), pool, B,
+                                  max(5, kt // 2), wt)
+            train["torch_adam"] = {k: t_adam[k] for k in ("value", "unit", "ms_per_step", "final_loss")}
+            del tm
+        # BASELINE configs[3]: FIXED global batch of 4 096 graphs (strong scaling): 4096 / N graphs per GPU
+        gb_fixed = 4096
+        if gb_fixed % world == 0:
+            per = gb_fixed // world
+            fpool = pool if per == B else make_pool(per, 2, seed=77 + 1000 * rank, device=dev)
+            fm = I.model_map["HybridModelv2"](vae_input_dim=VAE_IN, device=dev).to(dev)
+            fm.load_state_dict(state0)
+            fixed = run_training(fm, I.FusedAdam(fm.parameters(), lr=1e-3), GradientAllReducer(fm.parameters()), fpool, per,
+                                 5, 3)
+            fixed.update({"scaling": "strong", "batch_per_gpu": per, "optimizer": "immunostruct_b200.FusedAdam"})
+            train["fixed_global_batch_4096"] = fixed
+            del fm, fpool
+        model.load_state_dict(state0)
         model.eval()
 
     # ---- BASELINE configs[2]: cancer fine-tune step (train_Cancer_wFT.py / procedures/train.py:84-123) ---------
@@ -365,7 +490,7 @@ def main():
         P = B // 2
         torch.manual_seed(1)
         cmodel = I.model_map["HybridModelv2_Comparative"](vae_input_dim=VAE_IN, device=dev, use_wt_for_downstream=True).to(dev).train()
-        copt = torch.optim.AdamW(cmodel.parameters(), lr=1e-4, weight_decay=1e-6)
+        copt = I.FusedAdamW(cmodel.parameters(), lr=1e-4, weight_decay=1e-6)
         closs = I.Losses(VAE_IN, [0.81, 0.19], sequence=True)
         pcl = I.PairedContrastiveLoss(embedding_dim=104, device=dev)
         cpool = make_pool(P, 4, seed=4001, device=dev)
@@ -379,7 +504,7 @@ def main():
             lc = closs.BCE_loss(recons[0], dc["seq"], mus[0], lvs[0], out, y)
             lw = closs.BCE_loss(recons[1], dw["seq"], mus[1], lvs[1], out, y)
             loss = (lc + lw) / 2 + 0.01 * pcl(embs[0], embs[1], y)
-            copt.zero_grad(set_to_none=True)
+            copt.zero_grad()
             loss.backward()
             copt.step()
             return loss
@@ -396,7 +521,7 @@ def main():
         barrier()
         ms_c = e0.elapsed_time(e1)
         train_cmp = {"value": P * kc / (ms_c / 1e3), "unit": "pairs/s", "graphs_per_s": 2 * P * kc / (ms_c / 1e3), "steps": kc,
-                     "ms_per_step": ms_c / kc, "pairs_per_step": P, "model": "HybridModelv2_Comparative", "optimizer": "AdamW",
+                     "ms_per_step": ms_c / kc, "pairs_per_step": P, "model": "HybridModelv2_Comparative", "optimizer": "immunostruct_b200.FusedAdamW",
                      "loss": "BCE_loss(sequence=True) on both members + 0.01 * PairedContrastiveLoss", "final_loss": float(loss.detach())}
         del cmodel, copt, cpool
 
@@ -438,6 +563,7 @@ def main():
             "bf16_gen1": lambda: _C.egnn_edge_fwd_tc(gb, PQ, x, arr["edge_attr"], 64, W1, W2, b2, W3, b3, w4, True, _C.PREC_BF16 | 16, hn, xo),
         }
         t_all = {k: time_kernel(fn) for k, fn in variants.items()}
+        ncu = ncu_record(args.precision)
         t_k = t_all[args.precision]
         flops = e * FLOP_PER_EDGE_EDGE_KERNEL
         nbytes = e * BYTES_PER_EDGE_EDGE_KERNEL + n * BYTES_PER_NODE_EDGE_KERNEL
@@ -451,13 +577,13 @@ def main():
         # 91 us of MUFU pipe per launch) and ~100 issued warp-instructions -- see `simt` below and
         # profiles/r01_ws_*_edge_fwd_full.md (issue slots 47 %, MUFU 45 %, tensor pipe 33 %, DRAM 3 %).
         roofline = {"kernel": kname, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": gbs / hbm_peak, "traffic": NCU_TRAFFIC_BYTES.get(args.precision) if B == BATCH else None,
+                    "frac": gbs / hbm_peak, "traffic": (ncu or {}).get("dram_bytes") if B == BATCH else None,
                     "peak_source": src, "launch_ms": t_k * 1e3, "edges_per_launch": e,
                     "algorithmic_bytes_per_launch": nbytes, "algorithmic_flops_per_launch": flops,
                     "tensor": {"achieved": flops / t_k / 1e12, "peak": tensor_peak, "unit": "TFLOP/s",
                                "frac": flops / t_k / 1e12 / tensor_peak},
                     "l2_gather_gbs": e * GATHER_BYTES_PER_EDGE / t_k / 1e9,
-                    "ncu": NCU_PIPES.get(args.precision),
+                    "ncu": ncu,
                     "simt": {"mufu_floor_ms": e * 192 * (1 if args.precision == "bf16" else 2) / (148 * 16 * 1.965e9) * 1e3,
                              "note": "192 SiLU per edge, 1 (bf16: tanh.approx) or 2 (ex2 + rcp) MUFU ops each, 16 MUFU lanes / clk / SM"},
                     "roofline_time_ms": {"hbm": nbytes / hbm_peak / 1e6, "tensor": flops / tensor_peak / 1e9},
@@ -467,24 +593,35 @@ def main():
                             "x'); FLOPs = two 64x64 per-edge GEMMs + w4 dot (split-precision extra MMAs not counted); "
                             "traffic = ncu dram bytes of the same launch"}
 
-    # ---- CPU baseline (oracle port) on this box's host cores, rank 0 at N=1 only ------------------
+    # ---- CPU baseline on this box's host cores, rank 0 at N=1 only: the reference's CPU path (its own model code when
+    # baseline/_ref is present, else the oracle port), inference and -- BASELINE configs[0] -- fwd + bwd at batch 64 ---
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
+        ref = ReferenceCPU()
         sample = 64
         cpool = make_pool(sample, 1, seed=1, device="cpu")
-        params = {k: v.detach().cpu() for k, v in model.state_dict().items()}
         eps = torch.randn(sample, 32)
-        oracle_inference(params, *cpool[0], eps)
+        ref.infer(*cpool[0], eps)
         t0 = time.perf_counter()
         reps = 0
-        while reps < 3 or time.perf_counter() - t0 < 10.0:
-            ref_probs = oracle_inference(params, *cpool[0], eps)
+        while reps < 3 or time.perf_counter() - t0 < 8.0:
+            ref.infer(*cpool[0], eps)
             reps += 1
         dt = time.perf_counter() - t0
+        ref.train_step(*cpool[0], eps)
+        t1 = time.perf_counter()
+        reps_t = 0
+        while reps_t < 2 or time.perf_counter() - t1 < 10.0:
+            ref.train_step(*cpool[0], eps)
+            reps_t += 1
+        dt_t = time.perf_counter() - t1
         cpu_baseline = {"value": sample * reps / dt, "unit": "graphs/s", "cores": torch.get_num_threads(),
-                        "kind": "port", "sample": f"{reps} x {sample}-graph batches (same graph shape), "
-                                                  "oracle/reference_ops.py hybrid_forward, torch CPU fp32"}
+                        "kind": ref.kind, "sample": f"{reps} x {sample}-graph batches (same graph shape), {ref.describe()}, "
+                                                  "torch CPU fp32",
+                        "train": {"value": sample * reps_t / dt_t, "unit": "graphs/s", "ms_per_step": dt_t / reps_t * 1e3,
+                                  "sample": f"{reps_t} x fwd + bwd of a {sample}-graph batch, BCE_loss(sequence=True) "
+                                            "(BASELINE configs[0]), no optimizer step"}}
 
     # (last: a failed capture may leave the process RNG / allocator in capture mode)
     # ---- the same step captured once in a CUDA graph and replayed: fixed shapes, no host
@@ -546,8 +683,7 @@ def main():
             "precision": args.precision, "other_precisions": other,
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": "IEDB HybridModelv2 inference, batch 512 per GPU, 200-node 10-NN graphs, "
-                                   "283x21 sequence, fp32 (BASELINE configs[1])",
+            "config": {"workload": WORKLOAD,
                        "batch_per_gpu": B, "nodes_per_graph": N_NODES, "edges_per_graph": N_NODES * KNN,
                        "parallelism": f"dp{world}", "l2": f"{POOL} resident input batches (~42 MB each) cycled: inputs > L2"},
             "clocks": clk.summary(),
@@ -556,7 +692,10 @@ def main():
                     "compact_input": {"value": world * B * K / (ms_e2e_packed / 1e3), "unit": "graphs/s",
                                       "ms_per_step": ms_e2e_packed / K, "h2d_bytes_per_step": h2d_packed,
                                       "note": "same call path fed from immunostruct_b200.PackedGraphBatch / PackedSequence"}},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "scan_27000": scan,
+            "train_graphs_per_s": None if train is None else train["value"],
+            "train_fixed4096_graphs_per_s": None if train is None or "fixed_global_batch_4096" not in train
+            else train["fixed_global_batch_4096"]["value"],
             "train": train, "train_comparative": train_cmp, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }))
     if world > 1:

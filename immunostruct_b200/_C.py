@@ -56,9 +56,19 @@ def _check(rc: int, name: str):
         raise RuntimeError(f"{name} failed: {kind}")
 
 
+_dev_seen = None        # device index of the tensors of the call being assembled (checked in _call)
+
+
 def _t(t, dtype, name, contiguous=True):
+    global _dev_seen
     if t is None:
         return None
+    if t.is_cuda:
+        if _dev_seen is None:
+            _dev_seen = t.device.index
+        elif _dev_seen != t.device.index:
+            raise RuntimeError(f"{name}: tensors of one kernel call live on different devices "
+                               f"(cuda:{_dev_seen} and cuda:{t.device.index})")
     if not t.is_cuda:
         raise RuntimeError(f"{name}: expected a CUDA tensor (immunostruct_b200 has no CPU path), got {t.device}")
     if t.dtype != dtype:
@@ -70,8 +80,13 @@ def _t(t, dtype, name, contiguous=True):
 
 def _rows(t, name):
     """[n, k] fp32 view whose rows are contiguous (inner stride 1); returns (ptr, leading dim)."""
+    global _dev_seen
     if not t.is_cuda or t.dtype != torch.float32 or t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
         raise ValueError(f"{name}: expected a CUDA fp32 [n,k] tensor with unit inner stride")
+    if _dev_seen is None:
+        _dev_seen = t.device.index
+    elif _dev_seen != t.device.index:
+        raise RuntimeError(f"{name}: tensors of one kernel call live on different devices")
     return _vp(t.data_ptr()), _i64(t.stride(0))
 
 
@@ -85,10 +100,19 @@ _KERNELS_PER_CALL = {"is_collate_csr": 2, "is_loss_fwd": 2, "is_loss_bwd": 2, "i
 
 
 def _call(name, *args):
-    global LAUNCHES
+    """Enqueue one C-ABI launcher.  The tensors seen while the arguments were assembled must share one device; if that
+    device is not the current one (model on cuda:1 without set_device) the call runs under a device guard, because the
+    launchers use the current device and the stream handed over must belong to it."""
+    global LAUNCHES, _dev_seen
+    dev, _dev_seen = _dev_seen, None
     fn = getattr(lib(), name)
     fn.restype = ctypes.c_int
-    _check(fn(*args), name)
+    if dev is not None and dev != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            args = args[:-1] + (_stream(),)          # the stream argument is always last: re-take it on that device
+            _check(fn(*args), name)
+    else:
+        _check(fn(*args), name)
     LAUNCHES += _KERNELS_PER_CALL.get(name, 1)
 
 

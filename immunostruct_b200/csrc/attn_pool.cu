@@ -103,7 +103,8 @@ attn_fwd_kernel(const float* __restrict__ QKV, const int64_t* __restrict__ node_
     extern __shared__ __align__(16) float smem[];
     const int g = blockIdx.x;
     const int64_t n0 = node_off[g];
-    const int n = (int)(node_off[g + 1] - n0);
+    // clamped: an understated max_nodes (caught by GraphBatch validation) must not become a shared-memory overrun
+    const int n = min((int)(node_off[g + 1] - n0), IS_ATT_NMAX);
     float* Ks = smem;                               // [NMAX][68]
     float* Vs = Ks + IS_ATT_NMAX * IS_ATT_LD4;      // [NMAX][68]
     float* qs = Vs + IS_ATT_NMAX * IS_ATT_LD4;      // [8 warps][4][64]
@@ -196,7 +197,8 @@ attn_bwd_kernel(const float* __restrict__ QKV, const float* __restrict__ O /* or
     extern __shared__ __align__(16) float smem[];
     const int g = blockIdx.x;
     const int64_t n0 = node_off[g];
-    const int n = (int)(node_off[g + 1] - n0);
+    // clamped: an understated max_nodes (caught by GraphBatch validation) must not become a shared-memory overrun
+    const int n = min((int)(node_off[g + 1] - n0), IS_ATT_NMAX);
     float* S0 = smem;                               // pass A: K   ; pass B: Q      [NMAX][68]
     float* S1 = S0 + IS_ATT_NMAX * IS_ATT_LD4;      // pass A: V   ; pass B: gO     [NMAX][68]
     float* ra = S1 + IS_ATT_NMAX * IS_ATT_LD4;      // [8][4][64] pass A: q rows  ; pass B: k rows
@@ -391,7 +393,8 @@ attn_pool_infer_kernel(const float* __restrict__ QKV, const int64_t* __restrict_
     extern __shared__ __align__(16) float smem[];
     const int g = blockIdx.x;
     const int64_t n0 = node_off[g];
-    const int n = (int)(node_off[g + 1] - n0);
+    // clamped: an understated max_nodes (caught by GraphBatch validation) must not become a shared-memory overrun
+    const int n = min((int)(node_off[g + 1] - n0), IS_ATT_NMAX);
     float* Ks = smem;                               // [NMAX][68]
     float* qs = Ks + IS_ATT_NMAX * IS_ATT_LD4;      // [8 warps][4][64]
     float* part = qs + 8 * 4 * 64;                  // [8 warps][NMAX] column-sum partials

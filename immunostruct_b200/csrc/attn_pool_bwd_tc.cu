@@ -98,7 +98,7 @@ attn_pool_bwd_tc_kernel(const float* __restrict__ QKV, const int64_t* __restrict
 
     for (int g = blockIdx.x; g < n_graphs; g += gridDim.x) {
         const int64_t n0 = __ldg(node_off + g);
-        const int n = (int)(__ldg(node_off + g + 1) - n0);
+        const int n = min((int)(__ldg(node_off + g + 1) - n0), NPAD);      // clamped: see GraphBatch validation
         if (n <= 0) continue;
         if (tid < 64) g0_s[tid] = __ldg(g_pooled + (int64_t)g * 64 + tid) / (float)n;
         // ---- stage Q (scaled) and K rows; rows >= n are zero ---------------------------------------------------------
@@ -291,8 +291,7 @@ static int launch_attn_bwd_tc(const float* QKV, const int64_t* node_off, int n_g
     const size_t smem = 6 * (size_t)(NPAD / 8) * SBO + 3 * (size_t)G_BYTES + sizeof(float) * (4 * NPAD + 256 + 64);
     cudaError_t e = cudaFuncSetAttribute(attn_pool_bwd_tc_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int sms = current_num_sms();
     const int grid = n_graphs < sms ? n_graphs : sms;
     attn_pool_bwd_tc_kernel<NPAD><<<grid, NT, smem, st>>>(QKV, node_off, n_graphs, g_pooled, gQKV);
     e = cudaGetLastError();

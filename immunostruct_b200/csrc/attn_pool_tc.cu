@@ -85,7 +85,7 @@ attn_pool_tc_kernel(const float* __restrict__ QKV, const int64_t* __restrict__ n
 
     for (int g = blockIdx.x; g < n_graphs; g += gridDim.x) {
         const int64_t n0 = __ldg(node_off + g);
-        const int n = (int)(__ldg(node_off + g + 1) - n0);
+        const int n = min((int)(__ldg(node_off + g + 1) - n0), NPAD);      // clamped: see GraphBatch validation
         // ---- stage Q (scaled) and K rows; rows >= n are zero (zero scores, masked below) ----------------------
         for (int grp = warp; grp < NPAD / 8; grp += NT / 32) {
             float qv[2][8], kv[2][8];
@@ -208,8 +208,7 @@ static int launch_attn_tc(const float* QKV, const int64_t* node_off, int n_graph
     const size_t smem = (size_t)(NPAD / 128) * NS * QT_BYTES + (size_t)NS * (NPAD / 8) * SBO + sizeof(float) * (8 * NPAD + NPAD + 256);
     cudaError_t e = cudaFuncSetAttribute(attn_pool_tc_kernel<PREC, NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int sms = current_num_sms();
     const int grid = n_graphs < sms ? n_graphs : sms;
     attn_pool_tc_kernel<PREC, NPAD><<<grid, NT, smem, st>>>(QKV, node_off, n_graphs, pooled);
     e = cudaGetLastError();

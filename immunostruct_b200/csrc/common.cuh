@@ -31,6 +31,21 @@
 
 namespace is {
 
+// SM count of the CURRENT device (cached per device: the launch grids and the per-CTA partial buffers that the host
+// sizes with is_egnn_*_grid must agree, also when several devices are driven from one process)
+inline int current_num_sms() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (cached[dev] == 0) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cached[dev] = n > 0 ? n : 148;
+    }
+    return cached[dev];
+}
+
 // accurate exp + correctly rounded reciprocal: the fast intrinsics (__expf, __fdividef) cost ~1e-5 of
 // gradient parity against the fp32 reference (measured on the B200: tests/test_models_gpu.py)
 __device__ __forceinline__ float sigmoidf_fast(float z) { return __frcp_rn(1.0f + expf(-z)); }

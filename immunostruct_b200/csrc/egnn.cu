@@ -717,16 +717,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
 // =================================================================================================
 using namespace is;
 
-static int g_num_sms = 0;
-static int num_sms() {
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
-    }
-    return g_num_sms;
-}
+static int num_sms() { return current_num_sms(); }
 
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {

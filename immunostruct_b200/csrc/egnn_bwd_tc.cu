@@ -569,8 +569,7 @@ int is_egnn_edge_bwd_tc(const int* indptr, const int* csr_src, const int* csr_ds
     using C = TcCfg<PREC_BF16X3>;
     const size_t smem = 6 * (size_t)C::A_BYTES + 6 * (size_t)C::W_BYTES +
                         sizeof(float) * (IS_TM * IS_LD + 5 * 64 + 11 * IS_TM + BT_NW * 16) + 2 * sizeof(BwdMeta) + 128;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int sms = current_num_sms();
     int64_t g = (n_nodes + 31) / 32;
     if (g > sms) g = sms;
     const int grid = (int)(g < 1 ? 1 : g);

@@ -590,8 +590,7 @@ int is_egnn_node_post_bwd_tc(const float* gh_out, const float* h, int64_t ldh, i
     const size_t smem = 9 * (size_t)nb::T_BYTES + 9 * (size_t)nb::W_BYTES + sizeof(float) * (64 + 16 * 16);
     cudaError_t e = cudaFuncSetAttribute(node_post_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int sms = current_num_sms();
     const int64_t tiles = (n_nodes + IS_TM - 1) / IS_TM;
     const int grid = (int)(tiles < sms ? tiles : sms);
     node_post_bwd_tc_kernel<<<grid, nb::NT, smem, (cudaStream_t)stream>>>(gh_out, h, ldh, F, hn, W5, b5, W6, gh_direct, ghn, partials, n_nodes);
@@ -609,8 +608,7 @@ int is_egnn_node_pre_bwd_tc(const float* gz1, const float* gQ, const float* gD, 
     const size_t smem = 9 * (size_t)nb::T_BYTES + 6 * (size_t)nb::W_BYTES + (size_t)IS_TM * 64 * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(node_pre_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int sms = current_num_sms();
     const int64_t tiles = (n_nodes + IS_TM - 1) / IS_TM;
     const int grid = (int)(tiles < sms ? tiles : sms);
     node_pre_bwd_tc_kernel<<<grid, nb::NT, smem, (cudaStream_t)stream>>>(gz1, gQ, gD, gxd, gx_out, gh_direct, outptr, csc_pos, h, ldh, F,

@@ -198,8 +198,7 @@ static int launch_node_tc2(const float* h, int64_t ldh, int F, const float* hn, 
     const size_t smem = (size_t)C::NSPLIT * (C::A_BYTES + 6 * C::W_BYTES) + 5 * 64 * sizeof(float) + 128;
     cudaError_t e = cudaFuncSetAttribute(node_post_pre_tc_kernel<PREC, NT, FAST, NEXT_KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int sms = current_num_sms();
     int64_t tiles = (M + IS_TM - 1) / IS_TM;
     int64_t cap = (int64_t)sms * (NT == 256 ? 2 : 1);
     int grid = (int)(tiles < cap ? tiles : cap);

@@ -435,8 +435,7 @@ static int launch_wsk(const EdgeCommon& c, float* hn, float* x_out, int grid, cu
 // entry used by is_egnn_edge_fwd_tc (egnn_tc.cu) for the bf16 / bf16x3 precisions: warp-specialised kernel
 int launch_edge_fwd_ws(const EdgeCommon& c, float* hn, float* x_out, int precision, bool update_coords, bool fast,
                        cudaStream_t st) {
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int sms = current_num_sms();
     int64_t g = ((int64_t)c.n_nodes + 31) / 32;
     if (g > sms) g = sms;
     const int grid = (int)(g < 1 ? 1 : g);

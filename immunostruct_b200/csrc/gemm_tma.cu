@@ -340,9 +340,7 @@ extern "C" {
 
 // number of K slices that fills the GPU for an [M, N, Kp] problem (1 = no workspace needed)
 int is_gemm_tma_split_k(int64_t M, int64_t N, int64_t Kp) {
-    int sms = 148, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = current_num_sms();
     const int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
     const int64_t nkb = (Kp + BK - 1) / BK;
     int64_t s = tiles >= sms ? 1 : sms / tiles;

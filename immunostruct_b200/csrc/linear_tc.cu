@@ -230,8 +230,7 @@ extern "C" {
 
 // number of K slices that fills the GPU for an [M,N,K] problem (1 = no workspace needed)
 int is_linear_tc_split_k(int64_t M, int64_t N, int64_t K) {
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int sms = current_num_sms();
     const int64_t tiles = ((M + lin::BM - 1) / lin::BM) * ((N + lin::BN - 1) / lin::BN);
     const int64_t nkb = (K + lin::BK - 1) / lin::BK;
     int64_t s = tiles >= sms ? 1 : sms / tiles;

@@ -58,10 +58,7 @@ int is_fused_adam(float* p, const float* g, float* m, float* v, int64_t n, float
     if (n == 0) return IS_OK;
     if (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
           reinterpret_cast<uintptr_t>(v)) & 15) != 0) return IS_ERR_ARG;
-    int sms = 148;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = current_num_sms();
     int64_t blocks = ((n >> 2) + 255) / 256;
     if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
     if (blocks < 1) blocks = 1;

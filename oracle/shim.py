@@ -22,7 +22,11 @@ import torch.nn as nn
 
 from . import reference_ops as R
 
-REFERENCE_ROOT = "/root/reference/immunostruct"
+# The reference tree: /root/reference in the build container; on the GPU box (where /root/reference does not exist) the
+# copy that oracle/install_ref.py placed under baseline/_ref/ (git-ignored, travels with the snapshot).
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_CANDIDATES = ("/root/reference/immunostruct", os.path.join(_REPO, "baseline", "_ref", "immunostruct"))
+REFERENCE_ROOT = next((c for c in _CANDIDATES if os.path.isdir(os.path.join(c, "models"))), _CANDIDATES[0])
 
 
 def reference_available() -> bool:
@@ -128,7 +132,7 @@ def install():
 def load_reference():
     """Returns (model_map, Losses, PairedContrastiveLoss) from the reference's own files."""
     if not reference_available():
-        raise RuntimeError("/root/reference is not present on this box")
+        raise RuntimeError("no reference tree on this box (/root/reference or baseline/_ref, see oracle/install_ref.py)")
     install()
     import importlib
     mapping = importlib.import_module("models.mapping")
