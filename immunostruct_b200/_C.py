@@ -95,7 +95,7 @@ def _stream():
 
 
 LAUNCHES = 0          # number of immunostruct_b200 kernels enqueued so far (bench.py reports the delta)
-_KERNELS_PER_CALL = {"is_collate_csr": 2, "is_loss_fwd": 2, "is_loss_bwd": 2, "is_contrastive_fwd": 9,
+_KERNELS_PER_CALL = {"is_collate_csr": 1, "is_loss_fwd": 2, "is_loss_bwd": 2, "is_contrastive_fwd": 9,
                      "is_contrastive_bwd": 9}
 
 

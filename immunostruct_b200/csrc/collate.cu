@@ -15,34 +15,6 @@
 
 namespace is {
 
-// exclusive scan of two int64 count arrays with one CTA (B is a few thousand at most)
-__global__ void offsets_kernel(const int64_t* __restrict__ node_counts, const int64_t* __restrict__ edge_counts,
-                               int B, int64_t* __restrict__ node_off, int64_t* __restrict__ edge_off) {
-    __shared__ int64_t s_n[1024], s_e[1024];
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const int per = (B + nt - 1) / nt;
-    const int b0 = min(B, tid * per), b1 = min(B, b0 + per);
-    int64_t sn = 0, se = 0;
-    for (int b = b0; b < b1; ++b) { sn += node_counts[b]; se += edge_counts[b]; }
-    s_n[tid] = sn; s_e[tid] = se;
-    __syncthreads();
-    if (tid == 0) {
-        int64_t an = 0, ae = 0;
-        for (int t = 0; t < nt; ++t) {
-            int64_t vn = s_n[t], ve = s_e[t];
-            s_n[t] = an; s_e[t] = ae;
-            an += vn; ae += ve;
-        }
-        node_off[B] = an; edge_off[B] = ae;
-    }
-    __syncthreads();
-    sn = s_n[tid]; se = s_e[tid];
-    for (int b = b0; b < b1; ++b) {
-        node_off[b] = sn; edge_off[b] = se;
-        sn += node_counts[b]; se += edge_counts[b];
-    }
-}
-
 // ---- one warp walks one graph (graphs with more than CB_CAP nodes): counters / cursors in global scratch --------
 // globalise endpoints, histogram, scan, stable fill of CSR and CSC.  Integer arithmetic only.
 __device__ void collate_graph_warp(const int64_t* __restrict__ src_local, const int64_t* __restrict__ dst_local,
@@ -127,7 +99,8 @@ __device__ void collate_graph_warp(const int64_t* __restrict__ src_local, const 
 #define CB_CAP 512
 __global__ void __launch_bounds__(32 * CB_WARPS)
 collate_kernel(const int64_t* __restrict__ src_local, const int64_t* __restrict__ dst_local,
-               const int64_t* __restrict__ node_off, const int64_t* __restrict__ edge_off, int B,
+               const int64_t* __restrict__ node_counts, const int64_t* __restrict__ edge_counts, int B,
+               int64_t* __restrict__ node_off, int64_t* __restrict__ edge_off,
                int64_t* __restrict__ edge_index /* [2,E] */, int64_t E, int64_t* __restrict__ batch,
                int* __restrict__ indptr, int* __restrict__ csr_src, int* __restrict__ csr_dst, int* __restrict__ csr_eid,
                int* __restrict__ outptr, int* __restrict__ csc_pos,
@@ -135,9 +108,27 @@ collate_kernel(const int64_t* __restrict__ src_local, const int64_t* __restrict_
                int* __restrict__ stats) {
     __shared__ int s_cnt[2][CB_WARPS][CB_CAP];          // [in | out][warp][local node]: counts, then cursors (32 KB)
     __shared__ int s_wsum[2][CB_WARPS];
+    __shared__ int64_t s_off[2][CB_WARPS];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = blockIdx.x;
-    const int64_t n0 = node_off[g], n1 = node_off[g + 1], e0 = edge_off[g], e1 = edge_off[g + 1];
+    // segment offsets of this graph = sums of the counts of the graphs before it (every CTA reduces its own prefix:
+    // B is a few hundred to a few thousand, so this is cheaper than a separate scan launch)
+    {
+        int64_t sn = 0, se = 0;
+        for (int i = tid; i < g; i += 32 * CB_WARPS) { sn += node_counts[i]; se += edge_counts[i]; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { sn += __shfl_xor_sync(0xffffffffu, sn, o); se += __shfl_xor_sync(0xffffffffu, se, o); }
+        if (lane == 0) { s_off[0][w] = sn; s_off[1][w] = se; }
+        __syncthreads();
+    }
+    int64_t n0 = 0, e0 = 0;
+#pragma unroll
+    for (int ww = 0; ww < CB_WARPS; ++ww) { n0 += s_off[0][ww]; e0 += s_off[1][ww]; }
+    const int64_t n1 = n0 + node_counts[g], e1 = e0 + edge_counts[g];
+    if (tid == 0) {
+        node_off[g] = n0; edge_off[g] = e0;
+        if (g == B - 1) { node_off[B] = n1; edge_off[B] = e1; }
+    }
     const int ng = (int)(n1 - n0);
     if (tid == 0) {
         atomicMax(stats + 2, ng);
@@ -289,10 +280,8 @@ int is_collate_csr(const int64_t* src_local, const int64_t* dst_local, const int
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(stats, 0, 4 * sizeof(int), st);
     if (e != cudaSuccess) return (int)e;
-    offsets_kernel<<<1, 1024, 0, st>>>(node_counts, edge_counts, n_graphs, node_off, edge_off);
-    IS_LAUNCH_CHECK();
     collate_kernel<<<n_graphs, 32 * CB_WARPS, 0, st>>>(
-        src_local, dst_local, node_off, edge_off, n_graphs, edge_index, n_edges, batch, indptr, csr_src, csr_dst,
+        src_local, dst_local, node_counts, edge_counts, n_graphs, node_off, edge_off, edge_index, n_edges, batch, indptr, csr_src, csr_dst,
         csr_eid, outptr, csc_pos, scratch, scratch + n_nodes, stats);
     IS_LAUNCH_CHECK();
     return IS_OK;

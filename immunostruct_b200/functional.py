@@ -53,6 +53,12 @@ def cache_generation() -> int:
     return _cache_generation
 
 
+def _ops():
+    """The torch.library registration (ops.py), when routing through it has been switched on; else None."""
+    from . import ops
+    return ops if ops.enabled() else None
+
+
 def _new(like, *shape):
     return torch.empty(*shape, dtype=torch.float32, device=like.device)
 
@@ -250,6 +256,10 @@ class _EGNNStack(torch.autograd.Function):
 def egnn_stack(graph, x23, edge_attr, layer_params):
     """EGNN stack with autograd (training).  ``layer_params``: list of EGNNConv.kernel_params() tuples."""
     flat = [t for lp in layer_params for t in lp]
+    ops = _ops()
+    if ops is not None:
+        return ops.egnn_stack(x23, edge_attr, flat, ops.graph_tensors(graph), len(layer_params), graph.n_edges, graph.n_graphs,
+                              int(graph.max_nodes))[0]
     return _EGNNStack.apply(graph, len(layer_params), x23, edge_attr, *flat)
 
 
@@ -350,6 +360,9 @@ def attention_pool(graph, QKV, n_head=1, want_attn=False, want_nodes=False):
         else:
             _C.attn_pool_infer(QKV, graph.node_off, n_head, graph.max_nodes, pooled)
         return None, pooled, None
+    ops = _ops()
+    if ops is not None and not want_attn and not want_nodes:
+        return None, ops.attention_pool(QKV, graph.node_off, n_head, int(graph.max_nodes)), None
     return _AttnPool.apply(graph, n_head, want_attn, want_nodes, QKV)
 
 
@@ -380,6 +393,9 @@ class _FusionAttn(torch.autograd.Function):
 
 
 def fusion_attention(c, coef, n_head):
+    ops = _ops()
+    if ops is not None:
+        return ops.fusion_attention(c, coef, n_head)
     return _FusionAttn.apply(c, coef, n_head)
 
 
@@ -430,6 +446,13 @@ class _FusedLoss(torch.autograd.Function):
 
 
 def fused_loss(recon, seq, mu, logvar, logits, y, mode, pos_weight, w_pred, w_mse, w_kld, return_components=False):
+    ops = _ops()
+    if ops is not None:
+        if w_mse == 0.0 and w_kld == 0.0:
+            recon = seq = mu = logvar = None
+        comps = ops.fused_loss(recon, seq, mu, logvar, logits, y, int(mode), float(pos_weight), float(w_pred), float(w_mse),
+                               float(w_kld))
+        return (comps[0], comps.detach()) if return_components else comps[0]
     total, comps = _FusedLoss.apply(recon, seq, mu, logvar, logits, y, int(mode), float(pos_weight),
                                     float(w_pred), float(w_mse), float(w_kld))
     return (total, comps) if return_components else total
@@ -464,6 +487,9 @@ def segment_pool(graph_or_offsets, X, mode="mean"):
     node_off = getattr(graph_or_offsets, "node_off", graph_or_offsets)
     if mode not in _C.POOL_MODES:
         raise ValueError(f"mode must be one of {sorted(_C.POOL_MODES)}")
+    ops = _ops()
+    if ops is not None:
+        return ops.segment_pool(X, node_off, mode)
     return _SegmentPool.apply(X, node_off, mode)
 
 
@@ -572,4 +598,7 @@ class _LinearTC(torch.autograd.Function):
 
 def linear_tc(x, weight, bias=None, relu=False):
     """Differentiable ``relu?(F.linear(x, weight, bias))`` on the tensor cores; x [M, K] fp32 with unit inner stride."""
+    ops = _ops()
+    if ops is not None:
+        return ops.linear(x, weight, bias, relu)
     return _LinearTC.apply(x, weight, bias, relu)

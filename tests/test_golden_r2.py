@@ -26,7 +26,7 @@ def cpu_backend(monkeypatch):
     yield
 
 
-def run_class_case(cls, device, tol, grad_tol):
+def run_class_case(cls, device, tol, grad_tol, truth_factor=3.0):
     gd = load_golden(f"r2_{cls}")
     seed, pair = int(gd["meta"]["seed"]), bool(int(gd["meta"]["pair"]))
     model = I.model_map[cls](vae_input_dim=231, device=device, gcn_layers=1, vae_hidden_dim=32)
@@ -49,7 +49,7 @@ def run_class_case(cls, device, tol, grad_tol):
         assert rel_err(t, ref) < tol, (cls, i, rel_err(t, ref))
         assert rel_err(t, ref64) < tol, (cls, i, "fp64")
     objective(flat).backward()
-    assert_grads_close(named_grads(model), gd["grads"], grad_tol, truth=gd["grads64"])
+    assert_grads_close(named_grads(model), gd["grads"], grad_tol, truth=gd["grads64"], truth_factor=truth_factor)
 
 
 @pytest.mark.parametrize("cls", SINGLE + PAIR)
@@ -57,10 +57,26 @@ def test_class_golden_host_logic(cpu_backend, cls):
     run_class_case(cls, "cpu", 2e-5, 1e-4)
 
 
+# Gradient yardstick on the device: 1e-5 of the parameter's scale, or a multiple of the fp32 REFERENCE's own distance
+# from its fp64 run where that is larger (ill-conditioned parameters: the reference's fp32 gradients are 4e-5 off
+# there).  The fp32 SIMT mode is held to 3x (two independent fp32 roundings), the default bf16x3 tensor-core mode --
+# fp32 accumulation in TMEM truncates instead of rounding -- to 4x; measured worst cases 0.9x / 3.1x.
+PRECISIONS = [("fp32", 3.0), ("bf16x3", 4.0)]
+
+
+@pytest.fixture
+def precision(request):
+    prev = I.get_precision()
+    I.set_precision(request.param[0])
+    yield request.param
+    I.set_precision(prev)
+
+
 @pytest.mark.gpu
+@pytest.mark.parametrize("precision", PRECISIONS, indirect=True, ids=[p[0] for p in PRECISIONS])
 @pytest.mark.parametrize("cls", SINGLE + PAIR)
-def test_class_golden_gpu(cls):
-    run_class_case(cls, "cuda", 1e-5, 1e-5)
+def test_class_golden_gpu(cls, precision):
+    run_class_case(cls, "cuda", 1e-5, 1e-5, truth_factor=precision[1])
 
 
 def _split_sample(product_tensor, stored):
@@ -71,7 +87,7 @@ def _split_sample(product_tensor, stored):
     return s[0], s[1:], stored[0], stored[1:]
 
 
-def run_big_case(device, tol):
+def run_big_case(device, tol, truth_factor=3.0):
     gd = load_golden("r2_big_hybrid_v2")
     seed = int(gd["meta"]["seed"])
     model = I.model_map["HybridModelv2"](vae_input_dim=5943, device=device, gcn_layers=2)
@@ -100,7 +116,7 @@ def run_big_case(device, tol):
         truth[k] = t[1:] if n_g is not None else t
         if n_g is not None:                      # the two 3 M-element matrices: norm as well as the strided sample
             assert abs(float(n_g) - float(t[0])) < max(tol * float(t[0]), 3 * abs(float(n_ref) - float(t[0]))), k
-    assert_grads_close(got, ref, tol, truth=truth)
+    assert_grads_close(got, ref, tol, truth=truth, truth_factor=truth_factor)
     assert model.vae_fc1.weight.grad.shape == (512, 5943) and model.vae_fc4.weight.grad.shape == (5943, 512)
 
 
@@ -109,8 +125,9 @@ def test_production_width_golden_host_logic(cpu_backend):
 
 
 @pytest.mark.gpu
-def test_production_width_golden_gpu():
-    run_big_case("cuda", 1e-5)
+@pytest.mark.parametrize("precision", PRECISIONS, indirect=True, ids=[p[0] for p in PRECISIONS])
+def test_production_width_golden_gpu(precision):
+    run_big_case("cuda", 1e-5, truth_factor=precision[1])
 
 
 def test_train_mode_trace_matches_reference(cpu_backend):
