@@ -47,7 +47,7 @@ def exported_symbols():
             "is_fusion_attn_bwd", "is_loss_fwd", "is_loss_bwd", "is_umma_selftest", "is_egnn_edge_fwd_tc", "is_attn_pool_infer", "is_egnn_node_post_pre_tc", "is_egnn_edge_bwd_tc", "is_linear_tc", "is_linear_tc_split_k", "is_attn_pool_infer_tc", "is_vae_mid_infer", "is_head_infer", "is_unpack_nodes", "is_unpack_edges", "is_onehot_tokens", "is_egnn_node_post_bwd_tc", "is_egnn_node_pre_bwd_tc", "is_attn_pool_bwd_tc",
             "is_segment_pool_fwd", "is_segment_pool_bwd", "is_contrastive_scratch_floats", "is_contrastive_fwd",
             "is_contrastive_bwd", "is_fused_adam", "is_rotate_coords", "is_mask_single_residue", "is_mask_rows", "is_gemm_tma_split_k",
-            "is_split_planes", "is_gemm_planes_tma"]
+            "is_split_planes", "is_gemm_planes_tma", "is_egnn_set_ws_buffers"]
 
 
 def _check(rc: int, name: str):
@@ -60,33 +60,37 @@ _dev_seen = None        # device index of the tensors of the call being assemble
 
 
 def _t(t, dtype, name, contiguous=True):
+    """Device pointer of a checked tensor argument (None passes through as NULL).  Kept lean: a training step makes
+    ~300 calls with ~20 arguments each, so every attribute access here is paid thousands of times per step."""
     global _dev_seen
     if t is None:
         return None
-    if t.is_cuda:
-        if _dev_seen is None:
-            _dev_seen = t.device.index
-        elif _dev_seen != t.device.index:
-            raise RuntimeError(f"{name}: tensors of one kernel call live on different devices "
-                               f"(cuda:{_dev_seen} and cuda:{t.device.index})")
-    if not t.is_cuda:
+    d = t.get_device()                              # -1 for a CPU tensor
+    if d < 0:
         raise RuntimeError(f"{name}: expected a CUDA tensor (immunostruct_b200 has no CPU path), got {t.device}")
-    if t.dtype != dtype:
+    if t.dtype is not dtype:
         raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
     if contiguous and not t.is_contiguous():
         raise ValueError(f"{name}: expected a contiguous tensor")
+    if _dev_seen is None:
+        _dev_seen = d
+    elif _dev_seen != d:
+        seen, _dev_seen = _dev_seen, None
+        raise RuntimeError(f"{name}: tensors of one kernel call live on different devices (cuda:{seen} and cuda:{d})")
     return _vp(t.data_ptr())
 
 
 def _rows(t, name):
     """[n, k] fp32 view whose rows are contiguous (inner stride 1); returns (ptr, leading dim)."""
     global _dev_seen
-    if not t.is_cuda or t.dtype != torch.float32 or t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+    d = t.get_device()
+    if d < 0 or t.dtype is not torch.float32 or t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
         raise ValueError(f"{name}: expected a CUDA fp32 [n,k] tensor with unit inner stride")
     if _dev_seen is None:
-        _dev_seen = t.device.index
-    elif _dev_seen != t.device.index:
-        raise RuntimeError(f"{name}: tensors of one kernel call live on different devices")
+        _dev_seen = d
+    elif _dev_seen != d:
+        seen, _dev_seen = _dev_seen, None
+        raise RuntimeError(f"{name}: tensors of one kernel call live on different devices (cuda:{seen} and cuda:{d})")
     return _vp(t.data_ptr()), _i64(t.stride(0))
 
 
@@ -94,6 +98,7 @@ def _stream():
     return _vp(torch.cuda.current_stream().cuda_stream)
 
 
+_FN = {}              # launcher name -> ctypes function (restype set once)
 LAUNCHES = 0          # number of immunostruct_b200 kernels enqueued so far (bench.py reports the delta)
 _KERNELS_PER_CALL = {"is_collate_csr": 1, "is_loss_fwd": 2, "is_loss_bwd": 2, "is_contrastive_fwd": 9,
                      "is_contrastive_bwd": 9}
@@ -105,8 +110,10 @@ def _call(name, *args):
     launchers use the current device and the stream handed over must belong to it."""
     global LAUNCHES, _dev_seen
     dev, _dev_seen = _dev_seen, None
-    fn = getattr(lib(), name)
-    fn.restype = ctypes.c_int
+    fn = _FN.get(name)
+    if fn is None:
+        fn = _FN[name] = getattr(lib(), name)
+        fn.restype = ctypes.c_int
     if dev is not None and dev != torch.cuda.current_device():
         with torch.cuda.device(dev):
             args = args[:-1] + (_stream(),)          # the stream argument is always last: re-take it on that device
@@ -114,6 +121,13 @@ def _call(name, *args):
     else:
         _check(fn(*args), name)
     LAUNCHES += _KERNELS_PER_CALL.get(name, 1)
+
+
+def set_ws_buffers(n: int) -> None:
+    """Operand-buffer depth (2 default, 3 = measured alternative) of the warp-specialised edge forward kernel."""
+    fn = lib().is_egnn_set_ws_buffers
+    fn.restype = ctypes.c_int
+    _check(fn(_i32(n)), "is_egnn_set_ws_buffers")
 
 
 # ---- sizing queries ----------------------------------------------------------------------------

@@ -148,23 +148,30 @@ __device__ __forceinline__ void meta_edge(const EdgeCommon& p, Meta3& m, int j, 
 #endif
 #define WS_WAIT(bar, parity) mbar_wait_hint(bar, parity, IS_WS_WAIT_HINT_NS)
 
-template <int PREC, bool HAS_COORD, bool FAST>
+// NB = number of operand buffers.  NB = 2: the original ring (gather of tile i waits until MMA 2 / MMA 3 of tile i - 2 have
+// released buffer i & 1).  NB = 3 (bf16x3: 229.7 KB of shared memory, 2.7 KB below the limit): a third operand buffer
+// takes the t1 gather of tile i out of that dependency -- it only needs MMA 2 / 3 of tile i - 3 (a_free ring); the
+// selector tile S stays two deep, so it is built AFTER the row gather, behind a wait for tile i - 2 that has usually
+// passed by then.  TMEM accumulators stay two deep (indexed i & 1): a_full(i) is signalled after that wait, so MMA 1 of
+// tile i still cannot overwrite acc1 before epilogue 1 of tile i - 2 has read it.
+template <int PREC, bool HAS_COORD, bool FAST, int NB>
 __global__ void __launch_bounds__(e3::NT3, 1)
 edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_out) {
     using namespace e3;
     using C = TcCfg<PREC>;
     constexpr int NS = C::NSPLIT;
+    static_assert(NB == 2 || NB == 3, "two or three operand buffers");
     constexpr int CW = 32;                      // accumulator columns per epilogue thread (two column halves)
     constexpr uint32_t ABUF = NS * A_BYTES;     // one operand buffer (all split terms)
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t* sS = smem_raw;                                            // [2][S_BYTES]; rows 32..63 of a tile alias what follows
-    uint8_t* sA = sS + 2 * S_BYTES;                                    // [2][NS][A_BYTES] t1, then m
-    uint8_t* sW2 = sA + 2 * ABUF;                                      // [NS][W_BYTES]
+    uint8_t* sA = sS + 2 * S_BYTES;                                    // [NB][NS][A_BYTES] t1, then m
+    uint8_t* sW2 = sA + NB * ABUF;                                     // [NS][W_BYTES]
     uint8_t* sW3 = sW2 + NS * W_BYTES;
     float* vec = reinterpret_cast<float*>(sW3 + NS * W_BYTES);         // b2, b3, w4, wr, wa
     float* e_c = vec + 5 * 64;                                         // [2 buffers][2 halves][128] partial c
     Meta3* meta = reinterpret_cast<Meta3*>(e_c + 4 * IS_TM);           // [NM]
-    __shared__ __align__(8) uint64_t meta_full[NM], meta_free[NM], a_full[2], acc1_full[2], m_full[2], acc2_full[2], hn_full[2];
+    __shared__ __align__(8) uint64_t meta_full[NM], meta_free[NM], a_full[3], acc1_full[2], m_full[3], acc2_full[2], hn_full[2], a_free[3];
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -172,10 +179,8 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
     if (warp == 0) tmem_alloc(&s_tmem, 512);
     if (tid == 32) {
         for (int i = 0; i < NM; ++i) { mbar_init(&meta_full[i], NW_META); mbar_init(&meta_free[i], NW_EPI); }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&a_full[i], NW_PROD); mbar_init(&m_full[i], NW_EPI);
-            mbar_init(&acc1_full[i], 1); mbar_init(&acc2_full[i], 1); mbar_init(&hn_full[i], 1);
-        }
+        for (int i = 0; i < 3; ++i) { mbar_init(&a_full[i], NW_PROD); mbar_init(&m_full[i], NW_EPI); mbar_init(&a_free[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc1_full[i], 1); mbar_init(&acc2_full[i], 1); mbar_init(&hn_full[i], 1); }
     }
     stage_weight_block<PREC>(sW2, W_BYTES, p.W2, 64, 0, 64, tid, NT3);                 // W2 / W3 as B operands
     stage_weight_block<PREC>(sW3, W_BYTES, HAS_COORD ? p.W3 : nullptr, 64, 0, 64, tid, NT3);
@@ -230,30 +235,33 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
         const uint32_t s_addr = smem_u32(sS), a_addr = smem_u32(sA), w2_addr = smem_u32(sW2), w3_addr = smem_u32(sW3);
         const bool first = warp == W_MMA;
         bool done = false;
-        for (int i2 = 0; !done; i2 += 2) {
+        constexpr int UN = NB == 2 ? 2 : 6;              // lcm(2 TMEM sets, NB operand buffers)
+        for (int i2 = 0; !done; i2 += UN) {
 #pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                const int i = i2 + b;
+            for (int u = 0; u < UN; ++u) {
+                const int i = i2 + u;
+                const int b = u & 1, ab = u % NB;        // compile-time after unrolling (i2 is a multiple of UN)
                 WS_WAIT(&meta_full[i % NM], (i / NM) & 1);
                 done = meta[i % NM].tile[0] >= nend;
                 if (done) break;
                 if (first) {
-                    WS_WAIT(&a_full[b], (i >> 1) & 1);
+                    WS_WAIT(&a_full[ab], (i / NB) & 1);
                     fence_after_sync();
                     if (elect_one()) {
-                        issue_fwd<PREC>(tmem + TM_ACC1 + 64 * b, a_addr + b * ABUF, w2_addr);
+                        issue_fwd<PREC>(tmem + TM_ACC1 + 64 * b, a_addr + ab * ABUF, w2_addr);
                         mma_commit(&acc1_full[b]);
                     }
                 } else {
-                    WS_WAIT(&m_full[b], (i >> 1) & 1);
+                    WS_WAIT(&m_full[ab], (i / NB) & 1);
                     fence_after_sync();
                     if (elect_one()) {
                         if (HAS_COORD) {
-                            issue_fwd<PREC>(tmem + TM_ACC2 + 64 * b, a_addr + b * ABUF, w3_addr);
+                            issue_fwd<PREC>(tmem + TM_ACC2 + 64 * b, a_addr + ab * ABUF, w3_addr);
                             mma_commit(&acc2_full[b]);
                         }
-                        issue_segsum<PREC>(tmem + TM_HN + 64 * b, s_addr + b * S_BYTES, a_addr + b * ABUF, 8);
+                        issue_segsum<PREC>(tmem + TM_HN + 64 * b, s_addr + b * S_BYTES, a_addr + ab * ABUF, 8);
                         mma_commit(&hn_full[b]);
+                        if (NB == 3) mma_commit(&a_free[ab]);
                     }
                 }
                 __syncwarp();
@@ -268,14 +276,18 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
         const float4 wr0 = *reinterpret_cast<const float4*>(vec + 192 + 8 * kc), wr1 = *reinterpret_cast<const float4*>(vec + 196 + 8 * kc);
         const float4 wa0 = *reinterpret_cast<const float4*>(vec + 256 + 8 * kc), wa1 = *reinterpret_cast<const float4*>(vec + 260 + 8 * kc);
         for (int i = 0;; ++i) {
-            const int b = i & 1;
+            const int b = i & 1, ab = i % NB;
             WS_WAIT(&meta_full[i % NM], (i / NM) & 1);
             const Meta3& mt = meta[i % NM];
             const int n0 = mt.tile[0], ne = mt.tile[2];
             if (n0 >= nend) break;
-            if (i >= 2) WS_WAIT(&hn_full[b], ((i >> 1) - 1) & 1);        // MMA2 / MMA3 of tile i-2 are done with the buffer
-            uint8_t* A = sA + b * ABUF;
-            {   // selector tile: S[node][edge] = 1 for the node's in-edges (two 16-byte chunks per thread)
+            if (NB == 2) {
+                if (i >= 2) WS_WAIT(&hn_full[b], ((i >> 1) - 1) & 1);    // MMA2 / MMA3 of tile i-2 are done with the buffer
+            } else {
+                if (i >= 3) WS_WAIT(&a_free[ab], ((i / 3) - 1) & 1);     // MMA2 / MMA3 of tile i-3 are done with the buffer
+            }
+            uint8_t* A = sA + ab * ABUF;
+            auto build_selector = [&]() {   // S[node][edge] = 1 for the node's in-edges (two 16-byte chunks per thread)
                 const int jb = mt.nptr[lane], je = mt.nptr[lane + 1];         // rows beyond the tile: jb = je = ne
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
@@ -289,7 +301,8 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
                     w.w = ((mask >> 6) & 1u) * 0x3F80u + ((mask >> 7) & 1u) * 0x3F800000u;
                     *reinterpret_cast<uint4*>(sS + b * S_BYTES + (lane >> 3) * S_SBO + c * S_LBO + (lane & 7) * 16) = w;
                 }
-            }
+            };
+            if (NB == 2) build_selector();
 #pragma unroll
             for (int gi = 0; gi < 2; ++gi) {
                 const int g8 = 8 * (2 * pw + gi);
@@ -318,9 +331,13 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
                     store_chunk8<PREC>(A + (j >> 3) * SBO + (j & 7) * 16 + kc * LBO, A_BYTES, v);
                 }
             }
+            if (NB == 3) {
+                if (i >= 2) WS_WAIT(&hn_full[b], ((i >> 1) - 1) & 1);    // MMA 3 of tile i-2 is done with selector tile b
+                build_selector();
+            }
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&a_full[b]);
+            if (lane == 0) mbar_arrive(&a_full[ab]);
         }
     } else {
         // ================= epilogue: epilogue 1 of tile i, then epilogue 2 / hn rows / coordinates of tile i-1 =====
@@ -334,7 +351,7 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
                 // ---- epilogue 1: m = silu(acc1 + b2) -> operand buffer (A of MMA 2, transposed B of MMA 3) ----
                 WS_WAIT(&acc1_full[b], (i >> 1) & 1);
                 fence_after_sync();
-                uint8_t* A = sA + b * ABUF;
+                uint8_t* A = sA + (i % NB) * ABUF;
                 float z[CW];
                 tmem_ld<CW>(t_lane + TM_ACC1 + 64 * b, z);
 #pragma unroll
@@ -351,7 +368,7 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
                 fence_async_smem();
                 fence_before_sync();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&m_full[b]);
+                if (lane == 0) mbar_arrive(&m_full[i % NB]);
             }
             if (i >= 1) {
                 const int j = i - 1, bp = b ^ 1;
@@ -416,20 +433,32 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-template <int PREC>
+template <int PREC, int NB>
 static size_t ws_smem_bytes() {
     using namespace e3;
-    return 2 * (size_t)S_BYTES + (size_t)TcCfg<PREC>::NSPLIT * (2 * A_BYTES + 2 * W_BYTES) + sizeof(float) * (5 * 64 + 4 * IS_TM) + NM * sizeof(Meta3);
+    return 2 * (size_t)S_BYTES + (size_t)TcCfg<PREC>::NSPLIT * (NB * A_BYTES + 2 * W_BYTES) + sizeof(float) * (5 * 64 + 4 * IS_TM) + NM * sizeof(Meta3);
+}
+
+// operand buffers of the warp-specialised kernel (is_egnn_set_ws_buffers).  Measured on the B200 (scripts/ab_edge.py,
+// batch 512, bit-identical results): 3 buffers 225.4 vs 227.3 us (bf16x3 inference), 188.2 vs 192.5 us (last layer),
+// but 282 vs 252 us with the accurate training SiLU and 140 vs 135 us in bf16 -- the free-buffer wait is not on the
+// critical path, so the two-buffer ring stays the default.
+int g_ws_buffers = 2;
+
+template <int PREC, bool HAS_COORD, bool FAST, int NB>
+static int launch_wsk_nb(const EdgeCommon& c, float* hn, float* x_out, int grid, cudaStream_t st) {
+    const size_t smem = ws_smem_bytes<PREC, NB>();
+    cudaError_t e = cudaFuncSetAttribute(edge_fwd_ws_kernel<PREC, HAS_COORD, FAST, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    edge_fwd_ws_kernel<PREC, HAS_COORD, FAST, NB><<<grid, e3::NT3, smem, st>>>(c, hn, x_out);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
 }
 
 template <int PREC, bool HAS_COORD, bool FAST>
 static int launch_wsk(const EdgeCommon& c, float* hn, float* x_out, int grid, cudaStream_t st) {
-    const size_t smem = ws_smem_bytes<PREC>();
-    cudaError_t e = cudaFuncSetAttribute(edge_fwd_ws_kernel<PREC, HAS_COORD, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    edge_fwd_ws_kernel<PREC, HAS_COORD, FAST><<<grid, e3::NT3, smem, st>>>(c, hn, x_out);
-    e = cudaGetLastError();
-    return e == cudaSuccess ? 0 : (int)e;
+    return g_ws_buffers == 3 ? launch_wsk_nb<PREC, HAS_COORD, FAST, 3>(c, hn, x_out, grid, st)
+                             : launch_wsk_nb<PREC, HAS_COORD, FAST, 2>(c, hn, x_out, grid, st);
 }
 
 // entry used by is_egnn_edge_fwd_tc (egnn_tc.cu) for the bf16 / bf16x3 precisions: warp-specialised kernel
@@ -450,3 +479,10 @@ int launch_edge_fwd_ws(const EdgeCommon& c, float* hn, float* x_out, int precisi
 }
 
 }  // namespace is
+
+// number of operand buffers of the warp-specialised edge forward kernel: 2 (default) or 3 (A/B timing, see g_ws_buffers)
+extern "C" int is_egnn_set_ws_buffers(int n) {
+    if (n != 2 && n != 3) return IS_ERR_ARG;
+    is::g_ws_buffers = n;
+    return IS_OK;
+}

@@ -72,7 +72,7 @@ class BucketedGradientReducer:
                 self.buckets.append((lo, end))
                 lo = end
         self.count = [self.bucket_of.count(b) for b in range(len(self.buckets))]
-        self.pending = list(self.count)
+        self.pending = list(self.count)                  # mutated in place (the hooks hold a reference)
         self.works = [None] * len(self.buckets)
         self._world = dist.get_world_size(self.group)
         self._avg = dist.get_backend(self.group) == "nccl"
@@ -80,14 +80,16 @@ class BucketedGradientReducer:
             p.register_post_accumulate_grad_hook(self._make_hook(i))
 
     def _make_hook(self, i):
+        v, b = self.fg.views[i], self.bucket_of[i]
+        pending = self.pending
+
         def hook(p):
-            v = self.fg.views[i]
-            if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
-                v.copy_(p.grad)
+            g = p.grad
+            if g is not v and g is not None and g.data_ptr() != v.data_ptr():      # a fresh .grad tensor (set_to_none)
+                v.copy_(g)
                 p.grad = v
-            b = self.bucket_of[i]
-            self.pending[b] -= 1
-            if self.pending[b] == 0:
+            pending[b] -= 1
+            if pending[b] == 0:
                 self._launch(b)
         return hook
 
@@ -102,7 +104,7 @@ class BucketedGradientReducer:
             return
         if self.fg is None:
             self._setup()
-            self.pending = [0] * len(self.buckets)       # first step: nothing was launched from hooks
+            self.pending[:] = [0] * len(self.buckets)    # first step: nothing was launched from hooks
             self.overlapped_last_step = 0
         else:
             self.overlapped_last_step = sum(w is not None for w in self.works)
@@ -115,7 +117,7 @@ class BucketedGradientReducer:
                 lo, hi = self.buckets[b]
                 self.fg.flat[lo:hi].div_(self._world)
         self.works = [None] * len(self.buckets)
-        self.pending = list(self.count)
+        self.pending[:] = self.count
 
     def zero_grad(self) -> None:
         if self.fg is not None:

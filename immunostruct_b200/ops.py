@@ -360,9 +360,10 @@ def _egnn_backward(ctx, grads):
     graph = list(t[1 + 4 * n_layers + ctx.n_params:])
     gh = grads[0]
     if gh is None:
-        return None, None, [None] * ctx.n_params, None, None, None, None, None
+        return None, None, [None] * ctx.n_params, [None] * ctx.n_graph, None, None, None, None
     gp = egnn_stack_bwd(gh.contiguous(), edge_attr, saved, params, graph, *ctx.cfg)
-    return None, None, [None if g.numel() == 0 and p.numel() != 0 else g for g, p in zip(gp, params)], None, None, None, None, None
+    return (None, None, [None if g.numel() == 0 and p.numel() != 0 else g for g, p in zip(gp, params)], [None] * ctx.n_graph,
+            None, None, None, None)
 
 
 egnn_stack.register_autograd(_egnn_backward, setup_context=_egnn_setup)

@@ -28,7 +28,8 @@ class FlatGradients:
     """Gradients of ``params`` (those that have one) as views of a single buffer, in REVERSE parameter order:
     autograd finishes the last layers first, so the buffer fills front to back during the backward pass."""
 
-    def __init__(self, params: List[torch.nn.Parameter]):
+    def __init__(self, params: List[torch.nn.Parameter], alias: bool = True):
+        self.aliased = False
         self.params = [p for p in reversed(params) if p.grad is not None]
         if not self.params:
             raise RuntimeError("no parameter has a gradient yet: call after the first backward()")
@@ -40,12 +41,30 @@ class FlatGradients:
             o += (p.numel() + 3) // 4 * 4
         self.flat = torch.zeros(o, dtype=g0.dtype, device=g0.device)
         self.views = [self.flat[a:a + p.numel()].view_as(p) for a, p in zip(self.offsets, self.params)]
-        self.realias()
         for p in self.params:
             p._is_flat_grad = self
+        if alias:
+            self.realias()
+
+    def gather(self) -> None:
+        """Copy every parameter's current ``.grad`` into the flat buffer with one multi-tensor launch (no aliasing:
+        autograd keeps assigning fresh gradient tensors, which costs nothing, instead of ``view += grad`` per
+        parameter)."""
+        src, dst = [], []
+        for p, v in zip(self.params, self.views):
+            g = p.grad
+            if g is None:
+                v.zero_()
+            elif g is not v and g.data_ptr() != v.data_ptr():
+                src.append(g)
+                dst.append(v)
+        if src:
+            torch._foreach_copy_(dst, src)
 
     def realias(self) -> None:
-        """Make every ``p.grad`` the view of the flat buffer again (copying a foreign gradient tensor in)."""
+        """Make every ``p.grad`` the view of the flat buffer (copying a foreign gradient tensor in).  From then on
+        autograd accumulates in place, so slices of the buffer can be all-reduced while backward is still running."""
+        self.aliased = True
         for p, v in zip(self.params, self.views):
             g = p.grad
             if g is None:
@@ -66,15 +85,18 @@ class FlatGradients:
         raise KeyError("parameter not in this FlatGradients")
 
 
-def flatten_gradients(params: Iterable[torch.nn.Parameter]) -> FlatGradients:
+def flatten_gradients(params: Iterable[torch.nn.Parameter], alias: bool = True) -> FlatGradients:
     """The ``FlatGradients`` of ``params`` -- created on first use, shared by every later caller with the same
-    live parameter set (the gradient reducer and the optimiser of one model)."""
+    live parameter set (the gradient reducer and the optimiser of one model).  ``alias=True`` (the reducer) makes the
+    parameters' ``.grad`` views of the buffer; the optimiser alone does not need that and gathers instead."""
     params = [p for p in params if p.requires_grad]
     live = [p for p in params if p.grad is not None]
     fg = getattr(live[0], "_is_flat_grad", None) if live else None
     if fg is not None and len(fg.params) == len(live) and all(a is b for a, b in zip(fg.params, reversed(live))):
+        if alias and not fg.aliased:
+            fg.realias()
         return fg
-    return FlatGradients(params)
+    return FlatGradients(params, alias)
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -82,8 +104,8 @@ class FusedAdam(torch.optim.Optimizer):
 
     Same defaults, hyper-parameter names (``param_groups[i]['lr']`` is read every step, so LR schedulers work) and
     per-parameter state keys (``step``, ``exp_avg``, ``exp_avg_sq``) as torch's optimisers; ``amsgrad`` /
-    ``maximize`` are not supported.  ``zero_grad()`` zeroes the flat gradient buffer and keeps the views
-    (``set_to_none`` would break the aliasing the gradient reducer relies on)."""
+    ``maximize`` are not supported.  Without a gradient reducer the per-parameter gradients are gathered into the
+    flat buffer by one multi-tensor copy per step; with one (``distributed.BucketedGradientReducer``) they alias it."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False, grad_scale=1.0):
         if lr < 0 or eps < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1 or weight_decay < 0:
@@ -93,7 +115,7 @@ class FusedAdam(torch.optim.Optimizer):
         self._flat = {}       # group index -> dict(fg, p, m, v, runs, step)
 
     def _setup_group(self, gi, group):
-        fg = flatten_gradients(group["params"])
+        fg = flatten_gradients(group["params"], alias=False)
         mine = {id(p) for p in group["params"]}
         idx = [i for i, p in enumerate(fg.params) if id(p) in mine]
         n = sum((fg.params[i].numel() + 3) // 4 * 4 for i in idx)
@@ -132,14 +154,7 @@ class FusedAdam(torch.optim.Optimizer):
                 self._setup_group(gi, group)
             fl = self._flat[gi]
             fg = fl["fg"]
-            for i in fl["idx"]:                                   # a foreign .grad tensor (set_to_none happened): copy in
-                p, v = fg.params[i], fg.views[i]
-                if p.grad is None or p.grad.data_ptr() != v.data_ptr():
-                    if p.grad is None:
-                        v.zero_()
-                    else:
-                        v.copy_(p.grad)
-                    p.grad = v
+            fg.gather()                    # no-op when the gradients already live in the flat buffer (reducer attached)
             fl["step"] += 1
             t = fl["step"]
             b1, b2 = group["betas"]
@@ -156,14 +171,18 @@ class FusedAdam(torch.optim.Optimizer):
                 self.state[p]["step"] = torch.tensor(float(t))
         return loss
 
-    def zero_grad(self, set_to_none: bool = False):
-        done = set()
+    def zero_grad(self, set_to_none: bool = True):
+        """Gradients that alias the flat buffer (a gradient reducer is attached) are zeroed in one memset and keep
+        their views; otherwise torch's default (``set_to_none``) applies."""
+        done, aliased = set(), False
         for fl in self._flat.values():
-            if id(fl["fg"]) not in done:
-                fl["fg"].zero_()
-                done.add(id(fl["fg"]))
-        if not self._flat:
-            super().zero_grad(set_to_none=True)
+            fg = fl["fg"]
+            if fg.aliased and id(fg) not in done:
+                fg.zero_()
+                done.add(id(fg))
+                aliased = True
+        if not aliased:
+            super().zero_grad(set_to_none=set_to_none)
 
 
 class FusedAdamW(FusedAdam):

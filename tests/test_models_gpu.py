@@ -138,12 +138,12 @@ def test_benchmark_shape_against_full_model_oracle():
 
 def test_bf16_mode_within_1e_2_of_fp32_reference():
     """bf16 tensor-core mode (north star: 1e-2 relative): logits and loss at the benchmark shape against
-    the fp32 CPU oracle, inference path and training-forward path; gradients against the fp32-accurate
-    product run (the backward always recomputes in fp32, so only the forward activations differ)."""
+    the fp32 CPU oracle, inference path and training-forward path; gradients against the ORACLE's fp32 gradients
+    (the backward always recomputes in fp32, so only the forward activations carry bf16 rounding)."""
     b = 8
     arr, dense, model, eps = _bench_shape_case(b, seed=21)
     state = {k: v.cpu() for k, v in model.state_dict().items()}
-    recon, out, loss_ref, _ = _oracle_run(state, arr, dense, eps, torch.float32)
+    recon, out, loss_ref, grads_oracle = _oracle_run(state, arr, dense, eps, torch.float32)
     model = model.to(DEV).eval()
     gb = graph_batch(arr, DEV)
     losses = I.Losses(5943, [4.25, 1.0], sequence=True)
@@ -163,10 +163,18 @@ def test_bf16_mode_within_1e_2_of_fp32_reference():
             assert rel_err(o_inf, out) < tol and rel_err(o2, out) < tol and rel_err(loss, loss_ref) < tol, prec
     finally:
         I.set_precision("bf16x3")
-    gmax = max(float(v.abs().max()) for v in grads["fp32"].values())
-    for k, ref in grads["fp32"].items():
-        err = float((grads["bf16"][k] - ref).abs().max())
-        assert err <= 5e-2 * max(float(ref.abs().max()), 1e-2 * gmax), (k, err)
+    ref_grads = {k: v for k, v in grads_oracle.items() if v is not None}
+    gmax = max(float(v.abs().max()) for v in ref_grads.values())
+    worst = ("", 0.0)
+    for k, ref in ref_grads.items():
+        err = float((grads["bf16"][k].cpu() - ref).abs().max())
+        ratio = err / max(float(ref.abs().max()), 1e-2 * gmax)
+        worst = max(worst, (k, ratio), key=lambda t: t[1])
+    import os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/kernel_errors.txt", "a") as f:
+        f.write(f"test_bf16_mode | worst bf16 gradient vs oracle: {worst[0]} rel {worst[1]:.3e}\n")
+    assert worst[1] <= 1e-2, worst
 
 
 def test_full_batch_properties():
