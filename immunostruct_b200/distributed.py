@@ -6,11 +6,11 @@ list: inference scans need NO collective; training needs the gradient averaged a
 (6.33 M fp32 = 25.3 MB for HybridModelv2) between the two lines ``loss.backward()`` / ``optimizer.step()`` of
 reference procedures/train.py:27-28.
 
-``BucketedGradientReducer`` keeps the gradients in one flat buffer that the parameters' ``.grad`` alias
-(``optim.FlatGradients``: reverse parameter order, so it fills front to back during the backward pass), cuts it
-into buckets and launches each bucket's NCCL all-reduce IN PLACE from a post-accumulate-grad hook as soon as its
-last gradient is written: ``vae_fc4`` (12.2 MB, the first gradient autograd produces) is reduced under the whole
-GNN backward; only the last bucket (``vae_fc1`` + the first EGNN layer) is exposed.  No staging copies.
+``BucketedGradientReducer`` gives every gradient a slot in one flat buffer (``optim.FlatGradients``: reverse parameter
+order, so it fills front to back during the backward pass), cuts the buffer into buckets and, from a
+post-accumulate-grad hook, copies a bucket's gradients into their slots with one multi-tensor launch and starts the
+bucket's NCCL all-reduce as soon as its last gradient exists: the 24.5 MB of ``vae_fc4`` ... ``vae_fc1`` (the first
+gradients autograd produces) are reduced under the whole GNN backward; only the EGNN bucket (0.8 MB) is exposed.
 Parameters whose gradient is ``None`` (the last EGNN layer's coord_mlp) are left untouched on every rank, so
 optimizers skip them exactly as in the single-GPU run.
 """
@@ -45,10 +45,12 @@ class BucketedGradientReducer:
 
     Call ``step()`` between ``loss.backward()`` and ``optimizer.step()``.  The first call discovers which
     parameters receive gradients (identical on every rank: same model, same code path), builds the flat buffer
-    and reduces it in one piece; from the second step on the buckets are reduced from autograd hooks during the
-    backward pass and ``step()`` only waits for them.  One ``backward()`` per ``step()`` (as in the reference's
-    loops); use ``optimizer.zero_grad(set_to_none=False)`` / ``FusedAdam.zero_grad()`` / ``reducer.zero_grad()`` so
-    that the views survive (a fresh ``.grad`` tensor is copied back in, at the price of that copy).
+    and reduces it in one piece.  From the second step on a post-accumulate-grad hook counts the gradients of every
+    bucket; when a bucket's last gradient has been written, ONE multi-tensor copy moves the bucket's gradients into
+    their slots and the bucket's NCCL all-reduce is launched -- while the rest of the backward pass is still running.
+    ``step()`` waits for the buckets and makes every ``p.grad`` its (now averaged) slot, so any optimiser sees the
+    averaged gradients and ``FusedAdam`` reads them without another copy.  One ``backward()`` per ``step()`` (as in
+    the reference's loops).
     """
 
     def __init__(self, params: Iterable[torch.nn.Parameter], group=None, bucket_bytes: int = 13 << 20):
@@ -64,14 +66,17 @@ class BucketedGradientReducer:
         self.fg = flatten_gradients(self.params)
         fg = self.fg
         esz = fg.flat.element_size()
-        self.bucket_of, self.buckets, lo, cur = [], [], 0, 0
+        self.bucket_of, self.buckets, self.members, lo = [], [], [[]], 0
         for i, p in enumerate(fg.params):
             end = fg.offsets[i + 1] if i + 1 < len(fg.params) else fg.flat.numel()
             self.bucket_of.append(len(self.buckets))
+            self.members[-1].append(i)
             if (end - lo) * esz >= self.bucket_bytes or i + 1 == len(fg.params):
                 self.buckets.append((lo, end))
                 lo = end
-        self.count = [self.bucket_of.count(b) for b in range(len(self.buckets))]
+                if i + 1 < len(fg.params):
+                    self.members.append([])
+        self.count = [len(m) for m in self.members]
         self.pending = list(self.count)                  # mutated in place (the hooks hold a reference)
         self.works = [None] * len(self.buckets)
         self._world = dist.get_world_size(self.group)
@@ -80,20 +85,16 @@ class BucketedGradientReducer:
             p.register_post_accumulate_grad_hook(self._make_hook(i))
 
     def _make_hook(self, i):
-        v, b = self.fg.views[i], self.bucket_of[i]
-        pending = self.pending
+        b, pending = self.bucket_of[i], self.pending
 
         def hook(p):
-            g = p.grad
-            if g is not v and g is not None and g.data_ptr() != v.data_ptr():      # a fresh .grad tensor (set_to_none)
-                v.copy_(g)
-                p.grad = v
             pending[b] -= 1
             if pending[b] == 0:
                 self._launch(b)
         return hook
 
     def _launch(self, b):
+        self.fg.gather(self.members[b])                   # the bucket's gradients -> their slots (one launch)
         lo, hi = self.buckets[b]
         op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
         self.works[b] = dist.all_reduce(self.fg.flat[lo:hi], op=op, group=self.group, async_op=True)
@@ -116,12 +117,14 @@ class BucketedGradientReducer:
             if not self._avg:
                 lo, hi = self.buckets[b]
                 self.fg.flat[lo:hi].div_(self._world)
+        self.fg.point()                                    # p.grad = averaged slot (no copy)
         self.works = [None] * len(self.buckets)
         self.pending[:] = self.count
 
     def zero_grad(self) -> None:
-        if self.fg is not None:
-            self.fg.zero_()
+        """Drop the gradients (autograd then assigns fresh tensors: no per-parameter accumulation kernels)."""
+        for p in self.params:
+            p.grad = None
 
     @property
     def nbytes(self) -> int:

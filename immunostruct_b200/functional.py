@@ -550,10 +550,12 @@ def _planes_of_weight(weight, need_t):
     """Pre-split bf16 planes of a weight matrix, row-major ([out, in]: forward) and transposed ([in, out]: dgrad),
     cached per parameter version -- in inference the weights are constants, in training they change once per step."""
     n = _n_planes()
-    try:
-        key = (weight.data_ptr(), weight._version, n, _cache_generation)
-    except RuntimeError:
-        key = None
+    key = None
+    if isinstance(weight, torch.nn.Parameter):          # temporaries (e.g. a concatenated [Wq; Wk; Wv]) are not cached
+        try:
+            key = (weight.data_ptr(), weight._version, n, _cache_generation)
+        except RuntimeError:
+            key = None
     hit = _weight_planes.get(id(weight))
     if key is not None and hit is not None and hit[0] == key and (hit[2] is not None or not need_t):
         return hit[1], hit[2]

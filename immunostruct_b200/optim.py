@@ -3,10 +3,10 @@
 The reference steps ``torch.optim.Adam`` / ``AdamW`` over ~60 separate parameter tensors
 (train_IEDB_wFT.py:74,97; train_Cancer_wFT.py:98,122; procedures/train.py:28,122).  Here the parameters that
 receive gradients live in ONE flat fp32 buffer (each ``nn.Parameter`` is a view of it, so ``state_dict``,
-``torch.save`` and ``load_state_dict`` are unchanged), their gradients in a second flat buffer, and one launch of
-``is_fused_adam`` (csrc/optim.cu) updates everything.  The flat gradient buffer is shared with
-``distributed.BucketedGradientReducer``, which all-reduces slices of it in place while the backward pass is still
-running.
+``torch.save`` and ``load_state_dict`` are unchanged), their gradients are gathered into a second flat buffer, and one
+launch of ``is_fused_adam`` (csrc/optim.cu) updates everything.  The flat gradient buffer is shared with
+``distributed.BucketedGradientReducer``, which fills and all-reduces it bucket by bucket while the backward pass is
+still running.
 
 Parameters whose gradient is ``None`` after the first backward pass (the last EGNN layer's ``coord_mlp``,
 hybrid_models.py:323-326) stay outside the flat buffers and are never touched -- exactly what torch's optimisers do
@@ -25,16 +25,21 @@ __all__ = ["FlatGradients", "flatten_gradients", "FusedAdam", "FusedAdamW"]
 
 
 class FlatGradients:
-    """Gradients of ``params`` (those that have one) as views of a single buffer, in REVERSE parameter order:
-    autograd finishes the last layers first, so the buffer fills front to back during the backward pass."""
+    """One flat buffer with a slot (view) per parameter that has a gradient, in REVERSE parameter order: autograd
+    finishes the last layers first, so the buffer fills front to back during the backward pass.
 
-    def __init__(self, params: List[torch.nn.Parameter], alias: bool = True):
-        self.aliased = False
+    Gradients are not aliased by default: autograd keeps handing out fresh per-parameter tensors (free with
+    ``zero_grad(set_to_none=True)``), and ``gather`` copies a whole group of them into their slots with ONE multi-tensor
+    launch -- aliasing instead makes autograd run ``slot += grad`` once per parameter (~100 tiny kernels per step).
+    ``point`` makes ``p.grad`` the slots (after an all-reduce: every consumer of ``p.grad`` then sees the averaged
+    values); a gradient that already is its slot is skipped by ``gather``."""
+
+    def __init__(self, params: List[torch.nn.Parameter], alias: bool = False):
         self.params = [p for p in reversed(params) if p.grad is not None]
         if not self.params:
             raise RuntimeError("no parameter has a gradient yet: call after the first backward()")
         g0 = self.params[0].grad
-        # every view starts on a 16-byte boundary (vector accesses of the fused optimiser, NCCL alignment)
+        # every slot starts on a 16-byte boundary (vector accesses of the fused optimiser, NCCL alignment)
         self.offsets, o = [], 0
         for p in self.params:
             self.offsets.append(o)
@@ -46,13 +51,11 @@ class FlatGradients:
         if alias:
             self.realias()
 
-    def gather(self) -> None:
-        """Copy every parameter's current ``.grad`` into the flat buffer with one multi-tensor launch (no aliasing:
-        autograd keeps assigning fresh gradient tensors, which costs nothing, instead of ``view += grad`` per
-        parameter)."""
+    def gather(self, indices=None) -> None:
+        """Copy the current ``.grad`` of the given parameters (default: all) into their slots: one multi-tensor launch."""
         src, dst = [], []
-        for p, v in zip(self.params, self.views):
-            g = p.grad
+        for i in (range(len(self.params)) if indices is None else indices):
+            g, v = self.params[i].grad, self.views[i]
             if g is None:
                 v.zero_()
             elif g is not v and g.data_ptr() != v.data_ptr():
@@ -61,22 +64,19 @@ class FlatGradients:
         if src:
             torch._foreach_copy_(dst, src)
 
+    def point(self, indices=None) -> None:
+        """``p.grad = slot`` (no copy)."""
+        for i in (range(len(self.params)) if indices is None else indices):
+            self.params[i].grad = self.views[i]
+
     def realias(self) -> None:
-        """Make every ``p.grad`` the view of the flat buffer (copying a foreign gradient tensor in).  From then on
-        autograd accumulates in place, so slices of the buffer can be all-reduced while backward is still running."""
-        self.aliased = True
-        for p, v in zip(self.params, self.views):
-            g = p.grad
-            if g is None:
-                v.zero_()
-            elif g.data_ptr() != v.data_ptr():
-                v.copy_(g)
-            p.grad = v
+        """gather + point: every ``p.grad`` becomes its slot, holding the same values."""
+        self.gather()
+        self.point()
 
     def zero_(self) -> None:
         self.flat.zero_()
-        for p, v in zip(self.params, self.views):
-            p.grad = v
+        self.point()
 
     def index(self, p) -> int:
         for i, q in enumerate(self.params):
@@ -85,15 +85,14 @@ class FlatGradients:
         raise KeyError("parameter not in this FlatGradients")
 
 
-def flatten_gradients(params: Iterable[torch.nn.Parameter], alias: bool = True) -> FlatGradients:
+def flatten_gradients(params: Iterable[torch.nn.Parameter], alias: bool = False) -> FlatGradients:
     """The ``FlatGradients`` of ``params`` -- created on first use, shared by every later caller with the same
-    live parameter set (the gradient reducer and the optimiser of one model).  ``alias=True`` (the reducer) makes the
-    parameters' ``.grad`` views of the buffer; the optimiser alone does not need that and gathers instead."""
+    live parameter set (the gradient reducer and the optimiser of one model)."""
     params = [p for p in params if p.requires_grad]
     live = [p for p in params if p.grad is not None]
     fg = getattr(live[0], "_is_flat_grad", None) if live else None
     if fg is not None and len(fg.params) == len(live) and all(a is b for a, b in zip(fg.params, reversed(live))):
-        if alias and not fg.aliased:
+        if alias:
             fg.realias()
         return fg
     return FlatGradients(params, alias)
@@ -104,8 +103,8 @@ class FusedAdam(torch.optim.Optimizer):
 
     Same defaults, hyper-parameter names (``param_groups[i]['lr']`` is read every step, so LR schedulers work) and
     per-parameter state keys (``step``, ``exp_avg``, ``exp_avg_sq``) as torch's optimisers; ``amsgrad`` /
-    ``maximize`` are not supported.  Without a gradient reducer the per-parameter gradients are gathered into the
-    flat buffer by one multi-tensor copy per step; with one (``distributed.BucketedGradientReducer``) they alias it."""
+    ``maximize`` are not supported.  The per-parameter gradients are gathered into the flat buffer by one multi-tensor
+    copy per step -- or are already there when ``distributed.BucketedGradientReducer`` has all-reduced them."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False, grad_scale=1.0):
         if lr < 0 or eps < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1 or weight_decay < 0:
@@ -115,7 +114,7 @@ class FusedAdam(torch.optim.Optimizer):
         self._flat = {}       # group index -> dict(fg, p, m, v, runs, step)
 
     def _setup_group(self, gi, group):
-        fg = flatten_gradients(group["params"], alias=False)
+        fg = flatten_gradients(group["params"])
         mine = {id(p) for p in group["params"]}
         idx = [i for i, p in enumerate(fg.params) if id(p) in mine]
         n = sum((fg.params[i].numel() + 3) // 4 * 4 for i in idx)
@@ -154,7 +153,8 @@ class FusedAdam(torch.optim.Optimizer):
                 self._setup_group(gi, group)
             fl = self._flat[gi]
             fg = fl["fg"]
-            fg.gather()                    # no-op when the gradients already live in the flat buffer (reducer attached)
+            fg.gather(fl["idx"])           # one multi-tensor copy; skipped for gradients that already are their slots
+                                           # (a gradient reducer has all-reduced them in the flat buffer)
             fl["step"] += 1
             t = fl["step"]
             b1, b2 = group["betas"]
@@ -172,17 +172,7 @@ class FusedAdam(torch.optim.Optimizer):
         return loss
 
     def zero_grad(self, set_to_none: bool = True):
-        """Gradients that alias the flat buffer (a gradient reducer is attached) are zeroed in one memset and keep
-        their views; otherwise torch's default (``set_to_none``) applies."""
-        done, aliased = set(), False
-        for fl in self._flat.values():
-            fg = fl["fg"]
-            if fg.aliased and id(fg) not in done:
-                fg.zero_()
-                done.add(id(fg))
-                aliased = True
-        if not aliased:
-            super().zero_grad(set_to_none=set_to_none)
+        super().zero_grad(set_to_none=set_to_none)
 
 
 class FusedAdamW(FusedAdam):

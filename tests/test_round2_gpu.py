@@ -364,7 +364,8 @@ def test_linear_tc_autograd_matches_fp64(b, k, n, relu):
     x = torch.randn(b, k, generator=gen)
     w, bias = torch.randn(n, k, generator=gen) / k ** 0.5, torch.randn(n, generator=gen) * 0.1
     gy = torch.randn(b, n, generator=gen)
-    xd, wd, bd = (t.to(DEV).requires_grad_(True) for t in (x, w, bias))
+    xd = x.to(DEV).requires_grad_(True)
+    wd, bd = torch.nn.Parameter(w.to(DEV)), torch.nn.Parameter(bias.to(DEV))      # Parameters: their planes are cached
     y = IF.linear_tc(xd, wd, bd, relu)
     y.backward(gy.to(DEV))
     x64, w64, b64 = (t.double().requires_grad_(True) for t in (x, w, bias))

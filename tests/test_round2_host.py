@@ -114,19 +114,25 @@ def test_fused_adam_matches_torch_and_skips_gradless_parameters(cpu_backend, dec
     assert torch.allclose(st["exp_avg"], opt_t.state[a[0].weight]["exp_avg"], rtol=1e-5, atol=1e-8)
 
 
-def test_flat_gradients_are_shared_and_survive_set_to_none(cpu_backend):
+def test_flat_gradients_gather_point_and_sharing(cpu_backend):
     m = _toy()
     x = torch.randn(4, 7)
     m[2](m[0](x)).sum().backward()
     fg = flatten_gradients(m.parameters())
-    assert flatten_gradients(m.parameters()) is fg
+    assert flatten_gradients(m.parameters()) is fg                 # one object per live parameter set
     assert [p is q for p, q in zip(fg.params, [m[2].bias, m[2].weight, m[0].bias, m[0].weight])] == [True] * 4
     g0 = m[0].weight.grad.clone()
+    assert m[0].weight.grad.data_ptr() != fg.views[3].data_ptr()   # not aliased by default
+    fg.gather()
+    assert torch.equal(fg.views[3], g0)
+    fg.point()
     assert m[0].weight.grad.data_ptr() == fg.views[3].data_ptr()
     m.zero_grad(set_to_none=True)
-    m[2](m[0](x)).sum().backward()                              # fresh .grad tensors
+    m[2](m[0](2 * x)).sum().backward()                             # fresh .grad tensors again
+    fg.gather([3])                                                 # a single slot
+    assert torch.equal(fg.views[3], m[0].weight.grad) and not torch.equal(fg.views[1], m[2].weight.grad)
     fg.realias()
-    assert m[0].weight.grad.data_ptr() == fg.views[3].data_ptr() and torch.equal(m[0].weight.grad, g0)
+    assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(fg.params, fg.views))
 
 
 def _reducer_worker(rank, world, port, q):
