@@ -101,7 +101,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
             self.t.start()
@@ -299,22 +299,28 @@ def main():
     # ---- device-resident inference throughput (the headline `value`) ---------------------------
     model.eval()
     launches0 = None
+    # clocks / throttle reasons are sampled from before the warm-up until the end of the end-to-end loops: the timed
+    # region alone (K x 2.2 ms) can be shorter than nvidia-smi's sampling period, the whole stretch runs the same kernels
+    clk = ClockSampler(local)
+    clk.__enter__()
+    time.sleep(0.3)                               # nvidia-smi start-up: the first sample must not miss the load
     with torch.no_grad():
+        for i in range(20):                       # lead-in under the clock sampler (untimed, before the W warm-up steps)
+            infer_step(*pool[i % POOL])
         for i in range(W):
             infer_step(*pool[i % POOL])
         barrier()
         launches0 = _C.LAUNCHES
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local) as clk:
-            if args.profile:
-                torch.cuda.profiler.start()
-            e0.record()
-            for i in range(K):
-                probs = infer_step(*pool[i % POOL])
-            e1.record()
-            barrier()
-            if args.profile:
-                torch.cuda.profiler.stop()
+        if args.profile:
+            torch.cuda.profiler.start()
+        e0.record()
+        for i in range(K):
+            probs = infer_step(*pool[i % POOL])
+        e1.record()
+        barrier()
+        if args.profile:
+            torch.cuda.profiler.stop()
         ms = max_over_ranks(e0.elapsed_time(e1))
     launches = _C.LAUNCHES - launches0
     value = world * B * K / (ms / 1e3)
@@ -395,6 +401,7 @@ def main():
         e1.record()
         barrier()
         ms_e2e_packed = max_over_ranks(e0.elapsed_time(e1))
+    clk.__exit__()
 
     # ---- the same device-resident step in the other arithmetic modes (short runs) -----------------
     other = {}
