@@ -216,7 +216,7 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
     // sixteen values stay in registers (t1v) so that the second use of t1 (weight gradient of W2) is a re-store, not a
     // second gather + SiLU pass
     float t1v[2][8];
-    auto gather_t1 = [&](uint8_t* dst_tile, const BwdMeta& mt, int ne) {
+    auto gather_t1 = [&](uint8_t* dst_tile, const BwdMeta& mt, int ne, auto&& before_stores) {
         float pv[2][8], qv[2][8];
         float rr[2], aa[2];
 #pragma unroll
@@ -236,11 +236,16 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
             float d1[8];                                               // silu'(z1): parked in the fp32 tile for epilogue 4
 #pragma unroll
             for (int i = 0; i < 8; ++i) silu_both_acc(pv[u][i] + qv[u][i] + wr[i] * rr[u] + wa[i] * aa[u], t1v[u][i], d1[i]);
-            store_operand8<PREC_BF16X3>(dst_tile, ASPL, j, kc8, t1v[u]);    // rows >= ne: finite, multiplied by zero gradients
             float* dd = F32 + j * IS_LD + 8 * kc8;
             *reinterpret_cast<float4*>(dd) = make_float4(d1[0], d1[1], d1[2], d1[3]);
             *reinterpret_cast<float4*>(dd + 4) = make_float4(d1[4], d1[5], d1[6], d1[7]);
         }
+        // the row gathers and the SiLU evaluations above ran while the previous tile's weight-gradient MMAs (WG 2) were
+        // still reading the operand tiles; only the stores below have to wait for them
+        before_stores();
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+            store_operand8<PREC_BF16X3>(dst_tile, ASPL, u * 4 * BT_NW + warp * 4 + esub, kc8, t1v[u]);   // rows >= ne: finite, x 0
     };
     auto restore_t1 = [&](uint8_t* dst_tile) {
 #pragma unroll
@@ -281,10 +286,10 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
         if (n0 >= nend) break;
         const BwdMeta& mt = meta[cur];
         const bool row_valid = erow < ne;
-        wait_wg();              // WG 2 of the previous tile still reads X and Y
+        __syncthreads();        // the previous tile's destination-side sums are done with the fp32 tile
 
         // ---- t1 -> X ; MMA 1: z2 = t1 W2^T ; meanwhile prefetch the next tile's scalars ------------
-        gather_t1(sX, mt, ne);
+        gather_t1(sX, mt, ne, [&] { wait_wg(); });     // WG 2 of the previous tile still reads X and Y
         fence_async_smem();
         fence_before_sync();
         __syncthreads();

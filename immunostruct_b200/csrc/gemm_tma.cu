@@ -78,7 +78,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(&acc_full, 1);
     }
-    if (warp == 2) tmem_alloc(&s_tmem, BN);
+    if (warp == 2) tmem_alloc(&s_tmem, NPL == 3 ? 2 * BN : BN);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -110,17 +110,30 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 const uint32_t a_addr = base + s * STAGE_BYTES, b_addr = a_addr + OP_BYTES;
                 uint32_t acc = i > 0 ? 1u : 0u;
                 if (NPL == 3) {
-                    // (a-term, b-term), smallest products first: a3b1 a1b3 a2b2 a2b1 a1b2 a1b1
+                    // (a-term, b-term), smallest products first: a3b1 a1b3 a2b2 a2b1 a1b2 | a1b1.  TWO accumulators: the
+                    // five correction products (<= 2^-8 of the result) go to columns [BN, 2 BN), the leading product
+                    // a1 b1 alone to [0, BN).  Every accumulation step rounds at the accumulator's magnitude; keeping the
+                    // 20 correction steps per K block out of the leading accumulator leaves it 4 steps per block
+                    // instead of 24, and the corrections' own rounding is 2^-8 smaller.  The epilogue adds the two.
                     const uint32_t ta[6] = {2, 0, 1, 1, 0, 0}, tb[6] = {0, 2, 1, 0, 1, 0};
+                    uint32_t acc_c = acc;
+                    bool any_c = false;
 #pragma unroll
-                    for (int t = 0; t < 6; ++t) {
+                    for (int t = 0; t < 5; ++t) {
                         if ((a_exact && ta[t] != 0) || (b_exact && tb[t] != 0)) continue;
+                        any_c = true;
 #pragma unroll
                         for (int ks = 0; ks < BK / 16; ++ks) {
-                            mma_bf16(tmem, make_sw128_desc(a_addr + ta[t] * PLANE_BYTES + ks * 32),
-                                     make_sw128_desc(b_addr + tb[t] * PLANE_BYTES + ks * 32), idesc, acc);
-                            acc = 1;
+                            mma_bf16(tmem + BN, make_sw128_desc(a_addr + ta[t] * PLANE_BYTES + ks * 32),
+                                     make_sw128_desc(b_addr + tb[t] * PLANE_BYTES + ks * 32), idesc, acc_c);
+                            acc_c = 1;
                         }
+                    }
+                    (void)any_c;
+#pragma unroll
+                    for (int ks = 0; ks < BK / 16; ++ks) {
+                        mma_bf16(tmem, make_sw128_desc(a_addr + ks * 32), make_sw128_desc(b_addr + ks * 32), idesc, acc);
+                        acc = 1;
                     }
                 } else {
 #pragma unroll
@@ -137,6 +150,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     } else {
         // ================= epilogue (warps 2-5: TMEM lane quarter = warp % 4) =================
         constexpr int LDT = BN + 1;
+        const bool has_corr = !((a_resid_flag != nullptr && *a_resid_flag == 0) && (b_resid_flag != nullptr && *b_resid_flag == 0));
         float* T = reinterpret_cast<float*>(base_ptr);                        // 128 x 129 floats over the (idle) stage ring
         const int q = warp & 3, row = 32 * q + lane;
         if (nkb > 0) {
@@ -148,6 +162,12 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             float z[32];
             if (nkb > 0) {
                 tmem_ld<32>(tmem + ((uint32_t)(32 * q) << 16) + 32 * c, z);
+                if (NPL == 3 && has_corr) {                                   // + the correction accumulator
+                    float zc[32];
+                    tmem_ld<32>(tmem + ((uint32_t)(32 * q) << 16) + BN + 32 * c, zc);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) z[i] += zc[i];
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) z[i] = 0.0f;
@@ -180,7 +200,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem, BN);
+    if (warp == 2) tmem_dealloc(tmem, NPL == 3 ? 2 * BN : BN);
 }
 
 // C[m, n] = act(sum_s part[s][m][n] + b[n]) in slice order (deterministic)

@@ -95,9 +95,10 @@ class SelfAttention(nn.Module):
         return _cached_no_grad(self, "qkv", ps, lambda: (torch.cat(ps[:3], 0), torch.cat(ps[3:], 0)))
 
     def _qkv(self, h):
-        # (training path only: in inference the projections ride in the last node kernel.  Kept on torch's fp32 GEMM:
-        #  routed through the bf16x3 tensor-core GEMM the 64-wide projection is 1.3x faster but moves one tiny EGNN
-        #  gradient of the benchmark-shape parity test from 0.81x to 1.002x of its bound -- measured on the B200.)
+        # Training path only (in inference the projections ride in the last node kernel).  Kept on torch's fp32 GEMM:
+        # measured on the B200, routing this 64-wide projection and its three gradients through the TMA GEMM of
+        # csrc/gemm_tma.cu (128 x 128 tiles, one K block: epilogue-bound) leaves the 11.1 ms training step unchanged
+        # and moves one tiny EGNN gradient of the benchmark-shape parity test from 0.83x to 1.02x of its bound.
         return F.linear(h, *self.qkv_params())
 
     out_projection = None                       # SelfAttention has no w_concat
@@ -148,9 +149,10 @@ class MultiHeadAttention(nn.Module):
         return _cached_no_grad(self, "qkv", ps, lambda: (torch.cat(ps[:3], 0), torch.cat(ps[3:], 0)))
 
     def _qkv(self, h):
-        # (training path only: in inference the projections ride in the last node kernel.  Kept on torch's fp32 GEMM:
-        #  routed through the bf16x3 tensor-core GEMM the 64-wide projection is 1.3x faster but moves one tiny EGNN
-        #  gradient of the benchmark-shape parity test from 0.81x to 1.002x of its bound -- measured on the B200.)
+        # Training path only (in inference the projections ride in the last node kernel).  Kept on torch's fp32 GEMM:
+        # measured on the B200, routing this 64-wide projection and its three gradients through the TMA GEMM of
+        # csrc/gemm_tma.cu (128 x 128 tiles, one K block: epilogue-bound) leaves the 11.1 ms training step unchanged
+        # and moves one tiny EGNN gradient of the benchmark-shape parity test from 0.83x to 1.02x of its bound.
         return F.linear(h, *self.qkv_params())
 
     @property

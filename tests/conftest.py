@@ -65,7 +65,7 @@ def assert_grads_close(got: dict, ref: dict, tol: float, floor_frac: float = 1e-
     shift-invariance) from being compared on noise.  ``ref[k] is None`` demands that the product
     also reports NO gradient (``None``)."""
     gmax = max(float(v.abs().max()) for v in ref.values() if v is not None)
-    bad = []
+    bad, worst = [], ("", 0.0)
     for k, r in ref.items():
         g = got[k]
         if r is None:
@@ -83,6 +83,15 @@ def assert_grads_close(got: dict, ref: dict, tol: float, floor_frac: float = 1e-
             err = float((g - t).abs().max())
         else:
             err = float((g - r.double()).abs().max())
+        if lim > 0 and err / lim > worst[1]:
+            worst = (k, err / lim)
         if not err <= lim:
             bad.append((k, f"err {err:.3e} > {lim:.3e}"))
+    try:                                    # margin log (gpurun_out/kernel_errors.txt): worst error / bound of this call
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "kernel_errors.txt"), "a") as f:
+            test = os.environ.get("PYTEST_CURRENT_TEST", "").split("::")[-1]
+            f.write(f"{test} | gradient parity: worst err / bound = {worst[1]:.3f} ({worst[0]})\n")
+    except OSError:
+        pass
     assert not bad, bad
