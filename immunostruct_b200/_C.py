@@ -47,7 +47,7 @@ def exported_symbols():
             "is_fusion_attn_bwd", "is_loss_fwd", "is_loss_bwd", "is_umma_selftest", "is_egnn_edge_fwd_tc", "is_attn_pool_infer", "is_egnn_node_post_pre_tc", "is_egnn_edge_bwd_tc", "is_linear_tc", "is_linear_tc_split_k", "is_attn_pool_infer_tc", "is_vae_mid_infer", "is_head_infer", "is_unpack_nodes", "is_unpack_edges", "is_onehot_tokens", "is_egnn_node_post_bwd_tc", "is_egnn_node_pre_bwd_tc", "is_attn_pool_bwd_tc",
             "is_segment_pool_fwd", "is_segment_pool_bwd", "is_contrastive_scratch_floats", "is_contrastive_fwd",
             "is_contrastive_bwd", "is_fused_adam", "is_rotate_coords", "is_mask_single_residue", "is_mask_rows", "is_gemm_tma_split_k",
-            "is_split_planes", "is_gemm_planes_tma", "is_egnn_set_ws_buffers"]
+            "is_split_planes", "is_gemm_planes_tma", "is_egnn_set_ws_buffers", "is_reduce_partials3"]
 
 
 def _check(rc: int, name: str):
@@ -287,6 +287,15 @@ def reduce_partials(partials, out):
     f32 = torch.float32
     _call("is_reduce_partials", _t(partials, f32, "partials"), _i32(partials.shape[0]), _i64(partials.shape[1]),
           _t(out, f32, "out"), _stream())
+
+
+def reduce_partials3(parts, outs):
+    """Three (partials [n, stride], out [stride]) pairs reduced in CTA order by one launch."""
+    f32 = torch.float32
+    args = []
+    for p, o in zip(parts, outs):
+        args += [_t(p, f32, "partials"), _i32(p.shape[0]), _i64(p.shape[1]), _t(o, f32, "out")]
+    _call("is_reduce_partials3", *args, _stream())
 
 
 # ---- attention + pooling -----------------------------------------------------------------------

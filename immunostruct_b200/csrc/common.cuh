@@ -46,6 +46,26 @@ inline int current_num_sms() {
     return cached[dev];
 }
 
+// e^x with ONE MUFU and the product-rounding term compensated: x log2(e) is formed as t + lo (t = the rounded product,
+// lo = its exact rounding error + x * (log2 e - fl(log2 e))), 2^t comes from ex2.approx (2^-22.5 relative), and the
+// factor 2^lo = 1 + lo ln 2 is applied afterwards.  Six instructions against ~11 for expf(); the plain ex2.approx(x *
+// log2e) of the inference kernels carries |x| * 6e-8 of relative error from the product rounding, which was measured to
+// push parameter gradients past 1e-5 -- this form does not.  IS_EXP_LIBM restores expf().
+__device__ __forceinline__ float exp_comp(float x) {
+#ifdef IS_EXP_LIBM
+    return expf(x);
+#else
+    const float c1 = 1.4426950216293335f;              // fl(log2 e)
+    const float c2 = 1.9259629911266175e-8f;           // log2 e - c1
+    const float t = x * c1;
+    float lo = fmaf(x, c1, -t);
+    lo = fmaf(x, c2, lo);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+    return e * fmaf(lo, 0.6931471805599453f, 1.0f);      // (e may be 0 or inf: a product keeps them, e + e * x would not)
+#endif
+}
+
 // accurate exp + correctly rounded reciprocal: the fast intrinsics (__expf, __fdividef) cost ~1e-5 of
 // gradient parity against the fp32 reference (measured on the B200: tests/test_models_gpu.py)
 __device__ __forceinline__ float sigmoidf_fast(float z) { return __frcp_rn(1.0f + expf(-z)); }

@@ -706,8 +706,28 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= stride) return;
     float s = 0.0f;
+#pragma unroll 8
     for (int b = 0; b < nparts; ++b) s += partials[(size_t)b * stride + i];
     out[i] = s;
+}
+
+// the three partial buffers of one EGNN layer's backward (node_post, edge, node_pre) in ONE launch: blockIdx.y = set
+struct Partials3 {
+    const float* partials[3];
+    float* out[3];
+    int nparts[3];
+    int64_t stride[3];
+};
+__global__ void reduce_partials3_kernel(Partials3 a) {
+    const int k = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = a.stride[k];
+    if (i >= stride) return;
+    const float* __restrict__ p = a.partials[k];
+    const int n = a.nparts[k];
+    float s = 0.0f;
+#pragma unroll 8
+    for (int b = 0; b < n; ++b) s += p[(size_t)b * stride + i];        // ascending CTA order: deterministic
+    a.out[k][i] = s;
 }
 
 }  // namespace is
@@ -855,6 +875,22 @@ int is_egnn_node_pre_bwd(const float* gz1, const float* gQ, const float* gD, con
     if (rc) return rc;
     node_pre_bwd_kernel<<<node_grid(n_nodes), IS_THREADS, smem, (cudaStream_t)stream>>>(
         gz1, gQ, gD, gxd, gx_out, gh_direct, outptr, csc_pos, h, ldh, F, W1, gh, gx, partials, n_nodes);
+    IS_LAUNCH_CHECK();
+    return IS_OK;
+}
+
+int is_reduce_partials3(const float* p0, int n0, int64_t s0, float* o0, const float* p1, int n1, int64_t s1, float* o1,
+                        const float* p2, int n2, int64_t s2, float* o2, void* stream) {
+    if (n0 <= 0 || n1 <= 0 || n2 <= 0 || s0 <= 0 || s1 <= 0 || s2 <= 0) return IS_ERR_ARG;
+    Partials3 a;
+    a.partials[0] = p0; a.partials[1] = p1; a.partials[2] = p2;
+    a.out[0] = o0; a.out[1] = o1; a.out[2] = o2;
+    a.nparts[0] = n0; a.nparts[1] = n1; a.nparts[2] = n2;
+    a.stride[0] = s0; a.stride[1] = s1; a.stride[2] = s2;
+    int64_t smax = s0 > s1 ? s0 : s1;
+    if (s2 > smax) smax = s2;
+    dim3 grid((unsigned)((smax + 255) / 256), 3);
+    reduce_partials3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
     IS_LAUNCH_CHECK();
     return IS_OK;
 }

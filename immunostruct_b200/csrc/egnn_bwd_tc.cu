@@ -102,7 +102,7 @@ __device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
 // the training forward (tc_common.cuh act<PREC, false>), ~10 instructions instead of ~20 with a rounded reciprocal.
 __device__ __forceinline__ float sig_acc(float z) {
     float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + expf(-z)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + exp_comp(-z)));
     return r;
 }
 __device__ __forceinline__ float silu_acc(float z) { return z * sig_acc(z); }

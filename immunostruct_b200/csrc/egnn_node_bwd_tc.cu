@@ -106,7 +106,7 @@ __device__ __forceinline__ float colsum16(const float (&v)[16], int lane) {
 // accurate SiLU and derivative (same arithmetic as the SIMT kernels up to the approximate reciprocal, 1 ulp)
 __device__ __forceinline__ void silu_both_acc(float z, float& y, float& dy) {
     float s;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(1.0f + expf(-z)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(1.0f + exp_comp(-z)));
     y = z * s;
     dy = s * (1.0f + z * (1.0f - s));
 }

@@ -47,7 +47,7 @@ __device__ __forceinline__ float act(float z) {
     }
     float e, r;
     if (FAST) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
-    else e = expf(-z);      // training forward: gradient parity at 1e-5 needs the fully accurate exp
+    else e = exp_comp(-z);  // training forward: gradient parity at 1e-5 needs an exp without the product-rounding term
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
     return z * r;
 }

@@ -143,9 +143,7 @@ def _egnn_layer_backward(g, h, x, edge_attr, PQ, hn, params, gh_out, gx_out, nee
     (_C.egnn_node_pre_bwd_tc if tc else _C.egnn_node_pre_bwd)(gz1, gQ, gD, gxd, gx_out, gh_direct, g, h, W1, gh, gx, p_pre)
     # deterministic reduction of the per-CTA weight-gradient partials
     r_post, r_edge, r_pre = _new(h, p_post.shape[1]), _new(h, p_edge.shape[1]), _new(h, p_pre.shape[1])
-    _C.reduce_partials(p_post, r_post)
-    _C.reduce_partials(p_edge, r_edge)
-    _C.reduce_partials(p_pre, r_pre)
+    _C.reduce_partials3((p_post, p_edge, p_pre), (r_post, r_edge, r_pre))
 
     gW5 = r_post[:H * k].view(H, k)
     gb5 = r_post[H * k:H * k + H]

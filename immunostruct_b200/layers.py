@@ -70,6 +70,29 @@ class EGNNConv(nn.Module):
         return h_out, (x_out if update_coords else coord_feat)
 
 
+class _SegmentedLinear(torch.autograd.Function):
+    """``F.linear(h, W, b)`` for node rows [B * n, K] whose weight / bias gradients are contractions over ALL nodes of
+    the batch (102 400 rows at batch 512): autograd's single long-K GEMM and column reduction run 0.19 + 0.17 ms
+    there; per-graph partial products (one batched GEMM, [B, out, K]) summed over the graphs take a tenth of that.
+    Equal node counts per graph (the reference's own assumption, hybrid_models.py:86-92); fixed summation order."""
+
+    @staticmethod
+    def forward(ctx, h, w, b, n_graphs):
+        ctx.n_graphs = n_graphs
+        ctx.save_for_backward(h, w)
+        return F.linear(h, w, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        h, w = ctx.saved_tensors
+        bsz = ctx.n_graphs
+        g3, h3 = g.reshape(bsz, -1, g.shape[1]), h.reshape(bsz, -1, h.shape[1])
+        gh = g @ w if ctx.needs_input_grad[0] else None
+        gw = torch.bmm(g3.transpose(1, 2), h3).sum(0) if ctx.needs_input_grad[1] else None
+        gb = g3.sum(1).sum(0) if ctx.needs_input_grad[2] else None
+        return gh, gw, gb, None
+
+
 def _dense_attention(q, k, v):
     w = torch.softmax(q @ k.transpose(-2, -1) / math.sqrt(k.shape[-1]), dim=-1)
     return w @ v, w
@@ -94,19 +117,22 @@ class SelfAttention(nn.Module):
         ps = (self.query.weight, self.key.weight, self.value.weight, self.query.bias, self.key.bias, self.value.bias)
         return _cached_no_grad(self, "qkv", ps, lambda: (torch.cat(ps[:3], 0), torch.cat(ps[3:], 0)))
 
-    def _qkv(self, h):
+    def _qkv(self, h, graph=None):
         # Training path only (in inference the projections ride in the last node kernel).  Kept on torch's fp32 GEMM:
         # measured on the B200, routing this 64-wide projection and its three gradients through the TMA GEMM of
         # csrc/gemm_tma.cu (128 x 128 tiles, one K block: epilogue-bound) leaves the 11.1 ms training step unchanged
         # and moves one tiny EGNN gradient of the benchmark-shape parity test from 0.83x to 1.02x of its bound.
-        return F.linear(h, *self.qkv_params())
+        w, b = self.qkv_params()
+        if graph is not None and h.is_cuda and torch.is_grad_enabled() and graph.n_graphs * int(graph.max_nodes) == h.shape[0]:
+            return _SegmentedLinear.apply(h, w, b, graph.n_graphs)
+        return F.linear(h, w, b)
 
     out_projection = None                       # SelfAttention has no w_concat
 
     def pooled(self, graph, h, want_attn=False, want_nodes=False, qkv=None, project=True):
         """h [N_total,64] -> (per-graph mean of the attention output [B,64], weights|None, per-node out|None).
         ``qkv``: the projections [N,192] when a fused kernel has already computed them."""
-        O, pooled, attn = IF.attention_pool(graph, self._qkv(h) if qkv is None else qkv, 1, want_attn, want_nodes)
+        O, pooled, attn = IF.attention_pool(graph, self._qkv(h, graph) if qkv is None else qkv, 1, want_attn, want_nodes)
         if want_attn:
             attn = attn.squeeze(1)         # SelfAttention returns [B, n, n]
         return pooled, attn, (O if want_nodes else None)
@@ -148,12 +174,15 @@ class MultiHeadAttention(nn.Module):
         ps = (self.w_q.weight, self.w_k.weight, self.w_v.weight, self.w_q.bias, self.w_k.bias, self.w_v.bias)
         return _cached_no_grad(self, "qkv", ps, lambda: (torch.cat(ps[:3], 0), torch.cat(ps[3:], 0)))
 
-    def _qkv(self, h):
+    def _qkv(self, h, graph=None):
         # Training path only (in inference the projections ride in the last node kernel).  Kept on torch's fp32 GEMM:
         # measured on the B200, routing this 64-wide projection and its three gradients through the TMA GEMM of
         # csrc/gemm_tma.cu (128 x 128 tiles, one K block: epilogue-bound) leaves the 11.1 ms training step unchanged
         # and moves one tiny EGNN gradient of the benchmark-shape parity test from 0.83x to 1.02x of its bound.
-        return F.linear(h, *self.qkv_params())
+        w, b = self.qkv_params()
+        if graph is not None and h.is_cuda and torch.is_grad_enabled() and graph.n_graphs * int(graph.max_nodes) == h.shape[0]:
+            return _SegmentedLinear.apply(h, w, b, graph.n_graphs)
+        return F.linear(h, w, b)
 
     @property
     def out_projection(self):
@@ -166,7 +195,7 @@ class MultiHeadAttention(nn.Module):
         kernel has already computed them."""
         if self.feature_dim != 64 or self.input_dim != 64:
             raise NotImplementedError("fused per-graph attention is specialised for 64 channels")
-        O, pooled, attn = IF.attention_pool(graph, self._qkv(h) if qkv is None else qkv, self.n_head, want_attn, want_nodes)
+        O, pooled, attn = IF.attention_pool(graph, self._qkv(h, graph) if qkv is None else qkv, self.n_head, want_attn, want_nodes)
         nodes = self.w_concat(O) if want_nodes else None
         return (self.w_concat(pooled) if project else pooled), attn, nodes
 

@@ -103,6 +103,9 @@ int is_egnn_node_pre_bwd_tc(const float* gz1, const float* gQ, const float* gD, 
                          const int* outptr, const int* csc_pos, const float* h, int64_t ldh, int F,
                          const float* W1, float* gh, float* gx, float* partials, int64_t n_nodes, void* stream);
 int is_reduce_partials(const float* partials, int nparts, int64_t stride, float* out, void* stream);
+/* the three partial buffers of one layer's backward (node_post, edge, node_pre) reduced by one launch */
+int is_reduce_partials3(const float* p0, int n0, int64_t s0, float* o0, const float* p1, int n1, int64_t s1, float* o1,
+                        const float* p2, int n2, int64_t s2, float* o2, void* stream);
 
 /* ---- per-graph attention + global_mean_pool (models/layers.py:13-22,29-48,67-78;
  * models/hybrid_models.py:92-97 / 326-331).  QKV [n,192], O [n,64], LSE [n,H], pooled [B,64]. */
