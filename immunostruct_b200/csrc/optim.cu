@@ -13,10 +13,18 @@
 
 namespace is {
 
+__global__ void adam_tick_kernel(float* __restrict__ step) { *step += 1.0f; }
+
+// step_dev != NULL (CUDA-graph capture): the step count lives on the device and the bias corrections are formed here
 __global__ void __launch_bounds__(256)
 fused_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                   int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int decoupled,
-                  float step_size, float inv_bc2_sqrt, float grad_scale) {
+                  float step_size, float inv_bc2_sqrt, float grad_scale, const float* __restrict__ step_dev) {
+    if (step_dev != nullptr) {
+        const float t = *step_dev;
+        step_size = lr / (1.0f - powf(beta1, t));
+        inv_bc2_sqrt = rsqrtf(1.0f - powf(beta2, t));
+    }
     const int64_t n4 = n >> 2;
     const float omb1 = 1.0f - beta1, omb2 = 1.0f - beta2;
     const float decay = decoupled ? 1.0f - lr * weight_decay : 1.0f;
@@ -63,7 +71,28 @@ int is_fused_adam(float* p, const float* g, float* m, float* v, int64_t n, float
     if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
     if (blocks < 1) blocks = 1;
     fused_adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
-                                                                     decoupled, step_size, inv_bc2_sqrt, grad_scale);
+                                                                     decoupled, step_size, inv_bc2_sqrt, grad_scale, nullptr);
+    IS_LAUNCH_CHECK();
+    return IS_OK;
+}
+
+// Capturable form (the whole training step replayed from a CUDA graph): `step` is a device float holding the number of
+// steps taken so far; `tick` != 0 increments it first (once per optimiser step, before the first parameter run).
+int is_fused_adam_capturable(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                             float eps, float weight_decay, int decoupled, float* step, int tick, float grad_scale,
+                             void* stream) {
+    if (n < 0 || step == nullptr) return IS_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (tick) adam_tick_kernel<<<1, 1, 0, st>>>(step);
+    if (n == 0) return IS_OK;
+    if (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+          reinterpret_cast<uintptr_t>(v)) & 15) != 0) return IS_ERR_ARG;
+    const int sms = current_num_sms();
+    int64_t blocks = ((n >> 2) + 255) / 256;
+    if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+    if (blocks < 1) blocks = 1;
+    fused_adam_kernel<<<(int)blocks, 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, decoupled, 0.0f, 0.0f,
+                                                   grad_scale, step);
     IS_LAUNCH_CHECK();
     return IS_OK;
 }

@@ -106,11 +106,13 @@ class FusedAdam(torch.optim.Optimizer):
     ``maximize`` are not supported.  The per-parameter gradients are gathered into the flat buffer by one multi-tensor
     copy per step -- or are already there when ``distributed.BucketedGradientReducer`` has all-reduced them."""
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False, grad_scale=1.0):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False, grad_scale=1.0,
+                 capturable=False):
         if lr < 0 or eps < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1 or weight_decay < 0:
             raise ValueError("invalid Adam hyper-parameter")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, decoupled=decoupled))
         self.grad_scale = float(grad_scale)
+        self.capturable = bool(capturable)      # step count on the device: the step can be replayed from a CUDA graph
         self._flat = {}       # group index -> dict(fg, p, m, v, runs, step)
 
     def _setup_group(self, gi, group):
@@ -138,7 +140,8 @@ class FusedAdam(torch.optim.Optimizer):
             else:
                 runs.append((o, go, kp))
             o += kp
-        self._flat[gi] = dict(fg=fg, p=fp, m=fm, v=fv, runs=runs, step=0, idx=idx)
+        self._flat[gi] = dict(fg=fg, p=fp, m=fm, v=fv, runs=runs, step=0, idx=idx,
+                              step_dev=torch.zeros(1, dtype=torch.float32, device=dev) if self.capturable else None)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -159,13 +162,19 @@ class FusedAdam(torch.optim.Optimizer):
             t = fl["step"]
             b1, b2 = group["betas"]
             lr = float(group["lr"])
+            live = [fg.params[i] for i in fl["idx"]]
+            if self.capturable:
+                for k, (po, go, n) in enumerate(fl["runs"]):
+                    _C.fused_adam_capturable(fl["p"][po:po + n], fg.flat[go:go + n], fl["m"][po:po + n], fl["v"][po:po + n],
+                                             lr, b1, b2, group["eps"], group["weight_decay"], group["decoupled"],
+                                             fl["step_dev"], k == 0, self.grad_scale)
+                continue                        # (no host-side bookkeeping inside a captured step)
             step_size = lr / (1.0 - b1 ** t)
             inv_bc2_sqrt = 1.0 / math.sqrt(1.0 - b2 ** t)
             for po, go, n in fl["runs"]:
                 _C.fused_adam(fl["p"][po:po + n], fg.flat[go:go + n], fl["m"][po:po + n], fl["v"][po:po + n], lr, b1, b2,
                               group["eps"], group["weight_decay"], group["decoupled"], step_size, inv_bc2_sqrt,
                               self.grad_scale)
-            live = [fg.params[i] for i in fl["idx"]]
             torch.autograd.graph.increment_version(live)          # the kernel wrote through raw pointers: caches keyed on
             for p in live:                                        # the version counters must see the update
                 self.state[p]["step"] = torch.tensor(float(t))
@@ -176,5 +185,6 @@ class FusedAdam(torch.optim.Optimizer):
 
 
 class FusedAdamW(FusedAdam):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, grad_scale=1.0):
-        super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, decoupled=True, grad_scale=grad_scale)
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, grad_scale=1.0, capturable=False):
+        super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, decoupled=True, grad_scale=grad_scale,
+                         capturable=capturable)

@@ -228,6 +228,11 @@ int is_contrastive_bwd(const float* Ec, const float* Ew, int B, int D, int Z, co
 int is_fused_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                   float weight_decay, int decoupled, float step_size, float inv_bc2_sqrt, float grad_scale, void* stream);
 
+/* capturable form: the step count is a device float (`tick` != 0 increments it first), bias corrections on the device */
+int is_fused_adam_capturable(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                             float eps, float weight_decay, int decoupled, float* step, int tick, float grad_scale,
+                             void* stream);
+
 /* ---- on-device training augmentations (csrc/augment.cu) ------------------------------------
  * is_rotate_coords: RandomRotation (data/utils.py:148-155): x[:, c0:c0+3] @= Q_g, Q_g = Householder-QR orthogonal factor
  *   (LAPACK sign convention = numpy.linalg.qr) of the caller's 3x3 normal draw M_g; Qout [n_graphs, 9] or NULL.

@@ -560,6 +560,14 @@ def gemm_planes(a_planes, b_planes, bias=None, relu=False, out=None, a_flag=None
     return out
 
 
+def fused_adam_capturable(p, g, m, v, lr, beta1, beta2, eps, weight_decay, decoupled, step, tick, grad_scale=1.0):
+    if tick:
+        step += 1.0
+    t = float(step)
+    fused_adam(p, g, m, v, lr, beta1, beta2, eps, weight_decay, decoupled, lr / (1 - beta1 ** t),
+               1.0 / math.sqrt(1 - beta2 ** t), grad_scale)
+
+
 def reduce_partials3(parts, outs):
     for p, o in zip(parts, outs):
         reduce_partials(p, o)
@@ -569,4 +577,4 @@ ALL = ["num_sms", "egnn_node_grid", "egnn_edge_bwd_grid", "attn_max_nodes", "los
        "egnn_node_pre_fwd", "egnn_edge_fwd", "egnn_edge_fwd_tc", "egnn_node_post_pre_tc", "linear_tc", "vae_mid_infer", "head_infer", "unpack_nodes", "unpack_edges", "onehot_tokens", "egnn_node_post_fwd", "egnn_node_post_bwd", "egnn_node_post_bwd_tc", "egnn_node_pre_bwd_tc", "egnn_edge_bwd", "egnn_edge_bwd_tc",
        "egnn_node_pre_bwd", "reduce_partials", "attn_pool_fwd", "attn_pool_infer", "attn_pool_infer_tc", "attn_pool_bwd", "attn_pool_bwd_tc", "fusion_attn_fwd",
        "fusion_attn_bwd", "loss_fwd", "loss_bwd", "segment_pool_fwd", "segment_pool_bwd", "contrastive_scratch_floats",
-       "contrastive_fwd", "contrastive_bwd", "fused_adam", "rotate_coords", "mask_single_residue", "mask_rows", "split_planes", "gemm_planes", "reduce_partials3"]
+       "contrastive_fwd", "contrastive_bwd", "fused_adam", "rotate_coords", "mask_single_residue", "mask_rows", "split_planes", "gemm_planes", "reduce_partials3", "fused_adam_capturable"]

@@ -186,13 +186,14 @@ def test_contrastive_module_gate_buffers_and_determinism():
 
 
 # ---- fused Adam ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("capturable", [False, True])
 @pytest.mark.parametrize("decoupled,wd", [(False, 0.0), (False, 1e-6), (True, 1e-6), (True, 1e-2)])
-def test_fused_adam_matches_torch_on_the_model(decoupled, wd):
+def test_fused_adam_matches_torch_on_the_model(decoupled, wd, capturable):
     torch.manual_seed(1)
     a = I.model_map["HybridModelv2"](vae_input_dim=231, device=DEV, vae_hidden_dim=32).to(DEV)
     b = copy.deepcopy(a)
     opt_t = (torch.optim.AdamW if decoupled else torch.optim.Adam)(a.parameters(), lr=1e-3, weight_decay=wd)
-    opt_f = (FusedAdamW if decoupled else FusedAdam)(b.parameters(), lr=1e-3, weight_decay=wd)
+    opt_f = (FusedAdamW if decoupled else FusedAdam)(b.parameters(), lr=1e-3, weight_decay=wd, capturable=capturable)
     arr = synthetic_graph_arrays(3, 40, 5, seed=2, n_pad=2)
     gb = to_dev(arr)
     gen = torch.Generator().manual_seed(0)

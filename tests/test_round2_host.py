@@ -87,11 +87,12 @@ def _toy(seed=0):
     return torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Tanh(), torch.nn.Linear(5, 3), torch.nn.Linear(3, 3))
 
 
+@pytest.mark.parametrize("capturable", [False, True])
 @pytest.mark.parametrize("decoupled,wd", [(False, 0.0), (False, 1e-2), (True, 1e-2)])
-def test_fused_adam_matches_torch_and_skips_gradless_parameters(cpu_backend, decoupled, wd):
+def test_fused_adam_matches_torch_and_skips_gradless_parameters(cpu_backend, decoupled, wd, capturable):
     a, b = _toy(), _toy()
     opt_t = (torch.optim.AdamW if decoupled else torch.optim.Adam)(a.parameters(), lr=1e-2, weight_decay=wd)
-    opt_f = (FusedAdamW if decoupled else FusedAdam)(b.parameters(), lr=1e-2, weight_decay=wd)
+    opt_f = (FusedAdamW if decoupled else FusedAdam)(b.parameters(), lr=1e-2, weight_decay=wd, capturable=capturable)
     sched_t = torch.optim.lr_scheduler.StepLR(opt_t, 2, 0.5)
     sched_f = torch.optim.lr_scheduler.StepLR(opt_f, 2, 0.5)
     x = torch.randn(16, 7)
@@ -110,7 +111,8 @@ def test_fused_adam_matches_torch_and_skips_gradless_parameters(cpu_backend, dec
     c = _toy(1); c.load_state_dict(sd)
     assert torch.equal(c[0].weight, b[0].weight)
     st = opt_f.state[b[0].weight]
-    assert set(st) == {"step", "exp_avg", "exp_avg_sq"} and float(st["step"]) == 5
+    assert set(st) == {"step", "exp_avg", "exp_avg_sq"}
+    assert float(st["step"]) == 5 if not capturable else float(opt_f._flat[0]["step_dev"]) == 5
     assert torch.allclose(st["exp_avg"], opt_t.state[a[0].weight]["exp_avg"], rtol=1e-5, atol=1e-8)
 
 
