@@ -19,8 +19,7 @@
 // gradients are column sums over edge rows: each warp reduce-scatters its 32 rows with 16 shuffles and keeps
 // one running register per vector.
 // One 512-thread CTA per SM; shared memory: two bf16x3 operand tiles (X, Y), W2 / W3, one fp32 tile.
-#include "egnn_common.cuh"
-#include "tc_common.cuh"
+#include "egnn_bwd_common.cuh"
 
 namespace is {
 
@@ -68,77 +67,14 @@ __device__ __forceinline__ void load_bwd_meta(const EdgeCommon& p, const float* 
     m.v[j] = v0; m.v[IS_TM + j] = v1; m.v[2 * IS_TM + j] = v2;
 }
 
-// sum over the warp's 32 rows of 16 per-lane column values; afterwards lane L holds the total of column
-// (L >> 1) & 15 (both lanes of a pair hold the same value).  Fixed order -> deterministic.
-__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
-    float w8[8], w4[4], w2[2];
-    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float send = b4 ? v[i] : v[i + 8];
-        const float keep = b4 ? v[i + 8] : v[i];
-        w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float send = b3 ? w8[i] : w8[i + 4];
-        const float keep = b3 ? w8[i + 4] : w8[i];
-        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float send = b2 ? w4[i] : w4[i + 2];
-        const float keep = b2 ? w4[i + 2] : w4[i];
-        w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-    const float send = b1 ? w2[0] : w2[1];
-    const float keep = b1 ? w2[1] : w2[0];
-    float s = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    return s;
-}
-
-// SiLU and its derivative with the accurate expf and an approximate (1 ulp) reciprocal: the same arithmetic as
-// the training forward (tc_common.cuh act<PREC, false>), ~10 instructions instead of ~20 with a rounded reciprocal.
-__device__ __forceinline__ float sig_acc(float z) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + exp_comp(-z)));
-    return r;
-}
-__device__ __forceinline__ float silu_acc(float z) { return z * sig_acc(z); }
-__device__ __forceinline__ float dsilu_acc(float z) { const float s = sig_acc(z); return s * (1.0f + z * (1.0f - s)); }
-__device__ __forceinline__ void silu_both_acc(float z, float& y, float& dy) {
-    const float s = sig_acc(z);
-    y = z * s;
-    dy = s * (1.0f + z * (1.0f - s));
-}
-
-// ---- bf16x3 GEMM issue with explicit operand geometry (ONE thread) ------------------------------------------
-struct OpGeom {
-    uint32_t base;      // shared-memory address of split term 0
-    uint32_t split;     // bytes between split terms
-    uint32_t step;      // start-address advance per K step of 16
-    uint32_t lbo, sbo;  // descriptor fields (bytes)
-};
-__device__ __forceinline__ void issue_x3(uint32_t tmem_d, const OpGeom& a, const OpGeom& b, int nks, uint32_t idesc,
-                                         uint32_t accumulate) {
-    const uint32_t ta[6] = {2, 0, 1, 1, 0, 0}, tb[6] = {0, 2, 1, 0, 1, 0};     // smallest products first
-    uint32_t acc = accumulate;
-#pragma unroll
-    for (int t = 0; t < 6; ++t)
-#pragma unroll 8
-        for (int ks = 0; ks < nks; ++ks) {
-            mma_bf16(tmem_d, make_smem_desc(a.base + ta[t] * a.split + ks * a.step, a.lbo, a.sbo),
-                     make_smem_desc(b.base + tb[t] * b.split + ks * b.step, b.lbo, b.sbo), idesc, acc);
-            acc = 1;
-        }
-}
-
 template <bool HAS_COORD>
 __global__ void __launch_bounds__(BT_NT, 1)
 edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __restrict__ gx_out,
                    float* __restrict__ gz1, float* __restrict__ gQ, float* __restrict__ gD, float* __restrict__ gxd,
-                   float* __restrict__ partials) {
+                   float* __restrict__ partials, const int* __restrict__ gate) {
+    // gate (device, optional) = the batch's maximum in-degree: when the two-stream kernel of egnn_bwd_ws.cu can take
+    // the batch (every node fits one of its smaller tiles) this launch is its idle fallback and returns at once
+    if (gate != nullptr && __ldg(gate) <= IS_BWD_WS_TR) return;
     using C = TcCfg<PREC_BF16X3>;
     constexpr uint32_t ASPL = C::A_BYTES, WSPL = C::W_BYTES;
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -553,6 +489,32 @@ edge_bwd_tc_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
 
 }  // namespace is
 
+// shared launcher: is_egnn_edge_bwd_tc (gate = nullptr) and the fallback leg of is_egnn_edge_bwd_ws (egnn_bwd_ws.cu)
+namespace is {
+int launch_edge_bwd_tc(const EdgeCommon& c, const float* ghn, const float* gx_out, float* gz1, float* gQ, float* gD,
+                       float* gxd, float* partials, const int* gate, cudaStream_t st) {
+    using C = TcCfg<PREC_BF16X3>;
+    const size_t smem = 6 * (size_t)C::A_BYTES + 6 * (size_t)C::W_BYTES +
+                        sizeof(float) * (IS_TM * IS_LD + 5 * 64 + 11 * IS_TM + BT_NW * 16) + 2 * sizeof(BwdMeta) + 128;
+    const int sms = current_num_sms();
+    int64_t g = ((int64_t)c.n_nodes + 31) / 32;
+    if (g > sms) g = sms;
+    const int grid = (int)(g < 1 ? 1 : g);
+    cudaError_t e;
+    if (gx_out) {
+        e = cudaFuncSetAttribute(edge_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        edge_bwd_tc_kernel<true><<<grid, BT_NT, smem, st>>>(c, ghn, gx_out, gz1, gQ, gD, gxd, partials, gate);
+    } else {
+        e = cudaFuncSetAttribute(edge_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        edge_bwd_tc_kernel<false><<<grid, BT_NT, smem, st>>>(c, ghn, gx_out, gz1, gQ, gD, gxd, partials, gate);
+    }
+    IS_LAUNCH_CHECK();
+    return IS_OK;
+}
+}  // namespace is
+
 using namespace is;
 
 extern "C" {
@@ -571,26 +533,7 @@ int is_egnn_edge_bwd_tc(const int* indptr, const int* csr_src, const int* csr_ds
     c.indptr = indptr; c.csr_src = csr_src; c.csr_dst = csr_dst; c.csr_eid = csr_eid;
     c.PQ = PQ; c.x = x; c.ldx = ldx; c.edge_attr = edge_attr; c.W1 = W1; c.F = F;
     c.W2 = W2; c.b2 = b2; c.W3 = W3; c.b3 = b3; c.w4 = w4; c.n_nodes = (int)n_nodes; c.status = status;
-    using C = TcCfg<PREC_BF16X3>;
-    const size_t smem = 6 * (size_t)C::A_BYTES + 6 * (size_t)C::W_BYTES +
-                        sizeof(float) * (IS_TM * IS_LD + 5 * 64 + 11 * IS_TM + BT_NW * 16) + 2 * sizeof(BwdMeta) + 128;
-    const int sms = current_num_sms();
-    int64_t g = (n_nodes + 31) / 32;
-    if (g > sms) g = sms;
-    const int grid = (int)(g < 1 ? 1 : g);
-    cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e;
-    if (gx_out) {
-        e = cudaFuncSetAttribute(edge_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        edge_bwd_tc_kernel<true><<<grid, BT_NT, smem, st>>>(c, ghn, gx_out, gz1, gQ, gD, gxd, partials);
-    } else {
-        e = cudaFuncSetAttribute(edge_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        edge_bwd_tc_kernel<false><<<grid, BT_NT, smem, st>>>(c, ghn, gx_out, gz1, gQ, gD, gxd, partials);
-    }
-    IS_LAUNCH_CHECK();
-    return IS_OK;
+    return launch_edge_bwd_tc(c, ghn, gx_out, gz1, gQ, gD, gxd, partials, nullptr, (cudaStream_t)stream);
 }
 
 }  // extern "C"

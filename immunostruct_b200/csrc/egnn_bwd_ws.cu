@@ -1,0 +1,573 @@
+// EGNN edge BACKWARD on the tensor cores, TWO TILE STREAMS PER CTA (tcgen05 + TMEM, bf16x3 operand split, sm_100a).
+//
+// Same contract, outputs and per-CTA partial layout as is::edge_bwd_tc_kernel (egnn_bwd_tc.cu) and is::edge_bwd_kernel
+// (egnn.cu).  The lock-step kernel spends 36 % of its warp time waiting: a tile is a strict chain
+//     gather -> MMA 1 -> epilogue 1 -> MMA 2 -> epilogue 2 -> MMA 3 (+ WG 3) -> epilogue 3 -> MMA 4 (+ WG 2) -> epilogue 4
+// and with one tile in flight the tensor pipe (192 MMAs per tile) and the SIMT epilogues strictly alternate (ncu:
+// barrier stalls 5.4 of 13.4 cycles per issue, profiles/r02_edge_bwd_*).  Here the CTA runs two independent TEAMS of
+// 8 warps; team T owns the tiles T, T + 2, ... of the CTA's node range and walks the same chain on its own operand
+// buffers, accumulator columns and named barrier, so one team's MMAs run under the other team's epilogues and every
+// latency inside a team (MMA completion, L2 gathers, the scalar prefetch chain) is covered by the other team's work.
+//
+// What makes two tiles fit one SM:
+//   * tiles of <= 112 edges (IS_BWD_WS_TR): four bf16x3 operand buffers of 112 x 64 (42 KB each) + W2 / W3 (48 KB) =
+//     216 KB.  The M = 128 data MMAs read 16 rows past a buffer (the next buffer: finite or not, those accumulator
+//     rows are never read); the weight-gradient MMAs run over K = 112 edges exactly;
+//   * a thread owns one tile row and 32 columns in EVERY phase (gather included), so silu'(z1) never passes through
+//     shared memory: z1 is parked in the thread's own TMEM lane (64 spare columns per team) and t1 / silu'(z1) are
+//     re-derived from it where needed (the second use of t1, as the B operand of the W2 gradient, is a re-store);
+//   * the four data accumulators of a tile are consumed one after the other: they share ONE 64-column TMEM block;
+//   * the fp32 copy of gz1 that the destination-side sums read is written over the team's X buffer once the last
+//     weight-gradient MMA of the tile has completed;
+//   * per-edge scalars are single-buffered per team (their load is covered by the other team).
+// Nodes with more than 112 in-edges do not fit these tiles: the launcher is handed the batch's maximum in-degree on the
+// DEVICE (GraphBatch.stats[0]) and enqueues this kernel and the lock-step kernel back to back; each returns at once
+// when the batch is the other one's.
+//
+// TMEM (512 columns): ACC[team] 64 | DW2, DW3 [team] 2 x 64 (M = 64 weight-gradient accumulators) | PARK[team] 64.
+#include "egnn_bwd_common.cuh"
+
+namespace is {
+
+int launch_edge_bwd_tc(const EdgeCommon& c, const float* ghn, const float* gx_out, float* gz1, float* gQ, float* gD,
+                       float* gxd, float* partials, const int* gate, cudaStream_t st);     // egnn_bwd_tc.cu
+
+namespace bw {
+constexpr int TR = IS_BWD_WS_TR;                    // edge rows per tile
+constexpr int NT = 512, TT = 256, TWARPS = 8;       // CTA threads, team threads, team warps
+constexpr uint32_t LBO = 128, SBO = 8 * LBO;        // unpadded K-major tiles (a thread stores its own row: conflict free)
+constexpr uint32_t A_TERM = (TR / 8) * SBO;         // one split term of a 112-row operand tile (14 KB)
+constexpr uint32_t A_BUF = 3 * A_TERM;
+constexpr uint32_t W_TERM = 8 * 8 * umma::kLBO_W;   // one split term of a 64 x 64 weight tile (8 KB)
+constexpr uint32_t W_BUF = 3 * W_TERM;
+constexpr int F_LD = 68;                            // fp32 gz1 rows: padded leading dimension
+constexpr uint32_t F32_BYTES = TR * F_LD * 4;
+constexpr int NKW = TR / 16;                        // K steps of a weight-gradient MMA group
+constexpr int MAXN = 32;                            // destination nodes per tile
+constexpr uint32_t TM_ACC = 0, TM_DW2 = 128, TM_DW3 = 192, TM_PARK = 384;
+static_assert(F32_BYTES + 7 * TR * 4 <= A_BUF, "fp32 staging must fit the X buffer");
+static_assert(TR % 16 == 0 && TR <= 128, "tile rows");
+
+struct Meta {                   // per-edge scalars of the team's current tile
+    int src[TR];
+    int dst[TR];
+    float r[TR];
+    float a[TR];
+    float gc[TR];               // dL/dc = v . dhat
+    float dx[3 * TR];           // raw difference x_src - x_dst
+    float vn[3 * MAXN];         // gx_out[node] / max(deg, 1) for the tile's destination nodes
+};
+
+__device__ __forceinline__ void team_sync(int team) {
+    asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(TT) : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+#ifndef IS_BW_WAIT_HINT_NS
+#define IS_BW_WAIT_HINT_NS 1000
+#endif
+}  // namespace bw
+
+template <bool HAS_COORD>
+__global__ void __launch_bounds__(bw::NT, 1)
+edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __restrict__ gx_out,
+                   float* __restrict__ gz1, float* __restrict__ gQ, float* __restrict__ gD, float* __restrict__ gxd,
+                   float* __restrict__ partials, const int* __restrict__ gate) {
+    using namespace bw;
+    if (gate != nullptr && __ldg(gate) > TR) return;        // the lock-step kernel (128-edge tiles) takes this batch
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint8_t* sBuf = smem_raw;                                 // [team][X, Y][A_BUF]
+    uint8_t* sW2 = sBuf + 4 * A_BUF;                          // [3][W_TERM]
+    uint8_t* sW3 = sW2 + W_BUF;
+    float* vec = reinterpret_cast<float*>(sW3 + W_BUF);       // b2, b3, w4, wr, wa
+    Meta* metas = reinterpret_cast<Meta*>(vec + 5 * 64);      // [team]
+    __shared__ int s_tile[2][4];                              // the team's NEXT tile: n0, n1, p0, ne
+    __shared__ int s_started[2];
+    __shared__ __align__(8) uint64_t mbar_d[2];               // data MMAs (z2, z3, gm, gt1) of a team
+    __shared__ __align__(8) uint64_t mbar_wg[2];              // weight-gradient MMAs of a team
+    __shared__ uint32_t s_tmem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int team = tid >> 8, t = tid & (TT - 1), tw = t >> 5;
+    const int q = tw & 3, cq = tw >> 2, erow = 32 * q + lane;      // TMEM lane quarter (= CTA warp % 4), column half, tile row
+    const bool rowv = erow < TR;
+    const int ldw1 = 2 * p.F + 2;
+    if (warp == 0) tmem_alloc(&s_tmem, 512);
+    if (tid == 32) { mbar_init(&mbar_d[0], 1); mbar_init(&mbar_d[1], 1); mbar_init(&mbar_wg[0], 1); mbar_init(&mbar_wg[1], 1); }
+    stage_weight_block<PREC_BF16X3>(sW2, W_TERM, p.W2, 64, 0, 64, tid, NT);
+    stage_weight_block<PREC_BF16X3>(sW3, W_TERM, HAS_COORD ? p.W3 : nullptr, 64, 0, 64, tid, NT);
+    if (tid < 64) {
+        vec[tid] = p.b2[tid];
+        vec[64 + tid] = HAS_COORD ? p.b3[tid] : 0.0f;
+        vec[128 + tid] = HAS_COORD ? p.w4[tid] : 0.0f;
+        vec[192 + tid] = p.W1[tid * ldw1 + 2 * p.F];
+        vec[256 + tid] = p.W1[tid * ldw1 + 2 * p.F + 1];
+    }
+    const int chunk = (p.n_nodes + gridDim.x - 1) / gridDim.x;
+    const int nbeg = blockIdx.x * chunk;
+    const int nend = min(p.n_nodes, nbeg + chunk);
+    if (tw == TWARPS - 1) {                 // the team's first tile: tile `team` of the CTA's sequence
+        int a0, a1, ap, ae;
+        next_tile<TR>(p.indptr, nbeg, nend, p.status, lane, a0, a1, ap, ae);
+        if (team == 1) next_tile<TR>(p.indptr, a1, nend, p.status, lane, a0, a1, ap, ae);
+        if (lane == 0) { s_tile[team][0] = a0; s_tile[team][1] = a1; s_tile[team][2] = ap; s_tile[team][3] = ae; }
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = s_tmem;
+
+    uint8_t* X = sBuf + (size_t)team * 2 * A_BUF;             // t1 -> gz3 -> gz2 ; afterwards the fp32 copy of gz1
+    uint8_t* Y = X + A_BUF;                                   // m -> t1 (re-stored)
+    uint8_t* T1 = HAS_COORD ? X : Y;                          // without the coordinate branch t1 can stay where it is gathered
+    Meta& mt = metas[team];
+    float* F32 = reinterpret_cast<float*>(X);                 // [TR][F_LD]
+    float* e_gr = reinterpret_cast<float*>(X + F32_BYTES);    // [2][TR] partial gr per column half
+    float* e_c = e_gr + 2 * TR;                               // [2][TR] partial c per column half
+    float* e_gd = e_c + 2 * TR;                               // [3][TR]
+    uint64_t* bar_d = &mbar_d[team];
+    uint64_t* bar_wg = &mbar_wg[team];
+    const uint32_t t_acc = tmem + ((uint32_t)(32 * q) << 16) + TM_ACC + 64 * team + 32 * cq;
+    const uint32_t t_park = tmem + ((uint32_t)(32 * q) << 16) + TM_PARK + 64 * team + 32 * cq;
+    const uint32_t d_acc = tmem + TM_ACC + 64 * team, d_w2 = tmem + TM_DW2 + 128 * team, d_w3 = tmem + TM_DW3 + 128 * team;
+    const uint32_t rowoff = (uint32_t)((erow >> 3) * SBO + (erow & 7) * 16);
+    // operand geometries
+    const OpGeom gXk = {smem_u32(X), A_TERM, 2 * LBO, LBO, SBO};                   // K-major activation tile
+    const OpGeom gYk = {smem_u32(Y), A_TERM, 2 * LBO, LBO, SBO};
+    const OpGeom gT1k = {smem_u32(T1), A_TERM, 2 * LBO, LBO, SBO};
+    const OpGeom gXt = {smem_u32(X), A_TERM, 2 * SBO, SBO, LBO};                   // same tile, transposed (MN-major)
+    const OpGeom gYt = {smem_u32(Y), A_TERM, 2 * SBO, SBO, LBO};
+    const OpGeom gW2k = {smem_u32(sW2), W_TERM, 2 * kLBO_W, kLBO_W, 8 * kLBO_W};   // forward weight operand
+    const OpGeom gW3k = {smem_u32(sW3), W_TERM, 2 * kLBO_W, kLBO_W, 8 * kLBO_W};
+    const OpGeom gW2t = {smem_u32(sW2), W_TERM, 2 * 8 * kLBO_W, 8 * kLBO_W, kLBO_W};   // transposed view (dgrad)
+    const OpGeom gW3t = {smem_u32(sW3), W_TERM, 2 * 8 * kLBO_W, 8 * kLBO_W, kLBO_W};
+    const uint32_t id_fwd = make_instr_desc(1u, 128, 64, 0, 0);
+    const uint32_t id_dgrad = make_instr_desc(1u, 128, 64, 0, 1);
+    const uint32_t id_wgrad = make_instr_desc(1u, 64, 64, 1, 1);
+
+    // running vector gradients: after warp_colsum16 lane L holds column 32 cq + 16 h + ((L >> 1) & 15) of this warp's rows
+    float acc_gb2[2] = {0.f, 0.f}, acc_gb3[2] = {0.f, 0.f}, acc_gw4[2] = {0.f, 0.f};
+    float acc_gwr = 0.f, acc_gwa = 0.f;          // column t & 63, row block t >> 6 (fp32 staging pass)
+    uint32_t ph_d = 0, ph_wg = 0, started = 0;
+
+    auto wait_d = [&]() { mbar_wait_hint(bar_d, ph_d, IS_BW_WAIT_HINT_NS); ph_d ^= 1; fence_after_sync(); };
+    auto wait_wg = [&]() { mbar_wait_hint(bar_wg, ph_wg, IS_BW_WAIT_HINT_NS); ph_wg ^= 1; fence_after_sync(); };
+    // publish this team's operand stores, then one elected lane of team warp 0 issues `fn`
+    auto publish_and_issue = [&](auto&& fn) {
+        fence_async_smem();
+        fence_before_sync();
+        team_sync(team);
+        if (tw == 0) {
+            if (elect_one()) {
+                fence_after_sync();
+                fn();
+            }
+            __syncwarp();
+        }
+    };
+
+    while (true) {
+        const int n0 = s_tile[team][0], n1 = s_tile[team][1], p0 = s_tile[team][2], ne = s_tile[team][3];
+        if (n0 >= nend) break;
+        // ---- per-edge scalars of this tile (the other team's work covers the load chain) ---------------------------
+        if (t < TR) {
+            const int j = t;
+            int s = 0, d = 0;
+            float r = 0.f, a = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
+            if (j < ne) {
+                const int e = p0 + j;
+                s = __ldg(p.csr_src + e); d = __ldg(p.csr_dst + e);
+                a = __ldg(p.edge_attr + __ldg(p.csr_eid + e));
+                dx = __ldg(p.x + s * p.ldx + 0) - __ldg(p.x + d * p.ldx + 0);
+                dy = __ldg(p.x + s * p.ldx + 1) - __ldg(p.x + d * p.ldx + 1);
+                dz = __ldg(p.x + s * p.ldx + 2) - __ldg(p.x + d * p.ldx + 2);
+                r = dx * dx + dy * dy + dz * dz;
+            }
+            mt.src[j] = s; mt.dst[j] = d; mt.r[j] = r; mt.a[j] = a;
+            mt.dx[j] = dx; mt.dx[TR + j] = dy; mt.dx[2 * TR + j] = dz;
+        } else if (HAS_COORD && t >= 128 && t < 128 + 3 * MAXN) {
+            const int i = t - 128, nl = i / 3, comp = i - 3 * nl, node = n0 + nl;
+            float v = 0.0f;
+            if (node < n1) {
+                const int deg = __ldg(p.indptr + node + 1) - __ldg(p.indptr + node);
+                v = __ldg(gx_out + (size_t)node * 3 + comp) * (1.0f / (float)max(deg, 1));
+            }
+            mt.vn[i] = v;
+        }
+        team_sync(team);
+        if (HAS_COORD && t < TR) {
+            float gc = 0.0f;
+            if (t < ne) {
+                const int dl = mt.dst[t] - n0;
+                const float inv = 1.0f / (sqrtf(mt.r[t]) + 1e-30f);
+                gc = (mt.vn[3 * dl] * mt.dx[t] + mt.vn[3 * dl + 1] * mt.dx[TR + t] + mt.vn[3 * dl + 2] * mt.dx[2 * TR + t]) * inv;
+            }
+            mt.gc[t] = gc;          // read in epilogue 2, several team barriers from here
+        }
+        const bool valid = erow < ne;
+
+        // ---- gather: z1 = P[src] + Q[dst] + wr r + wa a -> parked in TMEM ; t1 = silu(z1) -> T1 ; MMA 1 ------------
+        {
+            float pv[32], qv[32];
+            float rr = 0.f, aa = 0.f;
+            if (valid) {
+                const int s = mt.src[erow], d = mt.dst[erow];
+                rr = mt.r[erow]; aa = mt.a[erow];
+                const float* pp = p.PQ + (size_t)s * 128 + 32 * cq;
+                const float* qp = p.PQ + (size_t)d * 128 + 64 + 32 * cq;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    ldg256(pp + 8 * g, *reinterpret_cast<float(*)[8]>(&pv[8 * g]));
+                    ldg256(qp + 8 * g, *reinterpret_cast<float(*)[8]>(&qv[8 * g]));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { pv[i] = 0.f; qv[i] = 0.f; }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float z[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int c = 32 * cq + 16 * h + i;
+                    z[i] = valid ? pv[16 * h + i] + qv[16 * h + i] + vec[192 + c] * rr + vec[256 + c] * aa : 0.0f;
+                }
+                tmem_st16(t_park + 16 * h, z);
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    float v8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v8[i] = silu_acc(z[8 * g + i]);          // rows beyond the tile: silu(0) = 0
+                    if (rowv) store_chunk8<PREC_BF16X3>(T1 + rowoff + (4 * cq + 2 * h + g) * LBO, A_TERM, v8);
+                }
+            }
+            tmem_st_wait();
+        }
+        publish_and_issue([&] {
+            issue_x3(d_acc, gT1k, gW2k, 4, id_fwd, 0);
+            mma_commit(bar_d);
+        });
+        if (tw == TWARPS - 1) {             // this team's next tile = the tile after the other team's next one
+            int a0, a1, ap, ae;
+            next_tile<TR>(p.indptr, n1, nend, p.status, lane, a0, a1, ap, ae);
+            next_tile<TR>(p.indptr, a1, nend, p.status, lane, a0, a1, ap, ae);
+            if (lane == 0) { s_tile[team][0] = a0; s_tile[team][1] = a1; s_tile[team][2] = ap; s_tile[team][3] = ae; }
+        }
+        wait_d();
+
+        // ---- epilogue 1: m = silu(z2 + b2) -> Y ; d2 = silu'(z2 + b2) stays in registers ---------------------------
+        float d2[32];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float z[16];
+            tmem_ld<16>(t_acc + 16 * h, z);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                float m8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    silu_both_acc(z[8 * g + i] + vec[32 * cq + 16 * h + 8 * g + i], m8[i], d2[16 * h + 8 * g + i]);
+                if (HAS_COORD && rowv) store_chunk8<PREC_BF16X3>(Y + rowoff + (4 * cq + 2 * h + g) * LBO, A_TERM, m8);
+            }
+        }
+        float cpart = 0.0f;
+        if (HAS_COORD) {
+            // ---- MMA 2: z3 = m W3^T ; epilogue 2: c, gz3 = gc w4 silu'(z3 + b3) -> X -------------------------------
+            publish_and_issue([&] {
+                issue_x3(d_acc, gYk, gW3k, 4, id_fwd, 0);
+                mma_commit(bar_d);
+            });
+            wait_d();
+            const float gc = valid ? mt.gc[erow] : 0.0f;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float z[16], g3[16], gu[16];
+                tmem_ld<16>(t_acc + 16 * h, z);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int c = 32 * cq + 16 * h + i;
+                    float u, d3;
+                    silu_both_acc(z[i] + vec[64 + c], u, d3);
+                    const float w = vec[128 + c];
+                    cpart = fmaf(w, u, cpart);
+                    g3[i] = valid ? gc * w * d3 : 0.0f;       // (accumulator rows beyond the tile may hold anything)
+                    gu[i] = valid ? gc * u : 0.0f;
+                }
+                acc_gb3[h] += warp_colsum16(g3, lane);
+                acc_gw4[h] += warp_colsum16(gu, lane);
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    float v8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v8[i] = g3[8 * g + i];
+                    if (rowv) store_chunk8<PREC_BF16X3>(X + rowoff + (4 * cq + 2 * h + g) * LBO, A_TERM, v8);   // MMA 1 is done with X
+                }
+            }
+            // ---- MMA 3: gm = gz3 W3 ; WG 3: gW3 += gz3^T m ---------------------------------------------------------
+            publish_and_issue([&] {
+                issue_x3(d_acc, gXk, gW3t, 4, id_dgrad, 0);
+                mma_commit(bar_d);
+                issue_x3(d_w3, gXt, gYt, NKW, id_wgrad, started);
+                mma_commit(bar_wg);
+            });
+            wait_d();
+        }
+        // ---- epilogue 3: gz2 = (gm + ghn[dst]) silu'(z2) -> X ; t1 re-derived from the parked z1 -> Y ---------------
+        float d1[32];
+        {
+            float g2[32];
+            const float* ghrow = ghn + (size_t)(valid ? mt.dst[erow] : 0) * 64 + 32 * cq;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float gm[16], gh[16];
+                if (HAS_COORD) {
+                    tmem_ld<16>(t_acc + 16 * h, gm);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) gm[i] = 0.0f;
+                }
+                if (valid) {
+                    ldg256(ghrow + 16 * h, *reinterpret_cast<float(*)[8]>(&gh[0]));
+                    ldg256(ghrow + 16 * h + 8, *reinterpret_cast<float(*)[8]>(&gh[8]));
+                }
+                float gs[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    gs[i] = valid ? (gm[i] + gh[i]) * d2[16 * h + i] : 0.0f;
+                    g2[16 * h + i] = gs[i];
+                }
+                acc_gb2[h] += warp_colsum16(gs, lane);
+            }
+            if (HAS_COORD) wait_wg();       // WG 3 must be done with X (gz3) and Y (m) before they are overwritten
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float v8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v8[i] = g2[8 * g + i];
+                if (rowv) store_chunk8<PREC_BF16X3>(X + rowoff + (4 * cq + g) * LBO, A_TERM, v8);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float z[16];
+                tmem_ld<16>(t_park + 16 * h, z);
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    float v8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) silu_both_acc(z[8 * g + i], v8[i], d1[16 * h + 8 * g + i]);
+                    if (HAS_COORD && rowv) store_chunk8<PREC_BF16X3>(Y + rowoff + (4 * cq + 2 * h + g) * LBO, A_TERM, v8);
+                }
+            }
+        }
+        // ---- MMA 4: gt1 = gz2 W2 ; WG 2: gW2 += gz2^T t1 ---------------------------------------------------------------
+        publish_and_issue([&] {
+            issue_x3(d_acc, gXk, gW2t, 4, id_dgrad, 0);
+            mma_commit(bar_d);
+            issue_x3(d_w2, gXt, gYt, NKW, id_wgrad, started);
+            mma_commit(bar_wg);
+        });
+        started = 1;
+        wait_d();
+        // ---- epilogue 4: gz1 = gt1 silu'(z1) -> global ; gr ; then (WG 2 done) the fp32 copy over X ------------------------
+        {
+            float grpart = 0.0f;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float gt1[16];
+                tmem_ld<16>(t_acc + 16 * h, gt1);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float gz = valid ? gt1[i] * d1[16 * h + i] : 0.0f;
+                    d1[16 * h + i] = gz;
+                    grpart = fmaf(vec[192 + 32 * cq + 16 * h + i], gz, grpart);
+                }
+            }
+            if (valid) {
+                float* go = gz1 + (size_t)(p0 + erow) * 64 + 32 * cq;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) stg256(go + 8 * g, *reinterpret_cast<const float(*)[8]>(&d1[8 * g]));
+            }
+            wait_wg();                      // WG 2 has read X and Y: both are free
+            if (rowv) {
+                float* fo = F32 + erow * F_LD + 32 * cq;
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                    *reinterpret_cast<float4*>(fo + 4 * g) = make_float4(d1[4 * g], d1[4 * g + 1], d1[4 * g + 2], d1[4 * g + 3]);
+                e_gr[cq * TR + erow] = grpart;
+                if (HAS_COORD) e_c[cq * TR + erow] = cpart;
+            }
+        }
+        fence_before_sync();
+        team_sync(team);
+        // ---- geometry backward (one thread per edge) ; gwr / gwa from the fp32 copy (column t & 63, rows of block t >> 6) ---
+        if (t < TR) {
+            const int j = t;
+            float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+            if (j < ne) {
+                const float dx = mt.dx[j], dy = mt.dx[TR + j], dz = mt.dx[2 * TR + j];
+                const float two_gr = 2.0f * (e_gr[j] + e_gr[TR + j]);
+                g0 = two_gr * dx; g1 = two_gr * dy; g2 = two_gr * dz;
+                if (HAS_COORD) {
+                    const float c = e_c[j] + e_c[TR + j];
+                    const float rho = sqrtf(mt.r[j]);
+                    const float inv = 1.0f / (rho + 1e-30f);
+                    const int dl = mt.dst[j] - n0;
+                    const float h0 = c * mt.vn[3 * dl], h1 = c * mt.vn[3 * dl + 1], h2 = c * mt.vn[3 * dl + 2];
+                    const float k = (h0 * dx + h1 * dy + h2 * dz) * inv * inv / rho;
+                    g0 += h0 * inv - k * dx; g1 += h1 * inv - k * dy; g2 += h2 * inv - k * dz;
+                }
+                gD[(size_t)(p0 + j) * 3 + 0] = g0;
+                gD[(size_t)(p0 + j) * 3 + 1] = g1;
+                gD[(size_t)(p0 + j) * 3 + 2] = g2;
+            }
+            e_gd[j] = g0; e_gd[TR + j] = g1; e_gd[2 * TR + j] = g2;
+        }
+        {
+            const int c = t & 63, rb = (t >> 6) * (TR / 4), re = min(ne, rb + TR / 4);
+            for (int row = rb; row < re; ++row) {
+                const float gz = F32[row * F_LD + c];
+                acc_gwr = fmaf(gz, mt.r[row], acc_gwr);
+                acc_gwa = fmaf(gz, mt.a[row], acc_gwa);
+            }
+        }
+        team_sync(team);
+        // ---- destination-side sums: gQ[d] = sum gz1 ; gxd[d] = -sum g_diff ----------------------------------------------
+        for (int node = n0 + tw; node < n1; node += TWARPS) {
+            const int jb = __ldg(p.indptr + node) - p0, je = __ldg(p.indptr + node + 1) - p0;
+            float2 s = make_float2(0.0f, 0.0f);
+            for (int j = jb; j < je; ++j) {
+                const float2 v = *reinterpret_cast<const float2*>(F32 + j * F_LD + 2 * lane);
+                s.x += v.x; s.y += v.y;
+            }
+            *reinterpret_cast<float2*>(gQ + (size_t)node * 64 + 2 * lane) = s;
+            if (lane < 3) {
+                float sx = 0.0f;
+                for (int j = jb; j < je; ++j) sx += e_gd[lane * TR + j];
+                gxd[(size_t)node * 3 + lane] = -sx;
+            }
+        }
+        team_sync(team);        // X, Y and the scalars are free for the team's next tile
+    }
+
+    // ---- per-CTA partials: weight gradients from TMEM (both teams), vector gradients from the running registers -----
+    if (t == 0) s_started[team] = (int)started;
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    float* P = partials + (size_t)blockIdx.x * (8192 + 5 * 64);
+    {
+        // M = 64 accumulators: row r lives in TMEM lane 32 (r / 16) + r % 16 -> lanes 0..15 of CTA warp w hold rows 16 (w & 3) + lane
+        const int wq = warp & 3, part = warp >> 2;
+        const bool st0 = s_started[0] != 0, st1 = s_started[1] != 0;
+        const uint32_t ta = tmem + ((uint32_t)(32 * wq) << 16) + 16 * part;
+        float w0[16], w1[16];
+        tmem_ld<16>(ta + TM_DW2, w0);
+        tmem_ld<16>(ta + TM_DW2 + 128, w1);
+        if (lane < 16) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) P[(16 * wq + lane) * 64 + 16 * part + i] = (st0 ? w0[i] : 0.0f) + (st1 ? w1[i] : 0.0f);
+        }
+        if (HAS_COORD) {
+            tmem_ld<16>(ta + TM_DW3, w0);
+            tmem_ld<16>(ta + TM_DW3 + 128, w1);
+        }
+        if (lane < 16) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                P[4096 + (16 * wq + lane) * 64 + 16 * part + i] = HAS_COORD ? (st0 ? w0[i] : 0.0f) + (st1 ? w1[i] : 0.0f) : 0.0f;
+        }
+    }
+    float* red = reinterpret_cast<float*>(sBuf);              // [3 vectors][2 teams][8 warps][2 halves][16]
+    float* red2 = red + 3 * 2 * TWARPS * 32;                  // [2 vectors][2 teams][4 row blocks][64]
+    if ((lane & 1) == 0) {
+        const int k = lane >> 1;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            red[((0 * 2 + team) * TWARPS + tw) * 32 + 16 * h + k] = acc_gb2[h];
+            red[((1 * 2 + team) * TWARPS + tw) * 32 + 16 * h + k] = acc_gb3[h];
+            red[((2 * 2 + team) * TWARPS + tw) * 32 + 16 * h + k] = acc_gw4[h];
+        }
+    }
+    red2[((0 * 2 + team) * 4 + (t >> 6)) * 64 + (t & 63)] = acc_gwr;
+    red2[((1 * 2 + team) * 4 + (t >> 6)) * 64 + (t & 63)] = acc_gwa;
+    __syncthreads();
+    if (tid < 5 * 64) {
+        const int v = tid >> 6, col = tid & 63;
+        float s = 0.0f;
+        if (v < 3) {
+            const int cqq = col >> 5, hk = col & 31;           // team warp = 4 cq + q
+#pragma unroll
+            for (int tm = 0; tm < 2; ++tm)
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) s += red[((v * 2 + tm) * TWARPS + 4 * cqq + qq) * 32 + hk];
+        } else {
+#pragma unroll
+            for (int tm = 0; tm < 2; ++tm)
+#pragma unroll
+                for (int rb = 0; rb < 4; ++rb) s += red2[(((v - 3) * 2 + tm) * 4 + rb) * 64 + col];
+        }
+        P[8192 + v * 64 + col] = s;
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace is
+
+using namespace is;
+
+extern "C" {
+
+// Two-stream tensor-core edge backward (same outputs and partial layout as is_egnn_edge_bwd / is_egnn_edge_bwd_tc).
+// max_in_degree = DEVICE pointer to the batch's maximum in-degree (GraphBatch.stats); the 112-edge-tile kernel runs when
+// it is <= 112, the 128-edge lock-step kernel otherwise (both are enqueued; the idle one returns at once).  NULL, or
+// pointers that miss the 32-byte alignment of the 256-bit row accesses: lock-step kernel only.
+int is_egnn_edge_bwd_ws(const int* indptr, const int* csr_src, const int* csr_dst, const int* csr_eid,
+                        const float* PQ, const float* x, int64_t ldx, const float* edge_attr,
+                        const float* W1, int F, const float* W2, const float* b2,
+                        const float* W3, const float* b3, const float* w4,
+                        const float* ghn, const float* gx_out,
+                        float* gz1, float* gQ, float* gD, float* gxd, float* partials,
+                        const int* max_in_degree, int64_t n_nodes, int* status, void* stream) {
+    if (!(F == 20 || F == 64) || n_nodes <= 0 || n_nodes > 0x7fffffff) return IS_ERR_ARG;
+    if (((reinterpret_cast<uintptr_t>(PQ) | reinterpret_cast<uintptr_t>(gz1)) & 31) != 0) return IS_ERR_ARG;   // 256-bit accesses
+    EdgeCommon c;
+    c.indptr = indptr; c.csr_src = csr_src; c.csr_dst = csr_dst; c.csr_eid = csr_eid;
+    c.PQ = PQ; c.x = x; c.ldx = ldx; c.edge_attr = edge_attr; c.W1 = W1; c.F = F;
+    c.W2 = W2; c.b2 = b2; c.W3 = W3; c.b3 = b3; c.w4 = w4; c.n_nodes = (int)n_nodes; c.status = status;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (max_in_degree == nullptr || (reinterpret_cast<uintptr_t>(ghn) & 31) != 0)
+        return launch_edge_bwd_tc(c, ghn, gx_out, gz1, gQ, gD, gxd, partials, nullptr, st);
+    const size_t smem = 4 * (size_t)bw::A_BUF + 2 * (size_t)bw::W_BUF + sizeof(float) * 5 * 64 + 2 * sizeof(bw::Meta);
+    const int sms = current_num_sms();
+    int64_t g = (n_nodes + 31) / 32;
+    if (g > sms) g = sms;
+    const int grid = (int)(g < 1 ? 1 : g);
+    cudaError_t e;
+    if (gx_out) {
+        e = cudaFuncSetAttribute(edge_bwd_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        edge_bwd_ws_kernel<true><<<grid, bw::NT, smem, st>>>(c, ghn, gx_out, gz1, gQ, gD, gxd, partials, max_in_degree);
+    } else {
+        e = cudaFuncSetAttribute(edge_bwd_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        edge_bwd_ws_kernel<false><<<grid, bw::NT, smem, st>>>(c, ghn, gx_out, gz1, gQ, gD, gxd, partials, max_in_degree);
+    }
+    IS_LAUNCH_CHECK();
+    return launch_edge_bwd_tc(c, ghn, gx_out, gz1, gQ, gD, gxd, partials, max_in_degree, st);
+}
+
+}  // extern "C"

@@ -55,13 +55,14 @@ struct EdgeCommon {
 // ---- tile walk: executed by one full warp; all lanes return the same values ------------------------
 // Longest run of consecutive destination nodes (<= 32) starting at n0 whose in-edges total <= 128.
 // tn0 >= nend means the CTA's node range is exhausted.  Nodes with more than 128 in-edges are
-// unsupported: flagged in *status and skipped.
+// unsupported: flagged in *status and skipped.  LIMIT = edge rows of the caller's tile (<= 128).
+template <int LIMIT = IS_TM>
 __device__ __forceinline__ void next_tile(const int* __restrict__ indptr, int n0, int nend, int* __restrict__ status,
                                           int lane, int& tn0, int& tn1, int& tp0, int& tne) {
     while (n0 < nend) {
         const int pbase = __ldg(indptr + n0);
         const int cand = n0 + lane + 1;
-        const bool ok = (cand <= nend) && (__ldg(indptr + (cand <= nend ? cand : nend)) - pbase <= IS_TM);
+        const bool ok = (cand <= nend) && (__ldg(indptr + (cand <= nend ? cand : nend)) - pbase <= LIMIT);
         const int cnt = __popc(__ballot_sync(0xffffffffu, ok));
         if (cnt == 0) {
             if (lane == 0 && status) atomicExch(status, 1);

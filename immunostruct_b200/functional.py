@@ -6,6 +6,8 @@ reductions; per-CTA partials summed in CTA order by ``is_reduce_partials``).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _C
@@ -33,6 +35,19 @@ def set_precision(name: str) -> None:
 
 def get_precision() -> str:
     return _precision
+
+
+# Tile streams of the tensor-core edge backward: 2 = csrc/egnn_bwd_ws.cu (two 112-edge tiles in flight per SM; batches
+# with a node of more than 112 in-edges fall through to the lock-step kernel on the device), 1 = the lock-step
+# kernel of csrc/egnn_bwd_tc.cu only (A/B timing).
+_edge_bwd_streams = int(os.environ.get("IS_EDGE_BWD_STREAMS", "2"))
+
+
+def set_edge_bwd_streams(n: int) -> None:
+    global _edge_bwd_streams
+    if n not in (1, 2):
+        raise ValueError("edge backward tile streams: 1 or 2")
+    _edge_bwd_streams = n
 
 
 # Generation counter of every parameter-derived cache (fused projection weights, fusion coefficients, pre-split weight
@@ -134,7 +149,7 @@ def _egnn_layer_backward(g, h, x, edge_attr, PQ, hn, params, gh_out, gx_out, nee
     # edge backward
     gz1, gQ, gD, gxd = _new(h, e, H), _new(h, n, H), _new(h, e, 3), _new(h, n, 3)
     p_edge = _new(h, grid_e, 2 * H * H + 5 * H)
-    bwd = _C.egnn_edge_bwd if _PRECISIONS[_precision] is None else _C.egnn_edge_bwd_tc
+    bwd = _C.egnn_edge_bwd if _PRECISIONS[_precision] is None else (_C.egnn_edge_bwd_ws if _edge_bwd_streams == 2 else _C.egnn_edge_bwd_tc)
     bwd(g, PQ, x, edge_attr, f, W1, W2, b2, W3, b3, w4, ghn, gx_out, gz1, gQ, gD, gxd, p_edge)
     # node_pre backward (source-side reduction through the CSC transpose)
     gh = _new(h, n, H) if need_gh else None

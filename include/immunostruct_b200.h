@@ -93,6 +93,16 @@ int is_egnn_edge_bwd_tc(const int* indptr, const int* csr_src, const int* csr_ds
                         const float* ghn, const float* gx_out,
                         float* gz1, float* gQ, float* gD, float* gxd, float* partials,
                         int64_t n_nodes, int* status, void* stream);
+/* Two tile streams per CTA (csrc/egnn_bwd_ws.cu): same outputs and partial layout.  max_in_degree = DEVICE pointer
+   to the batch's maximum in-degree (is_collate_csr's stats[0]): <= 112 runs the 112-edge-tile two-stream kernel,
+   otherwise the lock-step kernel above (both are enqueued, the idle one returns at once); NULL = lock-step only. */
+int is_egnn_edge_bwd_ws(const int* indptr, const int* csr_src, const int* csr_dst, const int* csr_eid,
+                        const float* PQ, const float* x, int64_t ldx, const float* edge_attr,
+                        const float* W1, int F, const float* W2, const float* b2,
+                        const float* W3, const float* b3, const float* w4,
+                        const float* ghn, const float* gx_out,
+                        float* gz1, float* gQ, float* gD, float* gxd, float* partials,
+                        const int* max_in_degree, int64_t n_nodes, int* status, void* stream);
 int is_egnn_node_pre_bwd(const float* gz1, const float* gQ, const float* gD, const float* gxd,
                          const float* gx_out, const float* gh_direct,
                          const int* outptr, const int* csc_pos, const float* h, int64_t ldh, int F,

@@ -237,6 +237,11 @@ def egnn_edge_bwd_tc(*args):
     egnn_edge_bwd(*args)
 
 
+def egnn_edge_bwd_ws(*args):
+    """Same contract again: the two-stream kernel changes the schedule (and the tile size), not the results."""
+    egnn_edge_bwd(*args)
+
+
 def egnn_node_pre_bwd(gz1, gQ, gD, gxd, gx_out, gh_direct, g, h, W1, gh, gx, partials):
     f = h.shape[1]
     n = h.shape[0]
@@ -574,7 +579,7 @@ def reduce_partials3(parts, outs):
 
 
 ALL = ["num_sms", "egnn_node_grid", "egnn_edge_bwd_grid", "attn_max_nodes", "loss_num_partials", "collate_csr",
-       "egnn_node_pre_fwd", "egnn_edge_fwd", "egnn_edge_fwd_tc", "egnn_node_post_pre_tc", "linear_tc", "vae_mid_infer", "head_infer", "unpack_nodes", "unpack_edges", "onehot_tokens", "egnn_node_post_fwd", "egnn_node_post_bwd", "egnn_node_post_bwd_tc", "egnn_node_pre_bwd_tc", "egnn_edge_bwd", "egnn_edge_bwd_tc",
+       "egnn_node_pre_fwd", "egnn_edge_fwd", "egnn_edge_fwd_tc", "egnn_node_post_pre_tc", "linear_tc", "vae_mid_infer", "head_infer", "unpack_nodes", "unpack_edges", "onehot_tokens", "egnn_node_post_fwd", "egnn_node_post_bwd", "egnn_node_post_bwd_tc", "egnn_node_pre_bwd_tc", "egnn_edge_bwd", "egnn_edge_bwd_tc", "egnn_edge_bwd_ws",
        "egnn_node_pre_bwd", "reduce_partials", "attn_pool_fwd", "attn_pool_infer", "attn_pool_infer_tc", "attn_pool_bwd", "attn_pool_bwd_tc", "fusion_attn_fwd",
        "fusion_attn_bwd", "loss_fwd", "loss_bwd", "segment_pool_fwd", "segment_pool_bwd", "contrastive_scratch_floats",
        "contrastive_fwd", "contrastive_bwd", "fused_adam", "rotate_coords", "mask_single_residue", "mask_rows", "split_planes", "gemm_planes", "reduce_partials3", "fused_adam_capturable"]

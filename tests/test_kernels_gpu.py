@@ -51,12 +51,13 @@ def random_multigraph_arrays(seed, node_counts, mean_deg):
             "node_counts": torch.tensor(node_counts), "edge_counts": torch.tensor(ecs)}
 
 
-def hub_and_isolated_arrays(seed):
+def hub_and_isolated_arrays(seed, hub=128):
     """Edge cases of the tile walk: a run of 80 isolated nodes (edge-less tiles), hubs with in-degree 128 (the tile
-    limit) and 100, many in-degree-1 nodes (32-node tiles far below 128 edges), a graph without any edge."""
+    limit; hub=112: the limit of the two-stream edge backward, which hands larger batches to the lock-step kernel) and
+    100, many in-degree-1 nodes (32-node tiles far below 128 edges), a graph without any edge."""
     gen = torch.Generator().manual_seed(seed)
     n0, n1 = 150, 90
-    dst = torch.cat([torch.full((128,), 80), torch.full((100,), 81), torch.arange(82, 150),
+    dst = torch.cat([torch.full((hub,), 80), torch.full((100,), 81), torch.arange(82, 150),
                      torch.randint(82, 150, (70,), generator=gen)])
     src = (dst + 1 + torch.randint(0, n0 - 1, (dst.numel(),), generator=gen)) % n0
     x = torch.zeros(n0 + n1, 23)
@@ -85,6 +86,7 @@ def out_hub_arrays(seed):
 
 CASES = {
     "hubs_isolated": lambda: hub_and_isolated_arrays(7),
+    "hubs_112": lambda: hub_and_isolated_arrays(9, hub=112),
     "out_hubs": lambda: out_hub_arrays(11),
     "knn_small": lambda: synthetic_graph_arrays(5, 37, 6, seed=3, n_pad=4, coord_scale=4.0),
     "knn_200": lambda: synthetic_graph_arrays(3, 200, 10, seed=4, n_pad=10),
@@ -326,12 +328,13 @@ def test_vae_mid_and_head_kernels(b):
 
 
 # ---- EGNN backward -----------------------------------------------------------------------------
-@pytest.mark.parametrize("tc", [False, True])
+@pytest.mark.parametrize("tc", [False, True, "ws"])
 @pytest.mark.parametrize("f,coord", [(64, True), (64, False), (20, True)])
 def test_egnn_backward_kernels(case, f, coord, tc):
-    """tc=True: the tcgen05 edge backward (bf16x3) against the same contract at the same tolerance."""
+    """tc=True: the tcgen05 edge backward (bf16x3) against the same contract at the same tolerance; "ws": its two-stream
+    successor (112-edge tiles; the in-degree-128 case exercises the device-side hand-over to the lock-step kernel)."""
     arrays, gb, cg = case
-    edge_bwd = _C.egnn_edge_bwd_tc if tc else _C.egnn_edge_bwd
+    edge_bwd = {False: _C.egnn_edge_bwd, True: _C.egnn_edge_bwd_tc, "ws": _C.egnn_edge_bwd_ws}[tc]
     gen = torch.Generator().manual_seed(13)
     n, e = gb.n_nodes, gb.n_edges
     w = egnn_weights(gen, f)
@@ -409,8 +412,10 @@ def test_egnn_backward_kernels(case, f, coord, tc):
     assert int(gb.status.item()) == 0
 
 
-def test_backward_is_deterministic(case):
-    """Same inputs twice -> bit-identical gradients (no floating-point atomics anywhere)."""
+@pytest.mark.parametrize("kernel", ["egnn_edge_bwd", "egnn_edge_bwd_ws"])
+def test_backward_is_deterministic(case, kernel):
+    """Same inputs twice -> bit-identical gradients (no floating-point atomics anywhere; the two tile streams of the
+    ws kernel accumulate into separate TMEM blocks that are added in a fixed order)."""
     arrays, gb, _ = case
     gen = torch.Generator().manual_seed(17)
     n, e = gb.n_nodes, gb.n_edges
@@ -421,7 +426,7 @@ def test_backward_is_deterministic(case):
     for _ in range(2):
         outs = [torch.empty(e, 64, device=DEV), torch.empty(n, 64, device=DEV), torch.empty(e, 3, device=DEV),
                 torch.empty(n, 3, device=DEV), torch.empty(_C.egnn_edge_bwd_grid(n), 8512, device=DEV)]
-        _C.egnn_edge_bwd(gb, PQ, x_d, ea, 64, w["W1"], w["W2"], w["b2"], w["W3"], w["b3"], w["w4"], ghn, gx_out, *outs)
+        getattr(_C, kernel)(gb, PQ, x_d, ea, 64, w["W1"], w["W2"], w["b2"], w["W3"], w["b3"], w["w4"], ghn, gx_out, *outs)
         red = torch.empty(8512, device=DEV)
         _C.reduce_partials(outs[4], red)
         res.append([o.clone() for o in outs[:4]] + [red])
