@@ -25,6 +25,8 @@
 // when the batch is the other one's.
 //
 // TMEM (512 columns): ACC[team] 64 | DW2, DW3 [team] 2 x 64 (M = 64 weight-gradient accumulators) | PARK[team] 64.
+#include <type_traits>
+
 #include "egnn_bwd_common.cuh"
 
 namespace is {
@@ -34,18 +36,18 @@ int launch_edge_bwd_tc(const EdgeCommon& c, const float* ghn, const float* gx_ou
 
 namespace bw {
 constexpr int TR = IS_BWD_WS_TR;                    // edge rows per tile
-constexpr int NT = 512, TT = 256, TWARPS = 8;       // CTA threads, team threads, team warps
 constexpr uint32_t LBO = 128, SBO = 8 * LBO;        // unpadded K-major tiles (a thread stores its own row: conflict free)
 constexpr uint32_t A_TERM = (TR / 8) * SBO;         // one split term of a 112-row operand tile (14 KB)
 constexpr uint32_t A_BUF = 3 * A_TERM;
 constexpr uint32_t W_TERM = 8 * 8 * umma::kLBO_W;   // one split term of a 64 x 64 weight tile (8 KB)
 constexpr uint32_t W_BUF = 3 * W_TERM;
 constexpr int F_LD = 68;                            // fp32 gz1 rows: padded leading dimension
+constexpr uint32_t F32_OFF = 2 * SBO;               // the fp32 copy starts behind the 16 rows a neighbour's M = 128 MMAs read
 constexpr uint32_t F32_BYTES = TR * F_LD * 4;
 constexpr int NKW = TR / 16;                        // K steps of a weight-gradient MMA group
 constexpr int MAXN = 32;                            // destination nodes per tile
 constexpr uint32_t TM_ACC = 0, TM_DW2 = 128, TM_DW3 = 192, TM_PARK = 384;
-static_assert(F32_BYTES + 7 * TR * 4 <= A_BUF, "fp32 staging must fit the X buffer");
+static_assert(F32_OFF + F32_BYTES + 7 * TR * 4 <= A_BUF, "fp32 staging must fit the X buffer");
 static_assert(TR % 16 == 0 && TR <= 128, "tile rows");
 
 struct Meta {                   // per-edge scalars of the team's current tile
@@ -58,33 +60,63 @@ struct Meta {                   // per-edge scalars of the team's current tile
     float vn[3 * MAXN];         // gx_out[node] / max(deg, 1) for the tile's destination nodes
 };
 
+template <int TT>
 __device__ __forceinline__ void team_sync(int team) {
     asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(TT) : "memory");
 }
 
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
     asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+        "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
         "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
         : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// sum over the warp's 32 rows of 8 per-lane column values; afterwards lane L holds the total of column (L >> 2) & 7
+// (all four lanes of a quad hold the same value).  Fixed order -> deterministic.
+__device__ __forceinline__ float warp_colsum8(const float (&v)[8], int lane) {
+    float w4[4], w2[2];
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = b4 ? v[i] : v[i + 4];
+        const float keep = b4 ? v[i + 4] : v[i];
+        w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = b3 ? w4[i] : w4[i + 2];
+        const float keep = b3 ? w4[i + 2] : w4[i];
+        w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const float send = b2 ? w2[0] : w2[1];
+    const float keep = b2 ? w2[1] : w2[0];
+    float s = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    return s;
+}
+
+// column chunks (8 features) per thread of column group g, and the group's first chunk, for a team of TWARPS warps
+// (4 TMEM lane quarters x TWARPS / 4 column groups): 8 warps: 4 + 4 | 12 warps: 3 + 3 + 2 | 16 warps: 2 + 2 + 2 + 2
+template <int TWARPS> __host__ __device__ constexpr int group_chunks(int g) { return TWARPS == 8 ? 4 : TWARPS == 16 ? 2 : (g < 2 ? 3 : 2); }
+template <int TWARPS> __host__ __device__ constexpr int group_first(int g) { return TWARPS == 8 ? 4 * g : TWARPS == 16 ? 2 * g : 3 * g; }
 
 #ifndef IS_BW_WAIT_HINT_NS
 #define IS_BW_WAIT_HINT_NS 1000
 #endif
 }  // namespace bw
 
-template <bool HAS_COORD>
-__global__ void __launch_bounds__(bw::NT, 1)
+template <bool HAS_COORD, int TWARPS>
+__global__ void __launch_bounds__(2 * 32 * TWARPS, 1)
 edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __restrict__ gx_out,
                    float* __restrict__ gz1, float* __restrict__ gQ, float* __restrict__ gD, float* __restrict__ gxd,
                    float* __restrict__ partials, const int* __restrict__ gate) {
     using namespace bw;
+    constexpr int TT = 32 * TWARPS, NT = 2 * TT;            // team threads, CTA threads
+    constexpr int NP = TT / 64, RP = (TR + NP - 1) / NP;    // row blocks of the gwr / gwa pass
     if (gate != nullptr && __ldg(gate) > TR) return;        // the lock-step kernel (128-edge tiles) takes this batch
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t* sBuf = smem_raw;                                 // [team][X, Y][A_BUF]
@@ -99,12 +131,16 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int team = tid >> 8, t = tid & (TT - 1), tw = t >> 5;
-    const int q = tw & 3, cq = tw >> 2, erow = 32 * q + lane;      // TMEM lane quarter (= CTA warp % 4), column half, tile row
+    const int team = tid >= TT ? 1 : 0, t = tid - team * TT, tw = t >> 5;
+    const int q = tw & 3, grp = tw >> 2, erow = 32 * q + lane;     // TMEM lane quarter (= CTA warp % 4), column group, tile row
     const bool rowv = erow < TR;
     const int ldw1 = 2 * p.F + 2;
     if (warp == 0) tmem_alloc(&s_tmem, 512);
     if (tid == 32) { mbar_init(&mbar_d[0], 1); mbar_init(&mbar_d[1], 1); mbar_init(&mbar_wg[0], 1); mbar_init(&mbar_wg[1], 1); }
+    // every byte the M = 128 MMAs can read is a finite bf16 from the start (and stays one: the fp32 copy of gz1 keeps clear
+    // of the first 16 rows of a buffer): accumulator rows beyond a tile (rows 112..127 come from the neighbouring
+    // buffer) then hold finite garbage, which the zero factors of the epilogues annihilate
+    for (int i = tid; i < (int)(4 * A_BUF / 16); i += NT) reinterpret_cast<uint4*>(sBuf)[i] = make_uint4(0u, 0u, 0u, 0u);
     stage_weight_block<PREC_BF16X3>(sW2, W_TERM, p.W2, 64, 0, 64, tid, NT);
     stage_weight_block<PREC_BF16X3>(sW3, W_TERM, HAS_COORD ? p.W3 : nullptr, 64, 0, 64, tid, NT);
     if (tid < 64) {
@@ -129,20 +165,33 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
     fence_after_sync();
     const uint32_t tmem = s_tmem;
 
+    float acc_gwr = 0.f, acc_gwa = 0.f;          // column t & 63, row block t >> 6 (fp32 staging pass)
+    float acc_v[3][4];                           // gb2, gb3, gw4: lane L holds column (L >> 2) & 7 of chunk ch of this warp's rows
+#pragma unroll
+    for (int v = 0; v < 3; ++v)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc_v[v][c] = 0.0f;
+    uint32_t started = 0;
+
+    auto team_main = [&](auto nch_tag) {
+    constexpr int NCH = decltype(nch_tag)::value;             // 8-column chunks of this thread
+    const int kc0 = group_first<TWARPS>(grp);                 // its first chunk
     uint8_t* X = sBuf + (size_t)team * 2 * A_BUF;             // t1 -> gz3 -> gz2 ; afterwards the fp32 copy of gz1
     uint8_t* Y = X + A_BUF;                                   // m -> t1 (re-stored)
     uint8_t* T1 = HAS_COORD ? X : Y;                          // without the coordinate branch t1 can stay where it is gathered
     Meta& mt = metas[team];
-    float* F32 = reinterpret_cast<float*>(X);                 // [TR][F_LD]
-    float* e_gr = reinterpret_cast<float*>(X + F32_BYTES);    // [2][TR] partial gr per column half
-    float* e_c = e_gr + 2 * TR;                               // [2][TR] partial c per column half
-    float* e_gd = e_c + 2 * TR;                               // [3][TR]
+    float* F32 = reinterpret_cast<float*>(X + F32_OFF);       // [TR][F_LD]; the first 2 KB of X always hold bf16 operand rows
+    float* e_gr = reinterpret_cast<float*>(X + F32_OFF + F32_BYTES);    // [TWARPS / 4][TR] partial gr per column group (<= 4)
+    float* e_c = e_gr + 4 * TR;                               // [<= 4][TR] partial c per column group
+    float* e_gd = e_c + 4 * TR;                               // [3][TR]
     uint64_t* bar_d = &mbar_d[team];
     uint64_t* bar_wg = &mbar_wg[team];
-    const uint32_t t_acc = tmem + ((uint32_t)(32 * q) << 16) + TM_ACC + 64 * team + 32 * cq;
-    const uint32_t t_park = tmem + ((uint32_t)(32 * q) << 16) + TM_PARK + 64 * team + 32 * cq;
+    const uint32_t t_acc = tmem + ((uint32_t)(32 * q) << 16) + TM_ACC + 64 * team + 8 * kc0;
+    const uint32_t t_park = tmem + ((uint32_t)(32 * q) << 16) + TM_PARK + 64 * team + 8 * kc0;
     const uint32_t d_acc = tmem + TM_ACC + 64 * team, d_w2 = tmem + TM_DW2 + 128 * team, d_w3 = tmem + TM_DW3 + 128 * team;
-    const uint32_t rowoff = (uint32_t)((erow >> 3) * SBO + (erow & 7) * 16);
+    uint8_t* rowX = X + (uint32_t)((erow >> 3) * SBO + (erow & 7) * 16) + kc0 * LBO;     // this thread's first chunk in X
+    uint8_t* rowY = rowX + A_BUF;
+    uint8_t* rowT1 = HAS_COORD ? rowX : rowY;
     // operand geometries
     const OpGeom gXk = {smem_u32(X), A_TERM, 2 * LBO, LBO, SBO};                   // K-major activation tile
     const OpGeom gYk = {smem_u32(Y), A_TERM, 2 * LBO, LBO, SBO};
@@ -156,19 +205,26 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
     const uint32_t id_fwd = make_instr_desc(1u, 128, 64, 0, 0);
     const uint32_t id_dgrad = make_instr_desc(1u, 128, 64, 0, 1);
     const uint32_t id_wgrad = make_instr_desc(1u, 64, 64, 1, 1);
+    uint32_t ph_d = 0, ph_wg = 0;
 
-    // running vector gradients: after warp_colsum16 lane L holds column 32 cq + 16 h + ((L >> 1) & 15) of this warp's rows
-    float acc_gb2[2] = {0.f, 0.f}, acc_gb3[2] = {0.f, 0.f}, acc_gw4[2] = {0.f, 0.f};
-    float acc_gwr = 0.f, acc_gwa = 0.f;          // column t & 63, row block t >> 6 (fp32 staging pass)
-    uint32_t ph_d = 0, ph_wg = 0, started = 0;
-
-    auto wait_d = [&]() { mbar_wait_hint(bar_d, ph_d, IS_BW_WAIT_HINT_NS); ph_d ^= 1; fence_after_sync(); };
-    auto wait_wg = [&]() { mbar_wait_hint(bar_wg, ph_wg, IS_BW_WAIT_HINT_NS); ph_wg ^= 1; fence_after_sync(); };
+    // one warp of the team polls the mbarrier, the others sleep at the team's hardware barrier
+    auto wait_d = [&]() {
+        if (tw == 0) mbar_wait_hint(bar_d, ph_d, IS_BW_WAIT_HINT_NS);
+        ph_d ^= 1;
+        team_sync<TT>(team);
+        fence_after_sync();
+    };
+    auto wait_wg = [&]() {
+        if (tw == 0) mbar_wait_hint(bar_wg, ph_wg, IS_BW_WAIT_HINT_NS);
+        ph_wg ^= 1;
+        team_sync<TT>(team);
+        fence_after_sync();
+    };
     // publish this team's operand stores, then one elected lane of team warp 0 issues `fn`
     auto publish_and_issue = [&](auto&& fn) {
         fence_async_smem();
         fence_before_sync();
-        team_sync(team);
+        team_sync<TT>(team);
         if (tw == 0) {
             if (elect_one()) {
                 fence_after_sync();
@@ -206,7 +262,7 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
             }
             mt.vn[i] = v;
         }
-        team_sync(team);
+        team_sync<TT>(team);
         if (HAS_COORD && t < TR) {
             float gc = 0.0f;
             if (t < ne) {
@@ -220,38 +276,32 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
 
         // ---- gather: z1 = P[src] + Q[dst] + wr r + wa a -> parked in TMEM ; t1 = silu(z1) -> T1 ; MMA 1 ------------
         {
-            float pv[32], qv[32];
+            float pv[NCH][8], qv[NCH][8];
             float rr = 0.f, aa = 0.f;
             if (valid) {
                 const int s = mt.src[erow], d = mt.dst[erow];
                 rr = mt.r[erow]; aa = mt.a[erow];
-                const float* pp = p.PQ + (size_t)s * 128 + 32 * cq;
-                const float* qp = p.PQ + (size_t)d * 128 + 64 + 32 * cq;
+                const float* pp = p.PQ + (size_t)s * 128 + 8 * kc0;
+                const float* qp = p.PQ + (size_t)d * 128 + 64 + 8 * kc0;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    ldg256(pp + 8 * g, *reinterpret_cast<float(*)[8]>(&pv[8 * g]));
-                    ldg256(qp + 8 * g, *reinterpret_cast<float(*)[8]>(&qv[8 * g]));
-                }
+                for (int ch = 0; ch < NCH; ++ch) { ldg256(pp + 8 * ch, pv[ch]); ldg256(qp + 8 * ch, qv[ch]); }
             } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) { pv[i] = 0.f; qv[i] = 0.f; }
+                for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { pv[ch][i] = 0.f; qv[ch][i] = 0.f; }
             }
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float z[16];
+            for (int ch = 0; ch < NCH; ++ch) {
+                float z[8], v8[8];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int c = 32 * cq + 16 * h + i;
-                    z[i] = valid ? pv[16 * h + i] + qv[16 * h + i] + vec[192 + c] * rr + vec[256 + c] * aa : 0.0f;
+                for (int i = 0; i < 8; ++i) {
+                    const int c = 8 * (kc0 + ch) + i;
+                    z[i] = pv[ch][i] + qv[ch][i] + vec[192 + c] * rr + vec[256 + c] * aa;       // rows beyond the tile: 0
+                    v8[i] = silu_acc(z[i]);                                                    // silu(0) = 0
                 }
-                tmem_st16(t_park + 16 * h, z);
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    float v8[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v8[i] = silu_acc(z[8 * g + i]);          // rows beyond the tile: silu(0) = 0
-                    if (rowv) store_chunk8<PREC_BF16X3>(T1 + rowoff + (4 * cq + 2 * h + g) * LBO, A_TERM, v8);
-                }
+                tmem_st8(t_park + 8 * ch, z);
+                if (rowv) store_chunk8<PREC_BF16X3>(rowT1 + ch * LBO, A_TERM, v8);
             }
             tmem_st_wait();
         }
@@ -268,19 +318,18 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
         wait_d();
 
         // ---- epilogue 1: m = silu(z2 + b2) -> Y ; d2 = silu'(z2 + b2) stays in registers ---------------------------
-        float d2[32];
+        float d2[NCH][8];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            float z[16];
-            tmem_ld<16>(t_acc + 16 * h, z);
+        for (int ch = 0; ch < NCH; ++ch) {
+            float z[8], m8[8];
+            tmem_ld<8>(t_acc + 8 * ch, z);
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                float m8[8];
+            for (int i = 0; i < 8; ++i) silu_both_acc(z[i] + vec[8 * (kc0 + ch) + i], m8[i], d2[ch][i]);
+            if (!valid) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    silu_both_acc(z[8 * g + i] + vec[32 * cq + 16 * h + 8 * g + i], m8[i], d2[16 * h + 8 * g + i]);
-                if (HAS_COORD && rowv) store_chunk8<PREC_BF16X3>(Y + rowoff + (4 * cq + 2 * h + g) * LBO, A_TERM, m8);
+                for (int i = 0; i < 8; ++i) d2[ch][i] = 0.0f;
             }
+            if (HAS_COORD && rowv) store_chunk8<PREC_BF16X3>(rowY + ch * LBO, A_TERM, m8);
         }
         float cpart = 0.0f;
         if (HAS_COORD) {
@@ -292,28 +341,22 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
             wait_d();
             const float gc = valid ? mt.gc[erow] : 0.0f;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float z[16], g3[16], gu[16];
-                tmem_ld<16>(t_acc + 16 * h, z);
+            for (int ch = 0; ch < NCH; ++ch) {
+                float z[8], g3[8], gu[8];
+                tmem_ld<8>(t_acc + 8 * ch, z);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int c = 32 * cq + 16 * h + i;
+                for (int i = 0; i < 8; ++i) {
+                    const int c = 8 * (kc0 + ch) + i;
                     float u, d3;
                     silu_both_acc(z[i] + vec[64 + c], u, d3);
                     const float w = vec[128 + c];
                     cpart = fmaf(w, u, cpart);
-                    g3[i] = valid ? gc * w * d3 : 0.0f;       // (accumulator rows beyond the tile may hold anything)
-                    gu[i] = valid ? gc * u : 0.0f;
+                    g3[i] = gc * w * d3;            // gc == 0 on rows beyond the tile (whose accumulator rows are finite)
+                    gu[i] = gc * u;
                 }
-                acc_gb3[h] += warp_colsum16(g3, lane);
-                acc_gw4[h] += warp_colsum16(gu, lane);
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    float v8[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v8[i] = g3[8 * g + i];
-                    if (rowv) store_chunk8<PREC_BF16X3>(X + rowoff + (4 * cq + 2 * h + g) * LBO, A_TERM, v8);   // MMA 1 is done with X
-                }
+                acc_v[1][ch] += warp_colsum8(g3, lane);
+                acc_v[2][ch] += warp_colsum8(gu, lane);
+                if (rowv) store_chunk8<PREC_BF16X3>(rowX + ch * LBO, A_TERM, g3);     // MMA 1 is done with X
             }
             // ---- MMA 3: gm = gz3 W3 ; WG 3: gW3 += gz3^T m ---------------------------------------------------------
             publish_and_issue([&] {
@@ -325,50 +368,39 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
             wait_d();
         }
         // ---- epilogue 3: gz2 = (gm + ghn[dst]) silu'(z2) -> X ; t1 re-derived from the parked z1 -> Y ---------------
-        float d1[32];
+        float d1[NCH][8];
         {
-            float g2[32];
-            const float* ghrow = ghn + (size_t)(valid ? mt.dst[erow] : 0) * 64 + 32 * cq;
+            const float* ghrow = ghn + (size_t)(valid ? mt.dst[erow] : 0) * 64 + 8 * kc0;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float gm[16], gh[16];
+            for (int ch = 0; ch < NCH; ++ch) {
+                float gm[8], gh[8];
                 if (HAS_COORD) {
-                    tmem_ld<16>(t_acc + 16 * h, gm);
+                    tmem_ld<8>(t_acc + 8 * ch, gm);
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) gm[i] = 0.0f;
+                    for (int i = 0; i < 8; ++i) gm[i] = 0.0f;
                 }
                 if (valid) {
-                    ldg256(ghrow + 16 * h, *reinterpret_cast<float(*)[8]>(&gh[0]));
-                    ldg256(ghrow + 16 * h + 8, *reinterpret_cast<float(*)[8]>(&gh[8]));
-                }
-                float gs[16];
+                    ldg256(ghrow + 8 * ch, gh);
+                } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    gs[i] = valid ? (gm[i] + gh[i]) * d2[16 * h + i] : 0.0f;
-                    g2[16 * h + i] = gs[i];
+                    for (int i = 0; i < 8; ++i) gh[i] = 0.0f;
                 }
-                acc_gb2[h] += warp_colsum16(gs, lane);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) d2[ch][i] = (gm[i] + gh[i]) * d2[ch][i];       // gz2 (0 on rows beyond the tile)
+                acc_v[0][ch] += warp_colsum8(d2[ch], lane);
             }
             if (HAS_COORD) wait_wg();       // WG 3 must be done with X (gz3) and Y (m) before they are overwritten
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                float v8[8];
+            for (int ch = 0; ch < NCH; ++ch)
+                if (rowv) store_chunk8<PREC_BF16X3>(rowX + ch * LBO, A_TERM, d2[ch]);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v8[i] = g2[8 * g + i];
-                if (rowv) store_chunk8<PREC_BF16X3>(X + rowoff + (4 * cq + g) * LBO, A_TERM, v8);
-            }
+            for (int ch = 0; ch < NCH; ++ch) {
+                float z[8], v8[8];
+                tmem_ld<8>(t_park + 8 * ch, z);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float z[16];
-                tmem_ld<16>(t_park + 16 * h, z);
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    float v8[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) silu_both_acc(z[8 * g + i], v8[i], d1[16 * h + 8 * g + i]);
-                    if (HAS_COORD && rowv) store_chunk8<PREC_BF16X3>(Y + rowoff + (4 * cq + 2 * h + g) * LBO, A_TERM, v8);
-                }
+                for (int i = 0; i < 8; ++i) silu_both_acc(z[i], v8[i], d1[ch][i]);
+                if (HAS_COORD && rowv) store_chunk8<PREC_BF16X3>(rowY + ch * LBO, A_TERM, v8);
             }
         }
         // ---- MMA 4: gt1 = gz2 W2 ; WG 2: gW2 += gz2^T t1 ---------------------------------------------------------------
@@ -383,48 +415,49 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
         // ---- epilogue 4: gz1 = gt1 silu'(z1) -> global ; gr ; then (WG 2 done) the fp32 copy over X ------------------------
         {
             float grpart = 0.0f;
+            float* go = gz1 + (size_t)(p0 + erow) * 64 + 8 * kc0;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float gt1[16];
-                tmem_ld<16>(t_acc + 16 * h, gt1);
+            for (int ch = 0; ch < NCH; ++ch) {
+                float gt1[8];
+                tmem_ld<8>(t_acc + 8 * ch, gt1);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float gz = valid ? gt1[i] * d1[16 * h + i] : 0.0f;
-                    d1[16 * h + i] = gz;
-                    grpart = fmaf(vec[192 + 32 * cq + 16 * h + i], gz, grpart);
+                for (int i = 0; i < 8; ++i) {
+                    const float gz = gt1[i] * d1[ch][i];      // rows ne..111: gz2 rows are zero, so gt1 == 0; rows >= 112 are never stored
+                    d1[ch][i] = gz;
+                    grpart = fmaf(vec[192 + 8 * (kc0 + ch) + i], gz, grpart);
                 }
-            }
-            if (valid) {
-                float* go = gz1 + (size_t)(p0 + erow) * 64 + 32 * cq;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) stg256(go + 8 * g, *reinterpret_cast<const float(*)[8]>(&d1[8 * g]));
+                if (valid) stg256(go + 8 * ch, d1[ch]);
             }
             wait_wg();                      // WG 2 has read X and Y: both are free
             if (rowv) {
-                float* fo = F32 + erow * F_LD + 32 * cq;
+                float* fo = F32 + erow * F_LD + 8 * kc0;
 #pragma unroll
-                for (int g = 0; g < 8; ++g)
-                    *reinterpret_cast<float4*>(fo + 4 * g) = make_float4(d1[4 * g], d1[4 * g + 1], d1[4 * g + 2], d1[4 * g + 3]);
-                e_gr[cq * TR + erow] = grpart;
-                if (HAS_COORD) e_c[cq * TR + erow] = cpart;
+                for (int ch = 0; ch < NCH; ++ch) {
+                    *reinterpret_cast<float4*>(fo + 8 * ch) = make_float4(d1[ch][0], d1[ch][1], d1[ch][2], d1[ch][3]);
+                    *reinterpret_cast<float4*>(fo + 8 * ch + 4) = make_float4(d1[ch][4], d1[ch][5], d1[ch][6], d1[ch][7]);
+                }
+                e_gr[grp * TR + erow] = grpart;
+                if (HAS_COORD) e_c[grp * TR + erow] = cpart;
             }
         }
         fence_before_sync();
-        team_sync(team);
+        team_sync<TT>(team);
         // ---- geometry backward (one thread per edge) ; gwr / gwa from the fp32 copy (column t & 63, rows of block t >> 6) ---
         if (t < TR) {
             const int j = t;
             float g0 = 0.f, g1 = 0.f, g2 = 0.f;
             if (j < ne) {
                 const float dx = mt.dx[j], dy = mt.dx[TR + j], dz = mt.dx[2 * TR + j];
-                const float two_gr = 2.0f * (e_gr[j] + e_gr[TR + j]);
+                float grs = 0.0f, cs = 0.0f;
+#pragma unroll
+                for (int gg = 0; gg < TWARPS / 4; ++gg) { grs += e_gr[gg * TR + j]; if (HAS_COORD) cs += e_c[gg * TR + j]; }
+                const float two_gr = 2.0f * grs;
                 g0 = two_gr * dx; g1 = two_gr * dy; g2 = two_gr * dz;
                 if (HAS_COORD) {
-                    const float c = e_c[j] + e_c[TR + j];
                     const float rho = sqrtf(mt.r[j]);
                     const float inv = 1.0f / (rho + 1e-30f);
                     const int dl = mt.dst[j] - n0;
-                    const float h0 = c * mt.vn[3 * dl], h1 = c * mt.vn[3 * dl + 1], h2 = c * mt.vn[3 * dl + 2];
+                    const float h0 = cs * mt.vn[3 * dl], h1 = cs * mt.vn[3 * dl + 1], h2 = cs * mt.vn[3 * dl + 2];
                     const float k = (h0 * dx + h1 * dy + h2 * dz) * inv * inv / rho;
                     g0 += h0 * inv - k * dx; g1 += h1 * inv - k * dy; g2 += h2 * inv - k * dz;
                 }
@@ -435,14 +468,14 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
             e_gd[j] = g0; e_gd[TR + j] = g1; e_gd[2 * TR + j] = g2;
         }
         {
-            const int c = t & 63, rb = (t >> 6) * (TR / 4), re = min(ne, rb + TR / 4);
+            const int c = t & 63, rb = (t >> 6) * RP, re = min(ne, rb + RP);
             for (int row = rb; row < re; ++row) {
                 const float gz = F32[row * F_LD + c];
                 acc_gwr = fmaf(gz, mt.r[row], acc_gwr);
                 acc_gwa = fmaf(gz, mt.a[row], acc_gwa);
             }
         }
-        team_sync(team);
+        team_sync<TT>(team);
         // ---- destination-side sums: gQ[d] = sum gz1 ; gxd[d] = -sum g_diff ----------------------------------------------
         for (int node = n0 + tw; node < n1; node += TWARPS) {
             const int jb = __ldg(p.indptr + node) - p0, je = __ldg(p.indptr + node + 1) - p0;
@@ -458,8 +491,11 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
                 gxd[(size_t)node * 3 + lane] = -sx;
             }
         }
-        team_sync(team);        // X, Y and the scalars are free for the team's next tile
+        team_sync<TT>(team);        // X, Y and the scalars are free for the team's next tile
     }
+    };   // team_main
+    if (group_chunks<TWARPS>(0) != group_chunks<TWARPS>(2) && grp == 2) team_main(std::integral_constant<int, group_chunks<TWARPS>(2)>{});
+    else team_main(std::integral_constant<int, group_chunks<TWARPS>(0)>{});
 
     // ---- per-CTA partials: weight gradients from TMEM (both teams), vector gradients from the running registers -----
     if (t == 0) s_started[team] = (int)started;
@@ -467,7 +503,7 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
     __syncthreads();
     fence_after_sync();
     float* P = partials + (size_t)blockIdx.x * (8192 + 5 * 64);
-    {
+    if (warp < 16) {
         // M = 64 accumulators: row r lives in TMEM lane 32 (r / 16) + r % 16 -> lanes 0..15 of CTA warp w hold rows 16 (w & 3) + lane
         const int wq = warp & 3, part = warp >> 2;
         const bool st0 = s_started[0] != 0, st1 = s_started[1] != 0;
@@ -489,40 +525,57 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
                 P[4096 + (16 * wq + lane) * 64 + 16 * part + i] = HAS_COORD ? (st0 ? w0[i] : 0.0f) + (st1 ? w1[i] : 0.0f) : 0.0f;
         }
     }
-    float* red = reinterpret_cast<float*>(sBuf);              // [3 vectors][2 teams][8 warps][2 halves][16]
-    float* red2 = red + 3 * 2 * TWARPS * 32;                  // [2 vectors][2 teams][4 row blocks][64]
-    if ((lane & 1) == 0) {
-        const int k = lane >> 1;
+    float* red = reinterpret_cast<float*>(sBuf);              // [3 vectors][2 teams][TWARPS][4 chunks][8]
+    float* red2 = red + 3 * 2 * TWARPS * 32;                  // [2 vectors][2 teams][NP row blocks][64]
+    if ((lane & 3) == 0) {
+        const int k = lane >> 2;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            red[((0 * 2 + team) * TWARPS + tw) * 32 + 16 * h + k] = acc_gb2[h];
-            red[((1 * 2 + team) * TWARPS + tw) * 32 + 16 * h + k] = acc_gb3[h];
-            red[((2 * 2 + team) * TWARPS + tw) * 32 + 16 * h + k] = acc_gw4[h];
-        }
+        for (int v = 0; v < 3; ++v)
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) red[((v * 2 + team) * TWARPS + tw) * 32 + 8 * ch + k] = acc_v[v][ch];
     }
-    red2[((0 * 2 + team) * 4 + (t >> 6)) * 64 + (t & 63)] = acc_gwr;
-    red2[((1 * 2 + team) * 4 + (t >> 6)) * 64 + (t & 63)] = acc_gwa;
+    red2[((0 * 2 + team) * NP + (t >> 6)) * 64 + (t & 63)] = acc_gwr;
+    red2[((1 * 2 + team) * NP + (t >> 6)) * 64 + (t & 63)] = acc_gwa;
     __syncthreads();
     if (tid < 5 * 64) {
         const int v = tid >> 6, col = tid & 63;
         float s = 0.0f;
         if (v < 3) {
-            const int cqq = col >> 5, hk = col & 31;           // team warp = 4 cq + q
+            const int kc = col >> 3, k = col & 7;
+            int gg = 0;                                        // column group that owns chunk kc, and the chunk's index in it
+#pragma unroll
+            for (int g2 = 1; g2 < TWARPS / 4; ++g2) if (kc >= group_first<TWARPS>(g2)) gg = g2;
+            const int ch = kc - group_first<TWARPS>(gg);
 #pragma unroll
             for (int tm = 0; tm < 2; ++tm)
 #pragma unroll
-                for (int qq = 0; qq < 4; ++qq) s += red[((v * 2 + tm) * TWARPS + 4 * cqq + qq) * 32 + hk];
+                for (int qq = 0; qq < 4; ++qq) s += red[((v * 2 + tm) * TWARPS + 4 * gg + qq) * 32 + 8 * ch + k];
         } else {
 #pragma unroll
             for (int tm = 0; tm < 2; ++tm)
 #pragma unroll
-                for (int rb = 0; rb < 4; ++rb) s += red2[(((v - 3) * 2 + tm) * 4 + rb) * 64 + col];
+                for (int rb = 0; rb < NP; ++rb) s += red2[(((v - 3) * 2 + tm) * NP + rb) * 64 + col];
         }
         P[8192 + v * 64 + col] = s;
     }
     fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// warps per team of the two-stream kernel: 8 (32 columns per thread, 128 registers), 12 (24 / 24 / 16 columns, 80
+// registers) or 16 (16 columns, 64 registers); is_egnn_set_bwd_ws_warps
+int g_bwd_ws_warps = 8;
+
+template <bool HAS_COORD, int TWARPS>
+static int launch_bwd_ws(const EdgeCommon& c, const float* ghn, const float* gx_out, float* gz1, float* gQ, float* gD,
+                         float* gxd, float* partials, const int* gate, int grid, cudaStream_t st) {
+    const size_t smem = 4 * (size_t)bw::A_BUF + 2 * (size_t)bw::W_BUF + sizeof(float) * 5 * 64 + 2 * sizeof(bw::Meta);
+    cudaError_t e = cudaFuncSetAttribute(edge_bwd_ws_kernel<HAS_COORD, TWARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    edge_bwd_ws_kernel<HAS_COORD, TWARPS><<<grid, 2 * 32 * TWARPS, smem, st>>>(c, ghn, gx_out, gz1, gQ, gD, gxd, partials, gate);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
 }
 
 }  // namespace is
@@ -551,23 +604,27 @@ int is_egnn_edge_bwd_ws(const int* indptr, const int* csr_src, const int* csr_ds
     cudaStream_t st = (cudaStream_t)stream;
     if (max_in_degree == nullptr || (reinterpret_cast<uintptr_t>(ghn) & 31) != 0)
         return launch_edge_bwd_tc(c, ghn, gx_out, gz1, gQ, gD, gxd, partials, nullptr, st);
-    const size_t smem = 4 * (size_t)bw::A_BUF + 2 * (size_t)bw::W_BUF + sizeof(float) * 5 * 64 + 2 * sizeof(bw::Meta);
     const int sms = current_num_sms();
     int64_t g = (n_nodes + 31) / 32;
     if (g > sms) g = sms;
     const int grid = (int)(g < 1 ? 1 : g);
-    cudaError_t e;
-    if (gx_out) {
-        e = cudaFuncSetAttribute(edge_bwd_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        edge_bwd_ws_kernel<true><<<grid, bw::NT, smem, st>>>(c, ghn, gx_out, gz1, gQ, gD, gxd, partials, max_in_degree);
-    } else {
-        e = cudaFuncSetAttribute(edge_bwd_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        edge_bwd_ws_kernel<false><<<grid, bw::NT, smem, st>>>(c, ghn, gx_out, gz1, gQ, gD, gxd, partials, max_in_degree);
-    }
-    IS_LAUNCH_CHECK();
+    int rc;
+    const int tw = g_bwd_ws_warps;
+#define IS_BW_LAUNCH(HC)                                                                                                   \
+    (tw == 8 ? launch_bwd_ws<HC, 8>(c, ghn, gx_out, gz1, gQ, gD, gxd, partials, max_in_degree, grid, st)                  \
+             : tw == 16 ? launch_bwd_ws<HC, 16>(c, ghn, gx_out, gz1, gQ, gD, gxd, partials, max_in_degree, grid, st)       \
+                        : launch_bwd_ws<HC, 12>(c, ghn, gx_out, gz1, gQ, gD, gxd, partials, max_in_degree, grid, st))
+    rc = gx_out ? IS_BW_LAUNCH(true) : IS_BW_LAUNCH(false);
+#undef IS_BW_LAUNCH
+    if (rc != 0) return rc;
     return launch_edge_bwd_tc(c, ghn, gx_out, gz1, gQ, gD, gxd, partials, max_in_degree, st);
+}
+
+// warps per team of the two-stream edge backward: 8 (default), 12 or 16 (A/B timing)
+int is_egnn_set_bwd_ws_warps(int n) {
+    if (n != 8 && n != 12 && n != 16) return IS_ERR_ARG;
+    is::g_bwd_ws_warps = n;
+    return IS_OK;
 }
 
 }  // extern "C"

@@ -26,7 +26,7 @@ from . import _C
 from . import functional as IF
 
 H = IF.H
-_GRAPH_FIELDS = ("indptr", "csr_src", "csr_dst", "csr_eid", "outptr", "csc_pos", "status", "node_off")
+_GRAPH_FIELDS = ("indptr", "csr_src", "csr_dst", "csr_eid", "outptr", "csc_pos", "status", "node_off", "stats")
 
 
 def graph_tensors(graph) -> List[Tensor]:

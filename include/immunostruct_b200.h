@@ -103,6 +103,9 @@ int is_egnn_edge_bwd_ws(const int* indptr, const int* csr_src, const int* csr_ds
                         const float* ghn, const float* gx_out,
                         float* gz1, float* gQ, float* gD, float* gxd, float* partials,
                         const int* max_in_degree, int64_t n_nodes, int* status, void* stream);
+/* warps per tile stream of is_egnn_edge_bwd_ws: 8 (default), 12 or 16 (A/B timing; results identical up to the
+   summation order of the bias-type gradients) */
+int is_egnn_set_bwd_ws_warps(int n);
 int is_egnn_node_pre_bwd(const float* gz1, const float* gQ, const float* gD, const float* gxd,
                          const float* gx_out, const float* gh_direct,
                          const int* outptr, const int* csc_pos, const float* h, int64_t ldh, int F,

@@ -29,7 +29,9 @@ def outs():
 
 res = {}
 for coord in (True, False):
-    for name, fn in (("tc", _C.egnn_edge_bwd_tc), ("ws", _C.egnn_edge_bwd_ws)):
+    for name, fn in (("tc", _C.egnn_edge_bwd_tc), ("ws8", _C.egnn_edge_bwd_ws), ("ws12", _C.egnn_edge_bwd_ws), ("ws16", _C.egnn_edge_bwd_ws)):
+        if name.startswith("ws"):
+            _C.set_bwd_ws_warps(int(name[2:]))
         o = outs()
         call = lambda: fn(gb, PQ, x, ea, 64, W1, W2, b2, W3, b3, w4, ghn, gxo if coord else None, *o)
         ts = []
@@ -44,8 +46,8 @@ for coord in (True, False):
         _C.reduce_partials(o[4], red)
         res[(coord, name)] = o[:4] + [red]
         print(f"edge_bwd {name} coord={coord}: {sum(ts) / len(ts):.1f} us  (min {min(ts):.1f})", flush=True)
-    a, b = res[(coord, "tc")], res[(coord, "ws")]
-    for nm, u, v in zip(("gz1", "gQ", "gD", "gxd", "partials"), a, b):
-        scale = float(u.abs().max()) + 1e-30
-        print(f"   coord={coord} {nm}: max |tc - ws| / scale = {float((u - v).abs().max()) / scale:.3e}")
+    for w in ("ws8", "ws12", "ws16"):
+        a, b = res[(coord, "tc")], res[(coord, w)]
+        print(f"   coord={coord} {w}: max |tc - ws| / scale: " + "  ".join(
+            f"{nm} {float((u - v).abs().max()) / (float(u.abs().max()) + 1e-30):.2e}" for nm, u, v in zip(("gz1", "gQ", "gD", "gxd", "partials"), a, b)))
 print("status", int(gb.status.item()))

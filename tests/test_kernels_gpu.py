@@ -86,7 +86,6 @@ def out_hub_arrays(seed):
 
 CASES = {
     "hubs_isolated": lambda: hub_and_isolated_arrays(7),
-    "hubs_112": lambda: hub_and_isolated_arrays(9, hub=112),
     "out_hubs": lambda: out_hub_arrays(11),
     "knn_small": lambda: synthetic_graph_arrays(5, 37, 6, seed=3, n_pad=4, coord_scale=4.0),
     "knn_200": lambda: synthetic_graph_arrays(3, 200, 10, seed=4, n_pad=10),
@@ -110,6 +109,18 @@ def cpu_graph(gb):
 @pytest.fixture(params=sorted(CASES))
 def case(request):
     arrays = CASES[request.param]()
+    gb = to_dev(arrays)
+    return arrays, gb, cpu_graph(gb)
+
+
+# the backward tests add the tile limit of the two-stream edge backward (in-degree 112; "hubs_isolated" with its
+# in-degree-128 hub exercises the device-side hand-over to the lock-step kernel)
+BWD_CASES = dict(CASES, hubs_112=lambda: hub_and_isolated_arrays(9, hub=112))
+
+
+@pytest.fixture(params=sorted(BWD_CASES))
+def bwd_case(request):
+    arrays = BWD_CASES[request.param]()
     gb = to_dev(arrays)
     return arrays, gb, cpu_graph(gb)
 
@@ -330,10 +341,10 @@ def test_vae_mid_and_head_kernels(b):
 # ---- EGNN backward -----------------------------------------------------------------------------
 @pytest.mark.parametrize("tc", [False, True, "ws"])
 @pytest.mark.parametrize("f,coord", [(64, True), (64, False), (20, True)])
-def test_egnn_backward_kernels(case, f, coord, tc):
+def test_egnn_backward_kernels(bwd_case, f, coord, tc):
     """tc=True: the tcgen05 edge backward (bf16x3) against the same contract at the same tolerance; "ws": its two-stream
     successor (112-edge tiles; the in-degree-128 case exercises the device-side hand-over to the lock-step kernel)."""
-    arrays, gb, cg = case
+    arrays, gb, cg = bwd_case
     edge_bwd = {False: _C.egnn_edge_bwd, True: _C.egnn_edge_bwd_tc, "ws": _C.egnn_edge_bwd_ws}[tc]
     gen = torch.Generator().manual_seed(13)
     n, e = gb.n_nodes, gb.n_edges
@@ -413,10 +424,10 @@ def test_egnn_backward_kernels(case, f, coord, tc):
 
 
 @pytest.mark.parametrize("kernel", ["egnn_edge_bwd", "egnn_edge_bwd_ws"])
-def test_backward_is_deterministic(case, kernel):
+def test_backward_is_deterministic(bwd_case, kernel):
     """Same inputs twice -> bit-identical gradients (no floating-point atomics anywhere; the two tile streams of the
     ws kernel accumulate into separate TMEM blocks that are added in a fixed order)."""
-    arrays, gb, _ = case
+    arrays, gb, _ = bwd_case
     gen = torch.Generator().manual_seed(17)
     n, e = gb.n_nodes, gb.n_edges
     w = {k: v.to(DEV) for k, v in egnn_weights(gen, 64).items()}
