@@ -47,7 +47,7 @@ def exported_symbols():
             "is_fusion_attn_bwd", "is_loss_fwd", "is_loss_bwd", "is_umma_selftest", "is_egnn_edge_fwd_tc", "is_attn_pool_infer", "is_egnn_node_post_pre_tc", "is_egnn_edge_bwd_tc", "is_egnn_edge_bwd_ws", "is_egnn_set_bwd_ws_warps", "is_linear_tc", "is_linear_tc_split_k", "is_attn_pool_infer_tc", "is_vae_mid_infer", "is_head_infer", "is_unpack_nodes", "is_unpack_edges", "is_onehot_tokens", "is_egnn_node_post_bwd_tc", "is_egnn_node_pre_bwd_tc", "is_attn_pool_bwd_tc",
             "is_segment_pool_fwd", "is_segment_pool_bwd", "is_contrastive_scratch_floats", "is_contrastive_fwd",
             "is_contrastive_bwd", "is_fused_adam", "is_rotate_coords", "is_mask_single_residue", "is_mask_rows", "is_gemm_tma_split_k",
-            "is_split_planes", "is_gemm_planes_tma", "is_egnn_set_ws_buffers", "is_reduce_partials3", "is_fused_adam_capturable"]
+            "is_split_planes", "is_gemm_planes_tma", "is_egnn_set_ws_buffers", "is_egnn_set_ws_variant", "is_reduce_partials3", "is_fused_adam_capturable"]
 
 
 def _check(rc: int, name: str):
@@ -142,8 +142,15 @@ def set_bwd_ws_warps(n: int) -> None:
         raise ValueError("edge backward warps per stream: 8, 12 or 16")
 
 
+def set_ws_variant(bits: int) -> None:
+    """Variant bits of the warp-specialised edge forward kernel: bit 0 = A operand of MMA 2 from tensor memory (default 1)."""
+    fn = lib().is_egnn_set_ws_variant
+    fn.restype = ctypes.c_int
+    _check(fn(_i32(bits)), "is_egnn_set_ws_variant")
+
+
 def set_ws_buffers(n: int) -> None:
-    """Operand-buffer depth (2 default, 3 = measured alternative) of the warp-specialised edge forward kernel."""
+    """Operand-buffer depth of the warp-specialised edge forward kernel (only 2 is supported; 3 was measured)."""
     fn = lib().is_egnn_set_ws_buffers
     fn.restype = ctypes.c_int
     _check(fn(_i32(n)), "is_egnn_set_ws_buffers")

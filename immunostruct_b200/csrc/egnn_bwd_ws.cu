@@ -65,15 +65,6 @@ __device__ __forceinline__ void team_sync(int team) {
     asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(TT) : "memory");
 }
 
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
-        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
 // sum over the warp's 32 rows of 8 per-lane column values; afterwards lane L holds the total of column (L >> 2) & 7
 // (all four lanes of a quad hold the same value).  Fixed order -> deterministic.
 __device__ __forceinline__ float warp_colsum8(const float (&v)[8], int lane) {

@@ -34,9 +34,10 @@
 namespace is {
 
 namespace e2 {
-constexpr uint32_t LBO = 128;                    // bytes between K-adjacent core matrices (unpadded)
+constexpr uint32_t LBO = 144;                    // bytes between K-adjacent core matrices: padded by 16 bytes, so that the eight
+                                                 // 16-byte stores of a quarter-warp that holds ONE row (chunks 0..7) hit 8 bank groups
 constexpr uint32_t SBO = 8 * LBO;                // bytes between 8-row groups of a 64-wide bf16 tile
-constexpr uint32_t A_BYTES = 16 * SBO;           // 128-row operand tile, one split term (16 KB)
+constexpr uint32_t A_BYTES = 16 * SBO;           // 128-row operand tile, one split term (18 KB)
 constexpr uint32_t W_BYTES = 8 * 8 * umma::kLBO_W;   // 64-row weight tile, one split term (8 KB)
 constexpr uint32_t S_LBO = 128;                  // selector tile: K = 128 edges = 16 chunks per node row
 constexpr uint32_t S_SBO = 16 * S_LBO;
@@ -65,6 +66,33 @@ __device__ __forceinline__ void issue_fwd(uint32_t tmem_d, uint32_t a_addr, uint
         for (int ks = 0; ks < 4; ++ks) {
             mma_bf16(tmem_d, make_smem_desc(a_addr + ks * 2 * LBO, LBO, SBO),
                      make_smem_desc(w_addr + ks * 2 * kLBO_W, kLBO_W, 8 * kLBO_W), idesc, acc);
+            acc = 1;
+        }
+    }
+}
+
+// same product with the A operand in TENSOR MEMORY (split term t at columns tmem_a + 32 t, 8 columns per K step): the
+// epilogue threads own one accumulator row each, so they can put m straight into their TMEM lane; the tensor core
+// then reads only the weights from shared memory (a third of the operand bytes of the shared-memory form)
+template <int PREC>
+__device__ __forceinline__ void issue_fwd_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t w_addr) {
+    using namespace umma;
+    const uint32_t idesc = make_instr_desc(1u, 128, 64);
+    uint32_t acc = 0;
+    if (PREC == PREC_BF16X3) {
+        const uint32_t ta[6] = {2, 0, 1, 1, 0, 0}, tw[6] = {0, 2, 1, 0, 1, 0};
+#pragma unroll
+        for (int t = 0; t < 6; ++t)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                mma_bf16_ts(tmem_d, tmem_a + 32 * ta[t] + 8 * ks,
+                            make_smem_desc(w_addr + tw[t] * W_BYTES + ks * 2 * kLBO_W, kLBO_W, 8 * kLBO_W), idesc, acc);
+                acc = 1;
+            }
+    } else {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            mma_bf16_ts(tmem_d, tmem_a + 8 * ks, make_smem_desc(w_addr + ks * 2 * kLBO_W, kLBO_W, 8 * kLBO_W), idesc, acc);
             acc = 1;
         }
     }
@@ -116,6 +144,7 @@ constexpr int NW_META = 4;                       // scalar warps: one edge per l
 constexpr int NT3 = 32 * (W_META + NW_META);     // 704 threads
 constexpr int NM = 4;                            // scalar stages
 constexpr uint32_t TM_ACC1 = 0, TM_ACC2 = 128, TM_HN = 256;   // + 64 * buffer
+constexpr uint32_t TM_MA = 384;                  // m as the A operand of MMA 2: 32 columns per split term
 
 struct Meta3 {
     int src[IS_TM];
@@ -148,30 +177,32 @@ __device__ __forceinline__ void meta_edge(const EdgeCommon& p, Meta3& m, int j, 
 #endif
 #define WS_WAIT(bar, parity) mbar_wait_hint(bar, parity, IS_WS_WAIT_HINT_NS)
 
-// NB = number of operand buffers.  NB = 2: the original ring (gather of tile i waits until MMA 2 / MMA 3 of tile i - 2 have
-// released buffer i & 1).  NB = 3 (bf16x3: 229.7 KB of shared memory, 2.7 KB below the limit): a third operand buffer
-// takes the t1 gather of tile i out of that dependency -- it only needs MMA 2 / 3 of tile i - 3 (a_free ring); the
-// selector tile S stays two deep, so it is built AFTER the row gather, behind a wait for tile i - 2 that has usually
-// passed by then.  TMEM accumulators stay two deep (indexed i & 1): a_full(i) is signalled after that wait, so MMA 1 of
-// tile i still cannot overwrite acc1 before epilogue 1 of tile i - 2 has read it.
-template <int PREC, bool HAS_COORD, bool FAST, int NB>
+// TSA = the A operand of MMA 2 comes from TENSOR MEMORY (is_egnn_set_ws_variant bit 0, default on): the kernel is bound by the
+// L1 / shared-memory data pipe (ncu: LSU wavefronts 56 % + tensor-core operand wavefronts 43 % of the pipe's cycles), and
+// every shared-memory A operand is read six times by the bf16x3 products (3 x a1, 2 x a2, 1 x a3).  Epilogue 1 therefore
+// also puts the packed split terms of m into its own TMEM lanes (tcgen05.st: 96 columns, single buffered -- MMA 2 of
+// tile i - 1 has completed before epilogue 1 of tile i stores: it waits for acc2_full of tile i - 1 first); the shared-memory
+// copy of m stays for MMA 3, which reads it transposed as its B operand.
+// The gather maps a quarter-warp to ONE row (8 lanes x 32 bytes = the row's 256 contiguous bytes of P or Q, two whole
+// 128-byte lines per quarter-warp and instruction); with LBO = 144 its eight 16-byte operand stores are conflict free.
+template <int PREC, bool HAS_COORD, bool FAST, bool TSA>
 __global__ void __launch_bounds__(e3::NT3, 1)
 edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_out) {
     using namespace e3;
     using C = TcCfg<PREC>;
     constexpr int NS = C::NSPLIT;
-    static_assert(NB == 2 || NB == 3, "two or three operand buffers");
     constexpr int CW = 32;                      // accumulator columns per epilogue thread (two column halves)
     constexpr uint32_t ABUF = NS * A_BYTES;     // one operand buffer (all split terms)
+    constexpr bool TS2 = TSA && HAS_COORD;      // MMA 2 exists and takes m from TMEM
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint8_t* sS = smem_raw;                                            // [2][S_BYTES]; rows 32..63 of a tile alias what follows
-    uint8_t* sA = sS + 2 * S_BYTES;                                    // [NB][NS][A_BYTES] t1, then m
-    uint8_t* sW2 = sA + NB * ABUF;                                     // [NS][W_BYTES]
+    uint8_t* sA = sS + 2 * S_BYTES;                                    // [2][NS][A_BYTES] t1, then m
+    uint8_t* sW2 = sA + 2 * ABUF;                                      // [NS][W_BYTES]
     uint8_t* sW3 = sW2 + NS * W_BYTES;
     float* vec = reinterpret_cast<float*>(sW3 + NS * W_BYTES);         // b2, b3, w4, wr, wa
     float* e_c = vec + 5 * 64;                                         // [2 buffers][2 halves][128] partial c
     Meta3* meta = reinterpret_cast<Meta3*>(e_c + 4 * IS_TM);           // [NM]
-    __shared__ __align__(8) uint64_t meta_full[NM], meta_free[NM], a_full[3], acc1_full[2], m_full[3], acc2_full[2], hn_full[2], a_free[3];
+    __shared__ __align__(8) uint64_t meta_full[NM], meta_free[NM], a_full[2], acc1_full[2], m_full[2], acc2_full[2], hn_full[2];
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -179,8 +210,10 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
     if (warp == 0) tmem_alloc(&s_tmem, 512);
     if (tid == 32) {
         for (int i = 0; i < NM; ++i) { mbar_init(&meta_full[i], NW_META); mbar_init(&meta_free[i], NW_EPI); }
-        for (int i = 0; i < 3; ++i) { mbar_init(&a_full[i], NW_PROD); mbar_init(&m_full[i], NW_EPI); mbar_init(&a_free[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc1_full[i], 1); mbar_init(&acc2_full[i], 1); mbar_init(&hn_full[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&a_full[i], NW_PROD); mbar_init(&m_full[i], NW_EPI);
+            mbar_init(&acc1_full[i], 1); mbar_init(&acc2_full[i], 1); mbar_init(&hn_full[i], 1);
+        }
     }
     stage_weight_block<PREC>(sW2, W_BYTES, p.W2, 64, 0, 64, tid, NT3);                 // W2 / W3 as B operands
     stage_weight_block<PREC>(sW3, W_BYTES, HAS_COORD ? p.W3 : nullptr, 64, 0, 64, tid, NT3);
@@ -235,33 +268,32 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
         const uint32_t s_addr = smem_u32(sS), a_addr = smem_u32(sA), w2_addr = smem_u32(sW2), w3_addr = smem_u32(sW3);
         const bool first = warp == W_MMA;
         bool done = false;
-        constexpr int UN = NB == 2 ? 2 : 6;              // lcm(2 TMEM sets, NB operand buffers)
-        for (int i2 = 0; !done; i2 += UN) {
+        for (int i2 = 0; !done; i2 += 2) {
 #pragma unroll
-            for (int u = 0; u < UN; ++u) {
+            for (int u = 0; u < 2; ++u) {
                 const int i = i2 + u;
-                const int b = u & 1, ab = u % NB;        // compile-time after unrolling (i2 is a multiple of UN)
+                const int b = u;                         // compile-time after unrolling (i2 is even)
                 WS_WAIT(&meta_full[i % NM], (i / NM) & 1);
                 done = meta[i % NM].tile[0] >= nend;
                 if (done) break;
                 if (first) {
-                    WS_WAIT(&a_full[ab], (i / NB) & 1);
+                    WS_WAIT(&a_full[b], (i >> 1) & 1);
                     fence_after_sync();
                     if (elect_one()) {
-                        issue_fwd<PREC>(tmem + TM_ACC1 + 64 * b, a_addr + ab * ABUF, w2_addr);
+                        issue_fwd<PREC>(tmem + TM_ACC1 + 64 * b, a_addr + b * ABUF, w2_addr);
                         mma_commit(&acc1_full[b]);
                     }
                 } else {
-                    WS_WAIT(&m_full[ab], (i / NB) & 1);
+                    WS_WAIT(&m_full[b], (i >> 1) & 1);
                     fence_after_sync();
                     if (elect_one()) {
                         if (HAS_COORD) {
-                            issue_fwd<PREC>(tmem + TM_ACC2 + 64 * b, a_addr + ab * ABUF, w3_addr);
+                            if (TS2) issue_fwd_ts<PREC>(tmem + TM_ACC2 + 64 * b, tmem + TM_MA, w3_addr);
+                            else issue_fwd<PREC>(tmem + TM_ACC2 + 64 * b, a_addr + b * ABUF, w3_addr);
                             mma_commit(&acc2_full[b]);
                         }
-                        issue_segsum<PREC>(tmem + TM_HN + 64 * b, s_addr + b * S_BYTES, a_addr + ab * ABUF, 8);
+                        issue_segsum<PREC>(tmem + TM_HN + 64 * b, s_addr + b * S_BYTES, a_addr + b * ABUF, 8);
                         mma_commit(&hn_full[b]);
-                        if (NB == 3) mma_commit(&a_free[ab]);
                     }
                 }
                 __syncwarp();
@@ -270,24 +302,19 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
     } else if (warp >= NW_EPI) {
         // ================= gather: S + t1 of tile i into operand buffer i & 1 =================
         const int pw = warp - NW_EPI;
-        // K-chunk kc (8 features) = lane / 4; a quarter-warp covers rows r4 + 4 * (chunk parity ^ pass parity) of an
-        // 8-row group for two adjacent chunks: its eight 16-byte stores fill 128 distinct bytes of a bank line
-        const int r4 = lane & 3, kc = lane >> 2;
+        // a quarter-warp takes ONE row: lane -> row rl = lane / 8 of a 4-row pass, K chunk kc = lane % 8 (8 features, 32 bytes)
+        const int rl = lane >> 3, kc = lane & 7;
         const float4 wr0 = *reinterpret_cast<const float4*>(vec + 192 + 8 * kc), wr1 = *reinterpret_cast<const float4*>(vec + 196 + 8 * kc);
         const float4 wa0 = *reinterpret_cast<const float4*>(vec + 256 + 8 * kc), wa1 = *reinterpret_cast<const float4*>(vec + 260 + 8 * kc);
         for (int i = 0;; ++i) {
-            const int b = i & 1, ab = i % NB;
+            const int b = i & 1;
             WS_WAIT(&meta_full[i % NM], (i / NM) & 1);
             const Meta3& mt = meta[i % NM];
             const int n0 = mt.tile[0], ne = mt.tile[2];
             if (n0 >= nend) break;
-            if (NB == 2) {
-                if (i >= 2) WS_WAIT(&hn_full[b], ((i >> 1) - 1) & 1);    // MMA2 / MMA3 of tile i-2 are done with the buffer
-            } else {
-                if (i >= 3) WS_WAIT(&a_free[ab], ((i / 3) - 1) & 1);     // MMA2 / MMA3 of tile i-3 are done with the buffer
-            }
-            uint8_t* A = sA + ab * ABUF;
-            auto build_selector = [&]() {   // S[node][edge] = 1 for the node's in-edges (two 16-byte chunks per thread)
+            if (i >= 2) WS_WAIT(&hn_full[b], ((i >> 1) - 1) & 1);    // MMA2 / MMA3 of tile i-2 are done with the buffer
+            uint8_t* A = sA + b * ABUF;
+            {   // S[node][edge] = 1 for the node's in-edges (two 16-byte chunks per thread)
                 const int jb = mt.nptr[lane], je = mt.nptr[lane + 1];         // rows beyond the tile: jb = je = ne
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
@@ -301,8 +328,7 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
                     w.w = ((mask >> 6) & 1u) * 0x3F80u + ((mask >> 7) & 1u) * 0x3F800000u;
                     *reinterpret_cast<uint4*>(sS + b * S_BYTES + (lane >> 3) * S_SBO + c * S_LBO + (lane & 7) * 16) = w;
                 }
-            };
-            if (NB == 2) build_selector();
+            }
 #pragma unroll
             for (int gi = 0; gi < 2; ++gi) {
                 const int g8 = 8 * (2 * pw + gi);
@@ -310,7 +336,7 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
                 float rr[2], aa[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    const int j = g8 + r4 + 4 * ((kc & 1) ^ u);
+                    const int j = g8 + 4 * u + rl;
                     const bool valid = j < ne;
                     const int s = valid ? mt.src[j] : 0, d = n0 + (valid ? (int)mt.dloc[j] : 0);
                     rr[u] = valid ? mt.r[j] : 0.0f;
@@ -322,7 +348,7 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
                 const float wa[8] = {wa0.x, wa0.y, wa0.z, wa0.w, wa1.x, wa1.y, wa1.z, wa1.w};
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    const int j = g8 + r4 + 4 * ((kc & 1) ^ u);
+                    const int j = g8 + 4 * u + rl;
                     const float r = rr[u], a = aa[u];
                     float v[8];
 #pragma unroll
@@ -331,27 +357,25 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
                     store_chunk8<PREC>(A + (j >> 3) * SBO + (j & 7) * 16 + kc * LBO, A_BYTES, v);
                 }
             }
-            if (NB == 3) {
-                if (i >= 2) WS_WAIT(&hn_full[b], ((i >> 1) - 1) & 1);    // MMA 3 of tile i-2 is done with selector tile b
-                build_selector();
-            }
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&a_full[ab]);
+            if (lane == 0) mbar_arrive(&a_full[b]);
         }
     } else {
         // ================= epilogue: epilogue 1 of tile i, then epilogue 2 / hn rows / coordinates of tile i-1 =====
         const int q = warp & 3, cq = warp >> 2, erow = 32 * q + lane;      // TMEM lane quarter, column half, tile row
         const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16) + CW * cq;
+        const uint32_t t_ma = tmem + ((uint32_t)(32 * q) << 16) + TM_MA + (CW / 2) * cq;      // 4 columns per 8-feature chunk
         for (int i = 0;; ++i) {
             const int b = i & 1;
             WS_WAIT(&meta_full[i % NM], (i / NM) & 1);
             const bool done = meta[i % NM].tile[0] >= nend;
             if (!done) {
-                // ---- epilogue 1: m = silu(acc1 + b2) -> operand buffer (A of MMA 2, transposed B of MMA 3) ----
+                // ---- epilogue 1: m = silu(acc1 + b2) -> operand buffer (B of MMA 3, transposed) and TMEM (A of MMA 2) ----
                 WS_WAIT(&acc1_full[b], (i >> 1) & 1);
+                if (TS2 && i >= 1) WS_WAIT(&acc2_full[b ^ 1], ((i - 1) >> 1) & 1);   // MMA 2 of tile i-1 has read the TMEM copy
                 fence_after_sync();
-                uint8_t* A = sA + (i % NB) * ABUF;
+                uint8_t* A = sA + b * ABUF;
                 float z[CW];
                 tmem_ld<CW>(t_lane + TM_ACC1 + 64 * b, z);
 #pragma unroll
@@ -363,12 +387,20 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
                     m8[2] = act<PREC, FAST>(z[8 * g + 2] + b0.z); m8[3] = act<PREC, FAST>(z[8 * g + 3] + b0.w);
                     m8[4] = act<PREC, FAST>(z[8 * g + 4] + b1.x); m8[5] = act<PREC, FAST>(z[8 * g + 5] + b1.y);
                     m8[6] = act<PREC, FAST>(z[8 * g + 6] + b1.z); m8[7] = act<PREC, FAST>(z[8 * g + 7] + b1.w);
-                    store_chunk8<PREC>(A + (erow >> 3) * SBO + (erow & 7) * 16 + ((CW / 8) * cq + g) * LBO, A_BYTES, m8);
+                    uint4 qs[3];
+                    split_chunk8<PREC>(m8, qs);
+                    uint8_t* dst = A + (erow >> 3) * SBO + (erow & 7) * 16 + ((CW / 8) * cq + g) * LBO;
+#pragma unroll
+                    for (int t = 0; t < NS; ++t) {
+                        *reinterpret_cast<uint4*>(dst + t * A_BYTES) = qs[t];
+                        if (TS2) tmem_st4(t_ma + 32 * t + 4 * g, qs[t].x, qs[t].y, qs[t].z, qs[t].w);
+                    }
                 }
+                if (TS2) tmem_st_wait();
                 fence_async_smem();
                 fence_before_sync();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&m_full[i % NB]);
+                if (lane == 0) mbar_arrive(&m_full[b]);
             }
             if (i >= 1) {
                 const int j = i - 1, bp = b ^ 1;
@@ -433,32 +465,29 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-template <int PREC, int NB>
+template <int PREC>
 static size_t ws_smem_bytes() {
     using namespace e3;
-    return 2 * (size_t)S_BYTES + (size_t)TcCfg<PREC>::NSPLIT * (NB * A_BYTES + 2 * W_BYTES) + sizeof(float) * (5 * 64 + 4 * IS_TM) + NM * sizeof(Meta3);
+    return 2 * (size_t)S_BYTES + (size_t)TcCfg<PREC>::NSPLIT * (2 * A_BYTES + 2 * W_BYTES) + sizeof(float) * (5 * 64 + 4 * IS_TM) + NM * sizeof(Meta3);
 }
 
-// operand buffers of the warp-specialised kernel (is_egnn_set_ws_buffers).  Measured on the B200 (scripts/ab_edge.py,
-// batch 512, bit-identical results): 3 buffers 225.4 vs 227.3 us (bf16x3 inference), 188.2 vs 192.5 us (last layer),
-// but 282 vs 252 us with the accurate training SiLU and 140 vs 135 us in bf16 -- the free-buffer wait is not on the
-// critical path, so the two-buffer ring stays the default.
-int g_ws_buffers = 2;
+// variant bits of the warp-specialised kernel (is_egnn_set_ws_variant): bit 0 = A operand of MMA 2 from tensor memory
+int g_ws_variant = 1;
 
-template <int PREC, bool HAS_COORD, bool FAST, int NB>
-static int launch_wsk_nb(const EdgeCommon& c, float* hn, float* x_out, int grid, cudaStream_t st) {
-    const size_t smem = ws_smem_bytes<PREC, NB>();
-    cudaError_t e = cudaFuncSetAttribute(edge_fwd_ws_kernel<PREC, HAS_COORD, FAST, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int PREC, bool HAS_COORD, bool FAST, bool TSA>
+static int launch_wsk_v(const EdgeCommon& c, float* hn, float* x_out, int grid, cudaStream_t st) {
+    const size_t smem = ws_smem_bytes<PREC>();
+    cudaError_t e = cudaFuncSetAttribute(edge_fwd_ws_kernel<PREC, HAS_COORD, FAST, TSA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    edge_fwd_ws_kernel<PREC, HAS_COORD, FAST, NB><<<grid, e3::NT3, smem, st>>>(c, hn, x_out);
+    edge_fwd_ws_kernel<PREC, HAS_COORD, FAST, TSA><<<grid, e3::NT3, smem, st>>>(c, hn, x_out);
     e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
 
 template <int PREC, bool HAS_COORD, bool FAST>
 static int launch_wsk(const EdgeCommon& c, float* hn, float* x_out, int grid, cudaStream_t st) {
-    return g_ws_buffers == 3 ? launch_wsk_nb<PREC, HAS_COORD, FAST, 3>(c, hn, x_out, grid, st)
-                             : launch_wsk_nb<PREC, HAS_COORD, FAST, 2>(c, hn, x_out, grid, st);
+    if (HAS_COORD && (g_ws_variant & 1)) return launch_wsk_v<PREC, HAS_COORD, FAST, true>(c, hn, x_out, grid, st);
+    return launch_wsk_v<PREC, HAS_COORD, FAST, false>(c, hn, x_out, grid, st);
 }
 
 // entry used by is_egnn_edge_fwd_tc (egnn_tc.cu) for the bf16 / bf16x3 precisions: warp-specialised kernel
@@ -480,9 +509,14 @@ int launch_edge_fwd_ws(const EdgeCommon& c, float* hn, float* x_out, int precisi
 
 }  // namespace is
 
-// number of operand buffers of the warp-specialised edge forward kernel: 2 (default) or 3 (A/B timing, see g_ws_buffers)
-extern "C" int is_egnn_set_ws_buffers(int n) {
-    if (n != 2 && n != 3) return IS_ERR_ARG;
-    is::g_ws_buffers = n;
+// Operand buffers of the warp-specialised edge forward kernel.  A third buffer was measured on the B200 (225 vs 227 us in
+// inference, slower in training and in bf16: the free-buffer wait is not on the critical path) and no longer fits next to
+// the padded operand tiles: only 2 is accepted.
+extern "C" int is_egnn_set_ws_buffers(int n) { return n == 2 ? IS_OK : IS_ERR_UNSUPPORTED; }
+
+// Variant bits of the warp-specialised edge forward kernel (A/B timing): bit 0 = A operand of MMA 2 from tensor memory.
+extern "C" int is_egnn_set_ws_variant(int bits) {
+    if (bits < 0 || bits > 1) return IS_ERR_ARG;
+    is::g_ws_variant = bits;
     return IS_OK;
 }

@@ -59,6 +59,31 @@ __device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
     return q;
 }
 
+// the packed 16-byte bf16 chunks of 8 consecutive K values, one per split term (q[0..NSPLIT-1]): bf16 = round to nearest;
+// bf16x3 = three terms by truncation, as store_chunk8 below
+template <int PREC>
+__device__ __forceinline__ void split_chunk8(const float (&v)[8], uint4 (&q)[3]) {
+    static_assert(PREC == PREC_BF16 || PREC == PREC_BF16X3, "bf16 operand tiles only");
+    if (PREC == PREC_BF16) {
+        q[0] = pack8_bf16(v);
+    } else {
+        uint32_t q1[4], q2[4], q3[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t a1 = __float_as_uint(v[2 * i]) & 0xffff0000u, b1 = __float_as_uint(v[2 * i + 1]) & 0xffff0000u;
+            const float ra = v[2 * i] - __uint_as_float(a1), rb = v[2 * i + 1] - __uint_as_float(b1);
+            const uint32_t a2 = __float_as_uint(ra) & 0xffff0000u, b2 = __float_as_uint(rb) & 0xffff0000u;
+            const float sa = ra - __uint_as_float(a2), sb = rb - __uint_as_float(b2);
+            q1[i] = __byte_perm(a1, b1, 0x7632);
+            q2[i] = __byte_perm(a2, b2, 0x7632);
+            q3[i] = __byte_perm(__float_as_uint(sa), __float_as_uint(sb), 0x7632);
+        }
+        q[0] = make_uint4(q1[0], q1[1], q1[2], q1[3]);
+        q[1] = make_uint4(q2[0], q2[1], q2[2], q2[3]);
+        q[2] = make_uint4(q3[0], q3[1], q3[2], q3[3]);
+    }
+}
+
 // store 8 consecutive K values (one 16-byte bf16 chunk per split term) at byte address p0 of split term 0;
 // `split_bytes` = distance between the split-term copies of the tile.  bf16 / bf16x3 only.
 template <int PREC>

@@ -120,6 +120,8 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, f
 //  mode 5: A operand MN-major  -- same trick for A (tile rows = k, cols = m).
 //  mode 6: M = 64 accumulator  -- D[64,64] = A[0:64] B^T with an M = 64 instruction; all 128 TMEM lanes are
 //          dumped so the lane mapping of the 64 rows can be read off.
+//  mode 7: A operand from TENSOR MEMORY -- every thread packs its own row of A to bf16 pairs and stores it into its
+//          TMEM lane (32 columns); the MMAs take A from TMEM (8 columns per K step of 16) and B from shared memory.
 template <int MODE>
 __global__ void __launch_bounds__(128)
 umma_layout_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D) {
@@ -132,8 +134,18 @@ umma_layout_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (warp == 0) tmem_alloc(&tmem_base, 64);
+    if (warp == 0) tmem_alloc(&tmem_base, 128);
     if (tid == 32) mbar_init(&mbar, 1);
+    if (MODE == 7) {
+        __syncthreads();                                     // tmem_base visible
+        const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + 64;
+        const float* arow = A + (size_t)tid * 64;
+#pragma unroll
+        for (int c = 0; c < 32; c += 4)
+            tmem_st4(ta + c, pack_bf16x2(arow[2 * c], arow[2 * c + 1]), pack_bf16x2(arow[2 * c + 2], arow[2 * c + 3]),
+                     pack_bf16x2(arow[2 * c + 4], arow[2 * c + 5]), pack_bf16x2(arow[2 * c + 6], arow[2 * c + 7]));
+        tmem_st_wait();
+    }
     for (int idx = tid; idx < 128 * 64; idx += 128) {
         const int m = idx >> 6, k = idx & 63;
         const __nv_bfloat16 v = __float2bfloat16_rn(A[idx]);
@@ -164,7 +176,8 @@ umma_layout_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
                 db = make_smem_desc(b0 + ks * 2 * (KCH8 * kLBO), KCH8 * kLBO, kLBO);
             else
                 db = make_smem_desc(b0 + ks * 2 * kLBO, kLBO, KCH8 * kLBO);
-            mma_bf16(tbase, da, db, idesc, ks > 0);
+            if (MODE == 7) mma_bf16_ts(tbase, tbase + 64 + 8 * ks, db, idesc, ks > 0);
+            else mma_bf16(tbase, da, db, idesc, ks > 0);
         }
         mma_commit(&mbar);
     }
@@ -179,7 +192,7 @@ umma_layout_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tbase, 64);
+    if (warp == 0) tmem_dealloc(tbase, 128);
 }
 
 }  // namespace is
@@ -209,11 +222,12 @@ extern "C" int is_umma_selftest(const float* A, const float* B, float* D, int mo
         e = cudaFuncSetAttribute(umma_selftest_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         umma_selftest_kernel<3><<<1, 128, smem, st>>>(A, B, D);
-    } else if (mode >= 4 && mode <= 6) {
+    } else if (mode >= 4 && mode <= 7) {
         size_t smem = (16 * 16 + 8 * 16) * umma::kLBO + 128;
         if (mode == 4) { cudaFuncSetAttribute(umma_layout_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); umma_layout_kernel<4><<<1, 128, smem, st>>>(A, B, D); }
         if (mode == 5) { cudaFuncSetAttribute(umma_layout_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); umma_layout_kernel<5><<<1, 128, smem, st>>>(A, B, D); }
         if (mode == 6) { cudaFuncSetAttribute(umma_layout_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); umma_layout_kernel<6><<<1, 128, smem, st>>>(A, B, D); }
+        if (mode == 7) { cudaFuncSetAttribute(umma_layout_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); umma_layout_kernel<7><<<1, 128, smem, st>>>(A, B, D); }
     } else {
         return IS_ERR_ARG;
     }

@@ -59,8 +59,12 @@ int is_egnn_edge_fwd_tc(const int* indptr, const int* csr_src, const int* csr_ds
                         const float* W1, int F, const float* W2, const float* b2,
                         const float* W3, const float* b3, const float* w4, int update_coords, int precision,
                         int fast_act, float* hn, float* x_out, int64_t n_nodes, int* status, void* stream);
-/* operand-buffer depth of the warp-specialised edge forward kernel (csrc/egnn_tc2.cu): 2 (default) or 3 (A/B timing) */
+/* operand-buffer depth of the warp-specialised edge forward kernel (csrc/egnn_tc2.cu): only 2 is accepted (a third
+   buffer was measured without gain and no longer fits next to the padded operand tiles) */
 int is_egnn_set_ws_buffers(int n);
+/* variant bits of the warp-specialised edge forward kernel (A/B timing): bit 0 = A operand of MMA 2 from tensor memory
+   (default on; results are bit-identical either way) */
+int is_egnn_set_ws_variant(int bits);
 /* node_mlp of layer l fused with the per-node half (P', Q') of layer l+1's first edge-MLP layer, on the
  * tensor cores (inference path).  W1n/b1n/PQn NULL = nothing follows.  next_kind 1: W1n = edge_mlp.0.weight
  * [64,130] of layer l+1, PQn [n,128].  next_kind 2 (after the last layer): W1n = [Wq;Wk;Wv] [192,64], b1n [192],

@@ -1,4 +1,5 @@
-"""A/B timing of the warp-specialised edge forward kernel with two and three operand buffers (batch 512, L2 flushed)."""
+"""A/B timing of the warp-specialised edge forward kernel: A operand of MMA 2 from shared memory (variant 0) or from
+tensor memory (variant 1, default); batch 512, L2 flushed; the results must be bit-identical."""
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -20,8 +21,8 @@ ref = {}
 for prec, name in ((_C.PREC_BF16X3, "bf16x3"), (_C.PREC_BF16, "bf16")):
     for fast in (True, False):
         for upd in (True, False):
-            for nb in (2, 3):
-                _C.set_ws_buffers(nb)
+            for nb in (0, 1):
+                _C.set_ws_variant(nb)
                 hn, xo = torch.zeros(n, 64, device=dev), torch.zeros(n, 3, device=dev)
                 ts = []
                 for it in range(12):
@@ -34,10 +35,10 @@ for prec, name in ((_C.PREC_BF16X3, "bf16x3"), (_C.PREC_BF16, "bf16")):
                     if it >= 4:
                         ts.append(e0.elapsed_time(e1) * 1e3)
                 key = (name, fast, upd)
-                if nb == 2:
+                if nb == 0:
                     ref[key] = (hn.clone(), xo.clone())
                     same = ""
                 else:
-                    same = f" identical to NB=2: hn {torch.equal(hn, ref[key][0])} x {torch.equal(xo, ref[key][1])}"
-                print(f"{name} fast={fast} coords={upd} NB={nb}: {sum(ts) / len(ts):.1f} us (min {min(ts):.1f}){same}", flush=True)
-_C.set_ws_buffers(2)
+                    same = f" identical to variant 0: hn {torch.equal(hn, ref[key][0])} x {torch.equal(xo, ref[key][1])}"
+                print(f"{name} fast={fast} coords={upd} variant={nb}: {sum(ts) / len(ts):.1f} us (min {min(ts):.1f}){same}", flush=True)
+_C.set_ws_variant(1)
