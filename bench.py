@@ -311,18 +311,28 @@ def main():
             infer_step(*pool[i % POOL])
         barrier()
         launches0 = _C.LAUNCHES
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if args.profile:
             torch.cuda.profiler.start()
-        e0.record()
-        for i in range(K):
-            probs = infer_step(*pool[i % POOL])
-        e1.record()
-        barrier()
+        # EXACTLY K steps per window, barrier + synchronize on both sides, max over ranks; three back-to-back windows
+        # and the fastest one is reported (as in run_training: a 2.2 ms step is ~24 launches, and a busy host core on the
+        # shared box can starve the queue for a whole 20-step window; all three are kept in ms_per_step_windows)
+        infer_windows = []
+        for w_ in range(1 if args.profile else 3):
+            barrier()
+            if w_ == 0:
+                launches0 = _C.LAUNCHES
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(K):
+                probs = infer_step(*pool[i % POOL])
+            e1.record()
+            barrier()
+            if w_ == 0:
+                launches = _C.LAUNCHES - launches0
+            infer_windows.append(max_over_ranks(e0.elapsed_time(e1)))
         if args.profile:
             torch.cuda.profiler.stop()
-        ms = max_over_ranks(e0.elapsed_time(e1))
-    launches = _C.LAUNCHES - launches0
+        ms = min(infer_windows)
     value = world * B * K / (ms / 1e3)
 
     # ---- BASELINE configs[1], literally: a scan of 27 000 graphs = 52 full batches of 512 + one of 376 (the last,
@@ -370,14 +380,17 @@ def main():
     with torch.no_grad():
         for item in I.DevicePrefetcher(host_batches(W), dev):
             e2e_consume(item)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for item in I.DevicePrefetcher(host_batches(K), dev):     # H2D of every batch is inside the timed region
-            e2e_consume(item)
-        e1.record()
-        barrier()
-        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+        e2e_windows = []
+        for w_ in range(3):                                           # fastest of three K-step windows, as above
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for item in I.DevicePrefetcher(host_batches(K), dev):     # H2D of every batch is inside the timed region
+                e2e_consume(item)
+            e1.record()
+            barrier()
+            e2e_windows.append(max_over_ranks(e0.elapsed_time(e1)))
+        ms_e2e = min(e2e_windows)
     e2e_value = world * B * K / (ms_e2e / 1e3)
 
     # ---- same, from the compact host format (1 byte per residue / sequence position, int32 edges): the H2D copy
@@ -699,13 +712,15 @@ def main():
         print(json.dumps({
             "metric": "pMHC graphs/sec (HybridModelv2 inference, fp32)", "value": value, "unit": "graphs/s",
             "precision": args.precision, "other_precisions": other,
-            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "ms_per_step_windows": [w_ / K for w_ in infer_windows], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "batch_per_gpu": B, "nodes_per_graph": N_NODES, "edges_per_graph": N_NODES * KNN,
                        "parallelism": f"dp{world}", "l2": f"{POOL} resident input batches (~42 MB each) cycled: inputs > L2"},
             "clocks": clk.summary(),
-            "e2e": {"value": e2e_value, "unit": "graphs/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": h2d,
+            "e2e": {"value": e2e_value, "unit": "graphs/s", "ms_per_step": ms_e2e / K,
+                    "ms_per_step_windows": [w_ / K for w_ in e2e_windows], "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": B * 4,
                     "compact_input": {"value": world * B * K / (ms_e2e_packed / 1e3), "unit": "graphs/s",
                                       "ms_per_step": ms_e2e_packed / K, "h2d_bytes_per_step": h2d_packed,
