@@ -29,7 +29,8 @@ def lib():
             raise ExtensionMissing(
                 f"{LIB_PATH} not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(nvcc, sm_100a). immunostruct_b200 has no CPU or eager fallback.")
-        _lib = ctypes.CDLL(LIB_PATH)
+        # IS_B200_DEBUG_LIB: a debug build of the same sources (e.g. -DIS_TRACE, scripts/trace_edge_fwd.sh); never set in tests / bench
+        _lib = ctypes.CDLL(os.environ.get("IS_B200_DEBUG_LIB", LIB_PATH))
     return _lib
 
 

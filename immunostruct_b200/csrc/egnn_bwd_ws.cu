@@ -58,6 +58,7 @@ struct Meta {                   // per-edge scalars of the team's current tile
     float gc[TR];               // dL/dc = v . dhat
     float dx[3 * TR];           // raw difference x_src - x_dst
     float vn[3 * MAXN];         // gx_out[node] / max(deg, 1) for the tile's destination nodes
+    int nptr[MAXN + 1];         // indptr[n0 + i] - p0: first tile row of node i (the destination-side sums walk these)
 };
 
 template <int TT>
@@ -95,6 +96,15 @@ __device__ __forceinline__ float warp_colsum8(const float (&v)[8], int lane) {
 template <int TWARPS> __host__ __device__ constexpr int group_chunks(int g) { return TWARPS == 8 ? 4 : TWARPS == 16 ? 2 : (g < 2 ? 3 : 2); }
 template <int TWARPS> __host__ __device__ constexpr int group_first(int g) { return TWARPS == 8 ? 4 * g : TWARPS == 16 ? 2 * g : 3 * g; }
 
+// Optional timeline tracing (debug builds: bash scripts/build_debug_lib.sh; scripts/trace_edge_bwd.py): thread 0 of each
+// team of CTA 0 records clock64() per (team, event, tile) into the buffer handed over by is_debug_set_trace_bwd.
+#ifdef IS_TRACE
+__device__ long long* g_trace_bwd = nullptr;
+#define TRB(ev) do { if (trc && t == 0 && tile_idx < 64) trc[((team * 20) + (ev)) * 64 + tile_idx] = clock64(); } while (0)
+#else
+#define TRB(ev) do { } while (0)
+#endif
+
 #ifndef IS_BW_WAIT_HINT_NS
 #define IS_BW_WAIT_HINT_NS 1000
 #endif
@@ -119,6 +129,7 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
     __shared__ int s_started[2];
     __shared__ __align__(8) uint64_t mbar_d[2];               // data MMAs (z2, z3, gm, gt1) of a team
     __shared__ __align__(8) uint64_t mbar_wg[2];              // weight-gradient MMAs of a team
+    __shared__ __align__(8) uint64_t mbar_kick;               // team 0 -> team 1: start half a tile later
     __shared__ uint32_t s_tmem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -127,7 +138,7 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
     const bool rowv = erow < TR;
     const int ldw1 = 2 * p.F + 2;
     if (warp == 0) tmem_alloc(&s_tmem, 512);
-    if (tid == 32) { mbar_init(&mbar_d[0], 1); mbar_init(&mbar_d[1], 1); mbar_init(&mbar_wg[0], 1); mbar_init(&mbar_wg[1], 1); }
+    if (tid == 32) { mbar_init(&mbar_d[0], 1); mbar_init(&mbar_d[1], 1); mbar_init(&mbar_wg[0], 1); mbar_init(&mbar_wg[1], 1); mbar_init(&mbar_kick, 1); }
     // every byte the M = 128 MMAs can read is a finite bf16 from the start (and stays one: the fp32 copy of gz1 keeps clear
     // of the first 16 rows of a buffer): accumulator rows beyond a tile (rows 112..127 come from the neighbouring
     // buffer) then hold finite garbage, which the zero factors of the epilogues annihilate
@@ -197,6 +208,10 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
     const uint32_t id_dgrad = make_instr_desc(1u, 128, 64, 0, 1);
     const uint32_t id_wgrad = make_instr_desc(1u, 64, 64, 1, 1);
     uint32_t ph_d = 0, ph_wg = 0;
+#ifdef IS_TRACE
+    long long* trc = blockIdx.x == 0 ? bw::g_trace_bwd : nullptr;
+    int tile_idx = -1;
+#endif
 
     // one warp of the team polls the mbarrier, the others sleep at the team's hardware barrier
     auto wait_d = [&]() {
@@ -225,9 +240,28 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
         }
     };
 
+    // The two teams must NOT run in phase (measured with -DIS_TRACE: started together they stay in lock-step, both in an
+    // epilogue or both waiting for their MMAs, and nothing overlaps): team 1 starts when team 0 is half way through its
+    // first tile; equal tile periods keep the offset.
+    bool kicked = false;
+    if (team == 1) {
+        if (tw == 0) mbar_wait_hint(&mbar_kick, 0, IS_BW_WAIT_HINT_NS);
+        team_sync<TT>(team);
+    }
+    // operands already published (a team barrier and fence_after_sync lie behind): the elected lane of team warp 0 issues
+    auto issue_only = [&](auto&& fn) {
+        if (tw == 0) {
+            if (elect_one()) fn();
+            __syncwarp();
+        }
+    };
     while (true) {
         const int n0 = s_tile[team][0], n1 = s_tile[team][1], p0 = s_tile[team][2], ne = s_tile[team][3];
         if (n0 >= nend) break;
+#ifdef IS_TRACE
+        ++tile_idx;
+#endif
+        TRB(0);
         // ---- per-edge scalars of this tile (the other team's work covers the load chain) ---------------------------
         if (t < TR) {
             const int j = t;
@@ -244,6 +278,7 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
             }
             mt.src[j] = s; mt.dst[j] = d; mt.r[j] = r; mt.a[j] = a;
             mt.dx[j] = dx; mt.dx[TR + j] = dy; mt.dx[2 * TR + j] = dz;
+            if (j <= MAXN) mt.nptr[j] = n0 + j <= n1 ? __ldg(p.indptr + n0 + j) - p0 : ne;
         } else if (HAS_COORD && t >= 128 && t < 128 + 3 * MAXN) {
             const int i = t - 128, nl = i / 3, comp = i - 3 * nl, node = n0 + nl;
             float v = 0.0f;
@@ -264,6 +299,7 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
             mt.gc[t] = gc;          // read in epilogue 2, several team barriers from here
         }
         const bool valid = erow < ne;
+        TRB(1);
 
         // ---- gather: z1 = P[src] + Q[dst] + wr r + wa a -> parked in TMEM ; t1 = silu(z1) -> T1 ; MMA 1 ------------
         {
@@ -296,10 +332,12 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
             }
             tmem_st_wait();
         }
+        TRB(2);
         publish_and_issue([&] {
             issue_x3(d_acc, gT1k, gW2k, 4, id_fwd, 0);
             mma_commit(bar_d);
         });
+        TRB(3);
         if (tw == TWARPS - 1) {             // this team's next tile = the tile after the other team's next one
             int a0, a1, ap, ae;
             next_tile<TR>(p.indptr, n1, nend, p.status, lane, a0, a1, ap, ae);
@@ -307,6 +345,7 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
             if (lane == 0) { s_tile[team][0] = a0; s_tile[team][1] = a1; s_tile[team][2] = ap; s_tile[team][3] = ae; }
         }
         wait_d();
+        TRB(4);
 
         // ---- epilogue 1: m = silu(z2 + b2) -> Y ; d2 = silu'(z2 + b2) stays in registers ---------------------------
         float d2[NCH][8];
@@ -323,6 +362,7 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
             if (HAS_COORD && rowv) store_chunk8<PREC_BF16X3>(rowY + ch * LBO, A_TERM, m8);
         }
         float cpart = 0.0f;
+        TRB(5);
         if (HAS_COORD) {
             // ---- MMA 2: z3 = m W3^T ; epilogue 2: c, gz3 = gc w4 silu'(z3 + b3) -> X -------------------------------
             publish_and_issue([&] {
@@ -330,6 +370,7 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
                 mma_commit(bar_d);
             });
             wait_d();
+            TRB(6);
             const float gc = valid ? mt.gc[erow] : 0.0f;
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
@@ -349,14 +390,25 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
                 acc_v[2][ch] += warp_colsum8(gu, lane);
                 if (rowv) store_chunk8<PREC_BF16X3>(rowX + ch * LBO, A_TERM, g3);     // MMA 1 is done with X
             }
+            TRB(7);
             // ---- MMA 3: gm = gz3 W3 ; WG 3: gW3 += gz3^T m ---------------------------------------------------------
+            // (the weight-gradient MMAs are issued only AFTER the data MMAs have completed: the two teams run nearly in
+            //  phase, and a team's 24 data MMAs must not queue behind the other team's 42 weight-gradient MMAs; the
+            //  weight gradients then run under the next epilogue's arithmetic)
             publish_and_issue([&] {
                 issue_x3(d_acc, gXk, gW3t, 4, id_dgrad, 0);
                 mma_commit(bar_d);
+            });
+            wait_d();
+            issue_only([&] {
                 issue_x3(d_w3, gXt, gYt, NKW, id_wgrad, started);
                 mma_commit(bar_wg);
             });
-            wait_d();
+            TRB(8);
+        }
+        if (team == 0 && !kicked) {
+            if (t == 0) mbar_arrive(&mbar_kick);
+            kicked = true;
         }
         // ---- epilogue 3: gz2 = (gm + ghn[dst]) silu'(z2) -> X ; t1 re-derived from the parked z1 -> Y ---------------
         float d1[NCH][8];
@@ -381,7 +433,9 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
                 for (int i = 0; i < 8; ++i) d2[ch][i] = (gm[i] + gh[i]) * d2[ch][i];       // gz2 (0 on rows beyond the tile)
                 acc_v[0][ch] += warp_colsum8(d2[ch], lane);
             }
+            TRB(9);
             if (HAS_COORD) wait_wg();       // WG 3 must be done with X (gz3) and Y (m) before they are overwritten
+            TRB(10);
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch)
                 if (rowv) store_chunk8<PREC_BF16X3>(rowX + ch * LBO, A_TERM, d2[ch]);
@@ -394,15 +448,19 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
                 if (HAS_COORD && rowv) store_chunk8<PREC_BF16X3>(rowY + ch * LBO, A_TERM, v8);
             }
         }
+        TRB(11);
         // ---- MMA 4: gt1 = gz2 W2 ; WG 2: gW2 += gz2^T t1 ---------------------------------------------------------------
         publish_and_issue([&] {
             issue_x3(d_acc, gXk, gW2t, 4, id_dgrad, 0);
             mma_commit(bar_d);
+        });
+        wait_d();
+        issue_only([&] {
             issue_x3(d_w2, gXt, gYt, NKW, id_wgrad, started);
             mma_commit(bar_wg);
         });
         started = 1;
-        wait_d();
+        TRB(12);
         // ---- epilogue 4: gz1 = gt1 silu'(z1) -> global ; gr ; then (WG 2 done) the fp32 copy over X ------------------------
         {
             float grpart = 0.0f;
@@ -419,7 +477,9 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
                 }
                 if (valid) stg256(go + 8 * ch, d1[ch]);
             }
+            TRB(13);
             wait_wg();                      // WG 2 has read X and Y: both are free
+            TRB(14);
             if (rowv) {
                 float* fo = F32 + erow * F_LD + 8 * kc0;
 #pragma unroll
@@ -433,6 +493,7 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
         }
         fence_before_sync();
         team_sync<TT>(team);
+        TRB(15);
         // ---- geometry backward (one thread per edge) ; gwr / gwa from the fp32 copy (column t & 63, rows of block t >> 6) ---
         if (t < TR) {
             const int j = t;
@@ -467,11 +528,13 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
             }
         }
         team_sync<TT>(team);
+        TRB(16);
         // ---- destination-side sums: gQ[d] = sum gz1 ; gxd[d] = -sum g_diff ----------------------------------------------
         for (int node = n0 + tw; node < n1; node += TWARPS) {
-            const int jb = __ldg(p.indptr + node) - p0, je = __ldg(p.indptr + node + 1) - p0;
+            const int jb = mt.nptr[node - n0], je = mt.nptr[node - n0 + 1];
             float2 s = make_float2(0.0f, 0.0f);
-            for (int j = jb; j < je; ++j) {
+#pragma unroll 4
+            for (int j = jb; j < je; ++j) {          // ascending row order, one accumulator: the sum order of the other kernels
                 const float2 v = *reinterpret_cast<const float2*>(F32 + j * F_LD + 2 * lane);
                 s.x += v.x; s.y += v.y;
             }
@@ -483,7 +546,9 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
             }
         }
         team_sync<TT>(team);        // X, Y and the scalars are free for the team's next tile
+        TRB(17);
     }
+    if (team == 0 && !kicked && t == 0) mbar_arrive(&mbar_kick);      // no tile at all: release team 1
     };   // team_main
     if (group_chunks<TWARPS>(0) != group_chunks<TWARPS>(2) && grp == 2) team_main(std::integral_constant<int, group_chunks<TWARPS>(2)>{});
     else team_main(std::integral_constant<int, group_chunks<TWARPS>(0)>{});
@@ -556,7 +621,7 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
 
 // warps per team of the two-stream kernel: 8 (32 columns per thread, 128 registers), 12 (24 / 24 / 16 columns, 80
 // registers) or 16 (16 columns, 64 registers); is_egnn_set_bwd_ws_warps
-int g_bwd_ws_warps = 8;
+int g_bwd_ws_warps = 16;
 
 template <bool HAS_COORD, int TWARPS>
 static int launch_bwd_ws(const EdgeCommon& c, const float* ghn, const float* gx_out, float* gz1, float* gQ, float* gD,
@@ -611,7 +676,15 @@ int is_egnn_edge_bwd_ws(const int* indptr, const int* csr_src, const int* csr_ds
     return launch_edge_bwd_tc(c, ghn, gx_out, gz1, gQ, gD, gxd, partials, max_in_degree, st);
 }
 
-// warps per team of the two-stream edge backward: 8 (default), 12 or 16 (A/B timing)
+#ifdef IS_TRACE
+// debug builds only: 2 teams x 20 events x 64 tiles of clock64() stamps written by CTA 0 of the two-stream edge backward
+int is_debug_set_trace_bwd(long long* buf) {
+    cudaError_t e = cudaMemcpyToSymbol(is::bw::g_trace_bwd, &buf, sizeof(buf));
+    return e == cudaSuccess ? IS_OK : (int)e;
+}
+#endif
+
+// warps per team of the two-stream edge backward: 8, 12 or 16 (default)
 int is_egnn_set_bwd_ws_warps(int n) {
     if (n != 8 && n != 12 && n != 16) return IS_ERR_ARG;
     is::g_bwd_ws_warps = n;
