@@ -85,8 +85,13 @@ __device__ __forceinline__ void silu_both(float z, float& y, float& dy) {
 // warp-wide access whose lanes touch different rows is still sector complete (two 128-bit accesses per lane hit every
 // sector twice, half a sector each).  p must be 32-byte aligned.
 __device__ __forceinline__ void ldg256(const float* __restrict__ p, float (&v)[8]) {
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(p));
+    // Two 128-bit loads, NOT one ld.global.nc.v8.f32: builds in which ptxas allocated the 256-bit form (LDG.E.ENL2.256) with
+    // its destination registers overlapping the address pair faulted on the B200 with "misaligned address" at that
+    // instruction (compute-sanitizer: an address inside the right allocation, off by 48 / 120 bytes; egnn_tc2.cu gather,
+    // only in some register allocations -- the same source with other flags ran clean); with 128-bit loads the same builds
+    // are clean and no slower (the two halves of a lane's 32-byte sector are requested back to back).
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 __device__ __forceinline__ void stg256(float* __restrict__ p, const float (&v)[8]) {
     asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"

@@ -312,8 +312,41 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
             const Meta3& mt = meta[i % NM];
             const int n0 = mt.tile[0], ne = mt.tile[2];
             if (n0 >= nend) break;
-            if (i >= 2) WS_WAIT(&hn_full[b], ((i >> 1) - 1) & 1);    // MMA2 / MMA3 of tile i-2 are done with the buffer
             uint8_t* A = sA + b * ABUF;
+            const float wr[8] = {wr0.x, wr0.y, wr0.z, wr0.w, wr1.x, wr1.y, wr1.z, wr1.w};
+            const float wa[8] = {wa0.x, wa0.y, wa0.z, wa0.w, wa1.x, wa1.y, wa1.z, wa1.w};
+            float pv[2][8], qv[2][8];
+            float rr[2], aa[2];
+            auto load_rows = [&](int gi) {          // P[src] and Q[dst] of this thread's two (row, chunk) items of 8-row group pair gi
+                const int g8 = 8 * (2 * pw + gi);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int j = g8 + 4 * u + rl;
+                    const bool valid = j < ne;
+                    const int s = valid ? mt.src[j] : 0, d = n0 + (valid ? (int)mt.dloc[j] : 0);
+                    rr[u] = valid ? mt.r[j] : 0.0f;
+                    aa[u] = valid ? mt.a[j] : 0.0f;
+                    ldg256(p.PQ + (size_t)s * 128 + 8 * kc, pv[u]);      // one whole 32-byte sector per lane
+                    ldg256(p.PQ + (size_t)d * 128 + 64 + 8 * kc, qv[u]);
+                }
+            };
+            auto store_rows = [&](int gi) {
+                const int g8 = 8 * (2 * pw + gi);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int j = g8 + 4 * u + rl;
+                    const float r = rr[u], a = aa[u];
+                    float v[8];
+#pragma unroll
+                    for (int i2 = 0; i2 < 8; ++i2) v[i2] = act<PREC, FAST>(pv[u][i2] + qv[u][i2] + wr[i2] * r + wa[i2] * a);
+                    // rows beyond the tile's edges hold finite values: the selector has zeros there
+                    store_chunk8<PREC>(A + (j >> 3) * SBO + (j & 7) * 16 + kc * LBO, A_BYTES, v);
+                }
+            };
+            // the first round of row loads needs the scalars only, not the operand buffer: it is in flight while this warp
+            // waits for MMA 2 / MMA 3 of tile i-2 to release the buffer
+            load_rows(0);
+            if (i >= 2) WS_WAIT(&hn_full[b], ((i >> 1) - 1) & 1);    // MMA2 / MMA3 of tile i-2 are done with the buffer
             {   // S[node][edge] = 1 for the node's in-edges (two 16-byte chunks per thread)
                 const int jb = mt.nptr[lane], je = mt.nptr[lane + 1];         // rows beyond the tile: jb = je = ne
 #pragma unroll
@@ -329,34 +362,9 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
                     *reinterpret_cast<uint4*>(sS + b * S_BYTES + (lane >> 3) * S_SBO + c * S_LBO + (lane & 7) * 16) = w;
                 }
             }
-#pragma unroll
-            for (int gi = 0; gi < 2; ++gi) {
-                const int g8 = 8 * (2 * pw + gi);
-                float pv[2][8], qv[2][8];
-                float rr[2], aa[2];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int j = g8 + 4 * u + rl;
-                    const bool valid = j < ne;
-                    const int s = valid ? mt.src[j] : 0, d = n0 + (valid ? (int)mt.dloc[j] : 0);
-                    rr[u] = valid ? mt.r[j] : 0.0f;
-                    aa[u] = valid ? mt.a[j] : 0.0f;
-                    ldg256(p.PQ + (size_t)s * 128 + 8 * kc, pv[u]);            // one whole 32-byte sector per lane
-                    ldg256(p.PQ + (size_t)d * 128 + 64 + 8 * kc, qv[u]);
-                }
-                const float wr[8] = {wr0.x, wr0.y, wr0.z, wr0.w, wr1.x, wr1.y, wr1.z, wr1.w};
-                const float wa[8] = {wa0.x, wa0.y, wa0.z, wa0.w, wa1.x, wa1.y, wa1.z, wa1.w};
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int j = g8 + 4 * u + rl;
-                    const float r = rr[u], a = aa[u];
-                    float v[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = act<PREC, FAST>(pv[u][i] + qv[u][i] + wr[i] * r + wa[i] * a);
-                    // rows beyond the tile's edges hold finite values: the selector has zeros there
-                    store_chunk8<PREC>(A + (j >> 3) * SBO + (j & 7) * 16 + kc * LBO, A_BYTES, v);
-                }
-            }
+            store_rows(0);
+            load_rows(1);
+            store_rows(1);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_full[b]);

@@ -248,6 +248,46 @@ def test_egnn_edge_forward_tensor_core(case, f, prec, tol):
     assert int(gb.status.item()) == 0
 
 
+def test_edge_kernels_at_benchmark_scale_match_the_simt_kernels():
+    """Size-independent property at the benchmark shape (256 graphs x 200 nodes x 10-NN: 512 000 edges, every CTA walks
+    ~30 tiles, both tile streams of the backward kernel busy): the tensor-core edge forward (bf16x3, both SiLU variants)
+    and the two-stream edge backward reproduce the fp32 SIMT kernels of csrc/egnn.cu -- a different schedule, tile size and
+    arithmetic path over the same CSR -- at the fp32 tolerance.  Catches wrong-row gathers that only appear at scale."""
+    from immunostruct_b200.synthetic import synthetic_graph_arrays
+    arr = synthetic_graph_arrays(256, 200, 10, seed=21, device=DEV)
+    gb = GraphBatch.from_arrays(*(arr[k] for k in ("x", "src", "dst", "edge_attr", "node_counts", "edge_counts")), max_nodes=200)
+    n, e = gb.n_nodes, gb.n_edges
+    gen = torch.Generator().manual_seed(43)
+    w = {k: v.to(DEV) for k, v in egnn_weights(gen, 64).items()}
+    PQ, ghn, gxo = dev(rnd(gen, n, 128), rnd(gen, n, 64), rnd(gen, n, 3))
+    x_d, ea = arr["x"][:, 20:], arr["edge_attr"].float()
+    ref_hn, ref_x = torch.empty(n, 64, device=DEV), torch.empty(n, 3, device=DEV)
+    _C.egnn_edge_fwd(gb, PQ, x_d, ea, 64, w["W1"], w["W2"], w["b2"], w["W3"], w["b3"], w["w4"], True, ref_hn, ref_x)
+    for fast in (False, True):
+        hn, xo = torch.full((n, 64), float("nan"), device=DEV), torch.full((n, 3), float("nan"), device=DEV)
+        _C.egnn_edge_fwd_tc(gb, PQ, x_d, ea, 64, w["W1"], w["W2"], w["b2"], w["W3"], w["b3"], w["w4"], True, _C.PREC_BF16X3,
+                            hn, xo, fast_act=fast)
+        close(hn, ref_hn.cpu(), 1e-5, what=f"scale hn fast={fast}")
+        close(xo - x_d, (ref_x - x_d).cpu(), 1e-5, what=f"scale x'-x fast={fast}")
+    grid = _C.egnn_edge_bwd_grid(n)
+    outs = {}
+    for name in ("egnn_edge_bwd", "egnn_edge_bwd_ws"):
+        o = [torch.full((e, 64), float("nan"), device=DEV), torch.full((n, 64), float("nan"), device=DEV),
+             torch.full((e, 3), float("nan"), device=DEV), torch.full((n, 3), float("nan"), device=DEV),
+             torch.zeros(grid, 8512, device=DEV)]
+        getattr(_C, name)(gb, PQ, x_d, ea, 64, w["W1"], w["W2"], w["b2"], w["W3"], w["b3"], w["w4"], ghn, gxo, *o)
+        red = torch.empty(8512, device=DEV)
+        _C.reduce_partials(o[4], red)
+        outs[name] = o[:4] + [red]
+    for nm, a, b in zip(("gz1", "gQ", "gD", "gxd"), outs["egnn_edge_bwd_ws"], outs["egnn_edge_bwd"]):
+        close(a, b.cpu(), 1e-5, what=f"scale {nm}")
+    ra, rb = outs["egnn_edge_bwd_ws"][4], outs["egnn_edge_bwd"][4].cpu()
+    for nm, lo, hi in (("gW2", 0, 4096), ("gW3", 4096, 8192), ("gb2", 8192, 8256), ("gb3", 8256, 8320), ("gw4", 8320, 8384),
+                       ("gwr", 8384, 8448), ("gwa", 8448, 8512)):
+        close(ra[lo:hi], rb[lo:hi], 2e-5, what=f"scale {nm}")       # 512 000-term fp32 sums in two different orders
+    assert int(gb.status.item()) == 0
+
+
 @pytest.mark.parametrize("prec,tol", [(_C.PREC_BF16X3, 1e-5), (_C.PREC_BF16, 1e-2)])
 @pytest.mark.parametrize("f,with_next", [(20, True), (64, True), (64, False)])
 def test_egnn_node_post_pre_tensor_core(case, f, with_next, prec, tol):
