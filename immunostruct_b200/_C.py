@@ -45,7 +45,7 @@ def exported_symbols():
             "is_loss_num_partials", "is_collate_csr", "is_egnn_node_pre_fwd", "is_egnn_edge_fwd",
             "is_egnn_node_post_fwd", "is_egnn_node_post_bwd", "is_egnn_edge_bwd", "is_egnn_node_pre_bwd",
             "is_reduce_partials", "is_attn_pool_fwd", "is_attn_pool_bwd", "is_fusion_attn_fwd",
-            "is_fusion_attn_bwd", "is_loss_fwd", "is_loss_bwd", "is_umma_selftest", "is_egnn_edge_fwd_tc", "is_attn_pool_infer", "is_egnn_node_post_pre_tc", "is_egnn_edge_bwd_tc", "is_egnn_edge_bwd_ws", "is_egnn_set_bwd_ws_warps", "is_linear_tc", "is_linear_tc_split_k", "is_attn_pool_infer_tc", "is_vae_mid_infer", "is_head_infer", "is_unpack_nodes", "is_unpack_edges", "is_onehot_tokens", "is_egnn_node_post_bwd_tc", "is_egnn_node_pre_bwd_tc", "is_attn_pool_bwd_tc",
+            "is_fusion_attn_bwd", "is_loss_fwd", "is_loss_bwd", "is_umma_selftest", "is_umma_timing", "is_egnn_edge_fwd_tc", "is_attn_pool_infer", "is_egnn_node_post_pre_tc", "is_egnn_edge_bwd_tc", "is_egnn_edge_bwd_ws", "is_egnn_set_bwd_ws_warps", "is_linear_tc", "is_linear_tc_split_k", "is_attn_pool_infer_tc", "is_vae_mid_infer", "is_head_infer", "is_unpack_nodes", "is_unpack_edges", "is_onehot_tokens", "is_egnn_node_post_bwd_tc", "is_egnn_node_pre_bwd_tc", "is_attn_pool_bwd_tc",
             "is_segment_pool_fwd", "is_segment_pool_bwd", "is_contrastive_scratch_floats", "is_contrastive_fwd",
             "is_contrastive_bwd", "is_fused_adam", "is_rotate_coords", "is_mask_single_residue", "is_mask_rows", "is_gemm_tma_split_k",
             "is_split_planes", "is_gemm_planes_tma", "is_egnn_set_ws_buffers", "is_egnn_set_ws_variant", "is_reduce_partials3", "is_fused_adam_capturable"]
@@ -484,6 +484,11 @@ def umma_selftest(A, B, D, mode):
     """D[128,64] = A[128,64] @ B[64,64]^T on the tensor cores; mode 0 bf16, 1 tf32, 2 3xTF32."""
     f32 = torch.float32
     _call("is_umma_selftest", _t(A, f32, "A"), _t(B, f32, "B"), _t(D, f32, "D"), _i32(mode), _stream())
+
+
+def umma_timing(out):
+    """Cycles per tcgen05.mma of 16 operand-layout / accumulator-rotation configurations into out[16] (csrc/umma_selftest.cu)."""
+    _call("is_umma_timing", _t(out, torch.float32, "out"), _stream())
 
 
 # ---- segment pooling -----------------------------------------------------------------------------

@@ -61,12 +61,14 @@ struct OpGeom {
     uint32_t step;      // start-address advance per K step of 16
     uint32_t lbo, sbo;  // descriptor fields (bytes)
 };
+// t0 = first of the six partial products (0: all; timing experiments drop the small ones)
+template <int T0 = 0>
 __device__ __forceinline__ void issue_x3(uint32_t tmem_d, const OpGeom& a, const OpGeom& b, int nks, uint32_t idesc,
                                          uint32_t accumulate) {
     const uint32_t ta[6] = {2, 0, 1, 1, 0, 0}, tb[6] = {0, 2, 1, 0, 1, 0};     // smallest products first
     uint32_t acc = accumulate;
 #pragma unroll
-    for (int t = 0; t < 6; ++t)
+    for (int t = T0; t < 6; ++t)
 #pragma unroll 8
         for (int ks = 0; ks < nks; ++ks) {
             mma_bf16(tmem_d, make_smem_desc(a.base + ta[t] * a.split + ks * a.step, a.lbo, a.sbo),

@@ -105,6 +105,12 @@ __device__ long long* g_trace_bwd = nullptr;
 #define TRB(ev) do { } while (0)
 #endif
 
+#ifndef IS_EXP_WG_T0
+#define IS_EXP_WG_T0 0          // timing experiment: first partial product of the weight-gradient MMAs (0 = all six)
+#endif
+#ifndef IS_EXP_DATA_T0
+#define IS_EXP_DATA_T0 0        // same for the data MMAs
+#endif
 #ifndef IS_BW_WAIT_HINT_NS
 #define IS_BW_WAIT_HINT_NS 1000
 #endif
@@ -230,7 +236,9 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
     auto publish_and_issue = [&](auto&& fn) {
         fence_async_smem();
         fence_before_sync();
+        TRB(18);
         team_sync<TT>(team);
+        TRB(19);
         if (tw == 0) {
             if (elect_one()) {
                 fence_after_sync();
@@ -334,7 +342,7 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
         }
         TRB(2);
         publish_and_issue([&] {
-            issue_x3(d_acc, gT1k, gW2k, 4, id_fwd, 0);
+            issue_x3<IS_EXP_DATA_T0>(d_acc, gT1k, gW2k, 4, id_fwd, 0);
             mma_commit(bar_d);
         });
         TRB(3);
@@ -366,7 +374,7 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
         if (HAS_COORD) {
             // ---- MMA 2: z3 = m W3^T ; epilogue 2: c, gz3 = gc w4 silu'(z3 + b3) -> X -------------------------------
             publish_and_issue([&] {
-                issue_x3(d_acc, gYk, gW3k, 4, id_fwd, 0);
+                issue_x3<IS_EXP_DATA_T0>(d_acc, gYk, gW3k, 4, id_fwd, 0);
                 mma_commit(bar_d);
             });
             wait_d();
@@ -396,12 +404,12 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
             //  phase, and a team's 24 data MMAs must not queue behind the other team's 42 weight-gradient MMAs; the
             //  weight gradients then run under the next epilogue's arithmetic)
             publish_and_issue([&] {
-                issue_x3(d_acc, gXk, gW3t, 4, id_dgrad, 0);
+                issue_x3<IS_EXP_DATA_T0>(d_acc, gXk, gW3t, 4, id_dgrad, 0);
                 mma_commit(bar_d);
             });
             wait_d();
             issue_only([&] {
-                issue_x3(d_w3, gXt, gYt, NKW, id_wgrad, started);
+                issue_x3<IS_EXP_WG_T0>(d_w3, gXt, gYt, NKW, id_wgrad, started);
                 mma_commit(bar_wg);
             });
             TRB(8);
@@ -451,12 +459,12 @@ edge_bwd_ws_kernel(EdgeCommon p, const float* __restrict__ ghn, const float* __r
         TRB(11);
         // ---- MMA 4: gt1 = gz2 W2 ; WG 2: gW2 += gz2^T t1 ---------------------------------------------------------------
         publish_and_issue([&] {
-            issue_x3(d_acc, gXk, gW2t, 4, id_dgrad, 0);
+            issue_x3<IS_EXP_DATA_T0>(d_acc, gXk, gW2t, 4, id_dgrad, 0);
             mma_commit(bar_d);
         });
         wait_d();
         issue_only([&] {
-            issue_x3(d_w2, gXt, gYt, NKW, id_wgrad, started);
+            issue_x3<IS_EXP_WG_T0>(d_w2, gXt, gYt, NKW, id_wgrad, started);
             mma_commit(bar_wg);
         });
         started = 1;

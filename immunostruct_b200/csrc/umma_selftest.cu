@@ -195,10 +195,91 @@ umma_layout_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
     if (warp == 0) tmem_dealloc(tbase, 128);
 }
 
+// Cycles per tcgen05.mma, issue to completion of 96 MMAs (N = 64, bf16, K = 16 each) issued by one elected thread from a
+// fully unrolled sequence with compile-time descriptors -- the way the edge kernels issue them.  NACC = number of TMEM
+// accumulators the sequence rotates over (1 = every MMA accumulates into the one before it: a dependent chain).
+template <int M, int AMN, int BMN, int ALBO, int ASBO, int BLBO, int BSBO, int TS, int NACC>
+__device__ __forceinline__ float umma_time_one(uint32_t tb, uint32_t a0, uint32_t b0, uint64_t* mbar, uint32_t& phase, int tid) {
+    using namespace umma;
+    long long t0 = 0;
+    if (tid < 32) {
+        if (elect_one()) {
+            const uint32_t idesc = make_instr_desc(1u, M, 64, AMN, BMN);
+            t0 = clock64();
+#pragma unroll
+            for (int i = 0; i < 96; ++i) {
+                const int ks = i & 3;
+                const uint64_t da = make_smem_desc(a0 + ks * 2 * ALBO, ALBO, ASBO);
+                const uint64_t db = make_smem_desc(b0 + ks * 2 * BLBO, BLBO, BSBO);
+                const uint32_t d = tb + 64 * (i % NACC);
+                if (TS) mma_bf16_ts(d, tb + 256 + 8 * ks, db, idesc, 1);
+                else mma_bf16(d, da, db, idesc, 1);
+            }
+            mma_commit(mbar);
+        }
+        __syncwarp();
+    }
+    mbar_wait(mbar, phase);
+    phase ^= 1;
+    const float r = (float)(clock64() - t0) / 96.0f;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(128)
+umma_timing_kernel(float* __restrict__ out) {
+    using namespace umma;
+    extern __shared__ __align__(128) uint8_t sm[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 96 * 1024 / 16; i += 128) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (warp == 0) tmem_alloc(&tmem_base, 512);
+    if (tid == 32) mbar_init(&mbar, 1);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tb = tmem_base, a0 = smem_u32(sm), b0 = smem_u32(sm + 48 * 1024);
+    uint32_t ph = 0;
+    float r[16];
+    //                 M   amn bmn albo  asbo  blbo  bsbo  ts nacc
+    r[0] = umma_time_one<128, 0, 0, 128, 1024, 128, 1024, 0, 1>(tb, a0, b0, &mbar, ph, tid);    // unpadded, one accumulator
+    r[1] = umma_time_one<128, 0, 0, 128, 1024, 128, 1024, 0, 2>(tb, a0, b0, &mbar, ph, tid);    // two accumulators
+    r[2] = umma_time_one<128, 0, 0, 128, 1024, 128, 1024, 0, 4>(tb, a0, b0, &mbar, ph, tid);    // four
+    r[3] = umma_time_one<128, 0, 0, 144, 1152, 128, 1024, 0, 1>(tb, a0, b0, &mbar, ph, tid);    // A padded
+    r[4] = umma_time_one<128, 0, 0, 144, 1152, 144, 1152, 0, 1>(tb, a0, b0, &mbar, ph, tid);    // both padded
+    r[5] = umma_time_one<128, 0, 0, 144, 1152, 144, 1152, 0, 4>(tb, a0, b0, &mbar, ph, tid);
+    r[6] = umma_time_one<128, 0, 0, 128, 1040, 128, 1040, 0, 1>(tb, a0, b0, &mbar, ph, tid);    // SBO padded
+    r[7] = umma_time_one<128, 0, 0, 128, 1024, 128, 1024, 1, 1>(tb, a0, b0, &mbar, ph, tid);    // A from TMEM
+    r[8] = umma_time_one<128, 0, 0, 128, 1024, 128, 1024, 1, 4>(tb, a0, b0, &mbar, ph, tid);
+    r[9] = umma_time_one<128, 0, 1, 128, 1024, 1024, 128, 0, 1>(tb, a0, b0, &mbar, ph, tid);    // dgrad: B MN-major view
+    r[10] = umma_time_one<128, 0, 1, 144, 1152, 1152, 144, 0, 1>(tb, a0, b0, &mbar, ph, tid);
+    r[11] = umma_time_one<64, 1, 1, 1024, 128, 1024, 128, 0, 1>(tb, a0, b0, &mbar, ph, tid);    // wgrad: M = 64, both MN-major
+    r[12] = umma_time_one<64, 1, 1, 1024, 128, 1024, 128, 0, 2>(tb, a0, b0, &mbar, ph, tid);
+    r[13] = umma_time_one<64, 1, 1, 1152, 144, 1152, 144, 0, 1>(tb, a0, b0, &mbar, ph, tid);
+    r[14] = umma_time_one<64, 0, 1, 128, 2048, 1152, 144, 0, 1>(tb, a0, b0, &mbar, ph, tid);    // segment sum of the edge forward
+    r[15] = umma_time_one<64, 0, 0, 128, 1024, 128, 1024, 0, 1>(tb, a0, b0, &mbar, ph, tid);    // M = 64 K-major
+    if (tid == 0)
+        for (int i = 0; i < 16; ++i) out[i] = r[i];
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tb, 512);
+}
+
 }  // namespace is
 
 using namespace is;
 
+// out[16]: cycles per MMA for 16 operand-layout / accumulator-rotation configurations (see umma_timing_kernel)
+extern "C" int is_umma_timing(float* out, void* stream) {
+    const size_t smem = 96 * 1024 + 4096;
+    cudaError_t e = cudaFuncSetAttribute(umma_timing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    umma_timing_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(out);
+    IS_LAUNCH_CHECK();
+    return IS_OK;
+}
 extern "C" int is_umma_selftest(const float* A, const float* B, float* D, int mode, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e;
@@ -234,3 +315,4 @@ extern "C" int is_umma_selftest(const float* A, const float* B, float* D, int mo
     IS_LAUNCH_CHECK();
     return IS_OK;
 }
+

@@ -196,6 +196,9 @@ int is_linear_tc_split_k(int64_t M, int64_t N, int64_t K);
 int is_linear_tc(const float* A, int64_t lda, const float* W, int64_t ldw, const float* bias, float* C, int64_t ldc,
                  int64_t M, int64_t N, int64_t K, int relu, int precision, int split_k, float* workspace, void* stream);
 int is_umma_selftest(const float* A, const float* B, float* D, int mode, void* stream);
+/* cycles per tcgen05.mma (96 MMAs of N = 64, bf16, issue to completion) for 16 operand-layout / accumulator-rotation
+   configurations of the edge kernels (csrc/umma_selftest.cu: umma_timing_kernel; scripts/umma_timing.py): out[16] */
+int is_umma_timing(float* out, void* stream);
 
 /* ---- TMA-fed tcgen05 GEMM for the dense Linear layers, forward and backward (csrc/gemm_tma.cu): the nn.Linear
  * layers of the sequence VAE (models/hybrid_models.py:63-74 / 297-308) and what autograd derives for them.

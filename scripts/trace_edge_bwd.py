@@ -49,6 +49,11 @@ for team in range(2):
         tot += m
         print(f"   {names[ev - 1]:>14} -> {names[ev]:<14} {m:8.0f} cycles")
     print(f"   sum {tot:.0f}")
+    # the LAST publish of a tile (MMA 4): thread 0's stores done -> its fences done -> team barrier passed -> MMAs issued + data ready
+    d1 = [int(t[team, 18, i] - t[team, 11, i]) for i in range(lo, hi)]
+    d2 = [int(t[team, 19, i] - t[team, 18, i]) for i in range(lo, hi)]
+    d3 = [int(t[team, 12, i] - t[team, 19, i]) for i in range(lo, hi)]
+    print(f"   publish of MMA 4: fences {sum(d1) / len(d1):.0f} | team barrier (slowest warp) {sum(d2) / len(d2):.0f} | issue + MMA 4 + wait {sum(d3) / len(d3):.0f}")
 # interleaving of the two teams: start stamps relative to team 0's tile 4
 b0 = int(t[0, 0, 0])
 print("team 0 starts:", [int(t[0, 0, i]) - b0 for i in range(0, 12)])
