@@ -40,7 +40,11 @@ if rep:
             "launch__registers_per_thread", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
             "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed.sum",
             "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "launch__block_size", "launch__grid_size",
-            "launch__shared_mem_per_block_dynamic"]
+            "launch__shared_mem_per_block_dynamic",
+            "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed",
+            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+            "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+            "lts__t_sector_hit_rate.pct", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"]
     lines = [f"# ncu --set full capture ({tag}): {rep}", ""]
     for r in rr[2:]:
         d = dict(zip(h, r))
@@ -54,5 +58,6 @@ if rep:
     seg = subprocess.run([sys.executable, "scripts/ncu_segments.py", rep], capture_output=True, text=True).stdout
     lines += ["## executed warp instructions / stall samples per code segment (split at barriers, TMEM loads, MMA commits)", "", "```"]
     lines += [l for l in seg.splitlines() if l[:4].strip().isdigit() or l.startswith("total")] + ["```", ""]
-    open(f"profiles/{tag}_edge_fwd_full.md", "w").write("\n".join(lines) + "\n")
+    suffix = sys.argv[4] if len(sys.argv) > 4 else "edge_fwd_full"
+    open(f"profiles/{tag}_{suffix}.md", "w").write("\n".join(lines) + "\n")
 print("wrote profiles/")
