@@ -176,6 +176,16 @@ __device__ __forceinline__ void meta_edge(const EdgeCommon& p, Meta3& m, int j, 
 #define IS_WS_WAIT_HINT_NS 2000
 #endif
 #define WS_WAIT(bar, parity) mbar_wait_hint(bar, parity, IS_WS_WAIT_HINT_NS)
+// Hardware named barriers for the two hand-overs whose producers are warps (gather -> MMA 1: ids 3, 4; epilogue 1 -> MMA 2 / 3:
+// ids 5, 6): the eight producer warps bar.arrive, the MMA warp bar.sync -- no polling of shared memory (ncu: the polled
+// mbarrier waits of the two MMA warps were 1.7 M of the kernel's 8 M poll iterations) and a wake-up within tens of cycles.
+// A barrier id is re-used two tiles later, after a completion of the consumer's MMAs that its producers wait for (hn_full /
+// acc1_full), so arrivals of different tiles never mix.  -DIS_WS_NAMED=0 restores the mbarriers (A/B timing: 214 -> 211 us).
+#ifndef IS_WS_NAMED
+#define IS_WS_NAMED 1
+#endif
+__device__ __forceinline__ void nbar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void nbar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // TSA = the A operand of MMA 2 comes from TENSOR MEMORY (is_egnn_set_ws_variant bit 0, default on): the kernel is bound by the
 // L1 / shared-memory data pipe (ncu: LSU wavefronts 56 % + tensor-core operand wavefronts 43 % of the pipe's cycles), and
@@ -277,14 +287,14 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
                 done = meta[i % NM].tile[0] >= nend;
                 if (done) break;
                 if (first) {
-                    WS_WAIT(&a_full[b], (i >> 1) & 1);
+                    if (IS_WS_NAMED) nbar_sync(3 + b, 32 * (NW_PROD + 1)); else WS_WAIT(&a_full[b], (i >> 1) & 1);
                     fence_after_sync();
                     if (elect_one()) {
                         issue_fwd<PREC>(tmem + TM_ACC1 + 64 * b, a_addr + b * ABUF, w2_addr);
                         mma_commit(&acc1_full[b]);
                     }
                 } else {
-                    WS_WAIT(&m_full[b], (i >> 1) & 1);
+                    if (IS_WS_NAMED) nbar_sync(5 + b, 32 * (NW_EPI + 1)); else WS_WAIT(&m_full[b], (i >> 1) & 1);
                     fence_after_sync();
                     if (elect_one()) {
                         if (HAS_COORD) {
@@ -367,7 +377,8 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
             store_rows(1);
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&a_full[b]);
+            if (IS_WS_NAMED) nbar_arrive(3 + b, 32 * (NW_PROD + 1));
+            else if (lane == 0) mbar_arrive(&a_full[b]);
         }
     } else {
         // ================= epilogue: epilogue 1 of tile i, then epilogue 2 / hn rows / coordinates of tile i-1 =====
@@ -408,7 +419,8 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
                 fence_async_smem();
                 fence_before_sync();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&m_full[b]);
+                if (IS_WS_NAMED) nbar_arrive(5 + b, 32 * (NW_EPI + 1));
+                else if (lane == 0) mbar_arrive(&m_full[b]);
             }
             if (i >= 1) {
                 const int j = i - 1, bp = b ^ 1;

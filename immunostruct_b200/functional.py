@@ -228,34 +228,70 @@ def _egnn_stack_forward(graph, x23, edge_attr, params, fast_act, keep, qkv=None)
     return h if qkv is None else (h, QKV)
 
 
+def _qkv_backward(n_graphs, max_nodes, h_fin, w, gqkv, need_w=True, need_b=True):
+    """Backward of ``QKV = h' W^T + b`` over all node rows of the batch -> (gh', gW, gb).  Equal node counts per graph (the
+    reference's own assumption, hybrid_models.py:86-92): the weight / bias gradients are per-graph partial products (one
+    batched GEMM, [B, out, K]) summed over the graphs in a fixed order -- a tenth of the time of autograd's single long-K
+    GEMM (K = 102 400 at batch 512) and column reduction."""
+    gqkv = gqkv.contiguous()
+    ghq = gqkv @ w
+    if n_graphs * max_nodes == h_fin.shape[0]:
+        g3, h3 = gqkv.reshape(n_graphs, -1, gqkv.shape[1]), h_fin.reshape(n_graphs, -1, h_fin.shape[1])
+        gw = torch.bmm(g3.transpose(1, 2), h3).sum(0) if need_w else None
+        gb = g3.sum(1).sum(0) if need_b else None
+    else:
+        gw = gqkv.t() @ h_fin if need_w else None
+        gb = gqkv.sum(0) if need_b else None
+    return ghq, gw, gb
+
+
 class _EGNNStack(torch.autograd.Function):
     """The whole ``for layer in self.GCN_layers`` loop (models/hybrid_models.py:89-90) as ONE autograd node:
     forward through the fused kernels (node side fused across layer boundaries on the tensor cores), backward
     layer by layer in reverse.  The last layer's coordinate branch is skipped, so its coord_mlp parameters get
     ``None`` gradients exactly as in the reference.
 
-    forward(graph, n_layers, x23, edge_attr, *flat_params) -> h_final [N,64]
+    forward(graph, n_layers, x23, edge_attr, qkv_w, qkv_b, *flat_params) -> (h_final [N,64], QKV [N,192] or None)
+
+    ``qkv_w`` [192,64] / ``qkv_b`` [192] (or None): the attention projections that follow the stack
+    (models/layers.py:13-16 / :67-69).  They ride in the last node kernel exactly as in inference (h' is still on chip:
+    +27 us instead of a 0.17 ms cuBLAS SIMT GEMM + bias kernel over 102 400 rows); their backward -- h' gets
+    ``gQKV W``, the weight / bias gradients are per-graph partial products summed in a fixed order -- runs here, before the
+    layer loop.  QKV is None when the node side runs on the SIMT kernels (fp32 mode): the caller projects itself.
     """
 
     @staticmethod
-    def forward(ctx, graph, n_layers, x23, edge_attr, *flat):
+    def forward(ctx, graph, n_layers, x23, edge_attr, qkv_w, qkv_b, *flat):
         params = [[t.contiguous() for t in flat[11 * l:11 * l + 11]] for l in range(n_layers)]
         edge_attr = edge_attr.contiguous()
         keep = []
-        h = _egnn_stack_forward(graph, x23, edge_attr, params, False, keep)
-        ctx.graph, ctx.n_layers = graph, n_layers
+        qkv = None if qkv_w is None else (qkv_w.contiguous(), qkv_b.contiguous())
+        out = _egnn_stack_forward(graph, x23, edge_attr, params, False, keep, qkv)
+        h, QKV = out if qkv is not None else (out, None)
+        ctx.graph, ctx.n_layers, ctx.has_qkv = graph, n_layers, QKV is not None
+        ctx.set_materialize_grads(False)
         saved = [edge_attr]
         for (hl, xl, PQl, hnl), pl in zip(keep, params):
             saved += [hl, xl, PQl, hnl, *pl]
+        if QKV is not None:
+            saved += [h, qkv[0]]
         ctx.save_for_backward(*saved)
-        return h
+        return h, QKV
 
     @staticmethod
-    def backward(ctx, gh):
+    def backward(ctx, gh, gqkv):
         saved = ctx.saved_tensors
         edge_attr = saved[0]
         nl = ctx.n_layers
         grads = [None] * (11 * nl)
+        gw = gb = None
+        if ctx.has_qkv and gqkv is not None:
+            ghq, gw, gb = _qkv_backward(ctx.graph.n_graphs, int(ctx.graph.max_nodes), saved[-2], saved[-1], gqkv,
+                                        ctx.needs_input_grad[4], ctx.needs_input_grad[5])
+            gh = ghq if gh is None else gh + ghq
+        if gh is None:
+            return (None,) * (6 + 11 * nl)
+        gh = gh.contiguous()
         gx = None
         for l in range(nl - 1, -1, -1):
             hl, xl, PQl, hnl, *pl = saved[1 + 15 * l:1 + 15 * (l + 1)]
@@ -263,17 +299,22 @@ class _EGNNStack(torch.autograd.Function):
             gh, gx_in, gl = _egnn_layer_backward(ctx.graph, hl, xl, edge_attr, PQl, hnl, pl, gh, gx, need, need)
             grads[11 * l:11 * l + 11] = gl
             gx = gx_in
-        return (None, None, None, None, *grads)
+        return (None, None, None, None, gw, gb, *grads)
 
 
-def egnn_stack(graph, x23, edge_attr, layer_params):
-    """EGNN stack with autograd (training).  ``layer_params``: list of EGNNConv.kernel_params() tuples."""
+def egnn_stack(graph, x23, edge_attr, layer_params, qkv=None):
+    """EGNN stack with autograd (training).  ``layer_params``: list of EGNNConv.kernel_params() tuples.  Returns the final
+    h [N,64]; with ``qkv`` = (W [192,64], b [192]) (differentiable) returns (h, QKV [N,192]) with the projections fused
+    into the last node kernel -- QKV is None where that kernel does not run (fp32 mode, registered-operator route)."""
     flat = [t for lp in layer_params for t in lp]
     ops = _ops()
     if ops is not None:
-        return ops.egnn_stack(x23, edge_attr, flat, ops.graph_tensors(graph), len(layer_params), graph.n_edges, graph.n_graphs,
-                              int(graph.max_nodes))[0]
-    return _EGNNStack.apply(graph, len(layer_params), x23, edge_attr, *flat)
+        out = ops.egnn_stack(x23, edge_attr, flat, ops.graph_tensors(graph), len(layer_params), graph.n_edges, graph.n_graphs,
+                             int(graph.max_nodes), [] if qkv is None else list(qkv))
+        return out[0] if qkv is None else (out[0], out[1] if out[1].numel() else None)
+    if qkv is None:
+        return _EGNNStack.apply(graph, len(layer_params), x23, edge_attr, None, None, *flat)[0]
+    return _EGNNStack.apply(graph, len(layer_params), x23, edge_attr, qkv[0], qkv[1], *flat)
 
 
 def egnn_stack_infer(graph, x23, edge_attr, layer_params, qkv=None):

@@ -296,22 +296,27 @@ fused_loss.register_autograd(_loss_backward, setup_context=_loss_setup)
 # ---- EGNN stack ----------------------------------------------------------------------------------------
 @torch.library.custom_op("immunostruct_b200::egnn_stack", mutates_args=())
 def egnn_stack(x23: Tensor, edge_attr: Tensor, params: List[Tensor], graph: List[Tensor], n_layers: int, n_edges: int,
-               n_graphs: int, max_nodes: int) -> List[Tensor]:
-    """-> [h_final, then per layer (h_in, x_in, PQ, hn)]: the intermediates are outputs so that autograd can keep them."""
+               n_graphs: int, max_nodes: int, qkv: List[Tensor]) -> List[Tensor]:
+    """-> [h_final, QKV, then per layer (h_in, x_in, PQ, hn)]: the intermediates are outputs so that autograd can keep them.
+    ``qkv`` = [W [192,64], b [192]] or []: the attention projections fused into the last node kernel; QKV is an empty
+    tensor when they were not computed (no ``qkv``, or the fp32 mode's SIMT node kernels)."""
     g = _graph_ns(graph, n_edges, n_graphs, max_nodes)
     pl = [[t.contiguous() for t in params[11 * l:11 * l + 11]] for l in range(n_layers)]
     keep: list = []
-    h = IF._egnn_stack_forward(g, x23, edge_attr.contiguous(), pl, False, keep)
-    out = [h]
+    res = IF._egnn_stack_forward(g, x23, edge_attr.contiguous(), pl, False, keep,
+                                 tuple(t.contiguous() for t in qkv) if qkv else None)
+    h, QKV = res if qkv else (res, None)
+    out = [h, x23.new_empty(0) if QKV is None else QKV]
     for hl, xl, pq, hn in keep:
         out += [hl.contiguous(), xl.contiguous(), pq, hn]       # (layer 0's h / x are strided views of x23)
     return out
 
 
 @egnn_stack.register_fake
-def _(x23, edge_attr, params, graph, n_layers, n_edges, n_graphs, max_nodes):
+def _(x23, edge_attr, params, graph, n_layers, n_edges, n_graphs, max_nodes, qkv):
     n = x23.shape[0]
-    out = [x23.new_empty(n, H)]
+    fused = bool(qkv) and IF.get_precision() != "fp32"
+    out = [x23.new_empty(n, H), x23.new_empty(n, 3 * H) if fused else x23.new_empty(0)]
     for l in range(n_layers):
         out += [x23.new_empty(n, 20 if l == 0 else H), x23.new_empty(n, 3), x23.new_empty(n, 2 * H), x23.new_empty(n, H)]
     return out
@@ -346,10 +351,12 @@ def _(gh, edge_attr, saved, params, graph, n_layers, n_edges, n_graphs, max_node
 
 
 def _egnn_setup(ctx, inputs, output):
-    x23, edge_attr, params, graph, n_layers, n_edges, n_graphs, max_nodes = inputs
+    x23, edge_attr, params, graph, n_layers, n_edges, n_graphs, max_nodes, qkv = inputs
     ctx.cfg = (n_layers, n_edges, n_graphs, max_nodes)
-    ctx.n_params, ctx.n_graph = len(params), len(graph)
-    ctx.save_for_backward(edge_attr, *output[1:], *params, *graph)
+    ctx.n_params, ctx.n_graph, ctx.n_qkv = len(params), len(graph), len(qkv)
+    ctx.has_qkv = bool(qkv) and output[1].numel() > 0
+    ctx.set_materialize_grads(False)
+    ctx.save_for_backward(edge_attr, *output[2:], *params, *graph, *((output[0], qkv[0]) if ctx.has_qkv else ()))
 
 
 def _egnn_backward(ctx, grads):
@@ -357,13 +364,18 @@ def _egnn_backward(ctx, grads):
     t = ctx.saved_tensors
     edge_attr, saved = t[0], list(t[1:1 + 4 * n_layers])
     params = list(t[1 + 4 * n_layers:1 + 4 * n_layers + ctx.n_params])
-    graph = list(t[1 + 4 * n_layers + ctx.n_params:])
-    gh = grads[0]
+    graph = list(t[1 + 4 * n_layers + ctx.n_params:1 + 4 * n_layers + ctx.n_params + ctx.n_graph])
+    gh, gqkv = grads[0], grads[1]
+    g_qkv_in = [None] * ctx.n_qkv
+    if ctx.has_qkv and gqkv is not None:                 # same arithmetic as functional._EGNNStack.backward
+        ghq, gw, gb = IF._qkv_backward(ctx.cfg[2], ctx.cfg[3], t[-2], t[-1], gqkv)
+        gh = ghq if gh is None else gh + ghq
+        g_qkv_in = [gw, gb]
     if gh is None:
-        return None, None, [None] * ctx.n_params, [None] * ctx.n_graph, None, None, None, None
+        return None, None, [None] * ctx.n_params, [None] * ctx.n_graph, None, None, None, None, g_qkv_in
     gp = egnn_stack_bwd(gh.contiguous(), edge_attr, saved, params, graph, *ctx.cfg)
     return (None, None, [None if g.numel() == 0 and p.numel() != 0 else g for g, p in zip(gp, params)], [None] * ctx.n_graph,
-            None, None, None, None)
+            None, None, None, None, g_qkv_in)
 
 
 egnn_stack.register_autograd(_egnn_backward, setup_context=_egnn_setup)

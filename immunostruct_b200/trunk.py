@@ -54,8 +54,13 @@ class StructureTrunk:
                                               project=project)
         # training: one autograd node for the whole stack (the last layer's coordinates are never consumed,
         # hybrid_models.py:323-326, so its coordinate branch is skipped and coord_mlp gets no gradient)
-        node_feat = IF.egnn_stack(graph_data, xin, edge_feat, [l.kernel_params() for l in self.GCN_layers])
-        return self.self_attention.pooled(graph_data, node_feat, want_attn=want_attn, want_nodes=want_nodes, project=project)
+        # (the attention projections ride in the last node kernel here too; their backward runs inside the same node)
+        fuse_qkv = getattr(self.self_attention, "feature_dim", self.gat_hidden_channels) == 64 and self.gat_hidden_channels == 64
+        out = IF.egnn_stack(graph_data, xin, edge_feat, [l.kernel_params() for l in self.GCN_layers],
+                            qkv=self.self_attention.qkv_params() if fuse_qkv else None)
+        node_feat, qkv = out if fuse_qkv else (out, None)
+        return self.self_attention.pooled(graph_data, node_feat, want_attn=want_attn, want_nodes=want_nodes, qkv=qkv,
+                                          project=project)
 
 
 def _tc_linear(layer, x, relu=False):

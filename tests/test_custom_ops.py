@@ -83,7 +83,11 @@ def _opcheck_all(device, tests=("test_schema", "test_faketensor", "test_autograd
     model = build_model("HybridModelv2", gd, device=device)
     flat = [t for l in model.GCN_layers for t in l.kernel_params()]
     torch.library.opcheck(ops.egnn_stack, (g.ndata["x"], g.edata["edge_attr"], flat, ops.graph_tensors(g), len(model.GCN_layers),
-                                           g.n_edges, g.n_graphs, int(g.max_nodes)), test_utils=tests)
+                                           g.n_edges, g.n_graphs, int(g.max_nodes), []), test_utils=tests)
+    # with the attention projections fused into the last node kernel (QKV is the operator's second output)
+    torch.library.opcheck(ops.egnn_stack, (g.ndata["x"], g.edata["edge_attr"], flat, ops.graph_tensors(g), len(model.GCN_layers),
+                                           g.n_edges, g.n_graphs, int(g.max_nodes), list(model.self_attention.qkv_params())),
+                          test_utils=tests)
 
 
 def test_registered_ops_pass_opcheck(cpu_backend):
