@@ -771,7 +771,11 @@ int is_egnn_node_pre_fwd(const float* h, int64_t ldh, int F, const float* W1, co
     size_t smem = sizeof(float) * (IS_TM * (F + 4) + 2 * F * 64);
     int rc = set_smem(node_pre_fwd_kernel, smem);
     if (rc) return rc;
-    node_pre_fwd_kernel<<<node_grid(n_nodes), IS_THREADS, smem, (cudaStream_t)stream>>>(h, ldh, F, W1, b1, PQ, n_nodes);
+    // a streaming kernel (20- or 64-wide rows in, 128-wide rows out, no per-CTA partials): four CTAs per SM hide the
+    // load -> barrier -> store chain of a tile that one CTA per SM (node_grid) leaves exposed
+    const int64_t tiles = (n_nodes + IS_TM - 1) / IS_TM, cap = 4 * (int64_t)num_sms();
+    const int grid = (int)(tiles < cap ? tiles : cap);
+    node_pre_fwd_kernel<<<grid < 1 ? 1 : grid, IS_THREADS, smem, (cudaStream_t)stream>>>(h, ldh, F, W1, b1, PQ, n_nodes);
     IS_LAUNCH_CHECK();
     return IS_OK;
 }

@@ -29,7 +29,7 @@ __device__ __forceinline__ void fusion_pair(const float* __restrict__ c, int L, 
     Z = 0.0f; S1 = 0.0f; S2 = 0.0f;
     for (int j = 0; j < L; ++j) {
         const float cj = c[j];
-        const float e = expf(gamma * cj - mx);
+        const float e = exp_comp(gamma * cj - mx);       // one MUFU, product rounding compensated (common.cuh)
         Z += e; S1 = fmaf(e, cj, S1); S2 = fmaf(e * cj, cj, S2);
     }
 }
@@ -112,7 +112,7 @@ fusion_bwd_kernel(const float* __restrict__ cin, int L, int H, const float* __re
         float var = 0.0f;
         for (int j = 0; j < L; ++j) {
             const float dcj = c[j] - E;
-            var = fmaf(expf(gamma * c[j] - mx), dcj * dcj, var);
+            var = fmaf(exp_comp(gamma * c[j] - mx), dcj * dcj, var);
         }
         var *= rz;
         s_gam[idx] = gamma; s_mx[idx] = mx; s_rz[idx] = rz; s_E[idx] = E;
@@ -135,20 +135,41 @@ fusion_bwd_kernel(const float* __restrict__ cin, int L, int H, const float* __re
         gdir[i] = s;
     }
     __syncthreads();
-    // dL/dc_j = gdir_j + sum_{i,h} go_i alpha_h p_ij (1 + gamma_ih (c_j - E_ih))
-    for (int j = tid; j < L; j += IS_THREADS) {
-        const float cj = c[j];
-        float s = gdir[j];
-        for (int i = 0; i < L; ++i) {
-            const float goi = go[i];
-            for (int h = 0; h < H; ++h) {
-                const int idx = i * H + h;
-                const float gam = s_gam[idx];
-                const float p = expf(gam * cj - s_mx[idx]) * s_rz[idx];
-                s = fmaf(goi * coef[2 * H + h] * p, 1.0f + gam * (cj - s_E[idx]), s);
+    // dL/dc_j = gdir_j + sum_{i,h} go_i alpha_h p_ij (1 + gamma_ih (c_j - E_ih)); two threads per j (the halves of the i
+    // range), combined in a fixed order
+    float* part = s_mx;                                       // re-used only after the loops that read it
+    const int half = tid & 1;
+    float sacc[2 * IS_FUS_LMAX / IS_THREADS];                 // L <= 256: two passes of 128 values of j
+#pragma unroll
+    for (int ps = 0; ps < 2 * IS_FUS_LMAX / IS_THREADS; ++ps) {
+        const int j = (tid >> 1) + ps * (IS_THREADS / 2);
+        float s = 0.0f;
+        if (j < L) {
+            const float cj = c[j];
+            const int ib = half ? (L + 1) / 2 : 0, ie = half ? L : (L + 1) / 2;
+            for (int i = ib; i < ie; ++i) {
+                const float goi = go[i];
+                for (int h = 0; h < H; ++h) {
+                    const int idx = i * H + h;
+                    const float gam = s_gam[idx];
+                    const float p = exp_comp(gam * cj - s_mx[idx]) * s_rz[idx];
+                    s = fmaf(goi * coef[2 * H + h] * p, 1.0f + gam * (cj - s_E[idx]), s);
+                }
             }
         }
-        gc[(int64_t)b * L + j] = s;
+        sacc[ps] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ps = 0; ps < 2 * IS_FUS_LMAX / IS_THREADS; ++ps) {
+        const int j = (tid >> 1) + ps * (IS_THREADS / 2);
+        if (j < L && half) part[j] = sacc[ps];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ps = 0; ps < 2 * IS_FUS_LMAX / IS_THREADS; ++ps) {
+        const int j = (tid >> 1) + ps * (IS_THREADS / 2);
+        if (j < L && !half) gc[(int64_t)b * L + j] = gdir[j] + (sacc[ps] + part[j]);
     }
 }
 

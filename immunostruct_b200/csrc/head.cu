@@ -20,15 +20,19 @@
 namespace is {
 
 // ---- vae_mid: SPB samples per CTA so that every weight row read from L2 serves SPB dot products ----------------
-constexpr int VM_SPB = 4;
+constexpr int VM_SPB = 2;      // 256 CTAs at batch 512: the phases below are latency chains, co-resident CTAs overlap them
 
+// SPEC: the reference's sizes (hidden 512, latent 32, 8 property features) as compile-time constants -- the dot-product loops
+// unroll completely and all their weight loads are in flight at once (the kernel is a chain of L2 latencies)
+template <bool SPEC>
 __global__ void __launch_bounds__(IS_THREADS)
 vae_mid_infer_kernel(const float* __restrict__ h1, const float* __restrict__ prop, const float* __restrict__ eps,
                      const float* __restrict__ Wp0, const float* __restrict__ bp0, const float* __restrict__ Wp3,
                      const float* __restrict__ bp3, const float* __restrict__ W21, const float* __restrict__ b21,
                      const float* __restrict__ W22, const float* __restrict__ b22, const float* __restrict__ W3,
                      const float* __restrict__ b3, float* __restrict__ mu, float* __restrict__ logvar,
-                     float* __restrict__ zv, float* __restrict__ h3, int B, int HD, int LD, int PD) {
+                     float* __restrict__ zv, float* __restrict__ h3, int B, int HD_, int LD_, int PD_) {
+    const int HD = SPEC ? 512 : HD_, LD = SPEC ? 32 : LD_, PD = SPEC ? 8 : PD_;
     extern __shared__ __align__(16) float sm[];
     float* sh = sm;                                  // [SPB][HD]
     float* se = sh + VM_SPB * HD;                    // [SPB][32] property hidden
@@ -54,6 +58,7 @@ vae_mid_infer_kernel(const float* __restrict__ h1, const float* __restrict__ pro
         float acc[VM_SPB];
 #pragma unroll
         for (int s = 0; s < VM_SPB; ++s) acc[s] = 0.0f;
+#pragma unroll
         for (int k = lane; k < HD; k += 32) {
             const float wk = __ldg(w + k);
 #pragma unroll
@@ -99,10 +104,25 @@ vae_mid_infer_kernel(const float* __restrict__ h1, const float* __restrict__ pro
 #pragma unroll
         for (int s = 0; s < VM_SPB; ++s) acc[s] = bo;
         const float* w = W3 + (int64_t)o * LZ;
-        for (int k = 0; k < LZ; ++k) {
-            const float wk = __ldg(w + k);
+        if ((LZ & 3) == 0 && (reinterpret_cast<uintptr_t>(W3) & 15) == 0) {
+            // 128-bit weight loads: a quarter of the (uncoalesced: one row per thread) load instructions, same k order
 #pragma unroll
-            for (int s = 0; s < VM_SPB; ++s) acc[s] = fmaf(wk, sz[s * LZ + k], acc[s]);
+            for (int k = 0; k < LZ; k += 4) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + k));
+#pragma unroll
+                for (int s = 0; s < VM_SPB; ++s) {
+                    acc[s] = fmaf(w4.x, sz[s * LZ + k], acc[s]);
+                    acc[s] = fmaf(w4.y, sz[s * LZ + k + 1], acc[s]);
+                    acc[s] = fmaf(w4.z, sz[s * LZ + k + 2], acc[s]);
+                    acc[s] = fmaf(w4.w, sz[s * LZ + k + 3], acc[s]);
+                }
+            }
+        } else {
+            for (int k = 0; k < LZ; ++k) {
+                const float wk = __ldg(w + k);
+#pragma unroll
+                for (int s = 0; s < VM_SPB; ++s) acc[s] = fmaf(wk, sz[s * LZ + k], acc[s]);
+            }
         }
 #pragma unroll
         for (int s = 0; s < VM_SPB; ++s)
@@ -159,7 +179,7 @@ head_infer_kernel(const float* __restrict__ pooled, const float* __restrict__ Wc
             float Z = 0.0f, S1 = 0.0f;
             for (int j = 0; j < L; ++j) {
                 const float cj = c[j];
-                const float e = expf(gamma * cj - mx);
+                const float e = exp_comp(gamma * cj - mx);
                 Z += e; S1 = fmaf(e, cj, S1);
             }
             Eh[idx] = S1 / Z;
@@ -207,12 +227,13 @@ int is_vae_mid_infer(const float* h1, const float* prop, const float* eps, const
     if (n_samples <= 0 || hidden <= 0 || latent <= 0 || prop_dim < 0 || VM_SPB * prop_dim > IS_THREADS) return IS_ERR_ARG;
     const size_t smem = sizeof(float) * (size_t)VM_SPB * (hidden + 32 + 2 * latent + latent + prop_dim);
     if (smem > 200 * 1024) return IS_ERR_UNSUPPORTED;
-    cudaError_t e = cudaFuncSetAttribute(vae_mid_infer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
     const int grid = (n_samples + VM_SPB - 1) / VM_SPB;
-    vae_mid_infer_kernel<<<grid, IS_THREADS, smem, (cudaStream_t)stream>>>(h1, prop, eps, Wp0, bp0, Wp3, bp3, W21, b21, W22, b22,
-                                                                           W3, b3, mu, logvar, z_vae, h3, n_samples, hidden,
-                                                                           latent, prop_dim);
+    const bool spec = hidden == 512 && latent == 32 && prop_dim == 8;
+    auto kern = spec ? vae_mid_infer_kernel<true> : vae_mid_infer_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<grid, IS_THREADS, smem, (cudaStream_t)stream>>>(h1, prop, eps, Wp0, bp0, Wp3, bp3, W21, b21, W22, b22, W3, b3, mu, logvar,
+                                                          z_vae, h3, n_samples, hidden, latent, prop_dim);
     IS_LAUNCH_CHECK();
     return IS_OK;
 }
