@@ -605,7 +605,9 @@ def main():
         # The byte term is the larger one, so "hbm" is the bound the schema asks for; in practice the
         # kernel is limited by the SIMT work per edge -- 192 SiLUs (2 MUFU each in the fp32-accurate mode:
         # 91 us of MUFU pipe per launch) and ~100 issued warp-instructions -- see `simt` below and
-        # profiles/r01_ws_*_edge_fwd_full.md (issue slots 47 %, MUFU 45 %, tensor pipe 33 %, DRAM 3 %).
+        # profiles/r02_ws_*_edge_fwd_full.md (issue slots 53 %, MUFU 50 %, tensor pipe 37 %, DRAM 5 %).  The unit that is
+        # nearly full is the shared-memory / L1 data pipe (128 B / clk / SM), which the LSU (operand stores, gathers, bias
+        # reads) and the tensor core's operand reads share: `ncu.l1_pipe_lsu_pct` + `ncu.l1_pipe_tensor_operand_pct`.
         roofline = {"kernel": kname, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
                     "frac": gbs / hbm_peak, "traffic": (ncu or {}).get("dram_bytes") if B == BATCH else None,
                     "peak_source": src, "launch_ms": t_k * 1e3, "edges_per_launch": e,

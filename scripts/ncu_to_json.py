@@ -16,7 +16,11 @@ KEYS = {"dram__bytes_read.sum": "dram_read", "dram__bytes_write.sum": "dram_writ
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active": "mufu_pipe_pct",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "tensor_pipe_pct",
         "smsp__inst_executed.sum": "warp_instructions", "launch__registers_per_thread": "registers_per_thread",
-        "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct"}
+        "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
+        # the shared-memory / L1 data pipe (128 B / clk / SM): LSU wavefronts (shared + global) and the tensor core's operand reads
+        "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed": "l1_pipe_lsu_pct",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed": "l1_pipe_lsu_shared_pct",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed": "l1_pipe_tensor_operand_pct"}
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
 
 
