@@ -133,6 +133,11 @@ __device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
         "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// shared memory -> tensor memory copy by the tensor core (ONE thread): 128 rows x 256 bits (8 columns) of the tile `sdesc`
+// describes (the A-operand descriptor of one K step of a K-major bf16 tile) into columns taddr .. taddr + 7 of all 128 lanes
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
 // arrive on `bar` once every previously issued MMA of this thread has completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

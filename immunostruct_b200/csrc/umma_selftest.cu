@@ -122,6 +122,9 @@ umma_selftest_kernel(const float* __restrict__ A, const float* __restrict__ B, f
 //          dumped so the lane mapping of the 64 rows can be read off.
 //  mode 7: A operand from TENSOR MEMORY -- every thread packs its own row of A to bf16 pairs and stores it into its
 //          TMEM lane (32 columns); the MMAs take A from TMEM (8 columns per K step of 16) and B from shared memory.
+//  mode 8: A operand copied shared memory -> TENSOR MEMORY by the tensor core's own copy (tcgen05.cp.128x256b: 128 rows x
+//          256 bits = one K step of the K-major bf16 tile per copy, same descriptor as the MMA's A operand), then as mode 7.
+//          Copies and MMAs of one thread execute in issue order: no barrier between them.
 template <int MODE>
 __global__ void __launch_bounds__(128)
 umma_layout_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D) {
@@ -176,7 +179,8 @@ umma_layout_kernel(const float* __restrict__ A, const float* __restrict__ B, flo
                 db = make_smem_desc(b0 + ks * 2 * (KCH8 * kLBO), KCH8 * kLBO, kLBO);
             else
                 db = make_smem_desc(b0 + ks * 2 * kLBO, kLBO, KCH8 * kLBO);
-            if (MODE == 7) mma_bf16_ts(tbase, tbase + 64 + 8 * ks, db, idesc, ks > 0);
+            if (MODE == 8) tmem_cp_128x256b(tbase + 64 + 8 * ks, da);
+            if (MODE == 7 || MODE == 8) mma_bf16_ts(tbase, tbase + 64 + 8 * ks, db, idesc, ks > 0);
             else mma_bf16(tbase, da, db, idesc, ks > 0);
         }
         mma_commit(&mbar);
@@ -303,11 +307,12 @@ extern "C" int is_umma_selftest(const float* A, const float* B, float* D, int mo
         e = cudaFuncSetAttribute(umma_selftest_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         umma_selftest_kernel<3><<<1, 128, smem, st>>>(A, B, D);
-    } else if (mode >= 4 && mode <= 7) {
+    } else if (mode >= 4 && mode <= 8) {
         size_t smem = (16 * 16 + 8 * 16) * umma::kLBO + 128;
         if (mode == 4) { cudaFuncSetAttribute(umma_layout_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); umma_layout_kernel<4><<<1, 128, smem, st>>>(A, B, D); }
         if (mode == 5) { cudaFuncSetAttribute(umma_layout_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); umma_layout_kernel<5><<<1, 128, smem, st>>>(A, B, D); }
         if (mode == 6) { cudaFuncSetAttribute(umma_layout_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); umma_layout_kernel<6><<<1, 128, smem, st>>>(A, B, D); }
+        if (mode == 8) { cudaFuncSetAttribute(umma_layout_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); umma_layout_kernel<8><<<1, 128, smem, st>>>(A, B, D); }
         if (mode == 7) { cudaFuncSetAttribute(umma_layout_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); umma_layout_kernel<7><<<1, 128, smem, st>>>(A, B, D); }
     } else {
         return IS_ERR_ARG;

@@ -7,7 +7,7 @@ from immunostruct_b200 import _C
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("mode,tol", [(0, 1e-2), (1, 2e-3), (2, 2e-6), (3, 2e-6), (4, 1e-2), (5, 1e-2), (7, 1e-2)])
+@pytest.mark.parametrize("mode,tol", [(0, 1e-2), (1, 2e-3), (2, 2e-6), (3, 2e-6), (4, 1e-2), (5, 1e-2), (7, 1e-2), (8, 1e-2)])
 def test_umma_selftest(mode, tol):
     gen = torch.Generator().manual_seed(5 + mode)
     A = torch.randn(128, 64, generator=gen).cuda()
