@@ -114,26 +114,6 @@ __device__ __forceinline__ void issue_segsum(uint32_t tmem_d, uint32_t s_addr, u
             acc = 1;
         }
 }
-
-// the same sums TRANSPOSED:  D[tmem_d] (M = 64 rows = FEATURES, N = 32 columns = nodes) = m^T[64, 16 nks] * S^T[16 nks, 32]:
-// A = the m tile read MN-major (the view MMA 3 used for its B operand), B = the selector tile as it is stored (K-major,
-// N = 32 node rows).  The tensor core then reads 2 + 1 KB of operands per MMA instead of 2 + 2 KB -- the M = 64 form above
-// reads 64 selector rows of which 32 exist -- and the accumulator takes 32 TMEM columns instead of 64.
-template <int PREC>
-__device__ __forceinline__ void issue_segsum_t(uint32_t tmem_d, uint32_t s_addr, uint32_t a_addr, int nks) {
-    using namespace umma;
-    const uint32_t idesc = make_instr_desc(1u, 64, MAX_TILE_NODES, 1, 0);
-    uint32_t acc = 0;
-    constexpr int NS = TcCfg<PREC>::NSPLIT;
-#pragma unroll
-    for (int t = NS - 1; t >= 0; --t)                       // smallest term first
-#pragma unroll 8
-        for (int ks = 0; ks < nks; ++ks) {
-            mma_bf16(tmem_d, make_smem_desc(a_addr + t * A_BYTES + ks * 2 * SBO, SBO, LBO),
-                     make_smem_desc(s_addr + ks * 2 * S_LBO, S_LBO, S_SBO), idesc, acc);
-            acc = 1;
-        }
-}
 }  // namespace e2
 
 // =====================================================================================================
@@ -196,15 +176,6 @@ __device__ __forceinline__ void meta_edge(const EdgeCommon& p, Meta3& m, int j, 
 #define IS_WS_WAIT_HINT_NS 2000
 #endif
 #define WS_WAIT(bar, parity) mbar_wait_hint(bar, parity, IS_WS_WAIT_HINT_NS)
-// Hand-overs between warps are mbarriers throughout.  Hardware named barriers (bar.arrive by the eight producer warps, bar.sync
-// by the MMA warp) for gather -> MMA 1 and epilogue 1 -> MMA 2 / 3 were measured at 214 -> 211 us and passed every parity test,
-// but FAULTED (misaligned address / invalid address space, clean under compute-sanitizer) as soon as the MMA 2 / 3 warp had
-// little to issue (MMA 3 in its transposed N = 32 form in the bf16 mode without the coordinate branch; no MMA 3 at all in a
-// timing experiment), while the same builds with mbarriers ran clean: removed (dead ends).
-// MMA 3 transposed (features x nodes, issue_segsum_t): -DIS_WS_HN_T=0 restores the nodes x features form
-#ifndef IS_WS_HN_T
-#define IS_WS_HN_T 1
-#endif
 
 // TSA = the A operand of MMA 2 comes from TENSOR MEMORY (is_egnn_set_ws_variant bit 0, default on): the kernel is bound by the
 // L1 / shared-memory data pipe (ncu: LSU wavefronts 56 % + tensor-core operand wavefronts 43 % of the pipe's cycles), and
@@ -321,8 +292,7 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
                             else issue_fwd<PREC>(tmem + TM_ACC2 + 64 * b, a_addr + b * ABUF, w3_addr);
                             mma_commit(&acc2_full[b]);
                         }
-                        if (IS_WS_HN_T) issue_segsum_t<PREC>(tmem + TM_HN + 64 * b, s_addr + b * S_BYTES, a_addr + b * ABUF, 8);
-                        else issue_segsum<PREC>(tmem + TM_HN + 64 * b, s_addr + b * S_BYTES, a_addr + b * ABUF, 8);
+                        issue_segsum<PREC>(tmem + TM_HN + 64 * b, s_addr + b * S_BYTES, a_addr + b * ABUF, 8);
                         mma_commit(&hn_full[b]);
                     }
                 }
@@ -466,18 +436,7 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
                 // ---- hn rows: M = 64 accumulator, node row r sits in TMEM lane 32 (r / 16) + r % 16 ----
                 WS_WAIT(&hn_full[bp], (j >> 1) & 1);
                 fence_after_sync();
-                if (IS_WS_HN_T) {
-                    // M = 64 accumulator of FEATURE rows: feature f sits in TMEM lane 32 (f / 16) + f % 16, node c in column c;
-                    // warp (q, cq) stores features 16 q .. 16 q + 15 of nodes 16 cq .. 16 cq + 15 (64 contiguous bytes per node)
-                    float z[16];
-                    tmem_ld<16>(tmem + ((uint32_t)(32 * q) << 16) + TM_HN + 64 * bp + 16 * cq, z);
-                    if (lane < 16) {
-                        float* hp = hn + (size_t)(n0 + 16 * cq) * 64 + 16 * q + lane;
-#pragma unroll
-                        for (int c = 0; c < 16; ++c)
-                            if (n0 + 16 * cq + c < n1) hp[c * 64] = z[c];
-                    }
-                } else if (q < 2) {
+                if (q < 2) {
                     float z[CW];
                     tmem_ld<CW>(t_lane + TM_HN + 64 * bp, z);
                     const int node = n0 + 16 * q + lane;
