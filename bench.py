@@ -70,7 +70,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "tf32x3", "bf16"],
+    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "fp16x2", "tf32x3", "bf16"],
                     help="EGNN GEMM arithmetic of the headline run (bf16x3 / tf32x3 = fp32-accurate tensor cores)")
     ap.add_argument("--profile", action="store_true",
                     help="bracket the timed inference region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
@@ -419,7 +419,7 @@ def main():
     # ---- the same device-resident step in the other arithmetic modes (short runs) -----------------
     other = {}
     with torch.no_grad():
-        for prec in ("fp32", "bf16x3", "tf32x3", "bf16"):
+        for prec in ("fp32", "bf16x3", "fp16x2", "tf32x3", "bf16"):
             if prec == args.precision:
                 continue
             I.set_precision(prec)
@@ -586,6 +586,7 @@ def main():
         variants = {
             "fp32": lambda: _C.egnn_edge_fwd(gb, PQ, x, arr["edge_attr"], 64, W1, W2, b2, W3, b3, w4, True, hn, xo),
             "bf16x3": lambda: _C.egnn_edge_fwd_tc(gb, PQ, x, arr["edge_attr"], 64, W1, W2, b2, W3, b3, w4, True, _C.PREC_BF16X3, hn, xo, fast_act=True),
+            "fp16x2": lambda: _C.egnn_edge_fwd_tc(gb, PQ, x, arr["edge_attr"], 64, W1, W2, b2, W3, b3, w4, True, _C.PREC_FP16X2, hn, xo, fast_act=True),
             "tf32x3": lambda: _C.egnn_edge_fwd_tc(gb, PQ, x, arr["edge_attr"], 64, W1, W2, b2, W3, b3, w4, True, _C.PREC_TF32X3, hn, xo, fast_act=True),
             "bf16": lambda: _C.egnn_edge_fwd_tc(gb, PQ, x, arr["edge_attr"], 64, W1, W2, b2, W3, b3, w4, True, _C.PREC_BF16, hn, xo),
             # first-generation tensor-core kernel (SIMT destination-side sums), for comparison

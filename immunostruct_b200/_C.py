@@ -219,7 +219,7 @@ def egnn_edge_fwd(g, PQ, x, edge_attr, F, W1, W2, b2, W3, b3, w4, update_coords,
           _t(x_out, f32, "x_out"), _i64(PQ.shape[0]), _t(g.status, torch.int32, "status"), _stream())
 
 
-PREC_BF16, PREC_TF32X3, PREC_BF16X3 = 0, 2, 3
+PREC_BF16, PREC_TF32X3, PREC_BF16X3, PREC_FP16X2 = 0, 2, 3, 4
 
 
 def egnn_node_post_pre_tc(h, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, precision, fast_act=True, next_kind=1):

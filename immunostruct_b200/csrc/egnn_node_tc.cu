@@ -236,6 +236,8 @@ int is_egnn_node_post_pre_tc(const float* h, int64_t ldh, int F, const float* hn
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == PREC_BF16)
         return launch_node_tc<PREC_BF16, 256, true>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, n_nodes, next_kind, st);
+    if (precision == PREC_FP16X2)          // fp16 hi / lo operand split: inference forward only
+        return launch_node_tc<PREC_FP16X2, 512, true>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, n_nodes, next_kind, st);
     if (precision == PREC_BF16X3 && fast_act)
         return launch_node_tc<PREC_BF16X3, 512, true>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, n_nodes, next_kind, st);
     if (precision == PREC_BF16X3)

@@ -320,7 +320,8 @@ int is_egnn_edge_fwd_tc(const int* indptr, const int* csr_src, const int* csr_ds
     if (!(F == 20 || F == 64) || n_nodes <= 0 || n_nodes > 0x7fffffff) return IS_ERR_ARG;
     const bool legacy = (precision & 16) != 0;
     precision &= ~16;
-    if (precision != PREC_BF16 && precision != PREC_TF32X3 && precision != PREC_BF16X3) return IS_ERR_ARG;
+    if (precision != PREC_BF16 && precision != PREC_TF32X3 && precision != PREC_BF16X3 && precision != PREC_FP16X2) return IS_ERR_ARG;
+    if (precision == PREC_FP16X2 && legacy) return IS_ERR_ARG;          // the fp16 hi / lo split exists in the warp-specialised kernel only
     EdgeCommon c;
     c.indptr = indptr; c.csr_src = csr_src; c.csr_dst = csr_dst; c.csr_eid = csr_eid;
     c.PQ = PQ; c.x = x; c.ldx = ldx; c.edge_attr = edge_attr; c.W1 = W1; c.F = F;

@@ -48,27 +48,20 @@ constexpr int MAX_TILE_NODES = 32;
 template <int PREC>
 __device__ __forceinline__ void issue_fwd(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr) {
     using namespace umma;
-    const uint32_t idesc = make_instr_desc(1u, 128, 64);
+    const uint32_t idesc = make_instr_desc(TcCfg<PREC>::FMT, 128, 64);
     uint32_t acc = 0;
-    if (PREC == PREC_BF16X3) {
-        // (a-term, w-term), smallest products first: a3w1 a1w3 a2w2 a2w1 a1w2 a1w1
-        const uint32_t ta[6] = {2, 0, 1, 1, 0, 0}, tw[6] = {0, 2, 1, 0, 1, 0};
+    // (a-term, w-term), smallest products first -- bf16x3: a3w1 a1w3 a2w2 a2w1 a1w2 a1w1; fp16x2: lo hi, hi lo, hi hi
+    constexpr int NP = PREC == PREC_BF16X3 ? 6 : PREC == PREC_FP16X2 ? 3 : 1;
+    const uint32_t ta[6] = {PREC == PREC_BF16X3 ? 2u : PREC == PREC_FP16X2 ? 1u : 0u, 0, PREC == PREC_BF16X3 ? 1u : 0u, 1, 0, 0};
+    const uint32_t tw[6] = {0, PREC == PREC_BF16X3 ? 2u : 1u, PREC == PREC_BF16X3 ? 1u : 0u, 0, 1, 0};
 #pragma unroll
-        for (int t = 0; t < 6; ++t)
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                mma_bf16(tmem_d, make_smem_desc(a_addr + ta[t] * A_BYTES + ks * 2 * LBO, LBO, SBO),
-                         make_smem_desc(w_addr + tw[t] * W_BYTES + ks * 2 * kLBO_W, kLBO_W, 8 * kLBO_W), idesc, acc);
-                acc = 1;
-            }
-    } else {
+    for (int t = 0; t < NP; ++t)
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-            mma_bf16(tmem_d, make_smem_desc(a_addr + ks * 2 * LBO, LBO, SBO),
-                     make_smem_desc(w_addr + ks * 2 * kLBO_W, kLBO_W, 8 * kLBO_W), idesc, acc);
+            mma_bf16(tmem_d, make_smem_desc(a_addr + ta[t] * A_BYTES + ks * 2 * LBO, LBO, SBO),
+                     make_smem_desc(w_addr + tw[t] * W_BYTES + ks * 2 * kLBO_W, kLBO_W, 8 * kLBO_W), idesc, acc);
             acc = 1;
         }
-    }
 }
 
 // same product with the A operand in TENSOR MEMORY (split term t at columns tmem_a + 32 t, 8 columns per K step): the
@@ -77,32 +70,26 @@ __device__ __forceinline__ void issue_fwd(uint32_t tmem_d, uint32_t a_addr, uint
 template <int PREC>
 __device__ __forceinline__ void issue_fwd_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t w_addr) {
     using namespace umma;
-    const uint32_t idesc = make_instr_desc(1u, 128, 64);
+    const uint32_t idesc = make_instr_desc(TcCfg<PREC>::FMT, 128, 64);
     uint32_t acc = 0;
-    if (PREC == PREC_BF16X3) {
-        const uint32_t ta[6] = {2, 0, 1, 1, 0, 0}, tw[6] = {0, 2, 1, 0, 1, 0};
+    constexpr int NP = PREC == PREC_BF16X3 ? 6 : PREC == PREC_FP16X2 ? 3 : 1;
+    const uint32_t ta[6] = {PREC == PREC_BF16X3 ? 2u : PREC == PREC_FP16X2 ? 1u : 0u, 0, PREC == PREC_BF16X3 ? 1u : 0u, 1, 0, 0};
+    const uint32_t tw[6] = {0, PREC == PREC_BF16X3 ? 2u : 1u, PREC == PREC_BF16X3 ? 1u : 0u, 0, 1, 0};
 #pragma unroll
-        for (int t = 0; t < 6; ++t)
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                mma_bf16_ts(tmem_d, tmem_a + 32 * ta[t] + 8 * ks,
-                            make_smem_desc(w_addr + tw[t] * W_BYTES + ks * 2 * kLBO_W, kLBO_W, 8 * kLBO_W), idesc, acc);
-                acc = 1;
-            }
-    } else {
+    for (int t = 0; t < NP; ++t)
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-            mma_bf16_ts(tmem_d, tmem_a + 8 * ks, make_smem_desc(w_addr + ks * 2 * kLBO_W, kLBO_W, 8 * kLBO_W), idesc, acc);
+            mma_bf16_ts(tmem_d, tmem_a + 32 * ta[t] + 8 * ks,
+                        make_smem_desc(w_addr + tw[t] * W_BYTES + ks * 2 * kLBO_W, kLBO_W, 8 * kLBO_W), idesc, acc);
             acc = 1;
         }
-    }
 }
 
 // hn tile:  D[tmem_d] (M = 64 rows = nodes) = S[64, 16 nks] * m[16 nks, 64]; m = the A tile read MN-major
 template <int PREC>
 __device__ __forceinline__ void issue_segsum(uint32_t tmem_d, uint32_t s_addr, uint32_t a_addr, int nks) {
     using namespace umma;
-    const uint32_t idesc = make_instr_desc(1u, 64, 64, 0, 1);
+    const uint32_t idesc = make_instr_desc(TcCfg<PREC>::FMT, 64, 64, 0, 1);
     uint32_t acc = 0;
     constexpr int NS = TcCfg<PREC>::NSPLIT;
 #pragma unroll
@@ -354,11 +341,12 @@ edge_fwd_ws_kernel(EdgeCommon p, float* __restrict__ hn, float* __restrict__ x_o
                     const int c = pw + 8 * u;
                     const int lo = min(max(jb - 8 * c, 0), 8), hi = min(max(je - 8 * c, 0), 8);
                     const uint32_t mask = (1u << hi) - (1u << lo);            // bits lo .. hi-1
+                    constexpr uint32_t ONE = PREC == PREC_FP16X2 ? 0x3C00u : 0x3F80u;      // 1.0 in the operand format
                     uint4 w;
-                    w.x = ((mask >> 0) & 1u) * 0x3F80u + ((mask >> 1) & 1u) * 0x3F800000u;
-                    w.y = ((mask >> 2) & 1u) * 0x3F80u + ((mask >> 3) & 1u) * 0x3F800000u;
-                    w.z = ((mask >> 4) & 1u) * 0x3F80u + ((mask >> 5) & 1u) * 0x3F800000u;
-                    w.w = ((mask >> 6) & 1u) * 0x3F80u + ((mask >> 7) & 1u) * 0x3F800000u;
+                    w.x = ((mask >> 0) & 1u) * ONE + ((mask >> 1) & 1u) * (ONE << 16);
+                    w.y = ((mask >> 2) & 1u) * ONE + ((mask >> 3) & 1u) * (ONE << 16);
+                    w.z = ((mask >> 4) & 1u) * ONE + ((mask >> 5) & 1u) * (ONE << 16);
+                    w.w = ((mask >> 6) & 1u) * ONE + ((mask >> 7) & 1u) * (ONE << 16);
                     *reinterpret_cast<uint4*>(sS + b * S_BYTES + (lane >> 3) * S_SBO + c * S_LBO + (lane & 7) * 16) = w;
                 }
             }
@@ -508,6 +496,9 @@ int launch_edge_fwd_ws(const EdgeCommon& c, float* hn, float* x_out, int precisi
     if (precision == PREC_BF16)
         return update_coords ? launch_wsk<PREC_BF16, true, true>(c, hn, x_out, grid, st)
                              : launch_wsk<PREC_BF16, false, true>(c, hn, x_out, grid, st);
+    if (precision == PREC_FP16X2)          // inference forward only (fast SiLU)
+        return update_coords ? launch_wsk<PREC_FP16X2, true, true>(c, hn, x_out, grid, st)
+                             : launch_wsk<PREC_FP16X2, false, true>(c, hn, x_out, grid, st);
     if (fast)
         return update_coords ? launch_wsk<PREC_BF16X3, true, true>(c, hn, x_out, grid, st)
                              : launch_wsk<PREC_BF16X3, false, true>(c, hn, x_out, grid, st);

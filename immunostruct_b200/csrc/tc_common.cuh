@@ -5,13 +5,20 @@
 //   PREC_BF16   (0): bf16 operands, fp32 accumulate, hardware-tanh SiLU        -- bf16 mode (1e-2)
 //   PREC_TF32X3 (2): a = hi + lo in tf32, D = lo*Bhi + hi*Blo + hi*Bhi          -- fp32 parity, 8 B/element
 //   PREC_BF16X3 (3): a = a1 + a2 + a3 in bf16, six partial products             -- fp32 parity, 6 B/element
+//   PREC_FP16X2 (4): a = hi + lo in fp16 (11 + 11 mantissa bits), D = lo*Bhi + hi*Blo + hi*Bhi -- fp32 parity (2^-22), 4 B/element:
+//                    two thirds of the operand bytes and HALF the MMAs of bf16x3, and a 3-instruction split instead of 5.5.
+//                    fp16 has 5 exponent bits: values beyond +-65504 become inf (-> NaN downstream, loudly), and a residual
+//                    below 2^-14 is kept to 2^-25 ABSOLUTE -- fine for O(1) forward activations and weights, not for
+//                    gradients: inference forward only ("fp16x2" mode of functional.set_precision).
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "umma.cuh"
 
 #define PREC_BF16 0
 #define PREC_TF32X3 2
 #define PREC_BF16X3 3
+#define PREC_FP16X2 4
 
 namespace is {
 
@@ -25,8 +32,8 @@ struct TcCfg {
     static constexpr uint32_t SBO_W = KCH * kLBO_W;                   // weight tiles (unpadded)
     static constexpr uint32_t A_BYTES = 16 * SBO;                     // 128-row operand tile (one split term)
     static constexpr uint32_t W_BYTES = 8 * SBO_W;                    // 64-row operand tile (one split term)
-    static constexpr int NSPLIT = PREC == PREC_BF16 ? 1 : PREC == PREC_TF32X3 ? 2 : 3;
-    static constexpr uint32_t FMT = PREC == PREC_TF32X3 ? 2u : 1u;
+    static constexpr int NSPLIT = PREC == PREC_BF16 ? 1 : (PREC == PREC_TF32X3 || PREC == PREC_FP16X2) ? 2 : 3;
+    static constexpr uint32_t FMT = PREC == PREC_TF32X3 ? 2u : PREC == PREC_FP16X2 ? 0u : 1u;       // instruction-descriptor operand format: 0 f16, 1 bf16, 2 tf32
     static constexpr bool ACCURATE = PREC != PREC_BF16;
 };
 
@@ -59,13 +66,31 @@ __device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
     return q;
 }
 
+// fp16 hi / lo split of 8 consecutive K values: hi = rn(v), lo = rn(v - hi) (the residual is exact in fp32); one packed
+// conversion per pair of values and term
+__device__ __forceinline__ void split8_fp16(const float (&v)[8], uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 h2 = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        const float2 hf = __half22float2(h2);
+        const __half2 l2 = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+        h[i] = *reinterpret_cast<const uint32_t*>(&h2);
+        l[i] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 // the packed 16-byte bf16 chunks of 8 consecutive K values, one per split term (q[0..NSPLIT-1]): bf16 = round to nearest;
 // bf16x3 = three terms by truncation, as store_chunk8 below
 template <int PREC>
 __device__ __forceinline__ void split_chunk8(const float (&v)[8], uint4 (&q)[3]) {
-    static_assert(PREC == PREC_BF16 || PREC == PREC_BF16X3, "bf16 operand tiles only");
+    static_assert(PREC == PREC_BF16 || PREC == PREC_BF16X3 || PREC == PREC_FP16X2, "16-bit operand tiles only");
     if (PREC == PREC_BF16) {
         q[0] = pack8_bf16(v);
+    } else if (PREC == PREC_FP16X2) {
+        split8_fp16(v, q[0], q[1]);
     } else {
         uint32_t q1[4], q2[4], q3[4];
 #pragma unroll
@@ -88,9 +113,14 @@ __device__ __forceinline__ void split_chunk8(const float (&v)[8], uint4 (&q)[3])
 // `split_bytes` = distance between the split-term copies of the tile.  bf16 / bf16x3 only.
 template <int PREC>
 __device__ __forceinline__ void store_chunk8(uint8_t* __restrict__ p0, uint32_t split_bytes, const float (&v)[8]) {
-    static_assert(PREC == PREC_BF16 || PREC == PREC_BF16X3, "bf16 operand tiles only");
+    static_assert(PREC == PREC_BF16 || PREC == PREC_BF16X3 || PREC == PREC_FP16X2, "16-bit operand tiles only");
     if (PREC == PREC_BF16) {
         *reinterpret_cast<uint4*>(p0) = pack8_bf16(v);
+    } else if (PREC == PREC_FP16X2) {
+        uint4 hi, lo;
+        split8_fp16(v, hi, lo);
+        *reinterpret_cast<uint4*>(p0) = hi;
+        *reinterpret_cast<uint4*>(p0 + split_bytes) = lo;
     } else {
         // three bf16 terms by truncation (top 16 bits); every residual is exact in fp32, so the sum of
         // the terms differs from v only by the truncation of the last one (2^-24 relative)
@@ -176,7 +206,7 @@ __device__ __forceinline__ void store_weight1(uint8_t* __restrict__ tile, uint32
 template <int PREC>
 __device__ __forceinline__ void stage_weight_block(uint8_t* __restrict__ tile, uint32_t split_bytes, const float* __restrict__ W,
                                                    int ldw, int col0, int kvalid, int tid, int nthreads) {
-    static_assert(PREC == PREC_BF16 || PREC == PREC_BF16X3, "bf16 weight tiles only");
+    static_assert(PREC == PREC_BF16 || PREC == PREC_BF16X3 || PREC == PREC_FP16X2, "16-bit weight tiles only");
     for (int idx = tid; idx < 64 * 8; idx += nthreads) {
         const int n = idx & 63, c = idx >> 6;
         float w[8];
@@ -193,6 +223,13 @@ __device__ __forceinline__ void stage_weight_block(uint8_t* __restrict__ tile, u
             }
         }
         uint8_t* dst = tile + (uint32_t)((n >> 3) * (8 * kLBO_W) + c * kLBO_W + (n & 7) * 16);
+        if (PREC == PREC_FP16X2) {
+            uint4 hi, lo;
+            split8_fp16(w, hi, lo);
+            *reinterpret_cast<uint4*>(dst) = hi;
+            *reinterpret_cast<uint4*>(dst + split_bytes) = lo;
+            continue;
+        }
         uint32_t q1[4], q2[4], q3[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -230,6 +267,17 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_addr, uin
         const uint32_t ta[8] = {2, 1, 2, 0, 1, 1, 0, 0}, tw[8] = {1, 2, 0, 2, 1, 0, 1, 0};
 #pragma unroll
         for (int t = FULL ? 0 : 2; t < 8; ++t)
+#pragma unroll
+            for (int ks = 0; ks < C::KCH / 2; ++ks) {
+                mma_bf16(tmem_d, make_smem_desc(a_addr + ta[t] * a_split + ks * 2 * kLBO, kLBO, C::SBO),
+                         make_smem_desc(w_addr + tw[t] * w_split + ks * 2 * kLBO_W, kLBO_W, C::SBO_W), idesc, acc);
+                acc = 1;
+            }
+    } else if (PREC == PREC_FP16X2) {
+        // (a-term, w-term), smallest products first: [lo lo] lo hi, hi lo, hi hi
+        const uint32_t ta[4] = {1, 1, 0, 0}, tw[4] = {1, 0, 1, 0};
+#pragma unroll
+        for (int t = FULL ? 0 : 1; t < 4; ++t)
 #pragma unroll
             for (int ks = 0; ks < C::KCH / 2; ++ks) {
                 mma_bf16(tmem_d, make_smem_desc(a_addr + ta[t] * a_split + ks * 2 * kLBO, kLBO, C::SBO),

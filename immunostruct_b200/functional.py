@@ -22,7 +22,10 @@ H = 64   # hidden width of the EGNN MLPs and of the node embedding (hybrid_model
 #              fp32-accurate, two CTAs per SM (csrc/egnn_tc.cu); the default
 #   "tf32x3" : tcgen05 tensor cores with the 3xTF32 split -- fp32-accurate, one 512-thread CTA per SM
 #   "bf16"   : tcgen05 tensor cores, bf16 operands, fp32 accumulate, fast SiLU (1e-2 tolerance mode)
-_PRECISIONS = {"fp32": None, "bf16x3": _C.PREC_BF16X3, "tf32x3": _C.PREC_TF32X3, "bf16": _C.PREC_BF16}
+# "fp16x2": the EGNN FORWARD of the no-grad path on fp16 hi / lo operand pairs (fp32-accurate to 2^-22, two thirds of the
+# operand bytes and half the MMAs of "bf16x3"; activations beyond +-65504 overflow to inf / NaN) -- everything else (training
+# forward and backward, attention, the dense layers) runs as in "bf16x3"
+_PRECISIONS = {"fp32": None, "bf16x3": _C.PREC_BF16X3, "tf32x3": _C.PREC_TF32X3, "bf16": _C.PREC_BF16, "fp16x2": _C.PREC_FP16X2}
 _precision = "bf16x3"
 
 
@@ -101,6 +104,8 @@ class _EGNNLayer(torch.autograd.Function):
         x_out = _new(h, n, 3) if update_coords else None
         _C.egnn_node_pre_fwd(h, W1, b1, PQ)
         prec = _PRECISIONS[_precision]
+        if prec == _C.PREC_FP16X2:
+            prec = _C.PREC_BF16X3              # (an autograd forward: see _PRECISIONS)
         if prec is None:
             _C.egnn_edge_fwd(graph, PQ, x, edge_attr, f, W1, W2, b2, W3, b3, w4, update_coords, hn, x_out)
         else:
@@ -189,7 +194,10 @@ def _egnn_stack_forward(graph, x23, edge_attr, params, fast_act, keep, qkv=None)
     h, x = x23[:, :20], x23[:, 20:]
     n = h.shape[0]
     prec = _PRECISIONS[_precision]
-    node_prec = {None: None, _C.PREC_BF16: _C.PREC_BF16, _C.PREC_TF32X3: _C.PREC_BF16X3, _C.PREC_BF16X3: _C.PREC_BF16X3}[prec]
+    if prec == _C.PREC_FP16X2 and keep is not None:
+        prec = _C.PREC_BF16X3                  # training: the backward kernels recompute the forward in the bf16x3 split
+    node_prec = {None: None, _C.PREC_BF16: _C.PREC_BF16, _C.PREC_TF32X3: _C.PREC_BF16X3, _C.PREC_BF16X3: _C.PREC_BF16X3,
+                 _C.PREC_FP16X2: _C.PREC_FP16X2}[prec]
     # (training forward: the fused tensor-core node kernel with the accurate SiLU and all eight bf16x3 partial
     #  products, fast_act = False -- with six products a handful of parameter gradients landed at 1.0-1.3e-5 of
     #  their scale on the B200, just outside the 1e-5 gradient tolerance)

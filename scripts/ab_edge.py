@@ -18,7 +18,7 @@ PQ = r(n, 128)
 x = arr["x"][:, 20:]
 flush = torch.empty(64 * 1024 * 1024, device=dev)
 ref = {}
-for prec, name in ((_C.PREC_BF16X3, "bf16x3"), (_C.PREC_BF16, "bf16")):
+for prec, name in ((_C.PREC_BF16X3, "bf16x3"), (_C.PREC_FP16X2, "fp16x2"), (_C.PREC_BF16, "bf16")):
     for fast in (True, False):
         for upd in (True, False):
             for nb in (0, 1):

@@ -1,5 +1,5 @@
 """Kernel timeline of the inference (default) or training step (argument `train`) from torch.profiler (CUPTI): per kernel its
-duration and the idle gap since the previous kernel ended; sums per step.  python scripts/step_timeline.py [train]"""
+duration and the idle gap since the previous kernel ended; sums per step.  python scripts/step_timeline.py [train] [bf16x3 | fp16x2 | bf16 | ...]"""
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -10,7 +10,7 @@ from immunostruct_b200.synthetic import synthetic_graph_arrays, synthetic_dense
 train = "train" in sys.argv[1:]
 dev = "cuda"
 B = 512
-I.set_precision("bf16x3")
+I.set_precision(next((a for a in sys.argv[1:] if a in ("bf16x3", "fp16x2", "bf16", "tf32x3", "fp32")), "bf16x3"))
 torch.manual_seed(1)
 model = I.model_map["HybridModelv2"](vae_input_dim=5943, device=dev).to(dev)
 arr = synthetic_graph_arrays(B, 200, 10, seed=1, device=dev)

@@ -18,10 +18,11 @@ for n_graphs, n_nodes, k in ((1, 200, 10), (7, 37, 3), (64, 200, 10), (300, 190,
     gb = GraphBatch.from_arrays(*(arr[kk] for kk in ("x", "src", "dst", "edge_attr", "node_counts", "edge_counts")), max_nodes=n_nodes)
     n = gb.n_nodes
     PQ, x = r(n, 128), arr["x"][:, 20:]
-    for prec, tol in ((_C.PREC_BF16X3, 2e-5), (_C.PREC_BF16, 3e-2)):
+    for prec, tol in ((_C.PREC_BF16X3, 2e-5), (_C.PREC_FP16X2, 2e-5), (_C.PREC_BF16, 3e-2)):
         for upd in (True, False):
             ref_hn, ref_x = torch.zeros(n, 64, device=dev), torch.zeros(n, 3, device=dev)
-            _C.egnn_edge_fwd_tc(gb, PQ, x, arr["edge_attr"], 64, W1, W2, b2, W3, b3, w4, upd, prec | 16, ref_hn, ref_x, fast_act=False)
+            _C.egnn_edge_fwd_tc(gb, PQ, x, arr["edge_attr"], 64, W1, W2, b2, W3, b3, w4, upd,
+                                (_C.PREC_BF16X3 if prec == _C.PREC_FP16X2 else prec) | 16, ref_hn, ref_x, fast_act=False)
             for fast in (True, False):
                 for var in (0, 1):
                     _C.set_ws_variant(var)

@@ -14,7 +14,7 @@ torch.manual_seed(1)
 model = I.model_map["HybridModelv2"](vae_input_dim=5943, device=dev).to(dev)
 losses = I.Losses(5943, [0.81, 0.19], sequence=True)
 n_fail = 0
-for prec in ("bf16x3", "bf16"):
+for prec in ("bf16x3", "fp16x2", "bf16"):
     I.set_precision(prec)
     for n_graphs, n_nodes, k in ((1, 200, 10), (2, 50, 4), (5, 190, 10), (17, 200, 10), (64, 128, 20), (129, 200, 10), (376, 200, 10), (512, 200, 10)):
         arr = synthetic_graph_arrays(n_graphs, n_nodes, k, seed=n_graphs, device=dev)

@@ -219,7 +219,7 @@ def test_egnn_forward_kernels(case, f):
     assert int(gb.status.item()) == 0
 
 
-@pytest.mark.parametrize("prec,tol", [(_C.PREC_BF16X3, 1e-5), (_C.PREC_TF32X3, 1e-5), (_C.PREC_BF16, 1e-2),
+@pytest.mark.parametrize("prec,tol", [(_C.PREC_BF16X3, 1e-5), (_C.PREC_TF32X3, 1e-5), (_C.PREC_BF16, 1e-2), (_C.PREC_FP16X2, 1e-5),
                                       (_C.PREC_BF16X3 | 16, 1e-5), (_C.PREC_BF16 | 16, 1e-2)])
 @pytest.mark.parametrize("f", [20, 64])
 def test_egnn_edge_forward_tensor_core(case, f, prec, tol):
@@ -288,7 +288,7 @@ def test_edge_kernels_at_benchmark_scale_match_the_simt_kernels():
     assert int(gb.status.item()) == 0
 
 
-@pytest.mark.parametrize("prec,tol", [(_C.PREC_BF16X3, 1e-5), (_C.PREC_BF16, 1e-2)])
+@pytest.mark.parametrize("prec,tol", [(_C.PREC_BF16X3, 1e-5), (_C.PREC_BF16, 1e-2), (_C.PREC_FP16X2, 1e-5)])
 @pytest.mark.parametrize("f,with_next", [(20, True), (64, True), (64, False)])
 def test_egnn_node_post_pre_tensor_core(case, f, with_next, prec, tol):
     """Fused node_post(l) + node_pre(l+1) tcgen05 kernel vs the CPU contracts of the two SIMT kernels."""
@@ -311,7 +311,7 @@ def test_egnn_node_post_pre_tensor_core(case, f, with_next, prec, tol):
         close(PQn_d, PQn, tol, what=f"node tc PQ' prec={prec} f={f}")
 
 
-@pytest.mark.parametrize("prec,tol", [(_C.PREC_BF16X3, 1e-5), (_C.PREC_BF16, 1e-2)])
+@pytest.mark.parametrize("prec,tol", [(_C.PREC_BF16X3, 1e-5), (_C.PREC_BF16, 1e-2), (_C.PREC_FP16X2, 1e-5)])
 def test_egnn_node_post_qkv_tensor_core(case, prec, tol):
     """Last-layer node kernel with the attention projections fused (next_kind = 2): h' and QKV = h' [Wq;Wk;Wv]^T + b."""
     arrays, gb, _ = case

@@ -149,7 +149,7 @@ def test_bf16_mode_within_1e_2_of_fp32_reference():
     losses = I.Losses(5943, [4.25, 1.0], sequence=True)
     grads = {}
     try:
-        for prec in ("bf16x3", "tf32x3", "fp32", "bf16"):
+        for prec in ("bf16x3", "tf32x3", "fp32", "fp16x2", "bf16"):
             I.set_precision(prec)
             inject_eps(model, eps, eps)
             with torch.no_grad():
