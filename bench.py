@@ -70,8 +70,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "fp16x2", "tf32x3", "bf16"],
-                    help="EGNN GEMM arithmetic of the headline run (bf16x3 / tf32x3 = fp32-accurate tensor cores)")
+    ap.add_argument("--precision", default="fp16x2", choices=["fp32", "bf16x3", "fp16x2", "tf32x3", "bf16"],
+                    help="EGNN GEMM arithmetic of the headline run; default = the package default: fp16x2 (fp16 hi / lo operand "
+                         "pairs in the no-grad forward, bf16x3 in training); fp16x2 / bf16x3 / tf32x3 = fp32-accurate tensor cores")
     ap.add_argument("--profile", action="store_true",
                     help="bracket the timed inference region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     ap.add_argument("--no-train", action="store_true")

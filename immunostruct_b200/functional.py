@@ -26,7 +26,7 @@ H = 64   # hidden width of the EGNN MLPs and of the node embedding (hybrid_model
 # operand bytes and half the MMAs of "bf16x3"; activations beyond +-65504 overflow to inf / NaN) -- everything else (training
 # forward and backward, attention, the dense layers) runs as in "bf16x3"
 _PRECISIONS = {"fp32": None, "bf16x3": _C.PREC_BF16X3, "tf32x3": _C.PREC_TF32X3, "bf16": _C.PREC_BF16, "fp16x2": _C.PREC_FP16X2}
-_precision = "bf16x3"
+_precision = "fp16x2"
 
 
 def set_precision(name: str) -> None:

@@ -1,11 +1,11 @@
 #!/bin/bash
-# Round-2 ncu evidence in one GPU-box visit: launch lists of the timed inference region (bf16x3 and bf16), of one training
+# Round-2 ncu evidence in one GPU-box visit: launch lists of the timed inference region (fp16x2, bf16x3 and bf16), of one training
 # step and of one cancer fine-tune step; full captures of the kernels under work (edge forward ws, edge backward ws, node
 # kernel, TMA GEMM); the tcgen05.mma timing probe.  Numbers printed under ncu are never bench values.
 mkdir -p gpurun_out
 python scripts/umma_timing.py > gpurun_out/umma_timing.txt 2>&1; cat gpurun_out/umma_timing.txt
 python scripts/prof_edge_bwd.py > gpurun_out/prof_edge_bwd.txt 2>&1; grep "edge_bwd" gpurun_out/prof_edge_bwd.txt
-for prec in bf16x3 bf16; do
+for prec in fp16x2 bf16x3 bf16; do
   ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
       --log-file gpurun_out/launches_${prec}.csv \
       python bench.py --steps 2 --warmup 3 --no-train --no-cpu-baseline --profile --precision ${prec} > gpurun_out/ncu_bench_${prec}.log 2>&1

@@ -6,7 +6,7 @@ from immunostruct_b200 import _C
 from immunostruct_b200.graph import GraphBatch
 from immunostruct_b200.synthetic import synthetic_graph_arrays
 
-prec = {"bf16": _C.PREC_BF16, "tf32x3": _C.PREC_TF32X3, "bf16x3": _C.PREC_BF16X3, "fp32": None}[sys.argv[1] if len(sys.argv) > 1 else "bf16"]
+prec = {"bf16": _C.PREC_BF16, "tf32x3": _C.PREC_TF32X3, "bf16x3": _C.PREC_BF16X3, "fp16x2": _C.PREC_FP16X2, "fp32": None}[sys.argv[1] if len(sys.argv) > 1 else "bf16"]
 dev = "cuda"
 arr = synthetic_graph_arrays(512, 200, 10, seed=1, device=dev)
 gb = GraphBatch.from_arrays(*(arr[k] for k in ("x", "src", "dst", "edge_attr", "node_counts", "edge_counts")), max_nodes=200)

@@ -148,6 +148,7 @@ def test_bf16_mode_within_1e_2_of_fp32_reference():
     gb = graph_batch(arr, DEV)
     losses = I.Losses(5943, [4.25, 1.0], sequence=True)
     grads = {}
+    default_precision = I.get_precision()
     try:
         for prec in ("bf16x3", "tf32x3", "fp32", "fp16x2", "bf16"):
             I.set_precision(prec)
@@ -162,7 +163,7 @@ def test_bf16_mode_within_1e_2_of_fp32_reference():
             tol = 1e-2 if prec == "bf16" else TOL
             assert rel_err(o_inf, out) < tol and rel_err(o2, out) < tol and rel_err(loss, loss_ref) < tol, prec
     finally:
-        I.set_precision("bf16x3")
+        I.set_precision(default_precision)
     ref_grads = {k: v for k, v in grads_oracle.items() if v is not None}
     gmax = max(float(v.abs().max()) for v in ref_grads.values())
     worst = ("", 0.0)
