@@ -119,9 +119,11 @@ attn_pool_tc_kernel(const float* __restrict__ QKV, const int64_t* __restrict__ n
         if (warp == 0) {
             if (elect_one()) {
                 fence_after_sync();
-                const uint32_t idesc = make_instr_desc(1u, 128, NPAD);
-                constexpr int NTERM = PREC == PREC_BF16X3 ? 6 : 1;
-                const uint32_t ta[6] = {2, 0, 1, 1, 0, 0}, tw[6] = {0, 2, 1, 0, 1, 0};   // smallest products first
+                const uint32_t idesc = make_instr_desc(C::FMT, 128, NPAD);
+                constexpr int NTERM = PREC == PREC_BF16X3 ? 6 : PREC == PREC_FP16X2 ? 3 : 1;
+                // (q-term, k-term), smallest products first -- bf16x3: six of the nine; fp16x2: lo hi, hi lo, hi hi
+                const uint32_t ta[6] = {PREC == PREC_FP16X2 ? 1u : 2u, 0, PREC == PREC_FP16X2 ? 0u : 1u, 1, 0, 0};
+                const uint32_t tw[6] = {0, PREC == PREC_FP16X2 ? 1u : 2u, PREC == PREC_FP16X2 ? 0u : 1u, 0, 1, 0};
 #pragma unroll
                 for (int m = 0; m < MT; ++m) {
                     uint32_t acc = 0;
@@ -129,7 +131,7 @@ attn_pool_tc_kernel(const float* __restrict__ QKV, const int64_t* __restrict__ n
                     for (int t = 0; t < NTERM; ++t)
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks) {
-                            const uint32_t at = PREC == PREC_BF16X3 ? ta[t] : 0, wt = PREC == PREC_BF16X3 ? tw[t] : 0;
+                            const uint32_t at = NTERM > 1 ? ta[t] : 0, wt = NTERM > 1 ? tw[t] : 0;
                             mma_bf16(tmem + m * NPAD,
                                      make_smem_desc(q_addr + (m * NS + at) * QT_BYTES + ks * 2 * LBO, LBO, SBO),
                                      make_smem_desc(k_addr + wt * KT_BYTES + ks * 2 * LBO, LBO, SBO), idesc, acc);
@@ -222,7 +224,7 @@ using namespace is;
 extern "C" {
 
 // Single-head variant of is_attn_pool_infer on the tensor cores: QKV [N_total, 192] (Q | K | V, 64 wide each),
-// node_off [n_graphs + 1] -> pooled [n_graphs, 64].  max_nodes <= 256.  precision 0 = bf16, 3 = bf16x3 (fp32-accurate).
+// node_off [n_graphs + 1] -> pooled [n_graphs, 64].  max_nodes <= 256.  precision 0 = bf16, 3 = bf16x3, 4 = fp16x2 (both fp32-accurate).
 int is_attn_pool_infer_tc(const float* QKV, const int64_t* node_off, int n_graphs, int max_nodes, int precision,
                           float* pooled, void* stream) {
     if (n_graphs <= 0 || max_nodes <= 0) return IS_ERR_ARG;
@@ -235,6 +237,9 @@ int is_attn_pool_infer_tc(const float* QKV, const int64_t* node_off, int n_graph
     if (precision == PREC_BF16X3)
         return max_nodes <= 128 ? launch_attn_tc<PREC_BF16X3, 128>(QKV, node_off, n_graphs, pooled, st)
                                 : launch_attn_tc<PREC_BF16X3, 256>(QKV, node_off, n_graphs, pooled, st);
+    if (precision == PREC_FP16X2)          // fp16 hi / lo pairs for the scores (no-grad forward)
+        return max_nodes <= 128 ? launch_attn_tc<PREC_FP16X2, 128>(QKV, node_off, n_graphs, pooled, st)
+                                : launch_attn_tc<PREC_FP16X2, 256>(QKV, node_off, n_graphs, pooled, st);
     return IS_ERR_ARG;
 }
 

@@ -366,8 +366,10 @@ class _AttnPool(torch.autograd.Function):
         prec = _PRECISIONS[_precision]
         if not want_attn and not want_nodes and n_head == 1 and prec is not None and graph.max_nodes <= 256:
             pooled = _new(QKV, b, H)
+            # (fp16x2: the no-grad forward only -- the backward kernel recomputes the scores in the bf16x3 split)
+            fwd_only = prec == _C.PREC_FP16X2 and not ctx.needs_input_grad[4]
             _C.attn_pool_infer_tc(QKV, graph.node_off, graph.max_nodes, pooled,
-                                  _C.PREC_BF16 if prec == _C.PREC_BF16 else _C.PREC_BF16X3)
+                                  _C.PREC_BF16 if prec == _C.PREC_BF16 else _C.PREC_FP16X2 if fwd_only else _C.PREC_BF16X3)
             ctx.pooled_only = True
             ctx.save_for_backward(QKV)
             return None, pooled, None
@@ -418,7 +420,7 @@ def attention_pool(graph, QKV, n_head=1, want_attn=False, want_nodes=False):
         if n_head == 1 and prec is not None and graph.max_nodes <= 256:
             # single head: Q K^T on the tensor cores, softmax statistics straight from TMEM (csrc/attn_pool_tc.cu)
             _C.attn_pool_infer_tc(QKV, graph.node_off, graph.max_nodes, pooled,
-                                  _C.PREC_BF16 if prec == _C.PREC_BF16 else _C.PREC_BF16X3)
+                                  prec if prec in (_C.PREC_BF16, _C.PREC_FP16X2) else _C.PREC_BF16X3)
         else:
             _C.attn_pool_infer(QKV, graph.node_off, n_head, graph.max_nodes, pooled)
         return None, pooled, None

@@ -501,11 +501,11 @@ def test_attention_pool_kernels(case, n_head):
     _C.attn_pool_infer(QKV.to(DEV), gb.node_off, n_head, gb.max_nodes, pooled_i)
     close(pooled_i, pooled, what="pooled (inference kernel)")
     if n_head == 1:
-        for prec, tol in ((_C.PREC_BF16X3, 1e-5), (_C.PREC_BF16, 1e-2)):
+        for prec, tol in ((_C.PREC_BF16X3, 1e-5), (_C.PREC_FP16X2, 1e-5), (_C.PREC_BF16, 1e-2)):
             pooled_t = torch.full((b, 64), float("nan"), device=DEV)
             _C.attn_pool_infer_tc(QKV.to(DEV), gb.node_off, gb.max_nodes, pooled_t, prec)
             close(pooled_t, pooled, tol, what=f"pooled (tensor-core inference kernel, prec={prec})")
-            if prec != _C.PREC_BF16X3:
+            if prec == _C.PREC_BF16:
                 # (no peaked-softmax case for plain bf16: with scores of magnitude ~100 the bf16 rounding of Q and K
                 #  alone moves a score by ~0.4, i.e. a probability by tens of percent -- a property of the input
                 #  format, not of the kernel; the 1e-2 bound is a statement about well-scaled activations)
