@@ -52,7 +52,8 @@ int is_egnn_edge_fwd(const int* indptr, const int* csr_src, const int* csr_dst, 
                      const float* W3, const float* b3, const float* w4, int update_coords,
                      float* hn, float* x_out, int64_t n_nodes, int* status, void* stream);
 /* tcgen05 / TMEM variant of is_egnn_edge_fwd: the two per-tile 128x64x64 GEMMs run on the tensor
- * cores.  precision 0 = bf16 operands (fp32 accumulate), 2 = 3xTF32, 3 = bf16x3 (both fp32-accurate);
+ * cores.  precision 0 = bf16 operands (fp32 accumulate), 2 = 3xTF32, 3 = bf16x3, 4 = fp16x2 (fp16 hi / lo operand pairs,
+ * inference forward only, activations beyond +-65504 overflow to inf) -- 2, 3, 4 are fp32-accurate;
  * fast_act != 0 selects the 5-instruction SiLU in the fp32-accurate modes (inference path). */
 int is_egnn_edge_fwd_tc(const int* indptr, const int* csr_src, const int* csr_dst, const int* csr_eid,
                         const float* PQ, const float* x, int64_t ldx, const float* edge_attr,
@@ -69,7 +70,7 @@ int is_egnn_set_ws_variant(int bits);
  * tensor cores (inference path).  W1n/b1n/PQn NULL = nothing follows.  next_kind 1: W1n = edge_mlp.0.weight
  * [64,130] of layer l+1, PQn [n,128].  next_kind 2 (after the last layer): W1n = [Wq;Wk;Wv] [192,64], b1n [192],
  * PQn = QKV [n,192], the projections of the per-graph attention (reference models/layers.py:13-16 / 67-69).
- * precision 0 = bf16, 3 = bf16x3. */
+ * precision 0 = bf16, 3 = bf16x3, 4 = fp16x2 (inference forward). */
 int is_egnn_node_post_pre_tc(const float* h, int64_t ldh, int F, const float* hn, const float* W5, const float* b5,
                              const float* W6, const float* b6, float* h_out, const float* W1n, const float* b1n,
                              float* PQn, int64_t n_nodes, int precision, int fast_act, int next_kind, void* stream);
@@ -157,7 +158,7 @@ int is_loss_bwd(const float* recon, const float* seq, int64_t n_recon, const flo
 /* Single-head per-graph attention + global mean pool on the tensor cores (inference: pooled rows only).  Same
  * result as is_attn_pool_infer with n_head = 1 (reference models/layers.py:13-22 / 67-78 + global_mean_pool,
  * hybrid_models.py:92-97 / 326-331).  QKV [N_total,192], node_off [n_graphs+1], pooled [n_graphs,64]; max_nodes <= 256;
- * precision 0 = bf16, 3 = bf16x3 (fp32-accurate). */
+ * precision 0 = bf16, 3 = bf16x3, 4 = fp16x2 (both fp32-accurate). */
 int is_attn_pool_infer_tc(const float* QKV, const int64_t* node_off, int n_graphs, int max_nodes, int precision,
                           float* pooled, void* stream);
 /* Backward of the pooled-rows-only single-head attention on the tensor cores (bf16x3, fp32-accurate;

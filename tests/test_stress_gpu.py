@@ -18,3 +18,31 @@ def test_stress(script):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", script)], cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.stdout[-3000:] + r.stderr[-3000:])
     assert "failures: 0" in r.stdout
+
+
+@pytest.mark.gpu
+def test_fp16x2_overflow_is_loud_not_silent():
+    """The default no-grad arithmetic splits operands into fp16 pairs: an activation beyond fp16's range (+-65 504) must
+    surface as non-finite output (NaN / inf), never as a finite wrong number; bf16x3 handles the same input exactly."""
+    import torch
+    from immunostruct_b200 import _C
+    from immunostruct_b200.graph import GraphBatch
+    from immunostruct_b200.synthetic import synthetic_graph_arrays
+    dev = "cuda"
+    arr = synthetic_graph_arrays(2, 50, 4, seed=3, device=dev)
+    gb = GraphBatch.from_arrays(*(arr[k] for k in ("x", "src", "dst", "edge_attr", "node_counts", "edge_counts")), max_nodes=50)
+    n = gb.n_nodes
+    g = torch.Generator(device=dev).manual_seed(0)
+    r = lambda *s: torch.randn(*s, device=dev, generator=g) * 0.2
+    W1, W2, b2, W3, b3, w4 = r(64, 130), r(64, 64), r(64), r(64, 64), r(64), r(1, 64)
+    PQ = r(n, 128)
+    PQ[:, 0] = 2.0e5                                   # t1[:, 0] = silu(~4e5) > 65504 on every edge
+    x = arr["x"][:, 20:]
+    out = {}
+    for name, prec in (("fp16x2", _C.PREC_FP16X2), ("bf16x3", _C.PREC_BF16X3)):
+        hn, xo = torch.zeros(n, 64, device=dev), torch.zeros(n, 3, device=dev)
+        _C.egnn_edge_fwd_tc(gb, PQ, x, arr["edge_attr"], 64, W1, W2, b2, W3, b3, w4, True, prec, hn, xo, fast_act=True)
+        out[name] = hn
+    assert bool(torch.isfinite(out["bf16x3"]).all())
+    has_edges = out["bf16x3"].abs().sum(1) > 0
+    assert not bool(torch.isfinite(out["fp16x2"][has_edges]).all(dim=1).any())      # every node with in-edges is flagged by NaN / inf
