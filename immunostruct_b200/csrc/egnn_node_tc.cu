@@ -28,8 +28,13 @@ node_post_pre_tc_kernel(const float* __restrict__ h, int64_t ldh, int F, const f
     constexpr int NW = NT / 32, CQ = NW / 4, CW = 64 / CQ;
     constexpr uint32_t ASPL = C::A_BYTES, WSPL = 6 * C::W_BYTES;          // split-term strides
     extern __shared__ __align__(128) uint8_t smem_raw[];
+    // TWO_BUF (one- and two-term operand splits: the three-term tiles leave no room): a second A-operand buffer, so that h
+    // and hn are staged together (their row loads overlap) and D1 = h W5h^T + hn W5n^T is ONE MMA group with one hand-over
+    // instead of two; the epilogues then alternate between the buffers.
+    constexpr bool TWO_BUF = C::NSPLIT <= 2;
     uint8_t* sA = smem_raw;                                   // [NSPLIT][A_BYTES]
-    uint8_t* sW = sA + C::NSPLIT * ASPL;                      // [NSPLIT][6 blocks][W_BYTES]: W5h W5n W6 | Ws' Wd' - or Wq Wk Wv
+    uint8_t* sA2 = TWO_BUF ? sA + C::NSPLIT * ASPL : sA;      // [NSPLIT][A_BYTES]
+    uint8_t* sW = sA2 + C::NSPLIT * ASPL;                     // [NSPLIT][6 blocks][W_BYTES]: W5h W5n W6 | Ws' Wd' - or Wq Wk Wv
     float* vec = reinterpret_cast<float*>(sW + C::NSPLIT * WSPL);   // b5, b6, next bias (64: b1' for Q' | 192: bq bk bv)
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t s_tmem;
@@ -61,14 +66,14 @@ node_post_pre_tc_kernel(const float* __restrict__ h, int64_t ldh, int F, const f
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem = s_tmem;
-    const uint32_t a_addr = smem_u32(sA), w_addr = smem_u32(sW);
+    const uint32_t a_addr = smem_u32(sA), a2_addr = smem_u32(sA2), w_addr = smem_u32(sW);
     const int q = warp & 3, cq = warp >> 2, erow = 32 * q + lane;
     const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
     const int rsub = lane >> 3, kc8 = lane & 7;
     uint32_t phase = 0;
 
     // stage a [128 x 64] fp32 tile (rows m0.., `ncols` valid columns, row stride ld) as the A operand
-    auto stage_rows = [&](const float* __restrict__ src, int64_t ld, int ncols, int64_t m0) {
+    auto stage_rows = [&](uint8_t* __restrict__ dstA, const float* __restrict__ src, int64_t ld, int ncols, int64_t m0) {
 #pragma unroll
         for (int pass = 0; pass < IS_TM / (4 * NW); ++pass) {
             const int r = pass * 4 * NW + warp * 4 + rsub;
@@ -88,17 +93,18 @@ node_post_pre_tc_kernel(const float* __restrict__ h, int64_t ldh, int F, const f
                     for (int i = 0; i < 8; ++i) v[i] = (8 * kc8 + i < ncols) ? __ldg(rp + i) : 0.0f;
                 }
             }
-            store_operand8<PREC>(sA, ASPL, r, kc8, v);
+            store_operand8<PREC>(dstA, ASPL, r, kc8, v);
         }
     };
-    auto run_gemm = [&](uint32_t tmem_d, int wblock, uint32_t ncols, uint32_t accumulate) {
+    // publish the staged operands, let one elected lane issue `issue_fn` (MMAs of one hand-over) and wait for them
+    auto run_gemms = [&](auto&& issue_fn) {
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
         if (tid < 32) {               // one elected lane of the converged warp issues (bare UTCHMMA, no election loop)
             if (elect_one()) {
                 fence_after_sync();
-                issue_gemm<PREC, !FAST>(tmem_d, a_addr, ASPL, w_addr + wblock * C::W_BYTES, WSPL, ncols, accumulate);
+                issue_fn();
                 mma_commit(&mbar);
             }
             __syncwarp();
@@ -108,15 +114,27 @@ node_post_pre_tc_kernel(const float* __restrict__ h, int64_t ldh, int F, const f
         __syncthreads();
         fence_after_sync();
     };
+    auto run_gemm = [&](uint32_t tmem_d, uint32_t a_tile, int wblock, uint32_t ncols, uint32_t accumulate) {
+        run_gemms([&] { issue_gemm<PREC, !FAST>(tmem_d, a_tile, ASPL, w_addr + wblock * C::W_BYTES, WSPL, ncols, accumulate); });
+    };
 
     const int64_t ntiles = (M + IS_TM - 1) / IS_TM;
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int64_t m0 = t * IS_TM;
         // ---- D1 = h W5h^T + hn W5n^T ---------------------------------------------------------------
-        stage_rows(h, ldh, F, m0);
-        run_gemm(tmem, 0, 64, 0);
-        stage_rows(hn, 64, 64, m0);
-        run_gemm(tmem, 1, 64, 1);
+        if (TWO_BUF) {
+            stage_rows(sA, h, ldh, F, m0);
+            stage_rows(sA2, hn, 64, 64, m0);
+            run_gemms([&] {
+                issue_gemm<PREC, !FAST>(tmem, a_addr, ASPL, w_addr + 0 * C::W_BYTES, WSPL, 64, 0);
+                issue_gemm<PREC, !FAST>(tmem, a2_addr, ASPL, w_addr + 1 * C::W_BYTES, WSPL, 64, 1);
+            });
+        } else {
+            stage_rows(sA, h, ldh, F, m0);
+            run_gemm(tmem, a_addr, 0, 64, 0);
+            stage_rows(sA, hn, 64, 64, m0);
+            run_gemm(tmem, a_addr, 1, 64, 1);
+        }
         // ---- t5 = silu(D1 + b5) -> A operand ; D2 = t5 W6^T -------------------------------------------
         {
             float z[CW];
@@ -129,7 +147,7 @@ node_post_pre_tc_kernel(const float* __restrict__ h, int64_t ldh, int F, const f
                 store_operand8<PREC>(sA, ASPL, erow, (CW / 8) * cq + g, v);
             }
         }
-        run_gemm(tmem + 64, 2, 64, 0);
+        run_gemm(tmem + 64, a_addr, 2, 64, 0);
         // ---- h' = D2 + b6 -> global (+ A operand for the next layer's P/Q) ------------------------------
         {
             float z[CW];
@@ -141,12 +159,12 @@ node_post_pre_tc_kernel(const float* __restrict__ h, int64_t ldh, int F, const f
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = z[8 * g + i] + vec[64 + CW * cq + 8 * g + i];
                 if (m < M) stg256(h_out + m * 64 + CW * cq + 8 * g, v);
-                if (has_next) store_operand8<PREC>(sA, ASPL, erow, (CW / 8) * cq + g, v);
+                if (has_next) store_operand8<PREC>(sA2, ASPL, erow, (CW / 8) * cq + g, v);
             }
         }
         if (has_next && next_kind == 2) {
             // ---- D3 = h' [Wq; Wk; Wv]^T (N = 192: blocks 3..5), written over the dead accumulators D1 / D2 ----
-            run_gemm(tmem, 3, 192, 0);
+            run_gemm(tmem, a2_addr, 3, 192, 0);
             const int64_t m = m0 + erow;
 #pragma unroll
             for (int part = 0; part < 3; ++part) {
@@ -165,7 +183,7 @@ node_post_pre_tc_kernel(const float* __restrict__ h, int64_t ldh, int F, const f
             }
         } else if (has_next) {
             // ---- D3 = h' [Ws'; Wd']^T (N = 128: weight blocks 3 and 4 are contiguous row groups) -------
-            run_gemm(tmem + 128, 3, 128, 0);
+            run_gemm(tmem + 128, a2_addr, 3, 128, 0);
             const int64_t m = m0 + erow;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -195,7 +213,7 @@ static int launch_node_tc2(const float* h, int64_t ldh, int F, const float* hn, 
                           const float* W6, const float* b6, float* h_out, const float* W1n, const float* b1n,
                           float* PQn, int64_t M, cudaStream_t st) {
     using C = TcCfg<PREC>;
-    const size_t smem = (size_t)C::NSPLIT * (C::A_BYTES + 6 * C::W_BYTES) + 5 * 64 * sizeof(float) + 128;
+    const size_t smem = (size_t)C::NSPLIT * ((C::NSPLIT <= 2 ? 2 : 1) * C::A_BYTES + 6 * C::W_BYTES) + 5 * 64 * sizeof(float) + 128;
     cudaError_t e = cudaFuncSetAttribute(node_post_pre_tc_kernel<PREC, NT, FAST, NEXT_KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const int sms = current_num_sms();
