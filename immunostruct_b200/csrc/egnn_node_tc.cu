@@ -26,15 +26,22 @@ node_post_pre_tc_kernel(const float* __restrict__ h, int64_t ldh, int F, const f
     constexpr int next_kind = NEXT_KIND;
     using C = TcCfg<PREC>;
     constexpr int NW = NT / 32, CQ = NW / 4, CW = 64 / CQ;
-    constexpr uint32_t ASPL = C::A_BYTES, WSPL = 6 * C::W_BYTES;          // split-term strides
+    constexpr int NBLK = NEXT_KIND == 2 ? 6 : 5;                          // resident weight blocks
+    constexpr uint32_t ASPL = C::A_BYTES, WSPL = NBLK * C::W_BYTES;       // split-term strides
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // TWO_BUF (one- and two-term operand splits: the three-term tiles leave no room): a second A-operand buffer, so that h
     // and hn are staged together (their row loads overlap) and D1 = h W5h^T + hn W5n^T is ONE MMA group with one hand-over
     // instead of two; the epilogues then alternate between the buffers.
     constexpr bool TWO_BUF = C::NSPLIT <= 2;
-    uint8_t* sA = smem_raw;                                   // [NSPLIT][A_BYTES]
-    uint8_t* sA2 = TWO_BUF ? sA + C::NSPLIT * ASPL : sA;      // [NSPLIT][A_BYTES]
-    uint8_t* sW = sA2 + C::NSPLIT * ASPL;                     // [NSPLIT][6 blocks][W_BYTES]: W5h W5n W6 | Ws' Wd' - or Wq Wk Wv
+    // NTILE (fp16x2: 2) tiles of 128 nodes share every hand-over: a tile's chain is a string of fixed latencies (barriers, MMA
+    // completion, the row loads' round trip) -- shortening its rows by 10 % did not change the kernel's time at all -- so two
+    // tiles per round halve the rounds (800 tiles on 148 CTAs: 6 -> 3) at little extra cost per round.  Needs both tiles'
+    // operand buffers (4 x 32 KB next to 96 KB of weights) and 2 x 256 TMEM columns.
+    constexpr int NTILE = (PREC == PREC_FP16X2 && NEXT_KIND == 1) ? 2 : 1;      // (the six blocks of the QKV tail leave no room)
+    constexpr uint32_t ABUF = C::NSPLIT * ASPL, ASTRIDE = (TWO_BUF ? 2 : 1) * ABUF, TCOLS = 256;
+    uint8_t* sA = smem_raw;                                   // [NTILE][1 or 2 buffers][NSPLIT][A_BYTES]
+    uint8_t* sA2 = TWO_BUF ? sA + ABUF : sA;
+    uint8_t* sW = sA + NTILE * ASTRIDE;                       // [NSPLIT][6 blocks][W_BYTES]: W5h W5n W6 | Ws' Wd' - or Wq Wk Wv
     float* vec = reinterpret_cast<float*>(sW + C::NSPLIT * WSPL);   // b5, b6, next bias (64: b1' for Q' | 192: bq bk bv)
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t s_tmem;
@@ -42,7 +49,7 @@ node_post_pre_tc_kernel(const float* __restrict__ h, int64_t ldh, int F, const f
     const bool has_next = W1n != nullptr;
     const int K5 = F + 64;
 
-    if (warp == 0) tmem_alloc(&s_tmem, 256);
+    if (warp == 0) tmem_alloc(&s_tmem, NTILE * TCOLS);
     if (tid == 32) mbar_init(&mbar, 1);
     // six resident weight blocks (16-byte chunk stores; W5's two K halves, W6, then the "next" weights)
     stage_weight_block<PREC>(sW + 0 * C::W_BYTES, WSPL, W5, K5, 0, F, tid, NT);
@@ -118,94 +125,120 @@ node_post_pre_tc_kernel(const float* __restrict__ h, int64_t ldh, int F, const f
         run_gemms([&] { issue_gemm<PREC, !FAST>(tmem_d, a_tile, ASPL, w_addr + wblock * C::W_BYTES, WSPL, ncols, accumulate); });
     };
 
-    const int64_t ntiles = (M + IS_TM - 1) / IS_TM;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int64_t m0 = t * IS_TM;
+    const int64_t ngroups = (M + NTILE * IS_TM - 1) / (NTILE * IS_TM);
+    for (int64_t t = blockIdx.x; t < ngroups; t += gridDim.x) {
+        const int64_t mg = t * NTILE * IS_TM;                 // first row of this group of NTILE tiles
         // ---- D1 = h W5h^T + hn W5n^T ---------------------------------------------------------------
         if (TWO_BUF) {
-            stage_rows(sA, h, ldh, F, m0);
-            stage_rows(sA2, hn, 64, 64, m0);
+#pragma unroll
+            for (int u = 0; u < NTILE; ++u) {
+                stage_rows(sA + u * ASTRIDE, h, ldh, F, mg + u * IS_TM);
+                stage_rows(sA2 + u * ASTRIDE, hn, 64, 64, mg + u * IS_TM);
+            }
             run_gemms([&] {
-                issue_gemm<PREC, !FAST>(tmem, a_addr, ASPL, w_addr + 0 * C::W_BYTES, WSPL, 64, 0);
-                issue_gemm<PREC, !FAST>(tmem, a2_addr, ASPL, w_addr + 1 * C::W_BYTES, WSPL, 64, 1);
+#pragma unroll
+                for (int u = 0; u < NTILE; ++u) {
+                    issue_gemm<PREC, !FAST>(tmem + u * TCOLS, a_addr + u * ASTRIDE, ASPL, w_addr + 0 * C::W_BYTES, WSPL, 64, 0);
+                    issue_gemm<PREC, !FAST>(tmem + u * TCOLS, a2_addr + u * ASTRIDE, ASPL, w_addr + 1 * C::W_BYTES, WSPL, 64, 1);
+                }
             });
         } else {
-            stage_rows(sA, h, ldh, F, m0);
+            stage_rows(sA, h, ldh, F, mg);
             run_gemm(tmem, a_addr, 0, 64, 0);
-            stage_rows(sA, hn, 64, 64, m0);
+            stage_rows(sA, hn, 64, 64, mg);
             run_gemm(tmem, a_addr, 1, 64, 1);
         }
         // ---- t5 = silu(D1 + b5) -> A operand ; D2 = t5 W6^T -------------------------------------------
-        {
+#pragma unroll
+        for (int u = 0; u < NTILE; ++u) {
             float z[CW];
-            tmem_ld<CW>(t_lane + CW * cq, z);
+            tmem_ld<CW>(t_lane + u * TCOLS + CW * cq, z);
 #pragma unroll
             for (int g = 0; g < CW / 8; ++g) {
                 float v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = act<PREC, FAST>(z[8 * g + i] + vec[CW * cq + 8 * g + i]);
-                store_operand8<PREC>(sA, ASPL, erow, (CW / 8) * cq + g, v);
+                store_operand8<PREC>(sA + u * ASTRIDE, ASPL, erow, (CW / 8) * cq + g, v);
             }
         }
-        run_gemm(tmem + 64, a_addr, 2, 64, 0);
+        run_gemms([&] {
+#pragma unroll
+            for (int u = 0; u < NTILE; ++u)
+                issue_gemm<PREC, !FAST>(tmem + u * TCOLS + 64, a_addr + u * ASTRIDE, ASPL, w_addr + 2 * C::W_BYTES, WSPL, 64, 0);
+        });
         // ---- h' = D2 + b6 -> global (+ A operand for the next layer's P/Q) ------------------------------
-        {
+#pragma unroll
+        for (int u = 0; u < NTILE; ++u) {
             float z[CW];
-            tmem_ld<CW>(t_lane + 64 + CW * cq, z);
-            const int64_t m = m0 + erow;
+            tmem_ld<CW>(t_lane + u * TCOLS + 64 + CW * cq, z);
+            const int64_t m = mg + u * IS_TM + erow;
 #pragma unroll
             for (int g = 0; g < CW / 8; ++g) {
                 float v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = z[8 * g + i] + vec[64 + CW * cq + 8 * g + i];
                 if (m < M) stg256(h_out + m * 64 + CW * cq + 8 * g, v);
-                if (has_next) store_operand8<PREC>(sA2, ASPL, erow, (CW / 8) * cq + g, v);
+                if (has_next) store_operand8<PREC>(sA2 + u * ASTRIDE, ASPL, erow, (CW / 8) * cq + g, v);
             }
         }
         if (has_next && next_kind == 2) {
             // ---- D3 = h' [Wq; Wk; Wv]^T (N = 192: blocks 3..5), written over the dead accumulators D1 / D2 ----
-            run_gemm(tmem, a2_addr, 3, 192, 0);
-            const int64_t m = m0 + erow;
+            run_gemms([&] {
 #pragma unroll
-            for (int part = 0; part < 3; ++part) {
-                float z[CW];
-                tmem_ld<CW>(t_lane + 64 * part + CW * cq, z);
-                if (m < M) {
+                for (int u = 0; u < NTILE; ++u)
+                    issue_gemm<PREC, !FAST>(tmem + u * TCOLS, a2_addr + u * ASTRIDE, ASPL, w_addr + 3 * C::W_BYTES, WSPL, 192, 0);
+            });
 #pragma unroll
-                    for (int g = 0; g < CW / 8; ++g) {
-                        const int c = 64 * part + CW * cq + 8 * g;
-                        float o[8];
+            for (int u = 0; u < NTILE; ++u) {
+                const int64_t m = mg + u * IS_TM + erow;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) o[i] = z[8 * g + i] + vec[128 + c + i];
-                        stg256(PQn + m * 192 + c, o);
+                for (int part = 0; part < 3; ++part) {
+                    float z[CW];
+                    tmem_ld<CW>(t_lane + u * TCOLS + 64 * part + CW * cq, z);
+                    if (m < M) {
+#pragma unroll
+                        for (int g = 0; g < CW / 8; ++g) {
+                            const int c = 64 * part + CW * cq + 8 * g;
+                            float o[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) o[i] = z[8 * g + i] + vec[128 + c + i];
+                            stg256(PQn + m * 192 + c, o);
+                        }
                     }
                 }
             }
         } else if (has_next) {
             // ---- D3 = h' [Ws'; Wd']^T (N = 128: weight blocks 3 and 4 are contiguous row groups) -------
-            run_gemm(tmem + 128, a2_addr, 3, 128, 0);
-            const int64_t m = m0 + erow;
+            run_gemms([&] {
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                float z[CW];
-                tmem_ld<CW>(t_lane + 128 + 64 * half + CW * cq, z);
-                if (m < M) {
+                for (int u = 0; u < NTILE; ++u)
+                    issue_gemm<PREC, !FAST>(tmem + u * TCOLS + 128, a2_addr + u * ASTRIDE, ASPL, w_addr + 3 * C::W_BYTES, WSPL, 128, 0);
+            });
 #pragma unroll
-                    for (int g = 0; g < CW / 8; ++g) {
-                        const int c = CW * cq + 8 * g;
-                        float o[8];
+            for (int u = 0; u < NTILE; ++u) {
+                const int64_t m = mg + u * IS_TM + erow;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) o[i] = z[8 * g + i] + (half ? vec[128 + c + i] : 0.0f);
-                        stg256(PQn + m * 128 + 64 * half + c, o);
+                for (int half = 0; half < 2; ++half) {
+                    float z[CW];
+                    tmem_ld<CW>(t_lane + u * TCOLS + 128 + 64 * half + CW * cq, z);
+                    if (m < M) {
+#pragma unroll
+                        for (int g = 0; g < CW / 8; ++g) {
+                            const int c = CW * cq + 8 * g;
+                            float o[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) o[i] = z[8 * g + i] + (half ? vec[128 + c + i] : 0.0f);
+                            stg256(PQn + m * 128 + 64 * half + c, o);
+                        }
                     }
                 }
             }
         }
-        fence_before_sync();      // TMEM reads of this tile are ordered before the next tile's MMAs
+        fence_before_sync();      // TMEM reads of this group are ordered before the next group's MMAs
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 256);
+    if (warp == 0) tmem_dealloc(tmem, NTILE * TCOLS);
 }
 
 template <int PREC, int NT, bool FAST, int NEXT_KIND>
@@ -213,11 +246,13 @@ static int launch_node_tc2(const float* h, int64_t ldh, int F, const float* hn, 
                           const float* W6, const float* b6, float* h_out, const float* W1n, const float* b1n,
                           float* PQn, int64_t M, cudaStream_t st) {
     using C = TcCfg<PREC>;
-    const size_t smem = (size_t)C::NSPLIT * ((C::NSPLIT <= 2 ? 2 : 1) * C::A_BYTES + 6 * C::W_BYTES) + 5 * 64 * sizeof(float) + 128;
+    constexpr int NTILE = (PREC == PREC_FP16X2 && NEXT_KIND == 1) ? 2 : 1;        // tiles per hand-over (see the kernel)
+    constexpr int NBLK = NEXT_KIND == 2 ? 6 : 5;
+    const size_t smem = (size_t)C::NSPLIT * (NTILE * (C::NSPLIT <= 2 ? 2 : 1) * C::A_BYTES + NBLK * C::W_BYTES) + 5 * 64 * sizeof(float) + 128;
     cudaError_t e = cudaFuncSetAttribute(node_post_pre_tc_kernel<PREC, NT, FAST, NEXT_KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const int sms = current_num_sms();
-    int64_t tiles = (M + IS_TM - 1) / IS_TM;
+    int64_t tiles = (M + NTILE * IS_TM - 1) / (NTILE * IS_TM);
     int64_t cap = (int64_t)sms * (NT == 256 ? 2 : 1);
     int grid = (int)(tiles < cap ? tiles : cap);
     node_post_pre_tc_kernel<PREC, NT, FAST, NEXT_KIND><<<grid < 1 ? 1 : grid, NT, smem, st>>>(h, ldh, F, hn, W5, b5, W6, b6, h_out, W1n, b1n, PQn, M);
