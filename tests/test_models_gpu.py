@@ -178,6 +178,31 @@ def test_bf16_mode_within_1e_2_of_fp32_reference():
     assert worst[1] <= 1e-2, worst
 
 
+def test_precision_modes_agree_at_the_full_batch():
+    """Batch 512 (the benchmark batch), no-grad forward: the default fp16x2 arithmetic, bf16x3, tf32x3 and the fp32 SIMT
+    kernels are four independent roundings of the same computation -- logits, reconstruction and latent statistics of all
+    512 graphs must agree within the fp32 tolerance (the oracle comparison above runs at batch 8)."""
+    b = 512
+    arr, dense, model, eps = _bench_shape_case(b, seed=13)
+    model = model.to(DEV).eval()
+    seq, prop = _d(dense["seq"]), _d(dense["prop"])
+    gb = graph_batch(arr, DEV)
+    default_precision = I.get_precision()
+    outs = {}
+    try:
+        with torch.no_grad():
+            for prec in ("fp32", "fp16x2", "bf16x3", "tf32x3"):
+                I.set_precision(prec)
+                inject_eps(model, eps)
+                outs[prec] = [t.clone() for t in model(gb, seq, prop)]
+    finally:
+        I.set_precision(default_precision)
+    for prec in ("fp16x2", "bf16x3", "tf32x3"):
+        for a, ref, what in zip(outs[prec], outs["fp32"], ("recon", "mu", "logvar", "logits")):
+            assert bool(torch.isfinite(a).all())
+            assert rel_err(a, ref) < TOL, (prec, what, rel_err(a, ref))
+
+
 def test_full_batch_properties():
     """Batch 512 (BASELINE inference batch): bit-determinism, edge-order invariance within tolerance,
     per-graph independence (a graph's output does not depend on its batch neighbours)."""
