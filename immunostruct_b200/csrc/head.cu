@@ -175,14 +175,28 @@ head_infer_kernel(const float* __restrict__ pooled, const float* __restrict__ Wc
         for (int idx = tid; idx < L * H; idx += IS_THREADS) {
             const int i = idx / H, h = idx - i * H;
             const float gamma = coef[h] * c[i] + coef[H + h];
-            const float mx = gamma > 0.0f ? gamma * cmax : gamma * cmin;
-            float Z = 0.0f, S1 = 0.0f;
-            for (int j = 0; j < L; ++j) {
-                const float cj = c[j];
-                const float e = exp_comp(gamma * cj - mx);
-                Z += e; S1 = fmaf(e, cj, S1);
+            // inference-only kernel: 2^(g2 c_j - m2) with ex2.approx, g2 = gamma log2 e (one FFMA + one MUFU per term; the
+            // rounding of g2 moves an exponent of magnitude <= ~20 by ~1e-6, an order below the 1e-5 parity bound, as in the
+            // fast SiLU of the inference EGNN kernels); two independent accumulator pairs
+            const float g2 = gamma * 1.4426950408889634f;
+            const float m2 = gamma > 0.0f ? g2 * cmax : g2 * cmin;
+            float Z0 = 0.0f, S0 = 0.0f, Z1 = 0.0f, S1 = 0.0f;
+            int j = 0;
+            for (; j + 1 < L; j += 2) {
+                const float c0 = c[j], c1 = c[j + 1];
+                float e0, e1;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(g2, c0, -m2)));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(g2, c1, -m2)));
+                Z0 += e0; S0 = fmaf(e0, c0, S0);
+                Z1 += e1; S1 = fmaf(e1, c1, S1);
             }
-            Eh[idx] = S1 / Z;
+            if (j < L) {
+                const float c0 = c[j];
+                float e0;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(g2, c0, -m2)));
+                Z0 += e0; S0 = fmaf(e0, c0, S0);
+            }
+            Eh[idx] = (S0 + S1) / (Z0 + Z1);
         }
         __syncthreads();
         for (int i = tid; i < L; i += IS_THREADS) {
