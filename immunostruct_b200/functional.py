@@ -19,12 +19,13 @@ H = 64   # hidden width of the EGNN MLPs and of the node embedding (hybrid_model
 # fp32-accurate bf16x3 split in every mode except "fp32" (which keeps the fp32 SIMT backward):
 #   "fp32"   : fp32 SIMT FMA kernels (csrc/egnn.cu)
 #   "bf16x3" : tcgen05 tensor cores, operands split into three bf16 terms, six partial products --
-#              fp32-accurate, two CTAs per SM (csrc/egnn_tc.cu); the default
+#              fp32-accurate (csrc/egnn_tc2.cu); what training runs in every tensor-core mode but "bf16"
 #   "tf32x3" : tcgen05 tensor cores with the 3xTF32 split -- fp32-accurate, one 512-thread CTA per SM
 #   "bf16"   : tcgen05 tensor cores, bf16 operands, fp32 accumulate, fast SiLU (1e-2 tolerance mode)
-# "fp16x2": the EGNN FORWARD of the no-grad path on fp16 hi / lo operand pairs (fp32-accurate to 2^-22, two thirds of the
-# operand bytes and half the MMAs of "bf16x3"; activations beyond +-65504 overflow to inf / NaN) -- everything else (training
-# forward and backward, attention, the dense layers) runs as in "bf16x3"
+#   "fp16x2" : THE DEFAULT.  The EGNN stack and the attention scores of the NO-GRAD forward on fp16 hi / lo operand pairs
+#              (fp32-accurate to 2^-22, two thirds of the operand bytes and half the MMAs of "bf16x3"; activations beyond
+#              +-65504 overflow to inf / NaN) -- everything else (training forward and backward, the dense layers) runs as
+#              in "bf16x3"
 _PRECISIONS = {"fp32": None, "bf16x3": _C.PREC_BF16X3, "tf32x3": _C.PREC_TF32X3, "bf16": _C.PREC_BF16, "fp16x2": _C.PREC_FP16X2}
 _precision = "fp16x2"
 
