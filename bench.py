@@ -664,36 +664,24 @@ def main():
     if world == 1 and not args.no_train:
         model.train()
         try:
-            arr_s = {k: pool[0][0][k].clone() for k in keys}
-            den_s = {k: v.clone() for k, v in pool[0][1].items()}
             opt_g = I.FusedAdam(model.parameters(), lr=1e-3, capturable=True)
-            loss_s = torch.zeros((), device=dev)
 
-            def graph_body():
-                gb = GraphBatch.from_arrays(*(arr_s[k] for k in keys), max_nodes=N_NODES)
+            def graph_body(t):
+                gb = GraphBatch.from_arrays(*(t[k] for k in keys), max_nodes=N_NODES)
                 opt_g.zero_grad(set_to_none=True)
-                recon, mu, logvar, out = model(gb, den_s["seq"], den_s["prop"])
-                loss = losses.BCE_loss(recon, den_s["seq"], mu, logvar, out, den_s["target"])
+                recon, mu, logvar, out = model(gb, t["seq"], t["prop"])
+                loss = losses.BCE_loss(recon, t["seq"], mu, logvar, out, t["target"])
                 loss.backward()
                 opt_g.step()
-                loss_s.copy_(loss.detach())
+                return loss
 
-            side = torch.cuda.Stream(dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
-                for _ in range(3):
-                    graph_body()
-            torch.cuda.current_stream(dev).wait_stream(side)
-            cg = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(cg):
-                graph_body()
+            captured = I.CapturedStep(graph_body, {**{k: pool[0][0][k] for k in keys},
+                                                   **{k: pool[0][1][k] for k in ("seq", "prop", "target")}})
+            loss_s = None
 
             def graph_step(arr, dense):
-                for k in keys:
-                    arr_s[k].copy_(arr[k])
-                for k in ("seq", "prop", "target"):
-                    den_s[k].copy_(dense[k])
-                cg.replay()
+                nonlocal loss_s
+                loss_s = captured({**{k: arr[k] for k in keys}, **{k: dense[k] for k in ("seq", "prop", "target")}})
 
             for i in range(wt):
                 graph_step(*pool[i % POOL])
@@ -706,8 +694,8 @@ def main():
             barrier()
             ms_g = e0.elapsed_time(e1)
             train["cuda_graph"] = {"value": B * kt / (ms_g / 1e3), "unit": "graphs/s", "ms_per_step": ms_g / kt,
-                                   "final_loss": float(loss_s), "note": "whole step (collation, fwd, loss, bwd, FusedAdam capturable) captured once, inputs copied into static buffers per step"}
-            del cg
+                                   "final_loss": float(loss_s), "note": "immunostruct_b200.CapturedStep: whole step (collation, fwd, loss, bwd, FusedAdam capturable) captured once, inputs copied into static buffers per step"}
+            del captured
         except Exception as exc:                      # capture is an optimisation: report, never fail the bench
             train["cuda_graph"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
             print("cuda graph capture failed:", repr(exc), file=sys.stderr)

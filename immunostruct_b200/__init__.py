@@ -11,6 +11,7 @@ from .loader import DevicePrefetcher  # noqa: F401
 from .packed import PackedGraphBatch, PackedGraphDataset, PackedSequence, pack_graph_batch, pack_sequence  # noqa: F401
 from .optim import FusedAdam, FusedAdamW  # noqa: F401
 from .augment import TrainAugment  # noqa: F401
+from .graphed import CapturedStep  # noqa: F401
 from . import augment, dataloading, nn, optim, ops  # noqa: F401
 from .ops import use_custom_ops  # noqa: F401
 from .functional import invalidate_caches  # noqa: F401

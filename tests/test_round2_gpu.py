@@ -392,3 +392,49 @@ def test_linear_tc_autograd_matches_fp64(b, k, n, relu):
         y2 = IF.linear_tc(xd, wd, bd, False)
     assert _weight_planes[id(wd)][0] != key0
     close(y2, torch.nn.functional.linear(x64, 2 * w64, b64), 1e-5, "linear_tc after in-place update")
+
+
+@pytest.mark.gpu
+def test_captured_step_reproduces_eager_steps():
+    """immunostruct_b200.CapturedStep (whole training step -- collation, forward, loss, backward, capturable FusedAdam -- in one
+    CUDA graph) against the same steps run eagerly: same losses and same parameters after warm-up + 3 steps on new batches
+    (dropout off and a fixed reparameterisation draw, so both runs are deterministic functions of the data)."""
+    from immunostruct_b200.synthetic import synthetic_dense
+    dev = "cuda"
+    keys = ("x", "src", "dst", "edge_attr", "node_counts", "edge_counts")
+    batches = []
+    for s in range(4):
+        arr = synthetic_graph_arrays(16, 60, 6, seed=40 + s, device=dev)
+        den = synthetic_dense(16, seed=40 + s, device=dev)
+        batches.append({**{k: arr[k] for k in keys}, "seq": den["seq"], "prop": den["prop"], "target": den["target"]})
+    eps = torch.randn(16, 32, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+    losses = I.Losses(5943, [0.81, 0.19], sequence=True)
+
+    def make():
+        torch.manual_seed(11)
+        model = I.model_map["HybridModelv2"](vae_input_dim=5943, device=dev).to(dev).eval()      # eval(): dropout off; autograd on
+        model.sample_eps = lambda like: eps.to(like.dtype)
+        opt = FusedAdam(model.parameters(), lr=1e-3, capturable=True)
+
+        def body(t):
+            gb = GraphBatch.from_arrays(*(t[k] for k in keys), max_nodes=60)
+            opt.zero_grad(set_to_none=True)
+            recon, mu, logvar, out = model(gb, t["seq"], t["prop"])
+            loss = losses.BCE_loss(recon, t["seq"], mu, logvar, out, t["target"])
+            loss.backward()
+            opt.step()
+            return loss
+        return model, body
+
+    model_e, body_e = make()
+    for _ in range(3):
+        body_e(batches[0])
+    eager = [float(body_e(b)) for b in batches[1:]]
+    model_c, body_c = make()
+    step = I.CapturedStep(body_c, batches[0], warmup=3)
+    assert step.warmup_steps == 3
+    captured = [float(step(b)) for b in batches[1:]]
+    for a, c in zip(eager, captured):
+        assert abs(a - c) <= 1e-6 * max(1.0, abs(a)), (eager, captured)
+    for (k, pe), (_, pc) in zip(model_e.named_parameters(), model_c.named_parameters()):
+        assert torch.allclose(pe, pc, rtol=1e-6, atol=1e-8), k
