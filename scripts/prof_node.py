@@ -9,7 +9,7 @@ g = torch.Generator(device=dev).manual_seed(0)
 r = lambda *s: torch.randn(*s, device=dev, generator=g) * 0.2
 W5, b5, W6, b6, W1n, b1n = r(64, 128), r(64), r(64, 64), r(64), r(64, 130), r(64)
 flush = torch.empty(64 * 1024 * 1024, device=dev)
-for prec in (_C.PREC_BF16X3, _C.PREC_BF16):
+for prec in (_C.PREC_FP16X2, _C.PREC_BF16X3, _C.PREC_BF16):
     for tiles_per_sm in (1, 2, 4, 5.4, 8, 16):
         n = int(128 * 148 * tiles_per_sm) if tiles_per_sm != 5.4 else 102400
         h, hn = r(n, 64), r(n, 64)
